@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py — ensemble trajectory-steps/s of the time-stepping hot path on N B200s (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lorenz_rk4|vdp_dopri5|heat_rk4] [--arith strict|fast]
+  python bench.py --impl reference ...      # the CPU restatement of the reference path on the host cores
+
+A "step" is ONE pass of the hot path over ONE batch: one kernel launch that advances every trajectory of a
+10^6-trajectory ensemble by one RK step (lorenz_rk4) / one adaptive attempt (vdp_dopri5), or one RK4 step of the
+2^26-point heat state (heat_rk4, 4 stage launches). The device-resident number (`value`) rotates over enough independent
+batches that the working set exceeds the 126 MB L2, so every launch streams its state from HBM. `e2e` is the same metric
+through the public API with HOST buffers: per e2e step one whole solve of the named config (upload from pinned memory,
+integrate, download) — see DESIGN.md §Measurement.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAJ = 1_000_000
+L2_MB = 126
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+class LorenzRK4:
+    name = "lorenz_rk4"
+    label = "config 2: fixed-step RK4, 10^6 Lorenz-63 trajectories per batch, f64, h=1e-3"
+    bytes_per_unit = 48.0  # read state + write state, 2*d*8
+    unit_name = "trajectory-step"
+    state_mb = 24
+    steps_per_solve = 1001  # t in [0,1], h = 1e-3: 1000 steps + the remainder step
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        self.vo, self.ctx = vo, ctx
+        self.tableau = vo.ButcherTableu.builtin("RK4")
+        self.rhs = vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+        first = rank * N_TRAJ
+        self.x0_host = vo.workloads.lorenz_x0(N_TRAJ, first=first)
+        self.x0 = vo.Ensemble.from_host(ctx, self.x0_host)
+        self.solvers = [vo.RK45Solver(self.rhs, 0.0, 1.0e9, self.x0, 1e-3, tableau=self.tableau) for _ in range(n_batches)]
+        vo.step_many(self.solvers, False, 1)  # the first call of every solver is the Chkpt event at t0 (no launch)
+
+    def run_steps(self, k):
+        nb = len(self.solvers)
+        if k >= nb:
+            self.vo.step_many(self.solvers, False, k // nb)
+        if k % nb:
+            self.vo.step_many(self.solvers[: k % nb], False, 1)
+
+    def units(self, k):
+        return float(k) * N_TRAJ
+
+    def e2e_setup(self):
+        import torch
+        self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_x0 = self.vo.Ensemble(self.ctx, 3, N_TRAJ)
+        self.e_solver = self.vo.RK45Solver(self.rhs, 0.0, 1.0, self.e_x0, 1e-3, tableau=self.tableau)
+
+    def e2e_step(self):
+        self.e_x0.upload(self.pin_in.numpy(), "aos")       # H2D from pinned memory (+ AoS->SoA on the device)
+        self.e_solver.reset(self.e_x0)
+        st = self.e_solver.run()
+        self.e_solver.current()[1].to_host("aos", out=self.pin_out.numpy())  # D2H of the result
+        return float(st.counts["Step"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
+
+
+class VdpDopri5:
+    name = "vdp_dopri5"
+    label = "config 3: adaptive DoPri5, 10^6 Van der Pol oscillators per batch (mu sweep 0.5..20), rtol 1e-6, per-trajectory control"
+    bytes_per_unit = 80.0  # state in/out + t,h,prev_h in/out
+    unit_name = "attempted trajectory-step"
+    state_mb = 60
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        self.vo, self.ctx = vo, ctx
+        self.tableau = vo.ButcherTableu.builtin("DOPRI5")
+        n_total = N_TRAJ * world
+        self.mu = vo.workloads.vdp_mu(n_total, N_TRAJ, rank * N_TRAJ)
+        self.rhs = vo.Rhs(ctx, "VDP", 2, [self.mu])
+        self.x0_host = vo.workloads.vdp_x0(N_TRAJ)
+        self.x0 = vo.Ensemble.from_host(ctx, self.x0_host)
+        self.solvers = [vo.RK45Solver(self.rhs, 0.0, 1.0e9, self.x0, 1e-3, tableau=self.tableau).with_tolerance(1e-6, 1e-6)
+                        for _ in range(n_batches)]
+        vo.step_many(self.solvers, True, 1)
+        self._attempts0 = None
+
+    def run_steps(self, k):
+        nb = len(self.solvers)
+        if k >= nb:
+            self.vo.step_many(self.solvers, True, k // nb)
+        if k % nb:
+            self.vo.step_many(self.solvers[: k % nb], True, 1)
+
+    def attempts(self):
+        tot = 0
+        for s in self.solvers:
+            st = s.stats()
+            tot += int(st["accepted"].sum()) + int(st["rejected"].sum())
+        return tot
+
+    def units(self, k):
+        return float(k) * N_TRAJ  # every lane is live (tf = 1e9): one attempt per trajectory per sweep
+
+    def e2e_setup(self):
+        import torch
+        self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_x0 = self.vo.Ensemble(self.ctx, 2, N_TRAJ)
+        self.e_solver = self.vo.RK45Solver(self.rhs, 0.0, 20.0, self.e_x0, 1e-3, tableau=self.tableau).with_tolerance(1e-6, 1e-6)
+
+    def e2e_step(self):
+        self.e_x0.upload(self.pin_in.numpy(), "aos")
+        self.e_solver.reset(self.e_x0)
+        st = self.e_solver.run(adaptive=True)
+        self.e_solver.current()[1].to_host("aos", out=self.pin_out.numpy())
+        return float(st.counts["Step"] + st.counts["Reject"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
+
+
+class HeatRK4:
+    name = "heat_rk4"
+    label = "config 4: RK4 on the semi-discretised 1-D heat equation, one state of 2^26 points, stage path"
+    bytes_per_unit = 104.0  # 13 vector passes x 8 B per grid-point-step
+    unit_name = "grid-point-step"
+    state_mb = 512
+    D = 1 << 26
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        self.vo, self.ctx = vo, ctx
+        self.tableau = vo.ButcherTableu.builtin("RK4")
+        self.rhs = vo.Rhs(ctx, "HEAT1D", self.D, [1.0])
+        self.x0_host = vo.workloads.heat_u0(self.D)[None, :]
+        self.x0 = vo.Ensemble.from_host(ctx, self.x0_host)
+        self.solvers = [vo.RK45Solver(self.rhs, 0.0, 1.0e9, self.x0, 0.25, tableau=self.tableau)]
+        self.solvers[0].step()
+
+    def run_steps(self, k):
+        self.vo.step_many(self.solvers, False, k)
+
+    def units(self, k):
+        return float(k) * self.D
+
+    def e2e_setup(self):
+        import torch
+        self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_x0 = self.vo.Ensemble(self.ctx, self.D, 1)
+        self.e_solver = self.vo.RK45Solver(self.rhs, 0.0, 25.0, self.e_x0, 0.25, tableau=self.tableau)
+
+    def e2e_step(self):
+        self.e_x0.upload(self.pin_in.numpy(), "soa")
+        self.e_solver.reset(self.e_x0)
+        st = self.e_solver.run()
+        self.e_solver.current()[1].to_host("soa", out=self.pin_out.numpy())
+        return float(st.counts["Step"]) * self.D, self.pin_in.numel() * 8, self.pin_out.numel() * 8
+
+
+WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle in the reference's un-fused shape (one solver object per trajectory), all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_run(workload, n_traj, n_steps, threads):
+    """Returns (units, seconds) for n_traj trajectories x n_steps RK steps (or attempts) on the host."""
+    from oracle import oracle_lib as ol
+    import vecode_b200 as vo
+    if workload == "lorenz_rk4":
+        x0 = vo.workloads.lorenz_x0(n_traj)
+        params = np.tile(vo.workloads.LORENZ_PARAMS, (n_traj, 1))
+        t0 = time.perf_counter()
+        r = ol.rk_ensemble("LORENZ63", params, ol.builtin_tableau(1), 0.0, 1.0e9, x0, 1e-3, n_threads=threads, max_calls=n_steps + 1)
+        dt = time.perf_counter() - t0
+        return float(r["accepted"].sum()), dt
+    if workload == "vdp_dopri5":
+        mu = vo.workloads.vdp_mu(N_TRAJ)[:: max(1, N_TRAJ // n_traj)][:n_traj]
+        x0 = vo.workloads.vdp_x0(len(mu))
+        t0 = time.perf_counter()
+        r = ol.rk_ensemble("VDP", mu[:, None], ol.builtin_tableau(2), 0.0, 1.0e9, x0, 1e-3, n_threads=threads, adaptive=True, rtol=1e-6,
+                           max_calls=n_steps + 1)
+        dt = time.perf_counter() - t0
+        return float(r["accepted"].sum() + r["rejected"].sum()), dt
+    if workload == "heat_rk4":
+        d = n_traj  # here: grid points
+        u0 = vo.workloads.heat_u0(d)
+        t0 = time.perf_counter()
+        _, out, _ = ol.rk_solve("HEAT1D", [1.0], ol.builtin_tableau(1), 0.0, 1.0e9, u0, 0.25, max_calls=n_steps + 1)
+        dt = time.perf_counter() - t0
+        return float(out.n_accept) * d, dt
+    raise KeyError(workload)
+
+
+def cpu_baseline(workload, budget_s=12.0):
+    from oracle import oracle_lib as ol
+    threads = ol.hardware_threads() if workload != "heat_rk4" else 1
+    if workload == "heat_rk4":
+        n, steps = 1 << 20, 2
+    else:
+        n, steps = 64 * threads, 50
+    units, dt = cpu_run(workload, n, steps, threads)  # calibration
+    rate = units / max(dt, 1e-6)
+    target = budget_s * rate  # units of work that fill the budget
+    if workload == "heat_rk4":
+        steps = int(min(40, max(2, target / n)))
+    else:
+        steps = 1000
+        n = int(min(N_TRAJ, max(n, target / steps)))
+    units, dt = cpu_run(workload, n, steps, threads)
+    what = f"{n} grid points x {steps} RK4 steps" if workload == "heat_rk4" else f"{n} trajectories x {steps} calls of step()"
+    return {"value": units / dt, "unit": f"{WORKLOADS[workload].unit_name}s/s", "cores": threads, "kind": "port",
+            "sample": f"{what}, one solver object per trajectory, un-fused LinearCombination passes ({dt:.1f} s)"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path. The crate is Rust and cannot be compiled in
+    this image, so this times the source-faithful C++ restatement (oracle/) with all host threads."""
+    if rank != 0:
+        return
+    from oracle import oracle_lib as ol
+    wl = args.workload
+    threads = ol.hardware_threads() if wl != "heat_rk4" else 1
+    total = args.steps + args.warmup
+    per_step_budget = min(0.5, 90.0 / max(total, 1))
+    if wl == "heat_rk4":
+        n, inner = 1 << 18, 1
+    else:
+        n, inner = 32 * threads, 20
+    units, dt = cpu_run(wl, n, inner, threads)
+    rate = units / max(dt, 1e-6)
+    grow = max(1.0, per_step_budget * rate / units)
+    n = int(min(N_TRAJ if wl != "heat_rk4" else (1 << 24), n * grow))
+    for _ in range(args.warmup):
+        cpu_run(wl, n, inner, threads)
+    tot_units, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        u, _ = cpu_run(wl, n, inner, threads)
+        tot_units += u
+    el = time.perf_counter() - t0
+    W = WORKLOADS[wl]
+    val = tot_units / el
+    sample = (f"each step = {n} {'grid points' if wl == 'heat_rk4' else 'trajectories'} x {inner} RK step(s) of the C++ restatement "
+              f"(one solver object per trajectory, un-fused passes)")
+    line = {"impl": "reference", "metric": "ensemble trajectory-steps/sec", "value": val, "unit": f"{W.unit_name}s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "what": W.label, "arith": "reference order (no FMA)"},
+            "cpu_baseline": {"value": val, "unit": f"{W.unit_name}s/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": f"{W.unit_name}s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lorenz_rk4", choices=sorted(WORKLOADS))
+    ap.add_argument("--arith", default="strict", choices=["strict", "fast"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--events-per-launch", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workload summary")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import vecode_b200 as vo
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = vo.Context.on_torch_stream(local, arith=args.arith)
+    W = WORKLOADS[args.workload]
+    n_batches = 1 if W is HeatRK4 else max(2, -(-3 * L2_MB // W.state_mb))  # working set >= 3x L2
+    w = W(vo, ctx, rank, world, n_batches)
+    for s in w.solvers:
+        s.set_events_per_launch(args.events_per_launch)
+
+    def timed(k):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = ctx.launch_count
+        ev0.record()
+        w.run_steps(k)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timed(args.warmup)
+    t_wall0 = time.time()
+    ms, launches = timed(args.steps)
+    # keep the same load up until the clock sampler has seen it (short timed regions are over before the first sample)
+    while time.time() - t_wall0 < 0.6:
+        w.run_steps(max(args.steps // 4, 16))
+        torch.cuda.synchronize()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    units_per_rank = w.units(args.steps) * args.events_per_launch
+    value = units_per_rank * world / (ms * 1e-3)
+    peak, peak_src = peaks()
+    launches_per_step = launches / max(args.steps, 1)
+    # dominant kernel: the step kernel itself (lorenz/vdp: the only launch; heat: 4 stage launches share the step evenly)
+    kernel_ms = ms / max(launches, 1)
+    bytes_per_launch = W.bytes_per_unit * (units_per_rank / max(launches, 1)) / args.events_per_launch
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
+                "peak_source": peak_src, "algorithmic_bytes_per_unit": W.bytes_per_unit, "kernel_us": kernel_ms * 1e3,
+                "note": "achieved = algorithmic bytes per launch / mean launch duration (CUDA events over the timed region, kernels back to back)"}
+
+    # ---- end to end through the public API with host buffers -----------------------------------------------------------
+    w.e2e_setup()
+    w.e2e_step()  # warm
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e_units, h2d, d2h = 0.0, 0, 0
+    for _ in range(args.e2e_steps):
+        u, h2d, d2h = w.e2e_step()
+        e_units += u
+    e1.record()
+    barrier()
+    e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+        u = torch.tensor([e_units], device="cuda", dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)  # the final reduction of the per-rank counters (NCCL over NVLink)
+        e_units = float(u.item())
+    e2e = {"value": e_units / (e_ms * 1e-3), "unit": f"{W.unit_name}s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
+           "what": "per e2e step: upload x0 from pinned host memory, one whole solve of the config through RK45Solver.run(), download the final state"}
+
+    also = None
+    if rank == 0 and world == 1 and not args.no_also and args.workload == "lorenz_rk4":
+        del w
+        also = {}
+        try:
+            w2 = VdpDopri5(vo, ctx, 0, 1, 6)
+            w2.run_steps(60)
+            torch.cuda.synchronize()
+            a0 = w2.attempts()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            w2.run_steps(1200)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms2 = ev0.elapsed_time(ev1)
+            att = w2.attempts() - a0
+            also["vdp_dopri5"] = {"value": att / (ms2 * 1e-3), "unit": "attempted trajectory-steps/s", "kernel_us": ms2 / 1200 * 1e3,
+                                  "hbm_gbs_algorithmic": 80.0 * att / (ms2 * 1e-3) / 1e9, "frac_of_peak": 80.0 * att / (ms2 * 1e-3) / 1e9 / peak}
+            del w2
+        except Exception as e:  # secondary figure only
+            also["vdp_dopri5"] = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args.workload)
+
+    if rank == 0:
+        line = {"metric": "ensemble trajectory-steps/sec", "value": value, "unit": f"{W.unit_name}s/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": N_TRAJ if W is not HeatRK4 else 1,
+                           "arith": args.arith, "events_per_launch": args.events_per_launch,
+                           "l2": f"{n_batches} independent batches of {W.state_mb} MB rotated per GPU (> {L2_MB} MB L2), so each launch streams from HBM"
+                           if W is not HeatRK4 else "state 512 MB per buffer > 126 MB L2",
+                           "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if also:
+            line["also"] = also
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+/* vecode_b200.h — C ABI of the B200-native batched ODE time-stepping engine.
+ *
+ * Drop-in boundary for the time-stepping path of hmunozb/vec-ode. Each entry point names the reference
+ * interface it replaces (paths relative to the crate root). Plain pointers and sizes only; every function
+ * returns an int32 status (0 = ok, < 0 = error) and never aborts or throws across the boundary; the
+ * message that the reference would put in `ODEError.msg` or a panic is available from vo_last_error().
+ *
+ * One `vo_ctx` = one CUDA device + one stream. Calls on a ctx are not re-entrant; different ctxs may be
+ * driven from different threads / processes (one process per GPU is the multi-GPU model).
+ *
+ * Data model: an ensemble (`vo_ens`) is N independent state vectors of dimension d stored
+ * structure-of-arrays, element (c, i) at `ptr[c * N + i]` (component c of trajectory i), f64. A single
+ * large state is the N = 1 case. Where the reference owns one solver object per trajectory, a
+ * `vo_solver` owns the whole ensemble and carries the per-trajectory controller state (t, h, prev_h,
+ * tgt_t, counters) on the device.
+ */
+#ifndef VECODE_B200_H
+#define VECODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VO_VERSION 100
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+#define VO_OK 0
+#define VO_ERR_BAD_ARG (-1)      /* precondition that panics in the reference (ode.rs:269,290,300; lc.rs:21-26) */
+#define VO_ERR_SHAPE (-2)        /* mismatched ensemble shapes / stage counts (rk.rs:106-108) */
+#define VO_ERR_CUDA (-3)
+#define VO_ERR_ALLOC (-4)
+#define VO_ERR_NOT_ADAPTIVE (-5) /* step_adaptive on a solver without x_err (ode.rs:312, rk.rs:317-319) */
+#define VO_ERR_UNSUPPORTED (-6)
+#define VO_ERR_STATE (-7)
+
+typedef struct vo_ctx_s* vo_ctx;
+typedef struct vo_ens_s* vo_ens;
+typedef struct vo_tableau_s* vo_tableau;
+typedef struct vo_rhs_s* vo_rhs;
+typedef struct vo_solver_s* vo_solver;
+typedef struct vo_split_s* vo_split;
+typedef struct vo_expsolver_s* vo_expsolver;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
+ * let the ctx create its own non-blocking stream. */
+int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out);
+int32_t vo_ctx_destroy(vo_ctx ctx);
+int32_t vo_ctx_sync(vo_ctx ctx);
+void* vo_ctx_stream(vo_ctx ctx);
+/* Message of the most recent failure on this ctx (NULL ctx: last failure of a create call on this thread).
+ * Replaces ODEError.msg (src/base/ode.rs:13-30) and the reference's panic messages. */
+const char* vo_last_error(vo_ctx ctx);
+int32_t vo_version(void);
+/* Number of kernels this ctx has launched since creation (bench.py's `gpu_launches`). */
+int64_t vo_ctx_launch_count(vo_ctx ctx);
+
+/* Arithmetic mode of every kernel launched on the ctx.
+ * VO_ARITH_STRICT: separate IEEE multiply and add in the reference's operation order, zero coefficients
+ *   kept — bit-identical to rustc's un-fused f64 code (src/impls/ndarray.rs:14-32).
+ * VO_ARITH_FAST: FMA contraction allowed and zero tableau coefficients skipped. */
+#define VO_ARITH_STRICT 0
+#define VO_ARITH_FAST 1
+int32_t vo_ctx_set_arith(vo_ctx ctx, int32_t mode);
+
+/* ---- ensembles (the `V` of the reference; `V: Clone`, src/base/ode.rs:79-80) ------------------- */
+#define VO_LAYOUT_SOA 0 /* host buffer [d][N] */
+#define VO_LAYOUT_AOS 1 /* host buffer [N][d] — one contiguous state per trajectory, as the reference holds them */
+int32_t vo_ens_create(vo_ctx ctx, int64_t d, int64_t n, vo_ens* out); /* zero-filled */
+int32_t vo_ens_wrap(vo_ctx ctx, void* device_ptr, int64_t d, int64_t n, vo_ens* out); /* non-owning view */
+int32_t vo_ens_clone(vo_ens src, vo_ens* out);                          /* V::clone */
+int32_t vo_ens_copy(vo_ens dst, vo_ens src);                            /* V::clone_from */
+int32_t vo_ens_destroy(vo_ens e);
+int32_t vo_ens_upload(vo_ens e, const double* host, int32_t layout);    /* synchronous on return */
+int32_t vo_ens_download(vo_ens e, double* host, int32_t layout);        /* synchronous on return */
+int32_t vo_ens_dims(vo_ens e, int64_t* d, int64_t* n);
+void* vo_ens_device_ptr(vo_ens e);
+
+/* ---- LinearCombination (src/lc.rs:7-55; element arithmetic of src/impls/ndarray.rs:14-32) ------ */
+int32_t vo_lc_scale(vo_ens v, double k);                                /* lc.rs:10  v *= k            */
+int32_t vo_lc_scalar_multiply_to(vo_ens v, double k, vo_ens target);    /* lc.rs:12  target = k*v      */
+int32_t vo_lc_add_scalar_mul(vo_ens v, double k, vo_ens u);             /* lc.rs:14  v = v + (k*u)     */
+int32_t vo_lc_add_assign_ref(vo_ens v, vo_ens u);                       /* lc.rs:16  v += u            */
+int32_t vo_lc_delta(vo_ens v, vo_ens y);                                /* lc.rs:18  v -= y            */
+/* lc.rs:20-54: v = k0*v0, then v = v + (ki*vi) left to right — ONE fused pass (n <= VO_MAX_TERMS).
+ * n == 0 returns VO_ERR_BAD_ARG (the reference panics / returns Err(())). v may alias none of v_arr. */
+#define VO_MAX_TERMS 16
+int32_t vo_lc_linear_combination(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n);
+/* Fused RK stage argument (rk.rs:121-124): v = (sum_j k_j v_j) * dt + x0, same operation order. */
+int32_t vo_lc_stage_combine(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n, double dt, vo_ens x0);
+
+/* ---- Normed (src/base/ode.rs:9-11): per-trajectory norm over the d components ------------------ */
+#define VO_NORM_L2 0    /* sqrt(sum_c e_c^2), left-to-right for d <= 64, tree-reduced above that */
+#define VO_NORM_LINF 1  /* max_c |e_c| */
+#define VO_NORM_L1 2
+#define VO_NORM_HYPOT 3 /* complex scalar stored as (re, im): hypot (rk.rs:209-214) */
+int32_t vo_norm(vo_ens e, int32_t kind, double* out_host /* [N] */);
+
+/* ---- ButcherTableu (src/base/rk.rs:22-78) ------------------------------------------------------ */
+#define VO_MAX_STAGES 16
+/* Same argument meaning as ButcherTableu::from_slices (rk.rs:31-42): ac is s*s row-major with a_ij below
+ * the diagonal and c_i ON the diagonal; b_err may be NULL. */
+int32_t vo_tableau_create(const double* ac, const double* b, const double* b_err, int32_t s, vo_tableau* out);
+#define VO_TABLEAU_RKF45_REF 0 /* RK45_AC/B/BERR literally as in src/dat/mod.rs:9-27 (incl. -3544./2526.) */
+#define VO_TABLEAU_RK4 1
+#define VO_TABLEAU_DOPRI5 2    /* 4th-order weights in b, 5th-order in b_err (local extrapolation under rk.rs:142-146) */
+int32_t vo_tableau_builtin(int32_t which, vo_tableau* out);
+int32_t vo_tableau_num_stages(vo_tableau t);                            /* rk.rs:55-57 */
+int32_t vo_tableau_get(vo_tableau t, double* ac, double* b, double* b_err, int32_t* has_err);
+int32_t vo_tableau_destroy(vo_tableau t);
+
+/* ---- right-hand sides: replace the closure `FnMut(T, &V, &mut V) -> Result<(),()>` (rk.rs:97) ---- */
+#define VO_RHS_DIAG_LINEAR 0 /* dx_c = p_c * x_c                      params: d                     */
+#define VO_RHS_HARMONIC2D 1  /* dx = v ; dv = -(k*x)                  params: k                     */
+#define VO_RHS_LORENZ63 2    /* sigma, rho, beta                      params: 3                     */
+#define VO_RHS_VDP 3         /* dx = v ; dv = (mu*(1-x*x))*v - x      params: mu                    */
+#define VO_RHS_HEAT1D 4      /* du_j = kappa*((u_{j-1}+u_{j+1}) - 2u_j), periodic in j; params: kappa */
+int32_t vo_rhs_create(vo_ctx ctx, int32_t kind, int32_t d, vo_rhs* out);
+int32_t vo_rhs_num_params(vo_rhs r);
+int32_t vo_rhs_set_param(vo_rhs r, int32_t idx, double value);                            /* shared by all trajectories */
+int32_t vo_rhs_set_param_array(vo_rhs r, int32_t idx, const double* host, int64_t n);     /* one value per trajectory */
+int32_t vo_rhs_eval(vo_rhs r, double t, vo_ens x, vo_ens dx);                             /* f(t, &x, &mut dx) */
+int32_t vo_rhs_destroy(vo_rhs r);
+
+/* ---- solver: RK45Solver + ODESolver + AdaptiveODESolver (rk.rs:158-320, ode.rs:208-344) --------- */
+/* ODEStep (ode.rs:42-48) */
+#define VO_EV_STEP 0
+#define VO_EV_CHKPT 1
+#define VO_EV_REJECT 2
+#define VO_EV_END 3
+#define VO_EV_ERR 4
+/* ODEState (ode.rs:34-38), aggregated over the ensemble: OK while any trajectory is still Ok. */
+#define VO_STATE_OK 0
+#define VO_STATE_DONE 1
+#define VO_STATE_ERR 2
+/* per-trajectory status bits (vo_solver_stats) */
+#define VO_TRAJ_DONE 1
+#define VO_TRAJ_NONFINITE 2   /* a non-finite error norm was seen (the reference accepts such steps, ode.rs:321-330) */
+#define VO_TRAJ_STUCK 4       /* rejected at h == min_dt: the reference would loop forever here */
+
+typedef struct vo_step_result {
+    int64_t n_step;    /* trajectories whose event was Step (accepted) in this call */
+    int64_t n_chkpt;
+    int64_t n_reject;
+    int64_t n_end;     /* trajectories that emitted End in this call */
+    int64_t n_active;  /* trajectories not Done after this call */
+    int32_t state;     /* VO_STATE_* */
+    int32_t launches;  /* kernels launched by this call */
+} vo_step_result;
+
+/* RK45Solver::new_with_lc (rk.rs:248-262) with the tableau as an argument; x0 is cloned. Defaults as the
+ * reference: x_err = Some, order 3.0, alpha 0.9, atol 1e-6, rtol 1e-4, min_dt 1e-6, max_dt 1.0,
+ * t_list = [t0, tf], tgt_t = 0. */
+int32_t vo_rk_create(vo_ctx ctx, vo_tableau tableau, vo_rhs rhs, double t0, double tf, vo_ens x0, double h,
+                     vo_solver* out);
+/* RK45Solver::new (rk.rs:229-231): the hard-wired RKF45 tables. */
+int32_t vo_rk45_create(vo_ctx ctx, vo_rhs rhs, double t0, double tf, vo_ens x0, double h, vo_solver* out);
+int32_t vo_solver_destroy(vo_solver s);
+int32_t vo_solver_no_adaptive(vo_solver s);                                  /* rk.rs:233-237 */
+int32_t vo_solver_with_tolerance(vo_solver s, double atol, double rtol);     /* ode.rs:298-306 */
+int32_t vo_solver_with_step_range(vo_solver s, double dt_min, double dt_max);/* ode.rs:267-285 */
+int32_t vo_solver_with_init_step(vo_solver s, double h);                     /* ode.rs:287-296 */
+int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n);  /* pub field ODEData.t_list, ode.rs:89 */
+int32_t vo_solver_set_order_alpha(vo_solver s, double order, double alpha);  /* ODEAdaptiveData::new / with_alpha, ode.rs:114-131 */
+int32_t vo_solver_set_norm(vo_solver s, int32_t norm_kind);                  /* the user `Normed` impl, rk.rs:302 */
+int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n); /* one initial step per trajectory */
+/* Events (calls of step()/step_adaptive()) fused per kernel launch by vo_run. 1 = one event per sweep. */
+int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k);
+/* 0 = whole-attempt register-resident kernel when the RHS/tableau allow it (default), 1 = force the
+ * stage-granular path (one fused kernel per RK stage over the K buffers). */
+int32_t vo_solver_set_path(vo_solver s, int32_t stage_path);
+
+/* ODESolver::step (ode.rs:249-253) / AdaptiveODESolver::step_adaptive (ode.rs:337-341) applied to every
+ * trajectory: ONE state-machine event per trajectory per call. res may be NULL. */
+int32_t vo_step(vo_solver s, vo_step_result* res);
+int32_t vo_step_adaptive(vo_solver s, vo_step_result* res);
+/* `while let ODEState::Ok(_) = solver.step() {}` for the whole ensemble. max_calls <= 0: until Done.
+ * res accumulates the event counts of all calls. */
+int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result* res);
+/* Round-robin stepping of several independent ensembles ("batches") that share one ctx: `rounds` times, each solver
+ * in turn advances by one launch (its events-per-launch calls of step()/step_adaptive()). Nothing is read back and
+ * nothing synchronises; counts and states are picked up later by vo_run / vo_solver_stats / vo_current. */
+int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int64_t rounds);
+/* ODESolver::current (ode.rs:216-218): borrowed view of x (valid until the next step) and the time range. */
+int32_t vo_current(vo_solver s, double* t_min, double* t_max, vo_ens* x);
+/* Per-trajectory controller state; any pointer may be NULL. Host arrays of length N. */
+int32_t vo_solver_stats(vo_solver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm,
+                        int32_t* status);
+/* Reset to (t0, x0, h) for another run (re-clones x0 like the constructor). */
+int32_t vo_solver_reset(vo_solver s, vo_ens x0);
+/* One bare rk_step (rk.rs:90-155) at (t, dt) on the solver's current x: writes next_x, x_err (NULL to skip)
+ * and the s stage derivatives K (NULL to skip) WITHOUT advancing. For kernel-level parity tests. */
+int32_t vo_rk_try_step(vo_solver s, double t, double dt, vo_ens next_x, vo_ens x_err, vo_ens* K);
+
+/* ---- exponential integrators (src/exp) ---------------------------------------------------------- */
+/* ExponentialSplit / Commutator / NormedExponentialSplit (exp/mod.rs:11-54) for batched dense complex
+ * systems on a shared basis: an operator L_i = sum_m coef[i][m] * B_m with M complex n x n matrices B_m
+ * shared by the ensemble; `L` values are coefficient ensembles, exp(L) is lazy and map_exp applies the
+ * scaled Taylor series of exp(L) to the state without forming U. States: complex n-vectors, AoS
+ * [N][n] interleaved (re, im). */
+int32_t vo_split_basis_create(vo_ctx ctx, int32_t n, int32_t M, const double* basis /* [M][n][n] (re,im) */,
+                              vo_split* out);
+int32_t vo_split_destroy(vo_split sp);
+/* structure constants for Commutator::commutator (exp/mod.rs:53): [B_a, B_b] = sum_c cs[a][b][c] B_c */
+int32_t vo_split_set_commutator(vo_split sp, const double* cs /* [M][M][M] */);
+int32_t vo_split_set_taylor_degree(vo_split sp, int32_t deg); /* 0 = automatic from theta = ||L||_1 bound */
+/* map_exp(&exp(L), &x) (exp/mod.rs:23-25) for every system: coef [N][M] complex (host), psi device [N][n] complex. */
+int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in_dev, void* psi_out_dev);
+
+/* Generator family replacing the closures of exp/magnus.rs:12,32 and exp/cfm.rs:54:
+ *   L_i(t) = B_0 + sum_{m=1}^{M_gen-1} amp_im * cos(omega_im * t + phase_im) * B_m ,  gp = [N][M_gen-1][3]. */
+#define VO_EXP_MIDPOINT 0 /* MidpointExpLinearSolver, exp/magnus.rs:85-148 */
+#define VO_EXP_CFM4 1     /* ExpCFMSolver, exp/cfm.rs:102-224 */
+#define VO_EXP_MAGNUS42 2 /* MagnusExpLinearSolver, exp/magnus.rs:151-285 */
+int32_t vo_exp_create(vo_ctx ctx, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N,
+                      double t0, double tf, const double* psi0_host /* [N][n] (re,im) */, double h, vo_expsolver* out);
+int32_t vo_exp_destroy(vo_expsolver s);
+int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */
+int32_t vo_exp_with_tolerance(vo_expsolver s, double atol, double rtol);
+int32_t vo_exp_with_step_range(vo_expsolver s, double dt_min, double dt_max);
+int32_t vo_exp_step(vo_expsolver s, vo_step_result* res);
+int32_t vo_exp_step_adaptive(vo_expsolver s, vo_step_result* res);
+int32_t vo_exp_run(vo_expsolver s, int32_t adaptive, int64_t max_calls, vo_step_result* res);
+int32_t vo_exp_current(vo_expsolver s, double* t_min, double* t_max, double* psi_host /* nullable */);
+int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm);
+void* vo_exp_state_device_ptr(vo_expsolver s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECODE_B200_H */

@@ -1,0 +1,65 @@
+"""The drop-in boundary: the shared library loads and exports every symbol include/vecode_b200.h declares; the host
+mirror binds all of them; nothing in the product path imports the oracle. No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vecode_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(vo):
+    if not os.path.exists(vo.SO_PATH):
+        vo.build()
+    lib = ctypes.CDLL(vo.SO_PATH)
+    names = _declared()
+    assert len(names) >= 60
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_host_binding_covers_header(vo):
+    assert sorted(vo._cabi.SIGNATURES) == _declared()
+    assert vo._cabi.lib().vo_version() == 100
+
+
+def test_no_cpu_fallback(vo):
+    """Without a CUDA device a context cannot be created and the error says so."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(vo.VecOdeError) as e:
+        vo.Context(0)
+    assert "no CPU fallback" in e.value.msg
+
+
+def test_tableau_handles_are_host_objects(vo, oracle):
+    """Tableaux need no device: from_slices round-trips, and the built-ins equal the oracle's constants bit for bit."""
+    for name, idx in oracle.TABLEAU_ID.items():
+        ac, b, be, s = vo.ButcherTableu.builtin(name).arrays()
+        oac, ob, obe, os_ = oracle.builtin_tableau(idx)
+        assert s == os_ and list(ac) == list(oac) and list(b) == list(ob)
+        assert (be is None) == (obe is None) and (be is None or list(be) == list(obe))
+    t = vo.ButcherTableu.from_slices([0, 0, 0.5, 0.5], [0.0, 1.0], None, 2)
+    assert t.num_stages() == 2 and t.arrays()[2] is None
+    with pytest.raises(vo.VecOdeError):
+        vo.ButcherTableu.from_slices([0.0] * 3, [1.0, 0.0], None, 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vec-ode_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                for line in open(os.path.join(dirpath, f)):
+                    code = line.split("//")[0].split("#", 1)[0] if not line.lstrip().startswith("#include") else line
+                    bad = ("oracle" in code) and any(k in code for k in ("import", "#include", "CDLL", "dlopen", "subprocess"))
+                    assert not bad and "libvecode_oracle" not in code, (f, line)

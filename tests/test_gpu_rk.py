@@ -1,0 +1,368 @@
+"""Runge-Kutta stepping path on the B200 against the CPU oracle (restatement of src/base/rk.rs + src/base/ode.rs).
+
+Bars: fixed-step = BIT-EXACT in strict mode (same operations, same order, no FMA) and <= 1e-12 relative in fast mode;
+adaptive = within the requested rtol at t_end, accepted/rejected counts compared and reported (the controller's
+`powf` comes from different libms on the two sides, so step sequences may differ in the last bits).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TABLEAUX = ["RKF45_REF", "RK4", "DOPRI5"]
+
+
+def _case(vo, name, n, seed=0):
+    """(rhs kind, d, params AoS [n][np], x0 AoS [n][d])"""
+    rng = np.random.default_rng(seed)
+    if name == "LORENZ63":
+        return name, 3, np.tile(vo.workloads.LORENZ_PARAMS, (n, 1)), vo.workloads.lorenz_x0(n)
+    if name == "VDP":
+        return name, 2, vo.workloads.vdp_mu(n)[:, None], vo.workloads.vdp_x0(n) + 0.01 * rng.standard_normal((n, 2))
+    if name == "HARMONIC2D":
+        return name, 2, 0.5 + rng.random((n, 1)), rng.standard_normal((n, 2))
+    if name.startswith("DIAG"):
+        d = int(name[4:])
+        return "DIAG_LINEAR", d, -rng.random((n, d)) * 2.0, rng.standard_normal((n, d))
+    raise KeyError(name)
+
+
+def _make_rhs(vo, ctx, kind, d, params, per_traj=True):
+    rhs = vo.Rhs(ctx, kind, d)
+    for q in range(params.shape[1]):
+        rhs.set_param(q, params[:, q].copy() if per_traj else float(params[0, q]))
+    return rhs
+
+
+@pytest.mark.parametrize("tab", TABLEAUX)
+@pytest.mark.parametrize("case", ["LORENZ63", "VDP", "HARMONIC2D", "DIAG1", "DIAG2", "DIAG4"])
+def test_try_step_stage_kernels_bit_exact(vo, ctx, oracle, tab, case):
+    """One rk_step (rk.rs:90-155) through the stage kernels: next_x, x_err and every K_i equal the oracle's bits."""
+    n = 257
+    kind, d, params, x0 = _case(vo, case, n, seed=3)
+    tableau = vo.ButcherTableu.builtin(tab)
+    otab = oracle.builtin_tableau(oracle.TABLEAU_ID[tab])
+    s = tableau.num_stages()
+    rhs = _make_rhs(vo, ctx, kind, d, params)
+    X0 = vo.Ensemble.from_host(ctx, x0)
+    solver = vo.RK45Solver(rhs, 0.0, 1.0, X0, 0.01, tableau=tableau)
+    nx, xe = vo.Ensemble(ctx, d, n), vo.Ensemble(ctx, d, n)
+    K = [vo.Ensemble(ctx, d, n) for _ in range(s)]
+    t, dt = 0.37, 0.0123
+    solver.try_step(t, dt, nx, xe if otab[2] is not None else None, K)
+    got_x, got_e = nx.to_host(), xe.to_host()
+    got_K = [k.to_host() for k in K]
+    for i in range(n):
+        rx, re, rK = oracle.rk_step(kind, params[i], otab, t, dt, x0[i])
+        assert np.array_equal(got_x[i], rx), (i, got_x[i], rx)
+        if re is not None:
+            assert np.array_equal(got_e[i], re)
+        for j in range(s):
+            assert np.array_equal(got_K[j][i], rK[j])
+
+
+@pytest.mark.parametrize("stage_path", [False, True])
+@pytest.mark.parametrize("tab,no_adaptive", [("RK4", False), ("RKF45_REF", False), ("RKF45_REF", True), ("DOPRI5", False)])
+def test_fixed_step_lorenz_bit_exact(vo, ctx, oracle, tab, no_adaptive, stage_path):
+    """Config 2 at a size the oracle finishes in seconds: N = 2048 Lorenz-63 trajectories, h = 1e-3, t in [0, 0.25]."""
+    n = 2048
+    kind, d, params, x0 = _case(vo, "LORENZ63", n)
+    tableau = vo.ButcherTableu.builtin(tab)
+    otab = oracle.builtin_tableau(oracle.TABLEAU_ID[tab])
+    rhs = _make_rhs(vo, ctx, kind, d, params, per_traj=False)
+    solver = vo.RK45Solver(rhs, 0.0, 0.25, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tableau)
+    if no_adaptive:
+        solver.no_adaptive()
+    solver.set_stage_path(stage_path)
+    st = solver.run()
+    assert st.kind == "Done"
+    ref = oracle.rk_ensemble(kind, params, otab, 0.0, 0.25, x0, 1e-3, n_threads=8, no_adaptive=no_adaptive)
+    (tmin, tmax), X = solver.current()
+    assert tmin == tmax == ref["t"][0]
+    assert st.counts["Step"] == int(ref["accepted"].sum())
+    assert np.array_equal(X.to_host(), ref["x"])
+    stats = solver.stats()
+    assert np.array_equal(stats["accepted"], ref["accepted"])
+
+
+def test_fixed_step_events_per_launch_and_step_calls(vo, ctx, oracle):
+    """k events fused per launch give the same bits as k separate step() calls; the first call is a Chkpt (ode.rs:144-145)."""
+    n = 1000
+    kind, d, params, x0 = _case(vo, "LORENZ63", n)
+    tableau = vo.ButcherTableu.builtin("RK4")
+    rhs = _make_rhs(vo, ctx, kind, d, params, per_traj=False)
+    a = vo.RK45Solver(rhs, 0.0, 0.05, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tableau)
+    first = a.step()
+    assert first.kind == "Ok" and first.counts["Chkpt"] == n and first.counts["Step"] == 0
+    calls = 1
+    while a.step().is_ok:
+        calls += 1
+    b = vo.RK45Solver(rhs, 0.0, 0.05, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tableau).set_events_per_launch(7)
+    st = b.run()
+    assert st.kind == "Done" and st.counts["Chkpt"] == n and st.counts["End"] == n
+    assert np.array_equal(a.current()[1].to_host(), b.current()[1].to_host())
+    ref = oracle.rk_ensemble(kind, params, oracle.builtin_tableau(1), 0.0, 0.05, x0, 1e-3, n_threads=4)
+    assert np.array_equal(b.current()[1].to_host(), ref["x"])
+    assert st.counts["Step"] == int(ref["accepted"].sum())
+    assert calls + 1 == int(ref["accepted"][0]) + 2  # accepted + Chkpt + End
+
+
+def test_reference_own_tests_golden(vo, ctx, oracle):
+    """The reference's three smoke tests (src/impls/nalgebra.rs:52-107) as fixed by the oracle."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rk_known_answers.json")))
+    # test_rk45_2: y' = (-y0, -2 y1), [0,2], h = 1e-4, step(), default constructor
+    case = g["test_rk45_2"]
+    rhs = vo.Rhs(ctx, "DIAG_LINEAR", 2, [-1.0, -2.0])
+    s = vo.RK45Solver(rhs, 0.0, 2.0, vo.Ensemble.from_host(ctx, [[1.0, 1.0]]), 1e-4)
+    st = s.run()
+    assert st.counts["Step"] == case["accepted"]
+    assert s.current()[1].to_host()[0].tolist() == case["x"]
+    # same with .no_adaptive() (propagates X_b and shows the 2526 typo)
+    case = g["test_rk45_2_no_adaptive"]
+    s = vo.RK45Solver(rhs, 0.0, 2.0, vo.Ensemble.from_host(ctx, [[1.0, 1.0]]), 1e-4).no_adaptive()
+    s.run()
+    assert s.current()[1].to_host()[0].tolist() == case["x"]
+    # test_rk45_1: complex Vector2 -> 4 real components, params (-1,-1,-2,-2)
+    case = g["test_rk45_1_complex"]
+    rhs4 = vo.Rhs(ctx, "DIAG_LINEAR", 4, [-1.0, -1.0, -2.0, -2.0])
+    s = vo.RK45Solver(rhs4, 0.0, 2.0, vo.Ensemble.from_host(ctx, [[1.0, 0.0, 1.0, 0.0]]), 1e-4)
+    s.run()
+    got = s.current()[1].to_host()[0]
+    assert np.array_equal(got, np.array(case["x"]))  # signed zeros compare equal
+    # test_rk45_f64: scalar, with_tolerance(1e-10, 1e-10), step_adaptive()
+    case = g["test_rk45_f64"]
+    rhs1 = vo.Rhs(ctx, "DIAG_LINEAR", 1, [-1.0])
+    s = vo.RK45Solver(rhs1, 0.0, 2.0, vo.Ensemble.from_host(ctx, [[1.0]]), 1e-4).with_tolerance(1e-10, 1e-10)
+    st = s.run(adaptive=True)
+    stats = s.stats()
+    x = s.current()[1].to_host()[0, 0]
+    assert abs(x - case["x"][0]) <= 1e-10
+    assert abs(int(stats["accepted"][0]) - case["accepted"]) <= 4 and int(stats["rejected"][0]) == case["rejected"]
+
+
+@pytest.mark.parametrize("rtol", [1e-6, 1e-8, 1e-10])
+def test_config1_harmonic_adaptive(vo, ctx, oracle, rtol):
+    """Config 1: adaptive RK45 (the reference's literal tableau) on x' = (v, -x), single trajectory."""
+    otab = oracle.builtin_tableau(0)
+    rx, ro, _ = oracle.rk_solve("HARMONIC2D", [1.0], otab, 0.0, 10.0, [1.0, 0.0], 1e-3, adaptive=True, rtol=rtol, atol=rtol)
+    rhs = vo.Rhs(ctx, "HARMONIC2D", 2, [1.0])
+    s = vo.RK45Solver(rhs, 0.0, 10.0, vo.Ensemble.from_host(ctx, [[1.0, 0.0]]), 1e-3).with_tolerance(rtol, rtol)
+    st = s.run(adaptive=True)
+    assert st.kind == "Done"
+    x = s.current()[1].to_host()[0]
+    stats = s.stats()
+    print(f"rtol={rtol}: gpu accepted/rejected {stats['accepted'][0]}/{stats['rejected'][0]}  oracle {ro.n_accept}/{ro.n_reject}")
+    assert abs(stats["t"][0] - 10.0) <= 1e-14 and abs(ro.t - 10.0) <= 1e-14
+    # absolute-error controller (ode.rs:320): per-step error <= rtol; global error grows with the step count
+    assert np.max(np.abs(x - rx)) <= rtol * 10
+    assert abs(int(stats["accepted"][0]) - ro.n_accept) <= max(2, ro.n_accept // 500)
+
+
+@pytest.mark.parametrize("tab", ["DOPRI5", "RKF45_REF"])
+@pytest.mark.parametrize("stage_path", [False, True])
+def test_config3_vdp_adaptive_ensemble(vo, ctx, oracle, tab, stage_path):
+    """Config 3 at oracle size: N = 512 Van der Pol oscillators, mu sweep, per-trajectory step control on the device."""
+    n, rtol, tf = 512, 1e-6, 20.0
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n)
+    tableau = vo.ButcherTableu.builtin(tab)
+    otab = oracle.builtin_tableau(oracle.TABLEAU_ID[tab])
+    ref = oracle.rk_ensemble("VDP", mu[:, None], otab, 0.0, tf, x0, 1e-3, n_threads=8, adaptive=True, rtol=rtol, atol=rtol)
+    rhs = vo.Rhs(ctx, "VDP", 2, [mu])
+    s = vo.RK45Solver(rhs, 0.0, tf, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tableau).with_tolerance(rtol, rtol)
+    s.set_stage_path(stage_path)
+    st = s.run(adaptive=True)
+    assert st.kind == "Done" and st.counts["End"] == n
+    x = s.current()[1].to_host()
+    stats = s.stats()
+    assert np.all(np.abs(stats["t"] - tf) <= 1e-13) and np.all(stats["status"] == 1)
+    acc_g, acc_r = stats["accepted"].sum(), ref["accepted"].sum()
+    rej_g, rej_r = stats["rejected"].sum(), ref["rejected"].sum()
+    print(f"{tab} stage_path={stage_path}: accepted gpu/oracle {acc_g}/{acc_r}, rejected {rej_g}/{rej_r}, launches {st.counts['launches']}")
+    assert st.counts["Step"] == acc_g and st.counts["Reject"] == rej_g
+    assert abs(acc_g - acc_r) <= 0.01 * acc_r and abs(rej_g - rej_r) <= 0.02 * rej_r + 8
+    # stiff-ish limit cycle: errors of a few hundred steps of size <= rtol each, amplified along the fast branches
+    err = np.abs(x - ref["x"]).max(axis=1)
+    assert np.quantile(err, 0.99) <= 200 * rtol, np.quantile(err, [0.5, 0.9, 0.99, 1.0])
+
+
+def test_small_and_stage_paths_agree_bitwise_adaptive(vo, ctx):
+    """Same device libm on both paths, so the register-resident and the stage-granular kernels must agree bit for bit,
+    step sequence included."""
+    n = 300
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n)
+    out = []
+    for stage_path in (False, True):
+        rhs = vo.Rhs(ctx, "VDP", 2, [mu])
+        s = vo.RK45Solver(rhs, 0.0, 5.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path).set_events_per_launch(1 if stage_path else 5)
+        s.run(adaptive=True)
+        out.append((s.current()[1].to_host(), s.stats()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("accepted", "rejected", "t", "h", "dx_norm"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_fast_mode_within_1e12(vo, oracle):
+    """FMA-contracted arithmetic with zero coefficients skipped: <= 1e-12 relative to the strict/oracle result."""
+    n = 4096
+    kind, d, params, x0 = _case(vo, "LORENZ63", n)
+    ref = oracle.rk_ensemble(kind, params, oracle.builtin_tableau(1), 0.0, 0.25, x0, 1e-3, n_threads=8)
+    c = vo.Context(0, arith="fast")
+    rhs = _make_rhs(vo, c, kind, d, params, per_traj=False)
+    s = vo.RK45Solver(rhs, 0.0, 0.25, vo.Ensemble.from_host(c, x0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    s.run()
+    x = s.current()[1].to_host()
+    rel = np.abs(x - ref["x"]).max() / np.abs(ref["x"]).max()
+    print("fast-mode max relative deviation:", rel)
+    assert rel <= 1e-12
+
+
+@pytest.mark.parametrize("d", [3, 1024, 1025, 4099, 1 << 16])
+@pytest.mark.parametrize("tab", ["RK4", "RKF45_REF"])
+def test_heat_stage_path_bit_exact(vo, ctx, oracle, d, tab):
+    """Config 4 at oracle size: periodic 1-D heat equation, stage kernels with the stencil fused, ragged tile tails."""
+    u0 = vo.workloads.heat_u0(d)
+    otab = oracle.builtin_tableau(oracle.TABLEAU_ID[tab])
+    steps = 6
+    rx, ro, _ = oracle.rk_solve("HEAT1D", [1.0], otab, 0.0, 0.25 * steps, u0, 0.25)
+    rhs = vo.Rhs(ctx, "HEAT1D", d, [1.0])
+    s = vo.RK45Solver(rhs, 0.0, 0.25 * steps, vo.Ensemble.from_host(ctx, u0[None, :]), 0.25, tableau=vo.ButcherTableu.builtin(tab))
+    st = s.run()
+    assert st.kind == "Done" and st.counts["Step"] == ro.n_accept
+    assert np.array_equal(s.current()[1].to_host()[0], rx)
+
+
+def test_heat_adaptive_single_state(vo, ctx, oracle):
+    """Large-state adaptive stepping: tree-reduced norm on the device, controller on the host (same libm as the oracle)."""
+    d = 4096
+    u0 = vo.workloads.heat_u0(d)
+    otab = oracle.builtin_tableau(0)
+    rx, ro, _ = oracle.rk_solve("HEAT1D", [1.0], otab, 0.0, 2.0, u0, 0.01, adaptive=True, rtol=1e-6, max_dt=0.3)
+    rhs = vo.Rhs(ctx, "HEAT1D", d, [1.0])
+    s = vo.RK45Solver(rhs, 0.0, 2.0, vo.Ensemble.from_host(ctx, u0[None, :]), 0.01).with_tolerance(1e-6, 1e-6)
+    s.with_step_range(1e-6, 0.3).with_init_step(0.01)
+    s.run(adaptive=True)
+    stats = s.stats()
+    print("heat adaptive accepted/rejected", stats["accepted"][0], stats["rejected"][0], "oracle", ro.n_accept, ro.n_reject)
+    np.testing.assert_allclose(s.current()[1].to_host()[0], rx, atol=1e-6)
+    assert abs(int(stats["accepted"][0]) - ro.n_accept) <= 3
+
+
+def test_heat_ensemble_kernel(vo, ctx, oracle):
+    n, d = 5, 96
+    rng = np.random.default_rng(1)
+    x0 = rng.standard_normal((n, d))
+    otab = oracle.builtin_tableau(1)
+    rhs = vo.Rhs(ctx, "HEAT1D", d, [0.7])
+    s = vo.RK45Solver(rhs, 0.0, 0.5, vo.Ensemble.from_host(ctx, x0), 0.1, tableau=vo.ButcherTableu.builtin("RK4"))
+    s.run()
+    got = s.current()[1].to_host()
+    for i in range(n):
+        rx, _, _ = oracle.rk_solve("HEAT1D", [0.7], otab, 0.0, 0.5, x0[i], 0.1)
+        assert np.array_equal(got[i], rx)
+
+
+def test_t_list_checkpoints(vo, ctx, oracle):
+    """Multi-entry t_list (pub field ODEData.t_list, ode.rs:89): steps are clipped to land on each entry, a Chkpt is
+    emitted there and h is restored from prev_h (ode.rs:192-195) — lock-step and per-trajectory control."""
+    n = 64
+    kind, d, params, x0 = _case(vo, "HARMONIC2D", n, seed=5)
+    t_list = [0.0, 0.35, 0.5, 1.0]
+    otab = oracle.builtin_tableau(0)
+    for adaptive in (False, True):
+        ref = oracle.rk_ensemble(kind, params, otab, 0.0, 1.0, x0, 0.01, n_threads=2, adaptive=adaptive, rtol=1e-7, t_list=t_list)
+        rhs = _make_rhs(vo, ctx, kind, d, params)
+        s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 0.01).with_tolerance(1e-7, 1e-7).set_t_list(t_list)
+        st = s.run(adaptive=adaptive)
+        assert st.kind == "Done" and st.counts["Chkpt"] == 3 * n and st.counts["End"] == n
+        x = s.current()[1].to_host()
+        if adaptive:
+            np.testing.assert_allclose(x, ref["x"], atol=1e-6)
+        else:
+            assert np.array_equal(x, ref["x"])
+
+
+def test_per_trajectory_initial_step(vo, ctx, oracle):
+    n = 128
+    kind, d, params, x0 = _case(vo, "HARMONIC2D", n, seed=9)
+    h0 = np.linspace(1e-3, 2e-2, n)
+    otab = oracle.builtin_tableau(2)
+    ref = oracle.rk_ensemble(kind, params, otab, 0.0, 1.0, x0, 0.0, h0_arr=h0, n_threads=2)
+    rhs = _make_rhs(vo, ctx, kind, d, params)
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5")).set_h_array(h0)
+    st = s.run()
+    assert st.kind == "Done"
+    assert np.array_equal(s.current()[1].to_host(), ref["x"])
+    assert np.array_equal(s.stats()["accepted"], ref["accepted"])
+
+
+def test_error_behaviour(vo, ctx):
+    rhs = vo.Rhs(ctx, "HARMONIC2D", 2)
+    x0 = vo.Ensemble.from_host(ctx, [[1.0, 0.0]])
+    s = vo.RK45Solver(rhs, 0.0, 1.0, x0, 1e-2)
+    with pytest.raises(vo.VecOdeError) as e:
+        s.with_tolerance(-1.0, 1e-3)  # ode.rs:299-301 panics
+    assert "Invalid tolerances" in e.value.msg
+    with pytest.raises(vo.VecOdeError) as e:
+        s.with_step_range(1.0, 0.5)  # ode.rs:268-270
+    assert "Invalid step range" in e.value.msg
+    with pytest.raises(vo.VecOdeError):
+        s.with_init_step(5.0)  # ode.rs:288-291: outside (min_dt, max_dt)
+    s.no_adaptive()
+    with pytest.raises(vo.VecOdeError) as e:
+        s.step_adaptive()  # ode.rs:312 `.expect("adaptive step validation failed")`
+    assert e.value.code == vo._cabi.VO_ERR_NOT_ADAPTIVE
+    with pytest.raises(vo.VecOdeError):
+        vo.RK45Solver(vo.Rhs(ctx, "LORENZ63", 3), 0.0, 1.0, x0, 1e-2)  # dimension mismatch
+    with pytest.raises(vo.VecOdeError):
+        vo.ButcherTableu.from_slices([0.0] * 4, [1.0], None, 2)
+
+
+def test_with_step_range_sets_geometric_mean(vo, ctx, oracle):
+    """with_step_range resets h to sqrt(min*max) (ode.rs:273-280)."""
+    rhs = vo.Rhs(ctx, "DIAG_LINEAR", 1, [-1.0])
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, [[1.0]]), 1e-4).with_step_range(1e-4, 1e-2)
+    assert s.stats()["h"][0] == np.sqrt(1e-4 * 1e-2)
+
+
+def test_nonfinite_and_stuck_flags(vo, ctx):
+    """NaN error norms are accepted like the reference (ode.rs:321-330) but flagged; a trajectory rejected at min_dt is
+    flagged STUCK and vo_run returns instead of spinning forever."""
+    rhs = vo.Rhs(ctx, "DIAG_LINEAR", 1, [-1.0])
+    s = vo.RK45Solver(rhs, 0.0, 0.01, vo.Ensemble.from_host(ctx, [[np.nan]]), 1e-2).set_events_per_launch(1000)
+    st = s.run(adaptive=True)
+    assert st.kind == "Done" and s.stats()["status"][0] & vo._cabi.TRAJ_NONFINITE
+    # huge decay rate, rtol tiny, min_dt == max reachable: every attempt is rejected at h == min_dt
+    rhs = vo.Rhs(ctx, "DIAG_LINEAR", 1, [-1.0e9])
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, [[1.0]]), 1e-3).with_tolerance(1e-30, 1e-30)
+    with pytest.raises(vo.VecOdeError):
+        s.run(adaptive=True)
+    assert s.stats()["status"][0] & vo._cabi.TRAJ_STUCK
+
+
+def test_full_size_properties_lorenz(vo, ctx):
+    """Config 2 at full size (N = 1e6): size-independent properties instead of an oracle run —
+    (i) permutation equivariance: shuffled trajectories give shuffled results, bit for bit;
+    (ii) splitting the ensemble into two shards (the multi-GPU decomposition) gives the same bits;
+    (iii) a 2048-trajectory prefix equals the standalone 2048-trajectory run (which the oracle test covers)."""
+    n = 1_000_000
+    x0 = vo.workloads.lorenz_x0(n)
+    tableau = vo.ButcherTableu.builtin("RK4")
+
+    def run(x):
+        rhs = vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+        s = vo.RK45Solver(rhs, 0.0, 0.1, vo.Ensemble.from_host(ctx, x), 1e-3, tableau=tableau)
+        st = s.run()
+        assert st.kind == "Done"
+        return s.current()[1].to_host()
+
+    full = run(x0)
+    assert np.all(np.isfinite(full))
+    perm = np.random.default_rng(0).permutation(n)
+    assert np.array_equal(run(x0[perm]), full[perm])
+    half = n // 2
+    assert np.array_equal(np.concatenate([run(x0[:half]), run(x0[half:])]), full)
+    assert np.array_equal(run(x0[:2048]), full[:2048])

@@ -1,0 +1,11 @@
+"""vecode_b200 — B200-native batched ODE time-stepping engine behind hmunozb/vec-ode's integrator API.
+
+The directory is `vec-ode_b200/` (not an importable name); `import vecode_b200` works through the shim module
+`vecode_b200.py` at the repository root.
+"""
+from . import _cabi, workloads
+from ._cabi import SO_PATH, StepResult, VecOdeError, build
+from .base import (ButcherTableu, Context, Ensemble, LinearCombination, ODEError, ODEState, RK45Solver, Rhs, step_many)
+
+__all__ = ["ButcherTableu", "Context", "Ensemble", "LinearCombination", "ODEError", "ODEState", "RK45Solver", "Rhs", "step_many",
+           "StepResult", "VecOdeError", "build", "workloads", "SO_PATH"]

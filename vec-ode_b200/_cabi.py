@@ -1,0 +1,159 @@
+"""ctypes binding of libvecode_b200.so (include/vecode_b200.h).
+
+This is the only place the Python host touches native code. There is NO CPU fallback: if the shared object is
+missing, or a context cannot be created because no CUDA device is present, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libvecode_b200.so")
+
+# status codes (include/vecode_b200.h)
+VO_OK = 0
+VO_ERR_BAD_ARG, VO_ERR_SHAPE, VO_ERR_CUDA, VO_ERR_ALLOC = -1, -2, -3, -4
+VO_ERR_NOT_ADAPTIVE, VO_ERR_UNSUPPORTED, VO_ERR_STATE = -5, -6, -7
+ARITH_STRICT, ARITH_FAST = 0, 1
+LAYOUT_SOA, LAYOUT_AOS = 0, 1
+NORM = {"L2": 0, "LINF": 1, "L1": 2, "HYPOT": 3}
+TABLEAU = {"RKF45_REF": 0, "RK4": 1, "DOPRI5": 2}
+RHS = {"DIAG_LINEAR": 0, "HARMONIC2D": 1, "LORENZ63": 2, "VDP": 3, "HEAT1D": 4}
+EXP_SCHEME = {"midpoint": 0, "cfm4": 1, "magnus42": 2}
+EV_STEP, EV_CHKPT, EV_REJECT, EV_END, EV_ERR = range(5)
+STATE_OK, STATE_DONE, STATE_ERR = range(3)
+TRAJ_DONE, TRAJ_NONFINITE, TRAJ_STUCK = 1, 2, 4
+
+_ERR_NAMES = {-1: "BAD_ARG", -2: "SHAPE", -3: "CUDA", -4: "ALLOC", -5: "NOT_ADAPTIVE", -6: "UNSUPPORTED", -7: "STATE"}
+
+
+class VecOdeError(RuntimeError):
+    """A non-zero status from the C ABI; `.msg` is what the reference puts in ODEError.msg or a panic message."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vecode_b200: {_ERR_NAMES.get(code, code)}: {msg}")
+        self.code, self.msg = code, msg
+
+
+class StepResult(C.Structure):
+    _fields_ = [("n_step", C.c_int64), ("n_chkpt", C.c_int64), ("n_reject", C.c_int64), ("n_end", C.c_int64),
+                ("n_active", C.c_int64), ("state", C.c_int32), ("launches", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes): every entry point of include/vecode_b200.h
+SIGNATURES = {
+    "vo_ctx_create": (_i32, [_i32, _vp, _pvp]),
+    "vo_ctx_destroy": (_i32, [_vp]),
+    "vo_ctx_sync": (_i32, [_vp]),
+    "vo_ctx_stream": (_vp, [_vp]),
+    "vo_last_error": (C.c_char_p, [_vp]),
+    "vo_version": (_i32, []),
+    "vo_ctx_launch_count": (_i64, [_vp]),
+    "vo_ctx_set_arith": (_i32, [_vp, _i32]),
+    "vo_ens_create": (_i32, [_vp, _i64, _i64, _pvp]),
+    "vo_ens_wrap": (_i32, [_vp, _vp, _i64, _i64, _pvp]),
+    "vo_ens_clone": (_i32, [_vp, _pvp]),
+    "vo_ens_copy": (_i32, [_vp, _vp]),
+    "vo_ens_destroy": (_i32, [_vp]),
+    "vo_ens_upload": (_i32, [_vp, _vp, _i32]),
+    "vo_ens_download": (_i32, [_vp, _vp, _i32]),
+    "vo_ens_dims": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "vo_ens_device_ptr": (_vp, [_vp]),
+    "vo_lc_scale": (_i32, [_vp, _f64]),
+    "vo_lc_scalar_multiply_to": (_i32, [_vp, _f64, _vp]),
+    "vo_lc_add_scalar_mul": (_i32, [_vp, _f64, _vp]),
+    "vo_lc_add_assign_ref": (_i32, [_vp, _vp]),
+    "vo_lc_delta": (_i32, [_vp, _vp]),
+    "vo_lc_linear_combination": (_i32, [_vp, _pvp, C.POINTER(_f64), _i32]),
+    "vo_lc_stage_combine": (_i32, [_vp, _pvp, C.POINTER(_f64), _i32, _f64, _vp]),
+    "vo_norm": (_i32, [_vp, _i32, _vp]),
+    "vo_tableau_create": (_i32, [_vp, _vp, _vp, _i32, _pvp]),
+    "vo_tableau_builtin": (_i32, [_i32, _pvp]),
+    "vo_tableau_num_stages": (_i32, [_vp]),
+    "vo_tableau_get": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "vo_tableau_destroy": (_i32, [_vp]),
+    "vo_rhs_create": (_i32, [_vp, _i32, _i32, _pvp]),
+    "vo_rhs_num_params": (_i32, [_vp]),
+    "vo_rhs_set_param": (_i32, [_vp, _i32, _f64]),
+    "vo_rhs_set_param_array": (_i32, [_vp, _i32, _vp, _i64]),
+    "vo_rhs_eval": (_i32, [_vp, _f64, _vp, _vp]),
+    "vo_rhs_destroy": (_i32, [_vp]),
+    "vo_rk_create": (_i32, [_vp, _vp, _vp, _f64, _f64, _vp, _f64, _pvp]),
+    "vo_rk45_create": (_i32, [_vp, _vp, _f64, _f64, _vp, _f64, _pvp]),
+    "vo_solver_destroy": (_i32, [_vp]),
+    "vo_solver_no_adaptive": (_i32, [_vp]),
+    "vo_solver_with_tolerance": (_i32, [_vp, _f64, _f64]),
+    "vo_solver_with_step_range": (_i32, [_vp, _f64, _f64]),
+    "vo_solver_with_init_step": (_i32, [_vp, _f64]),
+    "vo_solver_set_t_list": (_i32, [_vp, _vp, _i32]),
+    "vo_solver_set_order_alpha": (_i32, [_vp, _f64, _f64]),
+    "vo_solver_set_norm": (_i32, [_vp, _i32]),
+    "vo_solver_set_h_array": (_i32, [_vp, _vp, _i64]),
+    "vo_solver_set_events_per_launch": (_i32, [_vp, _i32]),
+    "vo_solver_set_path": (_i32, [_vp, _i32]),
+    "vo_step": (_i32, [_vp, C.POINTER(StepResult)]),
+    "vo_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
+    "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
+    "vo_step_many": (_i32, [_pvp, _i32, _i32, _i64]),
+    "vo_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _pvp]),
+    "vo_solver_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vo_solver_reset": (_i32, [_vp, _vp]),
+    "vo_rk_try_step": (_i32, [_vp, _f64, _f64, _vp, _vp, _pvp]),
+    "vo_split_basis_create": (_i32, [_vp, _i32, _i32, _vp, _pvp]),
+    "vo_split_destroy": (_i32, [_vp]),
+    "vo_split_set_commutator": (_i32, [_vp, _vp]),
+    "vo_split_set_taylor_degree": (_i32, [_vp, _i32]),
+    "vo_map_exp": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "vo_exp_create": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f64, _f64, _vp, _f64, _pvp]),
+    "vo_exp_destroy": (_i32, [_vp]),
+    "vo_exp_no_adaptive": (_i32, [_vp]),
+    "vo_exp_with_tolerance": (_i32, [_vp, _f64, _f64]),
+    "vo_exp_with_step_range": (_i32, [_vp, _f64, _f64]),
+    "vo_exp_step": (_i32, [_vp, C.POINTER(StepResult)]),
+    "vo_exp_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
+    "vo_exp_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
+    "vo_exp_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _vp]),
+    "vo_exp_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "vo_exp_state_device_ptr": (_vp, [_vp]),
+}
+
+_lib = None
+
+
+def build(force: bool = False, jobs: int = 8) -> str:
+    """Compile the CUDA sources in-tree with nvcc for sm_100a (csrc/Makefile)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), f"-j{jobs}"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return SO_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(vecode_b200 has no CPU fallback)")
+        l = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError here = the .so is stale w.r.t. the header
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(code: int, ctx=None):
+    if code != VO_OK:
+        msg = lib().vo_last_error(ctx)
+        if not msg and ctx is not None:
+            msg = lib().vo_last_error(None)
+        raise VecOdeError(code, (msg or b"").decode("utf-8", "replace"))

@@ -1,0 +1,394 @@
+"""Host-side mirror of vec-ode's integrator API for the time-stepping path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference crate (paths relative to its root):
+  ButcherTableu                src/base/rk.rs:22-78
+  RK45Solver                   src/base/rk.rs:158-320
+  ODESolver / AdaptiveODESolver  src/base/ode.rs:208-344   (step, step_adaptive, current, with_* builders)
+  ODEStep / ODEState / ODEError  src/base/ode.rs:13-76
+  LinearCombination            src/lc.rs:7-55
+  Normed                       src/base/ode.rs:9-11
+What differs by design: `V` is an `Ensemble` of N independent states on one B200 (SoA [d][N]); the RHS closure is a
+compiled-in device functor (`Rhs`); a panic in the reference is a `VecOdeError` here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import StepResult, VecOdeError, check, lib
+
+_vp = C.c_void_p
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + one stream. `stream` may be a raw cudaStream_t (int), e.g. torch's current stream."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None, arith: str = "strict"):
+        self._h = _vp()
+        check(lib().vo_ctx_create(device, _vp(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+        self.set_arith(arith)
+
+    @classmethod
+    def on_torch_stream(cls, device: int = 0, arith: str = "strict") -> "Context":
+        import torch
+        torch.cuda.set_device(device)
+        return cls(device, torch.cuda.current_stream(device).cuda_stream, arith)
+
+    def set_arith(self, mode: str):
+        """'strict': the reference's un-fused multiply/add order, bit-identical to the CPU restatement.
+        'fast': FMA contraction and zero tableau coefficients skipped."""
+        check(lib().vo_ctx_set_arith(self._h, {"strict": _cabi.ARITH_STRICT, "fast": _cabi.ARITH_FAST}[mode]), self._h)
+        self.arith = mode
+
+    def sync(self):
+        check(lib().vo_ctx_sync(self._h), self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().vo_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().vo_ctx_stream(self._h) or 0)
+
+    def close(self):
+        if self._h:
+            lib().vo_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ensemble:
+    """The reference's `V`: N independent d-vectors, SoA on the device (component c of trajectory i at [c*N + i])."""
+
+    def __init__(self, ctx: Context, d: int, n: int, _handle=None, _owner=None):
+        self.ctx, self.d, self.n = ctx, int(d), int(n)
+        self._owner = _owner  # keeps a wrapped torch tensor / parent solver alive
+        self._borrowed = _handle is not None and _owner is not None and not isinstance(_owner, _TensorOwner)
+        if _handle is None:
+            self._h = _vp()
+            check(lib().vo_ens_create(ctx._h, self.d, self.n, C.byref(self._h)), ctx._h)
+        else:
+            self._h = _handle
+
+    @classmethod
+    def from_host(cls, ctx: Context, a, layout: str = "aos") -> "Ensemble":
+        """a: [N][d] (layout 'aos', one contiguous state per trajectory, as the reference holds them) or [d][N] ('soa')."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1) if layout == "aos" else a.reshape(-1, 1)
+        n, d = a.shape if layout == "aos" else a.shape[::-1]
+        e = cls(ctx, d, n)
+        e.upload(a, layout)
+        return e
+
+    @classmethod
+    def wrap_tensor(cls, ctx: Context, t) -> "Ensemble":
+        """Non-owning view of a CUDA float64 torch tensor of shape [d][N] (contiguous)."""
+        assert t.is_cuda and t.is_contiguous() and t.dtype.itemsize == 8 and t.dim() == 2
+        h = _vp()
+        check(lib().vo_ens_wrap(ctx._h, _vp(t.data_ptr()), t.shape[0], t.shape[1], C.byref(h)), ctx._h)
+        return cls(ctx, t.shape[0], t.shape[1], _handle=h, _owner=_TensorOwner(t))
+
+    def upload(self, a: np.ndarray, layout: str = "aos"):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.size != self.d * self.n:
+            raise VecOdeError(_cabi.VO_ERR_SHAPE, "upload: host array has the wrong number of elements")
+        check(lib().vo_ens_upload(self._h, _np_ptr(a), _cabi.LAYOUT_AOS if layout == "aos" else _cabi.LAYOUT_SOA), self.ctx._h)
+
+    def to_host(self, layout: str = "aos", out: Optional[np.ndarray] = None) -> np.ndarray:
+        shape = (self.n, self.d) if layout == "aos" else (self.d, self.n)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        check(lib().vo_ens_download(self._h, _np_ptr(out), _cabi.LAYOUT_AOS if layout == "aos" else _cabi.LAYOUT_SOA), self.ctx._h)
+        return out
+
+    def clone(self) -> "Ensemble":
+        h = _vp()
+        check(lib().vo_ens_clone(self._h, C.byref(h)), self.ctx._h)
+        return Ensemble(self.ctx, self.d, self.n, _handle=h)
+
+    def copy_from(self, src: "Ensemble"):
+        check(lib().vo_ens_copy(self._h, src._h), self.ctx._h)
+
+    @property
+    def device_ptr(self) -> int:
+        return int(lib().vo_ens_device_ptr(self._h) or 0)
+
+    def norm(self, kind: str = "L2") -> np.ndarray:
+        """Normed::norm (src/base/ode.rs:9-11) per trajectory."""
+        out = np.empty(self.n)
+        check(lib().vo_norm(self._h, _cabi.NORM[kind], _np_ptr(out)), self.ctx._h)
+        return out
+
+    def __del__(self):
+        try:
+            if self._h and not self._borrowed:
+                lib().vo_ens_destroy(self._h)
+        except Exception:
+            pass
+
+
+class _TensorOwner:
+    def __init__(self, t):
+        self.t = t
+
+
+class LinearCombination:
+    """src/lc.rs:7-55 — static methods, like the trait. Element arithmetic is src/impls/ndarray.rs:14-32."""
+
+    @staticmethod
+    def scale(v: Ensemble, k: float):
+        check(lib().vo_lc_scale(v._h, k), v.ctx._h)
+
+    @staticmethod
+    def scalar_multiply_to(v: Ensemble, k: float, target: Ensemble):
+        check(lib().vo_lc_scalar_multiply_to(v._h, k, target._h), v.ctx._h)
+
+    @staticmethod
+    def add_scalar_mul(v: Ensemble, k: float, other: Ensemble):
+        check(lib().vo_lc_add_scalar_mul(v._h, k, other._h), v.ctx._h)
+
+    @staticmethod
+    def add_assign_ref(v: Ensemble, other: Ensemble):
+        check(lib().vo_lc_add_assign_ref(v._h, other._h), v.ctx._h)
+
+    @staticmethod
+    def delta(v: Ensemble, y: Ensemble):
+        check(lib().vo_lc_delta(v._h, y._h), v.ctx._h)
+
+    @staticmethod
+    def linear_combination(v: Ensemble, v_arr: Sequence[Ensemble], k_arr: Sequence[float]):
+        """lc.rs:20-35 in ONE pass. Empty input is an error (the reference panics)."""
+        n = min(len(v_arr), len(k_arr))  # zip semantics of lc.rs:28-33
+        hs = (C.c_void_p * max(n, 1))(*[e._h.value for e in v_arr[:n]])
+        ks = (C.c_double * max(n, 1))(*[float(k) for k in k_arr[:n]])
+        check(lib().vo_lc_linear_combination(v._h, hs, ks, n), v.ctx._h)
+
+    @staticmethod
+    def stage_combine(v: Ensemble, v_arr: Sequence[Ensemble], k_arr: Sequence[float], dt: float, x0: Ensemble):
+        """rk.rs:121-124 fused: v = (sum k_j v_j) * dt + x0."""
+        n = min(len(v_arr), len(k_arr))
+        hs = (C.c_void_p * max(n, 1))(*[e._h.value for e in v_arr[:n]])
+        ks = (C.c_double * max(n, 1))(*[float(k) for k in k_arr[:n]])
+        check(lib().vo_lc_stage_combine(v._h, hs, ks, n, dt, x0._h), v.ctx._h)
+
+
+class ButcherTableu:
+    """src/base/rk.rs:22-78 (the reference's spelling). `ac` is s*s row-major with c_i ON the diagonal."""
+
+    def __init__(self, handle, s: int):
+        self._h, self.s = handle, s
+
+    @classmethod
+    def from_slices(cls, ac, b, b_err, s: int) -> "ButcherTableu":
+        ac = np.ascontiguousarray(ac, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        be = None if b_err is None else np.ascontiguousarray(b_err, dtype=np.float64)
+        if ac.size != s * s or b.size != s or (be is not None and be.size != s):
+            raise VecOdeError(_cabi.VO_ERR_SHAPE, "ButcherTableu: slice lengths do not match s")  # rk.rs:35-39 panics
+        h = _vp()
+        check(lib().vo_tableau_create(_np_ptr(ac), _np_ptr(b), _np_ptr(be), s, C.byref(h)))
+        return cls(h, s)
+
+    from_vecs = from_slices  # rk.rs:44-53
+
+    @classmethod
+    def builtin(cls, name: str) -> "ButcherTableu":
+        h = _vp()
+        check(lib().vo_tableau_builtin(_cabi.TABLEAU[name], C.byref(h)))
+        return cls(h, int(lib().vo_tableau_num_stages(h)))
+
+    def num_stages(self) -> int:  # rk.rs:55-57
+        return int(lib().vo_tableau_num_stages(self._h))
+
+    def arrays(self):
+        s = self.s
+        ac, b, be, he = np.zeros(s * s), np.zeros(s), np.zeros(s), C.c_int32()
+        check(lib().vo_tableau_get(self._h, _np_ptr(ac), _np_ptr(b), _np_ptr(be), C.byref(he)))
+        return ac, b, (be if he.value else None), s
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vo_tableau_destroy(self._h)
+        except Exception:
+            pass
+
+
+class Rhs:
+    """Replaces the closure `FnMut(T, &V, &mut V) -> Result<(),()>` (src/base/rk.rs:97): a compiled-in device functor
+    chosen by name, with parameters that are shared scalars or per-trajectory arrays."""
+
+    def __init__(self, ctx: Context, kind: str, d: int, params=None):
+        self.ctx, self.kind, self.d = ctx, kind, d
+        self._h = _vp()
+        check(lib().vo_rhs_create(ctx._h, _cabi.RHS[kind], d, C.byref(self._h)), ctx._h)
+        self.num_params = int(lib().vo_rhs_num_params(self._h))
+        if params is not None:
+            for i, p in enumerate(params):
+                self.set_param(i, p)
+
+    def set_param(self, idx: int, value):
+        if np.ndim(value) == 0:
+            check(lib().vo_rhs_set_param(self._h, idx, float(value)), self.ctx._h)
+        else:
+            a = np.ascontiguousarray(value, dtype=np.float64)
+            check(lib().vo_rhs_set_param_array(self._h, idx, _np_ptr(a), a.size), self.ctx._h)
+
+    def __call__(self, t: float, x: Ensemble, dx: Ensemble):
+        check(lib().vo_rhs_eval(self._h, t, x._h, dx._h), self.ctx._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vo_rhs_destroy(self._h)
+        except Exception:
+            pass
+
+
+# ---- ODEStep / ODEState / ODEError (src/base/ode.rs:13-76), aggregated over the ensemble ------------------------
+@dataclass
+class ODEError(Exception):
+    msg: str
+
+
+@dataclass
+class ODEState:
+    """kind: 'Ok' while any trajectory still steps, 'Done' when all have emitted End, 'Err'. `counts` holds how many
+    trajectories saw each ODEStep variant in this call (Step / Chkpt / Reject / End)."""
+    kind: str
+    counts: dict
+
+    @property
+    def is_ok(self):
+        return self.kind == "Ok"
+
+
+def _state_of(res: StepResult) -> ODEState:
+    kind = {_cabi.STATE_OK: "Ok", _cabi.STATE_DONE: "Done", _cabi.STATE_ERR: "Err"}[res.state]
+    return ODEState(kind, dict(Step=res.n_step, Chkpt=res.n_chkpt, Reject=res.n_reject, End=res.n_end, active=res.n_active,
+                               launches=res.launches))
+
+
+class RK45Solver:
+    """RK45Solver (src/base/rk.rs:158-320) over an ensemble. `RK45Solver(f, t0, tf, x0, h)` hard-wires the reference's
+    RKF45 tables exactly like `RK45Solver::new`; pass `tableau=` for any other ButcherTableu."""
+
+    def __init__(self, f: Rhs, t0: float, tf: float, x0: Ensemble, h: float, tableau: Optional[ButcherTableu] = None):
+        self.ctx, self.f, self.tableau = x0.ctx, f, tableau
+        self._h = _vp()
+        if tableau is None:
+            check(lib().vo_rk45_create(self.ctx._h, f._h, t0, tf, x0._h, h, C.byref(self._h)), self.ctx._h)
+        else:
+            check(lib().vo_rk_create(self.ctx._h, tableau._h, f._h, t0, tf, x0._h, h, C.byref(self._h)), self.ctx._h)
+        self.d, self.n = x0.d, x0.n
+
+    # builders (consume-and-return like the reference) ------------------------------------------------------------
+    def no_adaptive(self):  # rk.rs:233-237
+        check(lib().vo_solver_no_adaptive(self._h), self.ctx._h)
+        return self
+
+    def with_tolerance(self, atol: float, rtol: float):  # ode.rs:298-306
+        check(lib().vo_solver_with_tolerance(self._h, atol, rtol), self.ctx._h)
+        return self
+
+    def with_step_range(self, dt_min: float, dt_max: float):  # ode.rs:267-285
+        check(lib().vo_solver_with_step_range(self._h, dt_min, dt_max), self.ctx._h)
+        return self
+
+    def with_init_step(self, h: float):  # ode.rs:287-296
+        check(lib().vo_solver_with_init_step(self._h, h), self.ctx._h)
+        return self
+
+    def with_norm(self, kind: str):  # the user-supplied `Normed` impl (rk.rs:302)
+        check(lib().vo_solver_set_norm(self._h, _cabi.NORM[kind]), self.ctx._h)
+        return self
+
+    def with_order_alpha(self, order: float, alpha: float):  # ode.rs:114-131
+        check(lib().vo_solver_set_order_alpha(self._h, order, alpha), self.ctx._h)
+        return self
+
+    def set_t_list(self, t_list):  # pub field ODEData.t_list (ode.rs:89)
+        a = np.ascontiguousarray(t_list, dtype=np.float64)
+        check(lib().vo_solver_set_t_list(self._h, _np_ptr(a), a.size), self.ctx._h)
+        return self
+
+    def set_h_array(self, h):
+        a = np.ascontiguousarray(h, dtype=np.float64)
+        check(lib().vo_solver_set_h_array(self._h, _np_ptr(a), a.size), self.ctx._h)
+        return self
+
+    def set_events_per_launch(self, k: int):
+        check(lib().vo_solver_set_events_per_launch(self._h, k), self.ctx._h)
+        return self
+
+    def set_stage_path(self, on: bool = True):
+        check(lib().vo_solver_set_path(self._h, 1 if on else 0), self.ctx._h)
+        return self
+
+    # stepping ------------------------------------------------------------------------------------------------------
+    def step(self) -> ODEState:  # ode.rs:249-253
+        res = StepResult()
+        check(lib().vo_step(self._h, C.byref(res)), self.ctx._h)
+        return _state_of(res)
+
+    def step_adaptive(self) -> ODEState:  # ode.rs:337-341
+        res = StepResult()
+        check(lib().vo_step_adaptive(self._h, C.byref(res)), self.ctx._h)
+        return _state_of(res)
+
+    def run(self, adaptive: bool = False, max_calls: int = 0) -> ODEState:
+        """`while let ODEState::Ok(_) = solver.step() {}` for the whole ensemble."""
+        res = StepResult()
+        check(lib().vo_run(self._h, 1 if adaptive else 0, max_calls, C.byref(res)), self.ctx._h)
+        return _state_of(res)
+
+    def current(self):  # ode.rs:216-218 -> ((t_min, t_max), borrowed Ensemble)
+        tmin, tmax, h = C.c_double(), C.c_double(), _vp()
+        check(lib().vo_current(self._h, C.byref(tmin), C.byref(tmax), C.byref(h)), self.ctx._h)
+        return (tmin.value, tmax.value), Ensemble(self.ctx, self.d, self.n, _handle=h, _owner=self)
+
+    def stats(self) -> dict:
+        n = self.n
+        acc, rej = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        t, h, dxn, st = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+        check(lib().vo_solver_stats(self._h, _np_ptr(acc), _np_ptr(rej), _np_ptr(t), _np_ptr(h), _np_ptr(dxn), _np_ptr(st)), self.ctx._h)
+        return dict(accepted=acc, rejected=rej, t=t, h=h, dx_norm=dxn, status=st)
+
+    def reset(self, x0: Ensemble):
+        check(lib().vo_solver_reset(self._h, x0._h), self.ctx._h)
+
+    def try_step(self, t: float, dt: float, next_x: Ensemble, x_err: Optional[Ensemble] = None, K: Optional[Sequence[Ensemble]] = None):
+        """One bare rk_step (rk.rs:90-155) on the current x, without advancing."""
+        ks = None
+        if K is not None:
+            ks = (C.c_void_p * len(K))(*[e._h.value for e in K])
+        check(lib().vo_rk_try_step(self._h, t, dt, next_x._h, None if x_err is None else x_err._h, ks), self.ctx._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vo_solver_destroy(self._h)
+        except Exception:
+            pass
+
+
+def step_many(solvers: Sequence[RK45Solver], adaptive: bool = False, rounds: int = 1):
+    """Round-robin one launch per solver, `rounds` times, with no read-back (vo_step_many)."""
+    hs = (C.c_void_p * len(solvers))(*[s._h.value for s in solvers])
+    check(lib().vo_step_many(hs, len(solvers), 1 if adaptive else 0, rounds), solvers[0].ctx._h)

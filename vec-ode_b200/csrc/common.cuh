@@ -1,0 +1,120 @@
+// common.cuh — handle definitions, error plumbing and arithmetic-mode helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/vecode_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// Handles
+// ------------------------------------------------------------------------------------------------
+struct vo_ctx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int arith = VO_ARITH_STRICT;
+    int sm_count = 148;
+    int64_t launches = 0;
+    std::string err;
+    // small pinned scratch for result read-back and a device mirror
+    void* pinned = nullptr;   // 4 KiB
+    void* dscratch = nullptr; // 4 KiB
+};
+
+struct vo_ens_s {
+    vo_ctx ctx = nullptr;
+    double* p = nullptr;
+    int64_t d = 0, n = 0;
+    bool owns = true;
+    int64_t elems() const { return d * n; }
+};
+
+struct vo_tableau_s {
+    int s = 0;
+    bool has_err = false;
+    double ac[VO_MAX_STAGES * VO_MAX_STAGES];
+    double b[VO_MAX_STAGES];
+    double b_err[VO_MAX_STAGES];
+};
+
+#define VO_MAX_PARAMS 8
+struct vo_rhs_s {
+    vo_ctx ctx = nullptr;
+    int kind = 0, d = 0, np = 0;
+    double shared[VO_MAX_PARAMS];      // shared value of each parameter
+    double* per_traj[VO_MAX_PARAMS];   // device array or nullptr
+    int64_t per_traj_n[VO_MAX_PARAMS];
+};
+
+// Device-side view of the RHS parameters, passed by value to kernels.
+struct RhsParams {
+    double shared[VO_MAX_PARAMS];
+    const double* per_traj[VO_MAX_PARAMS];
+};
+
+// Device-side tableau, passed by value (constant bank): compile-time-unrolled indices become c[0x0][..] operands.
+struct TableauDev {
+    double ac[VO_MAX_STAGES * VO_MAX_STAGES];
+    double b[VO_MAX_STAGES];
+    double b_err[VO_MAX_STAGES];
+    int s;
+    int has_err;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Errors
+// ------------------------------------------------------------------------------------------------
+extern thread_local std::string g_vo_tls_err;
+
+static inline int32_t vo_fail(vo_ctx ctx, int32_t code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_vo_tls_err = msg;
+    return code;
+}
+
+#define VO_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return vo_fail((ctx), VO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+#define VO_CHECK_LAUNCH(ctx)                                                                            \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return vo_fail((ctx), VO_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+        (ctx)->launches++;                                                                              \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Arithmetic modes. STRICT: explicit round-to-nearest multiply and add (never contracted by nvcc), the
+// reference's operation order. FAST: ordinary operators, nvcc is free to emit DFMA.
+// ------------------------------------------------------------------------------------------------
+template <bool STRICT> struct Ar {
+    static __device__ __forceinline__ double mul(double a, double b) { return STRICT ? __dmul_rn(a, b) : a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return STRICT ? __dadd_rn(a, b) : a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return STRICT ? __dsub_rn(a, b) : a - b; }
+    // y + (k*x)   (src/impls/ndarray.rs:23)
+    static __device__ __forceinline__ double axpy(double y, double k, double x) {
+        return STRICT ? __dadd_rn(y, __dmul_rn(k, x)) : fma(k, x, y);
+    }
+};
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

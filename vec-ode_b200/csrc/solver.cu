@@ -1,0 +1,853 @@
+// solver.cu — the ensemble Runge-Kutta solver: RK45Solver + ODESolver + AdaptiveODESolver
+// (src/base/rk.rs:158-320, src/base/ode.rs:208-344) for N independent trajectories held SoA on the device.
+//
+// Where the reference owns one solver object per trajectory, one vo_solver owns the whole ensemble. Control
+// state (t, h, prev_h, tgt_t, counters) is either
+//   * LOCK-STEP ("uniform"): every trajectory shares the scalars — true for step() on a freshly built solver,
+//     because the state machine of ode.rs:165-206 then never looks at the state. The scalars live on the host,
+//     are advanced there with the reference's arithmetic, and the kernels read them as launch parameters: the
+//     only HBM traffic of a step is the state itself; or
+//   * PER-TRAJECTORY: device arrays of length N, entered on the first step_adaptive() (or when per-trajectory
+//     initial steps are set). Rejected / finished lanes are masked inside the kernels.
+//
+// Two kernel paths:
+//   * small systems (compiled-in pointwise RHS, d <= 4): rk_small_kernel — a whole attempt (all stages, error
+//     estimate, norm, controller, commit) per thread in registers, k events per launch;
+//   * stage path (any d; the only path for HEAT1D): one fused kernel per stage over K buffers in HBM, then a
+//     norm + controller/commit step.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "rk_small_launch.cuh"
+#include "rk_stage.cuh"
+
+int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap);
+
+namespace {
+
+constexpr double F64_EPS = 2.220446049250313e-16;
+constexpr int PARTIAL_CAP = 1 << 14;
+
+}  // namespace
+
+struct vo_solver_s {
+    vo_ctx ctx = nullptr;
+    vo_tableau_s tab;
+    vo_rhs rhs = nullptr;
+    int64_t d = 0, n = 0;
+    double t0 = 0, tf = 0, h_init = 0;
+    vo_ens x = nullptr, next_x = nullptr, x_err = nullptr;
+    std::vector<vo_ens> K;  // stage path, allocated on first use
+    bool has_x_err = true;  // Option<V> x_err (rk.rs:249 Some; rk.rs:233-237 None)
+    // ODEAdaptiveData (ode.rs:98-110)
+    double atol = 1.0e-6, rtol = 1.0e-4, alpha = 0.9, pw = 1.0 / 3.0, min_dt = 1.0e-6, max_dt = 1.0;
+    std::vector<double> t_list;
+    double* t_list_dev = nullptr;
+    int norm_kind = VO_NORM_L2;
+    // lock-step control
+    bool uniform = true;
+    double u_t = 0, u_h = 0, u_prev_h = 0, u_dx_norm = 0;
+    int u_tgt = 0;
+    bool u_done = false;
+    int64_t u_accept = 0, u_reject = 0;
+    // per-trajectory control
+    CtlArrays ca{};
+    uint8_t* evv = nullptr;  // stage path: event of the current call per trajectory
+    double* dtv = nullptr;   // stage path: dt of the current call per trajectory
+    double* norm_partial = nullptr;
+    EvSlot* ev_dev = nullptr;
+    EvSlot* ev_host = nullptr;  // pinned
+    EvSlot ev_seen{};           // counter totals at the last read (device counters are cumulative)
+    int64_t n_done = 0;         // per-trajectory mode: trajectories that have emitted End
+    int k_events = 1;
+    int stage_path = 0;
+};
+
+namespace {
+
+bool rhs_is_small(const vo_rhs_s* r) { return r->kind != VO_RHS_HEAT1D && r->d <= 4; }
+bool use_small(const vo_solver_s* s) { return !s->stage_path && rhs_is_small(s->rhs); }
+bool use_err(const vo_solver_s* s) { return s->tab.has_err && s->has_x_err; }
+
+TableauDev make_tableau_dev(const vo_tableau_s& t) {
+    TableauDev d;
+    std::memcpy(d.ac, t.ac, sizeof d.ac), std::memcpy(d.b, t.b, sizeof d.b), std::memcpy(d.b_err, t.b_err, sizeof d.b_err);
+    d.s = t.s, d.has_err = t.has_err ? 1 : 0;
+    return d;
+}
+
+CtlShared make_ctl_shared(const vo_solver_s* s, int adaptive, int k_events) {
+    CtlShared cs;
+    std::memset(&cs, 0, sizeof cs);
+    cs.rtol = s->rtol, cs.alpha = s->alpha, cs.pw = s->pw, cs.min_dt = s->min_dt, cs.max_dt = s->max_dt;
+    cs.n_tlist = (int)s->t_list.size();
+    for (int i = 0; i < VO_INLINE_TLIST && i < cs.n_tlist; ++i) cs.t_list_inline[i] = s->t_list[i];
+    cs.t_list = s->t_list_dev;
+    cs.norm_kind = s->norm_kind;
+    cs.adaptive = adaptive;
+    cs.use_err = use_err(s) ? 1 : 0;
+    cs.k_events = k_events;
+    cs.count_events = 1;
+    cs.u_t = s->u_t, cs.u_h = s->u_h, cs.u_prev_h = s->u_prev_h, cs.u_tgt = s->u_tgt;
+    return cs;
+}
+
+// ---- host copy of the state machine for lock-step control (ode.rs:165-176, 389-399, 184-195) ----------
+int uni_step_size(const vo_solver_s* s, double* dt) {
+    if (s->u_tgt >= (int)s->t_list.size()) return VO_EV_END;
+    const double rem = s->t_list[s->u_tgt] - s->u_t;
+    if (std::fabs(rem) <= F64_EPS) return s->u_tgt >= (int)s->t_list.size() - 1 ? VO_EV_END : VO_EV_CHKPT;
+    *dt = rem < s->u_h ? rem : s->u_h;
+    return VO_EV_STEP;
+}
+void uni_checkpoint(vo_solver_s* s, bool end) {
+    s->u_tgt += 1, s->u_h = s->u_prev_h;
+    if (end) s->u_done = true;
+}
+
+// ---- per-trajectory control helpers ---------------------------------------------------------------------
+__global__ void ctl_fill_kernel(CtlArrays ca, int64_t N, double t, double h, double prev_h, double dxn, uint32_t acc, uint32_t rej, uint32_t word) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    ca.t[i] = t, ca.h[i] = h, ca.prev_h[i] = prev_h, ca.dx_norm[i] = dxn;
+    ca.n_accept[i] = acc, ca.n_reject[i] = rej, ca.word[i] = word;
+}
+
+// stage path, per-trajectory: step_size_of (ode.rs:165-176) for every live trajectory.
+__global__ void ctl_prepare_kernel(CtlArrays ca, const __grid_constant__ CtlShared cs, int64_t N, uint8_t* __restrict__ evv, double* __restrict__ dtv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t word = ca.word[i];
+    if ((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE) {
+        evv[i] = 255;
+        return;
+    }
+    const int tgt = (int)(word & VO_WORD_TGT_MASK);
+    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    int evk;
+    double dt = 0.0;
+    if (tgt >= cs.n_tlist) {
+        evk = VO_EV_END;
+    } else {
+        const double rem = tl[tgt] - ca.t[i], h = ca.h[i];
+        if (fabs(rem) <= 2.220446049250313e-16) evk = (tgt >= cs.n_tlist - 1) ? VO_EV_END : VO_EV_CHKPT;
+        else dt = rem < h ? rem : h, evk = VO_EV_STEP;
+    }
+    evv[i] = (uint8_t)evk, dtv[i] = dt;
+}
+
+// stage path, per-trajectory (d <= 64): error norm, handle_step_adaptive (ode.rs:311-334) and apply_step
+// (ode.rs:402-428) with a masked commit next_x -> x for accepted lanes.
+template <bool STRICT>
+__global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restrict__ next_x, const double* __restrict__ x_err, int64_t d, int64_t N,
+                                  CtlArrays ca, const __grid_constant__ CtlShared cs, const uint8_t* __restrict__ evv, const double* __restrict__ dtv,
+                                  EvSlot* __restrict__ ev) {
+    using A = Ar<STRICT>;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    if (i < N && evv[i] != 255) {
+        int evk = evv[i];
+        const uint32_t word = ca.word[i];
+        int tgt = (int)(word & VO_WORD_TGT_MASK);
+        uint32_t status = word >> VO_WORD_STATUS_SHIFT;
+        if (evk == VO_EV_STEP) {
+            if (cs.adaptive) {
+                double acc = 0.0;
+                if (cs.norm_kind == VO_NORM_HYPOT && d == 2) {
+                    acc = hypot(x_err[i], x_err[N + i]);
+                } else if (cs.norm_kind == VO_NORM_HYPOT) {
+                    for (int64_t c = 0; c + 1 < d; c += 2) {
+                        const double m = hypot(x_err[c * N + i], x_err[(c + 1) * N + i]);
+                        acc = A::add(acc, A::mul(m, m));
+                    }
+                    acc = sqrt(acc);
+                } else {
+                    for (int64_t c = 0; c < d; ++c) {
+                        const double e = x_err[c * N + i];
+                        if (cs.norm_kind == VO_NORM_L2) acc = A::add(acc, A::mul(e, e));
+                        else if (cs.norm_kind == VO_NORM_LINF) acc = fmax(acc, fabs(e));
+                        else acc = A::add(acc, fabs(e));
+                    }
+                    if (cs.norm_kind == VO_NORM_L2) acc = sqrt(acc);
+                }
+                const double h = ca.h[i];
+                const double f = cs.rtol / acc;
+                const double fp_lim = fmin(fmax(cs.alpha * pow(f, cs.pw), 0.3), 2.0);
+                const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+                if (!(acc == acc)) status |= VO_TRAJ_NONFINITE;
+                if (f <= 1.0) {
+                    evk = VO_EV_REJECT;
+                    if (h <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
+                }
+                ca.prev_h[i] = h, ca.h[i] = new_h, ca.dx_norm[i] = acc;
+            }
+            if (evk == VO_EV_STEP) {
+                for (int64_t c = 0; c < d; ++c) x[c * N + i] = next_x[c * N + i];
+                ca.t[i] += dtv[i];
+                ca.n_accept[i] += 1, ++c_step;
+            } else {
+                ca.n_reject[i] += 1, ++c_rej;
+            }
+        } else {
+            tgt += 1, ca.h[i] = ca.prev_h[i];
+            if (evk == VO_EV_END) status |= VO_TRAJ_DONE, ++c_end;
+            else ++c_chkpt;
+        }
+        const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
+        if (nw != word) ca.word[i] = nw;
+    }
+    c_step = __reduce_add_sync(0xffffffffu, c_step), c_chkpt = __reduce_add_sync(0xffffffffu, c_chkpt);
+    c_rej = __reduce_add_sync(0xffffffffu, c_rej), c_end = __reduce_add_sync(0xffffffffu, c_end);
+    c_stuck = __reduce_add_sync(0xffffffffu, c_stuck);
+    if ((threadIdx.x & 31) == 0) {
+        EvSlot* slot = ev + (blockIdx.x % VO_EV_SLOTS);
+        if (c_step) atomicAdd(&slot->n_step, (unsigned long long)c_step);
+        if (c_chkpt) atomicAdd(&slot->n_chkpt, (unsigned long long)c_chkpt);
+        if (c_rej) atomicAdd(&slot->n_reject, (unsigned long long)c_rej);
+        if (c_end) atomicAdd(&slot->n_end, (unsigned long long)c_end);
+        if (c_stuck) atomicAdd(&slot->n_stuck, (unsigned long long)c_stuck);
+    }
+}
+
+int32_t alloc_ctl(vo_solver_s* s) {
+    if (s->ca.t) return VO_OK;
+    vo_ctx c = s->ctx;
+    const size_t n = (size_t)s->n;
+    if (cudaMalloc(&s->ca.t, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.h, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.prev_h, 8 * n) != cudaSuccess ||
+        cudaMalloc(&s->ca.dx_norm, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.n_accept, 4 * n) != cudaSuccess ||
+        cudaMalloc(&s->ca.n_reject, 4 * n) != cudaSuccess || cudaMalloc(&s->ca.word, 4 * n) != cudaSuccess)
+        return vo_fail(c, VO_ERR_ALLOC, "solver: per-trajectory control allocation failed");
+    return VO_OK;
+}
+
+void free_ctl(vo_solver_s* s) {
+    cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm);
+    cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
+    s->ca = CtlArrays{};
+}
+
+// lock-step -> per-trajectory: every trajectory inherits the shared scalars.
+int32_t materialize(vo_solver_s* s) {
+    if (!s->uniform) return VO_OK;
+    if (s->t_list.size() > VO_WORD_TGT_MASK) return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "solver: t_list too long for per-trajectory control");
+    int32_t r = alloc_ctl(s);
+    if (r != VO_OK) return r;
+    vo_ctx c = s->ctx;
+    const uint32_t word = ((uint32_t)s->u_tgt & VO_WORD_TGT_MASK) | ((s->u_done ? (uint32_t)VO_TRAJ_DONE : 0u) << VO_WORD_STATUS_SHIFT);
+    ctl_fill_kernel<<<(unsigned)ceil_div(s->n, 256), 256, 0, c->stream>>>(s->ca, s->n, s->u_t, s->u_h, s->u_prev_h, s->u_dx_norm, (uint32_t)s->u_accept,
+                                                                         (uint32_t)s->u_reject, word);
+    VO_CHECK_LAUNCH(c);
+    s->n_done = s->u_done ? s->n : 0;
+    s->uniform = false;
+    return VO_OK;
+}
+
+void ev_sum(const EvSlot* h, EvSlot* out) {
+    std::memset(out, 0, sizeof *out);
+    for (int i = 0; i < VO_EV_SLOTS; ++i)
+        out->n_step += h[i].n_step, out->n_chkpt += h[i].n_chkpt, out->n_reject += h[i].n_reject, out->n_end += h[i].n_end, out->n_stuck += h[i].n_stuck;
+}
+
+// The device counters are cumulative since creation / reset; ev_read returns what was added since the previous
+// read (synchronises the stream), so launches made without a read-back (vo_step_many) are never lost.
+int32_t ev_read(vo_solver_s* s, EvSlot* out) {
+    vo_ctx c = s->ctx;
+    VO_CUDA(c, cudaMemcpyAsync(s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    EvSlot tot;
+    ev_sum(s->ev_host, &tot);
+    out->n_step = tot.n_step - s->ev_seen.n_step, out->n_chkpt = tot.n_chkpt - s->ev_seen.n_chkpt;
+    out->n_reject = tot.n_reject - s->ev_seen.n_reject, out->n_end = tot.n_end - s->ev_seen.n_end;
+    out->n_stuck = tot.n_stuck - s->ev_seen.n_stuck;
+    s->ev_seen = tot;
+    return VO_OK;
+}
+
+void res_add(vo_step_result* res, int64_t st, int64_t ck, int64_t rj, int64_t en, int launches) {
+    if (!res) return;
+    res->n_step += st, res->n_chkpt += ck, res->n_reject += rj, res->n_end += en, res->launches += launches;
+}
+
+// ---- small path ---------------------------------------------------------------------------------------------
+int32_t launch_small(vo_solver_s* s, const CtlShared& cs) {
+    vo_ctx c = s->ctx;
+    const TableauDev tb = make_tableau_dev(s->tab);
+    const RhsParams rp = make_rhs_params(s->rhs);
+    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, &cs, s->ev_dev, s->uniform};
+    int32_t r = VO_ERR_UNSUPPORTED;
+    switch (s->rhs->kind) {
+        case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
+        case VO_RHS_HARMONIC2D: r = launch_small_harmonic(L); break;
+        case VO_RHS_LORENZ63: r = launch_small_lorenz(L); break;
+        case VO_RHS_VDP: r = launch_small_vdp(L); break;
+    }
+    if (r != VO_OK) return vo_fail(c, r, "solver: no register-resident kernel for this RHS");
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+// Lock-step small path: advance the shared scalars through up to k events on the host exactly as the kernel
+// does per thread, launching the kernel only when at least one of them is a Step.
+int32_t small_uniform_events(vo_solver_s* s, int k, vo_step_result* res, int64_t* calls_done) {
+    const CtlShared cs = make_ctl_shared(s, 0, k);
+    bool any_step = false;
+    int64_t calls = 0;
+    for (int e = 0; e < k && !s->u_done; ++e) {
+        double dt = 0.0;
+        const int ev = uni_step_size(s, &dt);
+        ++calls;
+        if (ev == VO_EV_STEP) {
+            s->u_t += dt, s->u_accept += 1, any_step = true;
+            res_add(res, s->n, 0, 0, 0, 0);
+        } else {
+            uni_checkpoint(s, ev == VO_EV_END);
+            res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
+        }
+    }
+    if (calls_done) *calls_done = calls;
+    if (any_step) {
+        int32_t r = launch_small(s, cs);
+        if (r != VO_OK) return r;
+        res_add(res, 0, 0, 0, 0, 1);
+    }
+    return VO_OK;
+}
+
+// ---- stage path ---------------------------------------------------------------------------------------------
+int32_t ensure_K(vo_solver_s* s, int count) {
+    while ((int)s->K.size() < count) {
+        vo_ens k = nullptr;
+        int32_t r = vo_ens_create(s->ctx, s->d, s->n, &k);
+        if (r != VO_OK) return r;
+        s->K.push_back(k);
+    }
+    return VO_OK;
+}
+
+template <class RHS, bool TAIL> void launch_pointwise(vo_ctx c, const double* x0, int64_t N, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
+                                                       double* xe) {
+    const unsigned grid = (unsigned)ceil_div(N, 128);
+    if (c->arith == VO_ARITH_STRICT) stage_pointwise_kernel<RHS, true, TAIL><<<grid, 128, 0, c->stream>>>(x0, N, sa, rp, k_out, nx, xe);
+    else stage_pointwise_kernel<RHS, false, TAIL><<<grid, 128, 0, c->stream>>>(x0, N, sa, rp, k_out, nx, xe);
+}
+
+template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs& sa, double* k_out, double* nx, double* xe) {
+    vo_ctx c = s->ctx;
+    const vo_rhs_s* r = s->rhs;
+    const double* x0 = s->x->p;
+    const RhsParams rp = make_rhs_params(r);
+    switch (r->kind) {
+        case VO_RHS_DIAG_LINEAR:
+            switch (r->d) {
+                case 1: launch_pointwise<RhsF<VO_RHS_DIAG_LINEAR, 1>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+                case 2: launch_pointwise<RhsF<VO_RHS_DIAG_LINEAR, 2>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+                case 3: launch_pointwise<RhsF<VO_RHS_DIAG_LINEAR, 3>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+                case 4: launch_pointwise<RhsF<VO_RHS_DIAG_LINEAR, 4>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+                default: return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: DIAG_LINEAR needs d <= 4");
+            }
+            break;
+        case VO_RHS_HARMONIC2D: launch_pointwise<RhsF<VO_RHS_HARMONIC2D, 2>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+        case VO_RHS_LORENZ63: launch_pointwise<RhsF<VO_RHS_LORENZ63, 3>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+        case VO_RHS_VDP: launch_pointwise<RhsF<VO_RHS_VDP, 2>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+        case VO_RHS_HEAT1D: {
+            const double kappa = r->shared[0];
+            const bool strict = c->arith == VO_ARITH_STRICT;
+            if (s->n == 1) {
+                if (s->tab.s > 8) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: HEAT1D needs s <= 8");
+                const int64_t tiles = ceil_div(s->d, HEAT_TILE);
+                const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
+                if (strict) stage_heat_kernel<true, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
+                else stage_heat_kernel<false, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
+            } else {
+                const unsigned grid = (unsigned)ceil_div(s->d * s->n, 256);
+                if (strict) stage_heat_ens_kernel<true, TAIL><<<grid, 256, 0, c->stream>>>(x0, s->d, s->n, sa, kappa, k_out, nx, xe);
+                else stage_heat_ens_kernel<false, TAIL><<<grid, 256, 0, c->stream>>>(x0, s->d, s->n, sa, kappa, k_out, nx, xe);
+            }
+        } break;
+        default: return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: unknown RHS");
+    }
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+// One rk_step (rk.rs:90-155) through the stage kernels: s launches. K_out (nullable) receives all s stage
+// derivatives; otherwise K_{s-1} never leaves registers.
+int32_t stage_rk_step(vo_solver_s* s, double t, double dt, bool per_traj, double* nx, double* xe, vo_ens* K_out, int* launches) {
+    const vo_tableau_s& tb = s->tab;
+    const int S = tb.s;
+    const bool want_err = tb.has_err && xe != nullptr;
+    if (!K_out) {
+        int32_t r = ensure_K(s, std::max(1, S - 1));
+        if (r != VO_OK) return r;
+    }
+    StageArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    for (int j = 0; j < S; ++j) sa.K[j] = K_out ? K_out[j]->p : (j < (int)s->K.size() ? s->K[j]->p : nullptr);
+    sa.s = S, sa.dt = dt;
+    if (per_traj) sa.tv = s->ca.t, sa.dtv = s->dtv, sa.evv = s->evv;
+    for (int i = 0; i < S; ++i) {
+        const double* row = &tb.ac[i * S];
+        sa.i = i, sa.c_i = row[i];
+        sa.t_i = i == 0 ? t : t + row[i] * dt;  // rk.rs:119
+        for (int j = 0; j < i; ++j) sa.a[j] = row[j];
+        int32_t r;
+        if (i < S - 1) {
+            r = launch_stage_kernel<false>(s, sa, const_cast<double*>(sa.K[i]), nullptr, nullptr);
+        } else {
+            for (int j = 0; j < S; ++j) sa.b[j] = tb.b[j], sa.b_err[j] = tb.b_err[j];
+            sa.use_err = want_err ? 1 : 0;
+            r = launch_stage_kernel<true>(s, sa, K_out ? K_out[S - 1]->p : nullptr, nx, want_err ? xe : nullptr);
+        }
+        if (r != VO_OK) return r;
+        if (launches) ++*launches;
+    }
+    return VO_OK;
+}
+
+// Lock-step stage path: one event, controller on the host (the norm is read back for adaptive steps).
+int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) {
+    vo_ctx c = s->ctx;
+    double dt = 0.0;
+    int ev = uni_step_size(s, &dt);
+    int launches = 0;
+    if (ev == VO_EV_STEP) {
+        const double h = s->u_h;  // ode.rs:314
+        int32_t r = stage_rk_step(s, s->u_t, dt, false, s->next_x->p, use_err(s) ? s->x_err->p : nullptr, nullptr, &launches);
+        if (r != VO_OK) return r;
+        if (adaptive) {
+            double* out = (double*)c->dscratch;
+            if (s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: lock-step adaptive control needs N == 1");
+            const int64_t launches_before = c->launches;
+            r = vo_norm_device(s->x_err, s->norm_kind, out, s->norm_partial, PARTIAL_CAP);
+            if (r != VO_OK) return r;
+            launches += (int)(c->launches - launches_before);
+            VO_CUDA(c, cudaMemcpyAsync(c->pinned, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VO_CUDA(c, cudaStreamSynchronize(c->stream));
+            const double dxn = *(double*)c->pinned;
+            s->u_dx_norm = dxn;
+            const double f = s->rtol / dxn;                                                        // ode.rs:320
+            const double fp_lim = std::fmin(std::fmax(s->alpha * std::pow(f, s->pw), 0.3), 2.0);   // ode.rs:321-323
+            const double new_h = std::fmin(std::fmax(fp_lim * h, s->min_dt), s->max_dt);          // ode.rs:324
+            s->u_prev_h = s->u_h, s->u_h = new_h;                                                  // ode.rs:326
+            if (f <= 1.0) ev = VO_EV_REJECT;                                                       // ode.rs:328-330
+        }
+        if (ev == VO_EV_STEP) {
+            std::swap(s->x, s->next_x);  // advance, ode.rs:184-188
+            s->u_t += dt, s->u_accept += 1;
+            res_add(res, s->n, 0, 0, 0, launches);
+        } else {
+            s->u_reject += 1;
+            res_add(res, 0, 0, s->n, 0, launches);
+        }
+    } else {
+        uni_checkpoint(s, ev == VO_EV_END);
+        res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
+    }
+    return VO_OK;
+}
+
+// Per-trajectory stage path: prepare -> s stage kernels (masked) -> norm/controller/commit. One event per call.
+int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
+    vo_ctx c = s->ctx;
+    if (s->d > 64 || s->rhs->kind == VO_RHS_HEAT1D)
+        return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: per-trajectory control needs a pointwise RHS with d <= 64");
+    if (!s->evv) {
+        if (cudaMalloc(&s->evv, (size_t)s->n) != cudaSuccess || cudaMalloc(&s->dtv, 8 * (size_t)s->n) != cudaSuccess)
+            return vo_fail(c, VO_ERR_ALLOC, "stage path: event buffers");
+    }
+    const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, 1);
+    const unsigned grid = (unsigned)ceil_div(s->n, 256);
+    ctl_prepare_kernel<<<grid, 256, 0, c->stream>>>(s->ca, cs, s->n, s->evv, s->dtv);
+    VO_CHECK_LAUNCH(c);
+    ++*launches;
+    int32_t r = stage_rk_step(s, 0.0, 0.0, true, s->next_x->p, use_err(s) ? s->x_err->p : nullptr, nullptr, launches);
+    if (r != VO_OK) return r;
+    const double* xe = use_err(s) ? s->x_err->p : nullptr;
+    if (c->arith == VO_ARITH_STRICT) ctl_commit_kernel<true><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev);
+    else ctl_commit_kernel<false><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev);
+    VO_CHECK_LAUNCH(c);
+    ++*launches;
+    return VO_OK;
+}
+
+// validate_adaptive (ode.rs:312, rk.rs:317-319) and the switch from lock-step to per-trajectory control.
+int32_t prepare_mode(vo_solver_s* s, bool adaptive) {
+    vo_ctx c = s->ctx;
+    if (adaptive && !s->has_x_err) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // ode.rs:312
+    if (adaptive && !s->tab.has_err)
+        return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "step_adaptive: the tableau has no b_err, so no error estimate is ever formed");
+    if (s->uniform && adaptive && (use_small(s) || s->n > 1)) return materialize(s);
+    return VO_OK;
+}
+
+// One call of step()/step_adaptive() for every trajectory (or k fused calls on the small path).
+int32_t do_events(vo_solver_s* s, bool adaptive, int k, vo_step_result* res, int64_t* calls_done, bool read_back) {
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    int32_t pr = prepare_mode(s, adaptive);
+    if (pr != VO_OK) return pr;
+    const bool small = use_small(s);
+    if (s->uniform) {
+        if (small) return small_uniform_events(s, k, res, calls_done);
+        if (calls_done) *calls_done = 1;
+        if (s->u_done) return VO_OK;
+        return stage_uniform_event(s, adaptive, res);
+    }
+    // per-trajectory control
+    int launches = 0;
+    if (small) {
+        const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, k);
+        int32_t r = launch_small(s, cs);
+        if (r != VO_OK) return r;
+        launches = 1;
+        if (calls_done) *calls_done = k;
+    } else {
+        int32_t r = stage_pertraj_event(s, adaptive, &launches);
+        if (r != VO_OK) return r;
+        if (calls_done) *calls_done = 1;
+    }
+    if (res) res->launches += launches;
+    if (read_back) {
+        EvSlot sum;
+        int32_t r = ev_read(s, &sum);
+        if (r != VO_OK) return r;
+        s->n_done += (int64_t)sum.n_end;
+        res_add(res, (int64_t)sum.n_step, (int64_t)sum.n_chkpt, (int64_t)sum.n_reject, (int64_t)sum.n_end, 0);
+    }
+    return VO_OK;
+}
+
+void finish_result(vo_solver_s* s, vo_step_result* res) {
+    if (!res) return;
+    res->n_active = s->uniform ? (s->u_done ? 0 : s->n) : s->n - s->n_done;
+    res->state = res->n_active == 0 ? VO_STATE_DONE : VO_STATE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vo_rk_create(vo_ctx c, vo_tableau tableau, vo_rhs rhs, double t0, double tf, vo_ens x0, double h, vo_solver* out) {
+    if (!c || !tableau || !rhs || !x0 || !out) return vo_fail(c, VO_ERR_BAD_ARG, "vo_rk_create: NULL argument");
+    if (rhs->d != x0->d) return vo_fail(c, VO_ERR_SHAPE, "vo_rk_create: RHS dimension does not match the ensemble");
+    for (int q = 0; q < rhs->np; ++q)
+        if (rhs->per_traj[q] && rhs->per_traj_n[q] != x0->n) return vo_fail(c, VO_ERR_SHAPE, "vo_rk_create: per-trajectory parameter array length != N");
+    DeviceGuard g(c->device);
+    vo_solver s = new vo_solver_s();
+    s->ctx = c, s->tab = *tableau, s->rhs = rhs, s->d = x0->d, s->n = x0->n;
+    s->t0 = t0, s->tf = tf, s->h_init = h;
+    s->t_list = {t0, tf};  // ode.rs:144
+    s->u_t = t0, s->u_h = h, s->u_prev_h = h, s->u_tgt = 0;
+    int32_t r = vo_ens_clone(x0, &s->x);                      // ODEData::new clones x0 into x and next_x (ode.rs:141-150)
+    if (r == VO_OK) r = vo_ens_clone(x0, &s->next_x);
+    if (r == VO_OK && tableau->has_err) r = vo_ens_clone(x0, &s->x_err);  // Some(x0.clone()), rk.rs:249
+    if (r == VO_OK && cudaMalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: counters");
+    if (r == VO_OK && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: pinned counters");
+    if (r == VO_OK && cudaMalloc(&s->norm_partial, sizeof(double) * PARTIAL_CAP) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: norm scratch");
+    if (r == VO_OK) {
+        cudaError_t e = cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, c->stream);
+        if (e != cudaSuccess) r = vo_fail(c, VO_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (r != VO_OK) {
+        vo_solver_destroy(s);
+        return r;
+    }
+    *out = s;
+    return VO_OK;
+}
+
+int32_t vo_rk45_create(vo_ctx c, vo_rhs rhs, double t0, double tf, vo_ens x0, double h, vo_solver* out) {
+    vo_tableau t = nullptr;
+    int32_t r = vo_tableau_builtin(VO_TABLEAU_RKF45_REF, &t);  // rk.rs:250-254
+    if (r != VO_OK) return r;
+    r = vo_rk_create(c, t, rhs, t0, tf, x0, h, out);
+    vo_tableau_destroy(t);  // the solver keeps its own copy
+    return r;
+}
+
+int32_t vo_solver_destroy(vo_solver s) {
+    if (!s) return VO_OK;
+    DeviceGuard g(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
+    for (vo_ens k : s->K) vo_ens_destroy(k);
+    free_ctl(s);
+    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev);
+    cudaFreeHost(s->ev_host);
+    delete s;
+    return VO_OK;
+}
+
+int32_t vo_solver_no_adaptive(vo_solver s) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->has_x_err = false;  // rk.rs:233-237
+    return VO_OK;
+}
+
+int32_t vo_solver_with_tolerance(vo_solver s, double atol, double rtol) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (!(atol > 0.0) || !(rtol > 0.0)) return vo_fail(s->ctx, VO_ERR_BAD_ARG, "Invalid tolerances: atol=" + std::to_string(atol) + ", rtol=" + std::to_string(rtol));
+    s->atol = atol, s->rtol = rtol;  // ode.rs:298-306 (atol is stored and never read, as in the reference)
+    return VO_OK;
+}
+
+int32_t vo_solver_with_step_range(vo_solver s, double dt_min, double dt_max) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (!(dt_min > 0.0) || !(dt_max > 0.0) || !(dt_max > dt_min))
+        return vo_fail(s->ctx, VO_ERR_BAD_ARG, "Invalid step range: (" + std::to_string(dt_min) + ", " + std::to_string(dt_max) + ")");
+    if (!s->uniform) return vo_fail(s->ctx, VO_ERR_STATE, "with_step_range: builder called after per-trajectory stepping began");
+    s->min_dt = dt_min, s->max_dt = dt_max;
+    const double h = std::sqrt(dt_min * dt_max);  // ode.rs:273-280: reset_step_size(sqrt(min*max))
+    s->u_h = h, s->u_prev_h = h;
+    return VO_OK;
+}
+
+int32_t vo_solver_with_init_step(vo_solver s, double h) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (h < s->min_dt || h > s->max_dt)  // ode.rs:287-296
+        return vo_fail(s->ctx, VO_ERR_BAD_ARG, "Step " + std::to_string(h) + " is not inside the range (" + std::to_string(s->min_dt) + ", " + std::to_string(s->max_dt) + ")");
+    if (!s->uniform) return vo_fail(s->ctx, VO_ERR_STATE, "with_init_step: builder called after per-trajectory stepping began");
+    s->u_h = h, s->u_prev_h = h;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n) {
+    if (!s || !t_list || n < 1) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_t_list: bad argument");
+    if (n > (int32_t)VO_WORD_TGT_MASK) return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "vo_solver_set_t_list: list too long");
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    s->t_list.assign(t_list, t_list + n);
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(s->t_list_dev), s->t_list_dev = nullptr;
+    if (n > VO_INLINE_TLIST) {
+        if (cudaMalloc(&s->t_list_dev, sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_set_t_list: cudaMalloc");
+        VO_CUDA(c, cudaMemcpy(s->t_list_dev, t_list, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    return VO_OK;
+}
+
+int32_t vo_solver_set_order_alpha(vo_solver s, double order, double alpha) {
+    if (!s || !(order > 0.0)) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_order_alpha: bad argument");
+    s->pw = 1.0 / order, s->alpha = alpha;  // `order.recip()`, ode.rs:120; with_alpha, ode.rs:128-131
+    return VO_OK;
+}
+
+int32_t vo_solver_set_norm(vo_solver s, int32_t kind) {
+    if (!s || kind < 0 || kind > VO_NORM_HYPOT) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_norm: bad norm kind");
+    s->norm_kind = kind;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n) {
+    if (!s || !h_host || n != s->n) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_h_array: bad argument");
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    int32_t r = materialize(s);
+    if (r != VO_OK) return r;
+    VO_CUDA(c, cudaMemcpyAsync(s->ca.h, h_host, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(c, cudaMemcpyAsync(s->ca.prev_h, h_host, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VO_OK;
+}
+
+int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k) {
+    if (!s || k < 1 || k > (1 << 20)) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_events_per_launch: bad k");
+    s->k_events = k;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_path(vo_solver s, int32_t stage_path) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->stage_path = stage_path ? 1 : 0;
+    return VO_OK;
+}
+
+static int32_t step_impl(vo_solver s, bool adaptive, vo_step_result* res) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (res) std::memset(res, 0, sizeof *res);
+    int32_t r = do_events(s, adaptive, 1, res, nullptr, true);
+    if (r != VO_OK) return r;
+    finish_result(s, res);
+    return VO_OK;
+}
+
+int32_t vo_step(vo_solver s, vo_step_result* res) { return step_impl(s, false, res); }
+int32_t vo_step_adaptive(vo_solver s, vo_step_result* res) { return step_impl(s, true, res); }
+
+int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result* res) {
+    if (!s) return VO_ERR_BAD_ARG;
+    vo_step_result acc;
+    std::memset(&acc, 0, sizeof acc);
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    int64_t calls = 0;
+    const bool adp = adaptive != 0;
+    int32_t r = prepare_mode(s, adp);
+    if (r != VO_OK) return r;
+    // lock-step phase: no read-back is needed, the host knows every event
+    while (s->uniform && !s->u_done && (max_calls <= 0 || calls < max_calls)) {
+        int k = use_small(s) ? s->k_events : 1;
+        if (max_calls > 0) k = (int)std::min<int64_t>(k, max_calls - calls);
+        int64_t done = 0;
+        r = do_events(s, adp, k, &acc, &done, false);
+        if (r != VO_OK) return r;
+        calls += done;
+    }
+    if (!s->uniform) {
+        // per-trajectory phase: launch a batch of sweeps, then read the counters once. Finished lanes exit on
+        // their status word, so sweeps past the end of the slowest trajectory only cost 4 bytes per lane.
+        int batch = 4;
+        while (s->n_done < s->n && (max_calls <= 0 || calls < max_calls)) {
+            for (int b = 0; b < batch && (max_calls <= 0 || calls < max_calls); ++b) {
+                int k = use_small(s) ? s->k_events : 1;
+                if (max_calls > 0) k = (int)std::min<int64_t>(k, max_calls - calls);
+                int64_t done = 0;
+                r = do_events(s, adp, k, &acc, &done, false);
+                if (r != VO_OK) return r;
+                calls += done;
+            }
+            EvSlot sum;
+            r = ev_read(s, &sum);
+            if (r != VO_OK) return r;
+            s->n_done += (int64_t)sum.n_end;
+            res_add(&acc, (int64_t)sum.n_step, (int64_t)sum.n_chkpt, (int64_t)sum.n_reject, (int64_t)sum.n_end, 0);
+            if (sum.n_stuck && sum.n_step == 0 && sum.n_chkpt == 0 && sum.n_end == 0) {
+                // every live trajectory is rejecting at h == min_dt: the reference would spin forever (ode.rs:324-330)
+                finish_result(s, &acc);
+                acc.state = VO_STATE_ERR;
+                if (res) *res = acc;
+                return vo_fail(c, VO_ERR_STATE, "vo_run: all remaining trajectories are rejected at h == min_dt");
+            }
+            batch = std::min(batch * 2, 64);
+        }
+    }
+    finish_result(s, &acc);
+    if (res) *res = acc;
+    return VO_OK;
+}
+
+int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int64_t rounds) {
+    if (!solvers || n < 1 || rounds < 0) return VO_ERR_BAD_ARG;
+    for (int i = 0; i < n; ++i)
+        if (!solvers[i] || solvers[i]->ctx != solvers[0]->ctx) return vo_fail(solvers[0] ? solvers[0]->ctx : nullptr, VO_ERR_BAD_ARG, "vo_step_many: solvers must share one ctx");
+    DeviceGuard g(solvers[0]->ctx->device);
+    for (int i = 0; i < n; ++i) {
+        int32_t r = prepare_mode(solvers[i], adaptive != 0);
+        if (r != VO_OK) return r;
+    }
+    for (int64_t rd = 0; rd < rounds; ++rd)
+        for (int i = 0; i < n; ++i) {
+            vo_solver s = solvers[i];
+            int32_t r = do_events(s, adaptive != 0, use_small(s) ? s->k_events : 1, nullptr, nullptr, false);
+            if (r != VO_OK) return r;
+        }
+    return VO_OK;
+}
+
+int32_t vo_current(vo_solver s, double* t_min, double* t_max, vo_ens* x) {
+    if (!s) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    if (x) *x = s->x;
+    if (t_min || t_max) {
+        if (s->uniform) {
+            if (t_min) *t_min = s->u_t;
+            if (t_max) *t_max = s->u_t;
+        } else {
+            std::vector<double> t((size_t)s->n);
+            VO_CUDA(c, cudaMemcpyAsync(t.data(), s->ca.t, 8 * (size_t)s->n, cudaMemcpyDeviceToHost, c->stream));
+            VO_CUDA(c, cudaStreamSynchronize(c->stream));
+            const auto mm = std::minmax_element(t.begin(), t.end());
+            if (t_min) *t_min = *mm.first;
+            if (t_max) *t_max = *mm.second;
+        }
+    }
+    return VO_OK;
+}
+
+int32_t vo_solver_stats(vo_solver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm, int32_t* status) {
+    if (!s) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)s->n;
+    if (s->uniform) {
+        for (size_t i = 0; i < n; ++i) {
+            if (accepted) accepted[i] = s->u_accept;
+            if (rejected) rejected[i] = s->u_reject;
+            if (t) t[i] = s->u_t;
+            if (h) h[i] = s->u_h;
+            if (dx_norm) dx_norm[i] = s->u_dx_norm;
+            if (status) status[i] = s->u_done ? VO_TRAJ_DONE : 0;
+        }
+        return VO_OK;
+    }
+    std::vector<uint32_t> tmp(n);
+    if (accepted) {
+        VO_CUDA(c, cudaMemcpyAsync(tmp.data(), s->ca.n_accept, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+        VO_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) accepted[i] = tmp[i];
+    }
+    if (rejected) {
+        VO_CUDA(c, cudaMemcpyAsync(tmp.data(), s->ca.n_reject, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+        VO_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) rejected[i] = tmp[i];
+    }
+    if (status) {
+        VO_CUDA(c, cudaMemcpyAsync(tmp.data(), s->ca.word, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+        VO_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) status[i] = (int32_t)(tmp[i] >> VO_WORD_STATUS_SHIFT);
+    }
+    if (t) VO_CUDA(c, cudaMemcpyAsync(t, s->ca.t, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (h) VO_CUDA(c, cudaMemcpyAsync(h, s->ca.h, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (dx_norm) VO_CUDA(c, cudaMemcpyAsync(dx_norm, s->ca.dx_norm, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VO_OK;
+}
+
+int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
+    if (!s || !x0) return VO_ERR_BAD_ARG;
+    if (x0->d != s->d || x0->n != s->n) return vo_fail(s->ctx, VO_ERR_SHAPE, "vo_solver_reset: shape mismatch");
+    DeviceGuard g(s->ctx->device);
+    int32_t r = vo_ens_copy(s->x, x0);
+    if (r == VO_OK) r = vo_ens_copy(s->next_x, x0);
+    if (r == VO_OK && s->x_err) r = vo_ens_copy(s->x_err, x0);
+    if (r != VO_OK) return r;
+    s->uniform = true;
+    s->u_t = s->t0, s->u_h = s->h_init, s->u_prev_h = s->h_init, s->u_tgt = 0, s->u_done = false;
+    s->u_accept = s->u_reject = 0, s->u_dx_norm = 0.0, s->n_done = 0;
+    VO_CUDA(s->ctx, cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, s->ctx->stream));
+    std::memset(&s->ev_seen, 0, sizeof s->ev_seen);
+    return VO_OK;
+}
+
+int32_t vo_rk_try_step(vo_solver s, double t, double dt, vo_ens next_x, vo_ens x_err, vo_ens* K) {
+    if (!s || !next_x) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    if (next_x->d != s->d || next_x->n != s->n || (x_err && (x_err->d != s->d || x_err->n != s->n)))
+        return vo_fail(c, VO_ERR_SHAPE, "vo_rk_try_step: shape mismatch");
+    if (K)
+        for (int j = 0; j < s->tab.s; ++j)
+            if (!K[j] || K[j]->d != s->d || K[j]->n != s->n) return vo_fail(c, VO_ERR_SHAPE, "vo_rk_try_step: K must hold s ensembles of the solver's shape");
+    return stage_rk_step(s, t, dt, false, next_x->p, (x_err && s->has_x_err) ? x_err->p : nullptr, K, nullptr);
+}
+
+int32_t vo_rhs_eval(vo_rhs r, double t, vo_ens x, vo_ens dx) {
+    if (!r || !x || !dx) return VO_ERR_BAD_ARG;
+    vo_ctx c = r->ctx;
+    if (x->d != r->d || dx->d != x->d || dx->n != x->n) return vo_fail(c, VO_ERR_SHAPE, "vo_rhs_eval: shape mismatch");
+    DeviceGuard g(c->device);
+    // K_0 = f(t, x): stage 0 of the stage path on a throw-away solver view
+    vo_solver_s tmp;
+    tmp.ctx = c, tmp.rhs = r, tmp.d = x->d, tmp.n = x->n, tmp.x = x;
+    tmp.tab.s = 2;
+    StageArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    sa.s = 2, sa.i = 0, sa.t_i = t;
+    int32_t rc = launch_stage_kernel<false>(&tmp, sa, dx->p, nullptr, nullptr);
+    tmp.x = nullptr;
+    return rc;
+}
+
+}  // extern "C"
