@@ -61,13 +61,16 @@ class Context:
         return int(lib().vo_ctx_stream(self._h) or 0)
 
     def close(self):
+        """Drain the stream. The native context itself is released when the last Ensemble / Rhs / solver that refers to
+        it is gone (they hold a reference to this object), never while a child handle could still touch it."""
         if self._h:
-            lib().vo_ctx_destroy(self._h)
-            self._h = _vp()
+            self.sync()
 
     def __del__(self):
         try:
-            self.close()
+            if self._h:
+                lib().vo_ctx_destroy(self._h)
+                self._h = _vp()
         except Exception:
             pass
 
@@ -137,7 +140,7 @@ class Ensemble:
 
     def __del__(self):
         try:
-            if self._h and not self._borrowed:
+            if self._h and not self._borrowed and self.ctx._h:
                 lib().vo_ens_destroy(self._h)
         except Exception:
             pass
@@ -255,7 +258,7 @@ class Rhs:
 
     def __del__(self):
         try:
-            if self._h:
+            if self._h and self.ctx._h:
                 lib().vo_rhs_destroy(self._h)
         except Exception:
             pass
@@ -382,7 +385,7 @@ class RK45Solver:
 
     def __del__(self):
         try:
-            if self._h:
+            if self._h and self.ctx._h:
                 lib().vo_solver_destroy(self._h)
         except Exception:
             pass
