@@ -45,7 +45,7 @@ typedef struct vo_expsolver_s* vo_expsolver;
 
 /* ---- context ---------------------------------------------------------------------------------- */
 /* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
- * let the ctx create its own non-blocking stream. */
+ * let the ctx create its own non-blocking stream (use CUDA's cudaStreamLegacy handle, 0x1, to name the NULL stream). */
 int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out);
 int32_t vo_ctx_destroy(vo_ctx ctx);
 int32_t vo_ctx_sync(vo_ctx ctx);

@@ -41,7 +41,9 @@ class Context:
     def on_torch_stream(cls, device: int = 0, arith: str = "strict") -> "Context":
         import torch
         torch.cuda.set_device(device)
-        return cls(device, torch.cuda.current_stream(device).cuda_stream, arith)
+        # torch's default stream is the legacy NULL stream, whose handle 0 would mean "create your own" to vo_ctx_create:
+        # name it by CUDA's explicit handle cudaStreamLegacy (0x1) so that torch.cuda.Event timing sees our kernels.
+        return cls(device, torch.cuda.current_stream(device).cuda_stream or 1, arith)
 
     def set_arith(self, mode: str):
         """'strict': the reference's un-fused multiply/add order, bit-identical to the CPU restatement.

@@ -43,9 +43,8 @@ struct CtlShared {
     int use_err;       // tableau has b_err AND the solver still holds x_err (rk.rs:136-151)
     int k_events;      // calls fused into this launch
     int count_events;  // accumulate vo_step_result counters
-    // uniform (lock-step) control: every trajectory shares these scalars, nothing is loaded or stored
-    double u_t, u_h, u_prev_h;
-    int u_tgt;
+    int pw_is_third;   // pw == 1.0/3.0 exactly (the order RK45Solver hard-wires, rk.rs:258-260)
+    int record_dx_norm;  // keep ODEAdaptiveData.dx_norm (ode.rs:104) per trajectory
 };
 
 // Event counters, VO_EV_SLOTS copies 128 bytes apart to spread the atomics (host sums the slots).
@@ -97,11 +96,13 @@ __device__ __forceinline__ void combine(const double* __restrict__ k, int n, con
                 for (int c = 0; c < D; ++c) v[c] = A::axpy(v[c], k[j], K[j][c]);
             }
     } else {
+        // FMA chain. Zero coefficients are NOT tested for here: a data-dependent skip costs a DSETP + selects per term,
+        // more than the FMA it would save (the stage-path kernels, which save a whole HBM pass per zero, do skip).
 #pragma unroll
-        for (int c = 0; c < D; ++c) v[c] = 0.0;
+        for (int c = 0; c < D; ++c) v[c] = k[0] * K[0][c];
 #pragma unroll
-        for (int j = 0; j < SM; ++j)
-            if (j < n && k[j] != 0.0) {  // uniform predicate on a constant-bank value
+        for (int j = 1; j < SM; ++j)
+            if (j < n) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) v[c] = fma(k[j], K[j][c], v[c]);
             }
@@ -141,29 +142,95 @@ __device__ __forceinline__ void rk_attempt(const TableauDev& tb, bool use_err, d
     }
 }
 
-template <class RHS, int S, bool STRICT, bool UNIFORM>
-__global__ void __launch_bounds__(128) rk_small_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
-                                                       const __grid_constant__ RhsParams rp, const CtlArrays ca,
-                                                       const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev) {
-    constexpr int D = RHS::D;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
-    if (i < N) {
-        uint32_t word = UNIFORM ? (uint32_t)cs.u_tgt : ca.word[i];
-        if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
-            double xc[D], p[RHS::NP];
+// ---- lock-step fixed-step kernel -----------------------------------------------------------------------------
+// Every trajectory takes the same (t, dt) sequence, which the host has already derived with the reference's state
+// machine (ode.rs:165-176, 389-399), so the kernel carries no control arithmetic at all: per trajectory it moves
+// 2*d*8 bytes and executes the rk_step FLOPs, nothing else. Persistent grid: each thread walks trajectories
+// i, i+stride, ... and loads the NEXT trajectory's state before integrating the current one, so the HBM latency of
+// iteration n+1 hides behind the FP64 work of iteration n.
+#define VO_MAX_FUSED 32
+struct StepList {
+    int n;        // steps fused into this launch (<= VO_MAX_FUSED)
+    int use_err;  // propagate X_berr (rk.rs:142-146) instead of X_b
+    double t[VO_MAX_FUSED];
+    double dt[VO_MAX_FUSED];
+};
+
+template <class RHS> __device__ __forceinline__ void lane_load(const double* __restrict__ x, int64_t N, const RhsParams& rp, int64_t i,
+                                                               double (&xc)[RHS::D], double (&p)[RHS::NP]) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) xc[c] = x[c * N + i];
-            load_params<RHS::NP>(rp, i, p);
-            double t = UNIFORM ? cs.u_t : ca.t[i];
-            double h = UNIFORM ? cs.u_h : ca.h[i];
-            double prev_h = UNIFORM ? cs.u_prev_h : 0.0;
-            bool prev_h_loaded = UNIFORM, ctl_dirty = false, moved = false;
+    for (int c = 0; c < RHS::D; ++c) xc[c] = x[c * N + i];
+    load_params<RHS::NP>(rp, i, p);
+}
+
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(128) rk_fixed_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                       const __grid_constant__ RhsParams rp, const __grid_constant__ StepList sl) {
+    constexpr int D = RHS::D;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double xc[D], p[RHS::NP], xn[D], pn[RHS::NP];
+    if (i < N) lane_load<RHS>(x, N, rp, i, xc, p);
+    while (i < N) {
+        const int64_t j = i + stride;
+        if (j < N) lane_load<RHS>(x, N, rp, j, xn, pn);  // prefetch the next trajectory of this thread
+        for (int e = 0; e < sl.n; ++e) {
+            double xf[D], xe[D];
+            rk_attempt<RHS, S, STRICT>(tb, sl.use_err != 0, sl.t[e], sl.dt[e], xc, p, xf, xe);
+#pragma unroll
+            for (int c = 0; c < D; ++c) xc[c] = xf[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+#pragma unroll
+        for (int c = 0; c < D; ++c) xc[c] = xn[c];
+#pragma unroll
+        for (int q = 0; q < RHS::NP; ++q) p[q] = pn[q];
+        i = j;
+    }
+}
+
+// ---- per-trajectory control kernel ---------------------------------------------------------------------------
+// alpha * f^pw (ode.rs:133-135). STRICT keeps the general pow of the reference's `powf`; FAST takes the cube root
+// directly when pw is exactly 1/3 (the order RK45Solver hard-wires, rk.rs:258-260) — a few ulp apart, 4x fewer FP64 ops.
+template <bool STRICT> __device__ __forceinline__ double step_size_mul(double alpha, double f, double pw, int pw_is_third) {
+    if (!STRICT && pw_is_third) return alpha * cbrt(f);
+    return alpha * pow(f, pw);
+}
+
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                     const __grid_constant__ RhsParams rp, const CtlArrays ca, const __grid_constant__ CtlShared cs,
+                                                     EvSlot* __restrict__ ev) {
+    constexpr int D = RHS::D;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    // current / prefetched lane
+    uint32_t word = 0, word_n = 0;
+    double xc[D], p[RHS::NP], t = 0.0, h = 0.0, xn[D], pn[RHS::NP], t_n = 0.0, h_n = 0.0;
+    bool live = false, live_n = false;
+    if (i < N) {
+        word = ca.word[i];
+        live = !((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
+        if (live) lane_load<RHS>(x, N, rp, i, xc, p), t = ca.t[i], h = ca.h[i];
+    }
+    while (i < N) {
+        const int64_t j = i + stride;
+        if (j < N) {
+            word_n = ca.word[j];
+            live_n = !((word_n >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
+            if (live_n) lane_load<RHS>(x, N, rp, j, xn, pn), t_n = ca.t[j], h_n = ca.h[j];
+        }
+        if (live) {
+            double prev_h = 0.0;
+            bool prev_h_loaded = false, ctl_dirty = false, moved = false;
             int tgt = (int)(word & VO_WORD_TGT_MASK);
             uint32_t status = word >> VO_WORD_STATUS_SHIFT;
             double dxn = 0.0;
             bool dxn_set = false;
-            const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+            unsigned l_step = 0, l_rej = 0;
             for (int e = 0; e < cs.k_events; ++e) {
                 // ---- step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
                 int evk;
@@ -178,10 +245,10 @@ __global__ void __launch_bounds__(128) rk_small_kernel(double* __restrict__ x, i
                 if (evk == VO_EV_STEP) {
                     double xf[D], xe[D];
                     rk_attempt<RHS, S, STRICT>(tb, cs.use_err != 0, t, dt, xc, p, xf, xe);
-                    if (!UNIFORM && cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
+                    if (cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
                         dxn = err_norm<STRICT, D>(xe, cs.norm_kind), dxn_set = true;
                         const double f = cs.rtol / dxn;
-                        const double fp_lim = fmin(fmax(cs.alpha * pow(f, cs.pw), 0.3), 2.0);
+                        const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
                         const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
                         if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
                         if (f <= 1.0) {
@@ -194,9 +261,9 @@ __global__ void __launch_bounds__(128) rk_small_kernel(double* __restrict__ x, i
 #pragma unroll
                         for (int c = 0; c < D; ++c) xc[c] = xf[c];
                         t += dt;
-                        moved = true, ++c_step;
+                        moved = true, ++l_step;
                     } else {
-                        ++c_rej;
+                        ++l_rej;
                     }
                 } else {  // Chkpt / End -> checkpoint_update, ode.rs:192-195
                     if (!prev_h_loaded) prev_h = ca.prev_h[i], prev_h_loaded = true;
@@ -211,22 +278,28 @@ __global__ void __launch_bounds__(128) rk_small_kernel(double* __restrict__ x, i
             if (moved) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+                ca.t[i] = t;
             }
-            if (!UNIFORM) {
-                if (moved) ca.t[i] = t;
-                if (ctl_dirty) {
-                    ca.h[i] = h;
-                    ca.prev_h[i] = prev_h;
-                }
-                if (dxn_set) ca.dx_norm[i] = dxn;
-                if (c_step) ca.n_accept[i] += c_step;
-                if (c_rej) ca.n_reject[i] += c_rej;
-                const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
-                if (nw != word) ca.word[i] = nw;
+            if (ctl_dirty) {
+                ca.h[i] = h;
+                ca.prev_h[i] = prev_h;
             }
+            if (dxn_set && cs.record_dx_norm) ca.dx_norm[i] = dxn;
+            if (l_step) ca.n_accept[i] += l_step;
+            if (l_rej) ca.n_reject[i] += l_rej;
+            const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
+            if (nw != word) ca.word[i] = nw;
+            c_step += l_step, c_rej += l_rej;
         }
+        // rotate the prefetched lane in
+        word = word_n, live = (j < N) && live_n, t = t_n, h = h_n;
+#pragma unroll
+        for (int c = 0; c < D; ++c) xc[c] = xn[c];
+#pragma unroll
+        for (int q = 0; q < RHS::NP; ++q) p[q] = pn[q];
+        i = j;
     }
-    if (!UNIFORM && cs.count_events) {
+    if (cs.count_events) {
         // block-level reduction, then at most five atomics per block, spread over VO_EV_SLOTS lines
         __shared__ unsigned sm[5];
         if (threadIdx.x < 5) sm[threadIdx.x] = 0;

@@ -62,6 +62,7 @@ struct vo_solver_s {
     int64_t n_done = 0;         // per-trajectory mode: trajectories that have emitted End
     int k_events = 1;
     int stage_path = 0;
+    int record_dx_norm = 1;
 };
 
 namespace {
@@ -89,7 +90,8 @@ CtlShared make_ctl_shared(const vo_solver_s* s, int adaptive, int k_events) {
     cs.use_err = use_err(s) ? 1 : 0;
     cs.k_events = k_events;
     cs.count_events = 1;
-    cs.u_t = s->u_t, cs.u_h = s->u_h, cs.u_prev_h = s->u_prev_h, cs.u_tgt = s->u_tgt;
+    cs.pw_is_third = s->pw == 1.0 / 3.0 ? 1 : 0;
+    cs.record_dx_norm = s->record_dx_norm;
     return cs;
 }
 
@@ -270,11 +272,11 @@ void res_add(vo_step_result* res, int64_t st, int64_t ck, int64_t rj, int64_t en
 }
 
 // ---- small path ---------------------------------------------------------------------------------------------
-int32_t launch_small(vo_solver_s* s, const CtlShared& cs) {
+int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     vo_ctx c = s->ctx;
     const TableauDev tb = make_tableau_dev(s->tab);
     const RhsParams rp = make_rhs_params(s->rhs);
-    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, &cs, s->ev_dev, s->uniform};
+    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev};
     int32_t r = VO_ERR_UNSUPPORTED;
     switch (s->rhs->kind) {
         case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
@@ -290,28 +292,35 @@ int32_t launch_small(vo_solver_s* s, const CtlShared& cs) {
 // Lock-step small path: advance the shared scalars through up to k events on the host exactly as the kernel
 // does per thread, launching the kernel only when at least one of them is a Step.
 int32_t small_uniform_events(vo_solver_s* s, int k, vo_step_result* res, int64_t* calls_done) {
-    const CtlShared cs = make_ctl_shared(s, 0, k);
-    bool any_step = false;
+    StepList sl;
+    sl.n = 0, sl.use_err = use_err(s) ? 1 : 0;
     int64_t calls = 0;
+    auto flush = [&]() -> int32_t {
+        if (sl.n == 0) return VO_OK;
+        int32_t r = launch_small(s, nullptr, &sl);
+        sl.n = 0;
+        res_add(res, 0, 0, 0, 0, 1);
+        return r;
+    };
     for (int e = 0; e < k && !s->u_done; ++e) {
         double dt = 0.0;
         const int ev = uni_step_size(s, &dt);
         ++calls;
         if (ev == VO_EV_STEP) {
-            s->u_t += dt, s->u_accept += 1, any_step = true;
+            sl.t[sl.n] = s->u_t, sl.dt[sl.n] = dt, ++sl.n;
+            s->u_t += dt, s->u_accept += 1;  // advance, ode.rs:184-188
             res_add(res, s->n, 0, 0, 0, 0);
+            if (sl.n == VO_MAX_FUSED) {
+                int32_t r = flush();
+                if (r != VO_OK) return r;
+            }
         } else {
             uni_checkpoint(s, ev == VO_EV_END);
             res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
         }
     }
     if (calls_done) *calls_done = calls;
-    if (any_step) {
-        int32_t r = launch_small(s, cs);
-        if (r != VO_OK) return r;
-        res_add(res, 0, 0, 0, 0, 1);
-    }
-    return VO_OK;
+    return flush();
 }
 
 // ---- stage path ---------------------------------------------------------------------------------------------
@@ -498,7 +507,7 @@ int32_t do_events(vo_solver_s* s, bool adaptive, int k, vo_step_result* res, int
     int launches = 0;
     if (small) {
         const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, k);
-        int32_t r = launch_small(s, cs);
+        int32_t r = launch_small(s, &cs, nullptr);
         if (r != VO_OK) return r;
         launches = 1;
         if (calls_done) *calls_done = k;
