@@ -315,6 +315,7 @@ def run_reference(args, rank):
 
 
 def main():
+    global N_TRAJ
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20000)
@@ -324,10 +325,12 @@ def main():
     ap.add_argument("--arith", default="strict", choices=["strict", "fast"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--events-per-launch", type=int, default=1)
+    ap.add_argument("--n-traj", type=int, default=N_TRAJ, help="trajectories per batch (experiments only; the named configs use 10^6)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workload summary")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    N_TRAJ = args.n_traj
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
 
@@ -350,7 +353,8 @@ def main():
 
     ctx = vo.Context.on_torch_stream(local, arith=args.arith)
     W = WORKLOADS[args.workload]
-    n_batches = 1 if W is HeatRK4 else max(2, -(-3 * L2_MB // W.state_mb))  # working set >= 3x L2
+    state_mb = W.state_mb * N_TRAJ / 1.0e6 if W is not HeatRK4 else W.state_mb
+    n_batches = 1 if W is HeatRK4 else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
     w = W(vo, ctx, rank, world, n_batches)
     for s in w.solvers:
         s.set_events_per_launch(args.events_per_launch)

@@ -33,6 +33,15 @@ int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out) {
         c->owns_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // staging buffers of upload/download come from the stream-ordered pool: keep freed blocks cached across
+        // synchronisations instead of returning them to the driver every time (the default threshold is 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (cudaMallocHost(&c->pinned, 4096) != cudaSuccess || cudaMalloc(&c->dscratch, 4096) != cudaSuccess) {
         delete c;
         return vo_fail(nullptr, VO_ERR_ALLOC, "vo_ctx_create: scratch allocation failed");

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "rhs.cuh"
+#include "tile_pipe.cuh"
 
 #define VO_WORD_TGT_MASK 0xffffu
 #define VO_WORD_STATUS_SHIFT 16
@@ -198,6 +199,268 @@ template <bool STRICT> __device__ __forceinline__ double step_size_mul(double al
     return alpha * pow(f, pw);
 }
 
+// ---- staged (TMA bulk-copy) variants ---------------------------------------------------------------------------
+// Same arithmetic as the two kernels above; the difference is how state reaches the registers. One CTA = 128 lanes =
+// one tile of 128 consecutive trajectories; thread 0 keeps VO_STAGES tiles (every SoA row the kernel reads: the d state
+// components, per-trajectory RHS parameters, and for the control kernel t, h and the status word) in flight through
+// cp.async.bulk + mbarrier; lanes read their element from shared memory, integrate, and store straight to global.
+// Needs N even (row starts 16-byte aligned); the host falls back to the register-prefetch kernels otherwise.
+#define VO_STAGES 4
+#define VO_TILE 128
+
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                                  const __grid_constant__ RhsParams rp, const __grid_constant__ StepList sl) {
+    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE;
+    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T]
+    __shared__ __align__(8) uint64_t full[VO_STAGES];
+    int nrows = D;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) nrows += rp.per_traj[q] ? 1 : 0;
+    const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
+    const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
+        pipe::fence_mbar_init();
+    }
+    __syncthreads();
+    pipe::launch_dependents();
+    pipe::grid_wait();
+    auto issue = [&](int64_t k) {  // thread 0: all rows of this CTA's k-th tile into stage k % VO_STAGES
+        const int st = (int)(k % VO_STAGES);
+        const int64_t base = (first + k * G) * T;
+        double* dst = sbuf + (size_t)st * nrows * T;
+        pipe::mbar_expect_tx(&full[st], (uint32_t)(nrows * T * sizeof(double)));
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) pipe::bulk_g2s(dst + (r++) * T, x + c * N + base, T * sizeof(double), &full[st]);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (rp.per_traj[q]) pipe::bulk_g2s(dst + (r++) * T, rp.per_traj[q] + base, T * sizeof(double), &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < my_count && k < VO_STAGES; ++k) issue(k);
+    for (int64_t k = 0; k < my_count; ++k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t i = (first + k * G) * T + threadIdx.x;
+        pipe::mbar_wait(&full[st], (uint32_t)((k / VO_STAGES) & 1));
+        const double* src = sbuf + (size_t)st * nrows * T + threadIdx.x;
+        double xc[D], p[NP];
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) xc[c] = src[(r++) * T];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) p[q] = rp.per_traj[q] ? src[(r++) * T] : rp.shared[q];
+        __syncthreads();  // every lane has taken its element: the stage may be refilled
+        if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
+        for (int e = 0; e < sl.n; ++e) {
+            double xf[D], xe[D];
+            rk_attempt<RHS, S, STRICT>(tb, sl.use_err != 0, sl.t[e], sl.dt[e], xc, p, xf, xe);
+#pragma unroll
+            for (int c = 0; c < D; ++c) xc[c] = xf[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+    }
+    // ragged tail (N % 128 trajectories): plain loads, last CTA
+    const int64_t i = n_full * T + threadIdx.x;
+    if (blockIdx.x == G - 1 && i < N) {
+        double xc[D], p[NP];
+        lane_load<RHS>(x, N, rp, i, xc, p);
+        for (int e = 0; e < sl.n; ++e) {
+            double xf[D], xe[D];
+            rk_attempt<RHS, S, STRICT>(tb, sl.use_err != 0, sl.t[e], sl.dt[e], xc, p, xf, xe);
+#pragma unroll
+            for (int c = 0; c < D; ++c) xc[c] = xf[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+    }
+}
+
+// One lane of the per-trajectory control kernel: k_events calls of step()/step_adaptive() on registers, then the
+// masked write-back. Shared by the staged kernel body and its ragged tail.
+template <class RHS, int S, bool STRICT>
+__device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int64_t i, const TableauDev& tb, const CtlArrays& ca, const CtlShared& cs,
+                                         const double* __restrict__ tl, uint32_t word, double (&xc)[RHS::D], const double (&p)[RHS::NP], double t, double h,
+                                         uint32_t n_acc, uint32_t n_rej, unsigned& c_step, unsigned& c_chkpt, unsigned& c_rej, unsigned& c_end, unsigned& c_stuck) {
+    constexpr int D = RHS::D;
+    double prev_h = 0.0;
+    bool prev_h_loaded = false, ctl_dirty = false, moved = false;
+    int tgt = (int)(word & VO_WORD_TGT_MASK);
+    uint32_t status = word >> VO_WORD_STATUS_SHIFT;
+    double dxn = 0.0;
+    bool dxn_set = false;
+    unsigned l_step = 0, l_rej = 0;
+    for (int e = 0; e < cs.k_events; ++e) {
+        int evk;  // step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
+        double dt = 0.0;
+        if (tgt >= cs.n_tlist) {
+            evk = VO_EV_END;
+        } else {
+            const double rem = tl[tgt] - t;
+            if (fabs(rem) <= 2.220446049250313e-16) evk = (tgt >= cs.n_tlist - 1) ? VO_EV_END : VO_EV_CHKPT;
+            else dt = rem < h ? rem : h, evk = VO_EV_STEP;
+        }
+        if (evk == VO_EV_STEP) {
+            double xf[D], xe[D];
+            rk_attempt<RHS, S, STRICT>(tb, cs.use_err != 0, t, dt, xc, p, xf, xe);
+            if (cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
+                dxn = err_norm<STRICT, D>(xe, cs.norm_kind), dxn_set = true;
+                const double f = cs.rtol / dxn;
+                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
+                const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+                if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
+                if (f <= 1.0) {
+                    evk = VO_EV_REJECT;
+                    if (h <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
+                }
+                prev_h = h, h = new_h, prev_h_loaded = true, ctl_dirty = true;  // update_step_size, ode.rs:202-205
+            }
+            if (evk == VO_EV_STEP) {  // accept_step -> advance, ode.rs:184-188
+#pragma unroll
+                for (int c = 0; c < D; ++c) xc[c] = xf[c];
+                t += dt;
+                moved = true, ++l_step;
+            } else {
+                ++l_rej;
+            }
+        } else {  // Chkpt / End -> checkpoint_update, ode.rs:192-195
+            if (!prev_h_loaded) prev_h = ca.prev_h[i], prev_h_loaded = true;
+            tgt += 1, h = prev_h, ctl_dirty = true;
+            if (evk == VO_EV_END) {
+                status |= VO_TRAJ_DONE, ++c_end;
+                break;
+            }
+            ++c_chkpt;
+        }
+    }
+    if (moved) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+        ca.t[i] = t;
+    }
+    if (ctl_dirty) {
+        ca.h[i] = h;
+        ca.prev_h[i] = prev_h;
+    }
+    if (dxn_set && cs.record_dx_norm) ca.dx_norm[i] = dxn;
+    if (l_step) ca.n_accept[i] = n_acc + l_step;  // counters came in with the tile: no read-modify-write round trip here
+    if (l_rej) ca.n_reject[i] = n_rej + l_rej;
+    const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
+    if (nw != word) ca.word[i] = nw;
+    c_step += l_step, c_rej += l_rej;
+}
+
+__device__ __forceinline__ void ctl_count_events(const CtlShared& cs, EvSlot* __restrict__ ev, unsigned c_step, unsigned c_chkpt, unsigned c_rej,
+                                                 unsigned c_end, unsigned c_stuck) {
+    if (!cs.count_events) return;
+    // block-level reduction, then at most five atomics per block, spread over VO_EV_SLOTS lines
+    __shared__ unsigned sm[5];
+    if (threadIdx.x < 5) sm[threadIdx.x] = 0;
+    __syncthreads();
+    c_step = __reduce_add_sync(0xffffffffu, c_step), c_chkpt = __reduce_add_sync(0xffffffffu, c_chkpt);
+    c_rej = __reduce_add_sync(0xffffffffu, c_rej), c_end = __reduce_add_sync(0xffffffffu, c_end);
+    c_stuck = __reduce_add_sync(0xffffffffu, c_stuck);
+    if ((threadIdx.x & 31) == 0) {
+        if (c_step) atomicAdd(&sm[0], c_step);
+        if (c_chkpt) atomicAdd(&sm[1], c_chkpt);
+        if (c_rej) atomicAdd(&sm[2], c_rej);
+        if (c_end) atomicAdd(&sm[3], c_end);
+        if (c_stuck) atomicAdd(&sm[4], c_stuck);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && sm[threadIdx.x]) {
+        EvSlot* slot = ev + (blockIdx.x % VO_EV_SLOTS);
+        unsigned long long* dst = threadIdx.x == 0   ? &slot->n_step
+                                  : threadIdx.x == 1 ? &slot->n_chkpt
+                                  : threadIdx.x == 2 ? &slot->n_reject
+                                  : threadIdx.x == 3 ? &slot->n_end
+                                                     : &slot->n_stuck;
+        atomicAdd(dst, (unsigned long long)sm[threadIdx.x]);
+    }
+}
+
+#ifndef VO_CTL_MIN_BLOCKS
+#define VO_CTL_MIN_BLOCKS 6
+#endif
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                                const __grid_constant__ RhsParams rp, const CtlArrays ca,
+                                                                const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev) {
+    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE;
+    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T] doubles, then [VO_STAGES][T] status words
+    __shared__ __align__(8) uint64_t full[VO_STAGES];
+    int nrows = D + 2;  // state, t, h
+#pragma unroll
+    for (int q = 0; q < NP; ++q) nrows += rp.per_traj[q] ? 1 : 0;
+    uint32_t* wbuf = reinterpret_cast<uint32_t*>(sbuf + (size_t)VO_STAGES * nrows * T);
+    const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
+    const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
+    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
+        pipe::fence_mbar_init();
+    }
+    __syncthreads();
+    pipe::launch_dependents();
+    pipe::grid_wait();
+    auto issue = [&](int64_t k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t base = (first + k * G) * T;
+        double* dst = sbuf + (size_t)st * nrows * T;
+        pipe::mbar_expect_tx(&full[st], (uint32_t)(nrows * T * sizeof(double) + 3 * T * sizeof(uint32_t)));
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) pipe::bulk_g2s(dst + (r++) * T, x + c * N + base, T * sizeof(double), &full[st]);
+        pipe::bulk_g2s(dst + (r++) * T, ca.t + base, T * sizeof(double), &full[st]);
+        pipe::bulk_g2s(dst + (r++) * T, ca.h + base, T * sizeof(double), &full[st]);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (rp.per_traj[q]) pipe::bulk_g2s(dst + (r++) * T, rp.per_traj[q] + base, T * sizeof(double), &full[st]);
+        uint32_t* wdst = wbuf + (size_t)st * 3 * T;  // status word, accepted, rejected
+        pipe::bulk_g2s(wdst, ca.word + base, T * sizeof(uint32_t), &full[st]);
+        pipe::bulk_g2s(wdst + T, ca.n_accept + base, T * sizeof(uint32_t), &full[st]);
+        pipe::bulk_g2s(wdst + 2 * T, ca.n_reject + base, T * sizeof(uint32_t), &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < my_count && k < VO_STAGES; ++k) issue(k);
+    for (int64_t k = 0; k < my_count; ++k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t i = (first + k * G) * T + threadIdx.x;
+        pipe::mbar_wait(&full[st], (uint32_t)((k / VO_STAGES) & 1));
+        const double* src = sbuf + (size_t)st * nrows * T + threadIdx.x;
+        double xc[D], p[NP];
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) xc[c] = src[(r++) * T];
+        const double t = src[(r++) * T], h = src[(r++) * T];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) p[q] = rp.per_traj[q] ? src[(r++) * T] : rp.shared[q];
+        const uint32_t* wsrc = wbuf + (size_t)st * 3 * T + threadIdx.x;
+        const uint32_t word = wsrc[0], n_acc = wsrc[T], n_rej = wsrc[2 * T];
+        __syncthreads();
+        if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
+        if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE))
+            ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, n_acc, n_rej, c_step, c_chkpt, c_rej, c_end, c_stuck);
+    }
+    const int64_t i = n_full * T + threadIdx.x;  // ragged tail: plain loads, last CTA
+    if (blockIdx.x == G - 1 && i < N) {
+        const uint32_t word = ca.word[i];
+        if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
+            double xc[D], p[NP];
+            lane_load<RHS>(x, N, rp, i, xc, p);
+            ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
+                                     c_stuck);
+        }
+    }
+    ctl_count_events(cs, ev, c_step, c_chkpt, c_rej, c_end, c_stuck);
+}
+
+// Register-prefetch fallback of the control kernel (odd N: SoA rows are not 16-byte aligned for bulk copies).
 template <class RHS, int S, bool STRICT>
 __global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
                                                      const __grid_constant__ RhsParams rp, const CtlArrays ca, const __grid_constant__ CtlShared cs,
@@ -207,122 +470,28 @@ __global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
     const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
-    // current / prefetched lane
-    uint32_t word = 0, word_n = 0;
+    uint32_t word = 0, word_n = 0, na = 0, nr = 0, na_n = 0, nr_n = 0;
     double xc[D], p[RHS::NP], t = 0.0, h = 0.0, xn[D], pn[RHS::NP], t_n = 0.0, h_n = 0.0;
     bool live = false, live_n = false;
     if (i < N) {
         word = ca.word[i];
         live = !((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
-        if (live) lane_load<RHS>(x, N, rp, i, xc, p), t = ca.t[i], h = ca.h[i];
+        if (live) lane_load<RHS>(x, N, rp, i, xc, p), t = ca.t[i], h = ca.h[i], na = ca.n_accept[i], nr = ca.n_reject[i];
     }
     while (i < N) {
         const int64_t j = i + stride;
-        if (j < N) {
+        if (j < N) {  // prefetch the next trajectory of this thread
             word_n = ca.word[j];
             live_n = !((word_n >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
-            if (live_n) lane_load<RHS>(x, N, rp, j, xn, pn), t_n = ca.t[j], h_n = ca.h[j];
+            if (live_n) lane_load<RHS>(x, N, rp, j, xn, pn), t_n = ca.t[j], h_n = ca.h[j], na_n = ca.n_accept[j], nr_n = ca.n_reject[j];
         }
-        if (live) {
-            double prev_h = 0.0;
-            bool prev_h_loaded = false, ctl_dirty = false, moved = false;
-            int tgt = (int)(word & VO_WORD_TGT_MASK);
-            uint32_t status = word >> VO_WORD_STATUS_SHIFT;
-            double dxn = 0.0;
-            bool dxn_set = false;
-            unsigned l_step = 0, l_rej = 0;
-            for (int e = 0; e < cs.k_events; ++e) {
-                // ---- step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
-                int evk;
-                double dt = 0.0;
-                if (tgt >= cs.n_tlist) {
-                    evk = VO_EV_END;
-                } else {
-                    const double rem = tl[tgt] - t;
-                    if (fabs(rem) <= 2.220446049250313e-16) evk = (tgt >= cs.n_tlist - 1) ? VO_EV_END : VO_EV_CHKPT;
-                    else dt = rem < h ? rem : h, evk = VO_EV_STEP;
-                }
-                if (evk == VO_EV_STEP) {
-                    double xf[D], xe[D];
-                    rk_attempt<RHS, S, STRICT>(tb, cs.use_err != 0, t, dt, xc, p, xf, xe);
-                    if (cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
-                        dxn = err_norm<STRICT, D>(xe, cs.norm_kind), dxn_set = true;
-                        const double f = cs.rtol / dxn;
-                        const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
-                        const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
-                        if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
-                        if (f <= 1.0) {
-                            evk = VO_EV_REJECT;
-                            if (h <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
-                        }
-                        prev_h = h, h = new_h, prev_h_loaded = true, ctl_dirty = true;  // update_step_size, ode.rs:202-205
-                    }
-                    if (evk == VO_EV_STEP) {  // accept_step -> advance, ode.rs:184-188
-#pragma unroll
-                        for (int c = 0; c < D; ++c) xc[c] = xf[c];
-                        t += dt;
-                        moved = true, ++l_step;
-                    } else {
-                        ++l_rej;
-                    }
-                } else {  // Chkpt / End -> checkpoint_update, ode.rs:192-195
-                    if (!prev_h_loaded) prev_h = ca.prev_h[i], prev_h_loaded = true;
-                    tgt += 1, h = prev_h, ctl_dirty = true;
-                    if (evk == VO_EV_END) {
-                        status |= VO_TRAJ_DONE, ++c_end;
-                        break;
-                    }
-                    ++c_chkpt;
-                }
-            }
-            if (moved) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
-                ca.t[i] = t;
-            }
-            if (ctl_dirty) {
-                ca.h[i] = h;
-                ca.prev_h[i] = prev_h;
-            }
-            if (dxn_set && cs.record_dx_norm) ca.dx_norm[i] = dxn;
-            if (l_step) ca.n_accept[i] += l_step;
-            if (l_rej) ca.n_reject[i] += l_rej;
-            const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
-            if (nw != word) ca.word[i] = nw;
-            c_step += l_step, c_rej += l_rej;
-        }
-        // rotate the prefetched lane in
-        word = word_n, live = (j < N) && live_n, t = t_n, h = h_n;
+        if (live) ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, na, nr, c_step, c_chkpt, c_rej, c_end, c_stuck);
+        word = word_n, live = (j < N) && live_n, t = t_n, h = h_n, na = na_n, nr = nr_n;
 #pragma unroll
         for (int c = 0; c < D; ++c) xc[c] = xn[c];
 #pragma unroll
         for (int q = 0; q < RHS::NP; ++q) p[q] = pn[q];
         i = j;
     }
-    if (cs.count_events) {
-        // block-level reduction, then at most five atomics per block, spread over VO_EV_SLOTS lines
-        __shared__ unsigned sm[5];
-        if (threadIdx.x < 5) sm[threadIdx.x] = 0;
-        __syncthreads();
-        c_step = __reduce_add_sync(0xffffffffu, c_step), c_chkpt = __reduce_add_sync(0xffffffffu, c_chkpt);
-        c_rej = __reduce_add_sync(0xffffffffu, c_rej), c_end = __reduce_add_sync(0xffffffffu, c_end);
-        c_stuck = __reduce_add_sync(0xffffffffu, c_stuck);
-        if ((threadIdx.x & 31) == 0) {
-            if (c_step) atomicAdd(&sm[0], c_step);
-            if (c_chkpt) atomicAdd(&sm[1], c_chkpt);
-            if (c_rej) atomicAdd(&sm[2], c_rej);
-            if (c_end) atomicAdd(&sm[3], c_end);
-            if (c_stuck) atomicAdd(&sm[4], c_stuck);
-        }
-        __syncthreads();
-        if (threadIdx.x < 5 && sm[threadIdx.x]) {
-            EvSlot* slot = ev + (blockIdx.x % VO_EV_SLOTS);
-            unsigned long long* dst = threadIdx.x == 0   ? &slot->n_step
-                                      : threadIdx.x == 1 ? &slot->n_chkpt
-                                      : threadIdx.x == 2 ? &slot->n_reject
-                                      : threadIdx.x == 3 ? &slot->n_end
-                                                         : &slot->n_stuck;
-            atomicAdd(dst, (unsigned long long)sm[threadIdx.x]);
-        }
-    }
+    ctl_count_events(cs, ev, c_step, c_chkpt, c_rej, c_end, c_stuck);
 }

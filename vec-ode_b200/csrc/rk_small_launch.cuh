@@ -2,6 +2,7 @@
 // Each RHS family is instantiated in its own translation unit (rk_small_<family>.cu) so they compile in parallel.
 #pragma once
 #include <unordered_map>
+#include <utility>
 
 #include "rk_small.cuh"
 
@@ -19,25 +20,57 @@ struct SmallLaunch {
     EvSlot* ev;
 };
 
-// Persistent grid: every thread gets the same number of trajectories (no partial last wave), all CTAs resident.
-template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N) {
+// Persistent grid: every CTA gets the same number of 128-trajectory tiles (no partial last wave), all CTAs resident.
+template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem) {
     static std::unordered_map<const void*, int> cache;  // resident CTAs per SM of each kernel instantiation
     int& bps = cache[(const void*)kernel];
     if (bps == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, RK_SMALL_THREADS, 0) != cudaSuccess || bps < 1) bps = 1;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, RK_SMALL_THREADS, smem) != cudaSuccess || bps < 1) bps = 1;
     }
-    const int64_t slots = (int64_t)c->sm_count * bps * RK_SMALL_THREADS;
-    const int64_t iters = ceil_div(N, slots);
-    return (unsigned)ceil_div(N, iters * RK_SMALL_THREADS);
+    const int64_t tiles = ceil_div(N, RK_SMALL_THREADS);
+    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
+    return (unsigned)ceil_div(tiles, iters);
+}
+
+// Launch with programmatic stream serialisation: the kernel calls griddepcontrol.wait before touching global memory, so
+// its launch latency and prologue overlap the tail of the previous kernel of the stream.
+template <class... KArgs, class... Args> static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(RK_SMALL_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+static inline int per_traj_rows(const RhsParams& rp, int np) {
+    int n = 0;
+    for (int q = 0; q < np; ++q) n += rp.per_traj[q] ? 1 : 0;
+    return n;
 }
 
 template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunch& L) {
+    const bool staged = (L.N % 2 == 0) && L.N >= RK_SMALL_THREADS;  // SoA rows 16-byte aligned for bulk copies
     if (L.sl) {
-        auto k = rk_fixed_kernel<RHS, S, STRICT>;
-        k<<<persistent_grid(L.ctx, k, L.N), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, *L.sl);
+        if (staged) {
+            const size_t smem = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double);
+            auto k = rk_fixed_staged_kernel<RHS, S, STRICT>;
+            launch_pdl(k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl);
+        } else {
+            auto k = rk_fixed_kernel<RHS, S, STRICT>;
+            k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, *L.sl);
+        }
     } else {
-        auto k = rk_ctl_kernel<RHS, S, STRICT>;
-        k<<<persistent_grid(L.ctx, k, L.N), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
+        if (staged) {
+            const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
+            auto k = rk_ctl_staged_kernel<RHS, S, STRICT>;
+            launch_pdl(k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
+        } else {
+            auto k = rk_ctl_kernel<RHS, S, STRICT>;
+            k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
+        }
     }
 }
 
