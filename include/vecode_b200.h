@@ -225,6 +225,8 @@ int32_t vo_exp_step_adaptive(vo_expsolver s, vo_step_result* res);
 int32_t vo_exp_run(vo_expsolver s, int32_t adaptive, int64_t max_calls, vo_step_result* res);
 int32_t vo_exp_current(vo_expsolver s, double* t_min, double* t_max, double* psi_host /* nullable */);
 int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm);
+/* Back to (t0, psi0, h): psi0_host NULL re-uses the state given at creation, otherwise uploads a new one. */
+int32_t vo_exp_reset(vo_expsolver s, const double* psi0_host);
 void* vo_exp_state_device_ptr(vo_expsolver s);
 
 #ifdef __cplusplus

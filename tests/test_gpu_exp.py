@@ -1,0 +1,128 @@
+"""Exponential integrators (src/exp) on the B200 against the CPU oracle and an eigendecomposition reference.
+
+The reference pins only the SCHEME (nodes, weights, composition order); exp/map_exp/commutator are user-supplied there,
+so the arithmetic bar is floating-point: <= 1e-12 against (a) the oracle's scaled-Taylor restatement and (b)
+V diag(e^{lambda}) V^-1 from numpy/LAPACK for constant generators, plus unitarity of the propagated state."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_system(n):
+    rng = np.random.default_rng(n)
+    k = np.arange(n)
+    H0 = np.diag((k - (n - 1) / 2) * 0.05) + np.diag(np.full(n - 1, 0.5), 1) + np.diag(np.full(n - 1, 0.5), -1)
+    G = rng.uniform(-1, 1, (n, n)) + 1j * rng.uniform(-1, 1, (n, n))
+    return H0.astype(complex), (G + G.conj().T) / (2 * np.sqrt(n))
+
+
+def _system(vo, n, N, seed=3):
+    H0, H1 = vo.workloads.schrodinger_system(n) if n == 64 else _small_system(n)
+    gp = vo.workloads.schrodinger_drive(N)
+    rng = np.random.default_rng(seed)
+    psi0 = rng.standard_normal((N, n)) + 1j * rng.standard_normal((N, n))
+    psi0 /= np.linalg.norm(psi0, axis=1, keepdims=True)
+    return -1j * H0, -1j * H1, gp, psi0
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_map_exp_against_eigendecomposition(vo, ctx, n):
+    """map_exp(exp(L), x) == V diag(e^{lambda}) V^-1 x for L = c0 B0 + c1 B1 with per-system coefficients."""
+    import torch
+    N = 37  # ragged: not a multiple of the 16-system tile
+    B0, B1, _, psi0 = _system(vo, n, N)
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    rng = np.random.default_rng(5)
+    coef = np.zeros((N, 2), dtype=complex)
+    coef[:, 0] = rng.uniform(0.05, 1.2, N)          # up to ||L||_1 ~ 3: exercises sub-stepping
+    coef[:, 1] = rng.uniform(-0.3, 0.3, N) + 0.05j * rng.uniform(-1, 1, N)
+    x = torch.from_numpy(psi0.view(np.float64).reshape(N, n, 2).copy()).cuda()
+    y = torch.empty_like(x)
+    sp.map_exp(sp.exp(coef), x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    got = y.cpu().numpy().reshape(N, n * 2).view(np.complex128)
+    for i in range(N):
+        L = coef[i, 0] * B0 + coef[i, 1] * B1
+        lam, V = np.linalg.eig(L)
+        ref = V @ (np.exp(lam) * np.linalg.solve(V, psi0[i]))
+        assert np.abs(got[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (i, np.abs(got[i] - ref).max())
+
+
+@pytest.mark.parametrize("scheme,cls", [("midpoint", "MidpointExpLinearSolver"), ("cfm4", "ExpCFMSolver"), ("magnus42", "MagnusExpLinearSolver")])
+@pytest.mark.parametrize("n", [16, 64])
+def test_fixed_step_schemes_match_oracle(vo, ctx, oracle, scheme, cls, n):
+    """Config 5 at oracle size: fixed step h = 0.1, 20 steps, every scheme; <= 1e-12 vs the oracle, unitarity preserved."""
+    N = 40
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    if scheme == "magnus42":
+        basis, cs = vo.with_commutator_slot(B0, B1)
+        sp = vo.DenseBasisSplit(ctx, basis, commutator_structure=cs)
+    else:
+        basis, cs = np.stack([B0, B1]), None
+        sp = vo.DenseBasisSplit(ctx, basis)
+    ref = oracle.exp_ensemble(scheme, basis, gp, psi0, 0.0, 2.0, 0.1, M_gen=2, cs=cs, no_adaptive=True, n_threads=8)
+    s = getattr(vo, cls)(sp, gp, 0.0, 2.0, psi0, 0.1, M_gen=2).no_adaptive()
+    st = s.run()
+    assert st.kind == "Done" and st.counts["Step"] == int(ref["accepted"].sum()) and st.counts["Chkpt"] == N
+    (tmin, tmax), psi = s.current()
+    assert tmin == tmax == ref["t"][0]
+    err = np.abs(psi - ref["psi"]).max()
+    print(f"{scheme} n={n}: max |psi - oracle| = {err:.2e}")
+    assert err <= 1e-12
+    assert np.abs(np.linalg.norm(psi, axis=1) - 1.0).max() <= 1e-12
+
+
+def test_cfm4_converges_to_fine_reference(vo, ctx):
+    """Scheme order check independent of the oracle: CFM4 error falls ~16x when h halves (4th order)."""
+    n, N = 16, 16
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+
+    def solve(h):
+        s = vo.ExpCFMSolver(sp, gp, 0.0, 1.6, psi0, h).no_adaptive()
+        s.run()
+        return s.current()[1]
+
+    fine = solve(0.0125)
+    e1, e2 = np.abs(solve(0.2) - fine).max(), np.abs(solve(0.1) - fine).max()
+    print("cfm4 errors", e1, e2, "ratio", e1 / e2)
+    assert 10.0 < e1 / e2 < 24.0
+
+
+@pytest.mark.parametrize("scheme,cls", [("cfm4", "ExpCFMSolver"), ("magnus42", "MagnusExpLinearSolver")])
+def test_adaptive_schemes_match_oracle(vo, ctx, oracle, scheme, cls):
+    """Adaptive stepping with per-system step control: within rtol of the oracle at t_end, step counts close."""
+    n, N, rtol = 16, 48, 1e-7
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    if scheme == "magnus42":
+        basis, cs = vo.with_commutator_slot(B0, B1)
+        sp = vo.DenseBasisSplit(ctx, basis, commutator_structure=cs)
+    else:
+        basis, cs = np.stack([B0, B1]), None
+        sp = vo.DenseBasisSplit(ctx, basis)
+    ref = oracle.exp_ensemble(scheme, basis, gp, psi0, 0.0, 2.0, 0.05, M_gen=2, cs=cs, adaptive=True, no_adaptive=False, rtol=rtol, n_threads=8)
+    s = getattr(vo, cls)(sp, gp, 0.0, 2.0, psi0, 0.05, M_gen=2).with_tolerance(rtol, rtol)
+    st = s.run(adaptive=True)
+    assert st.kind == "Done"
+    psi = s.current()[1]
+    stats = s.stats()
+    print(f"{scheme}: accepted gpu/oracle {stats['accepted'].sum()}/{ref['accepted'].sum()} rejected {stats['rejected'].sum()}/{ref['rejected'].sum()}")
+    assert np.abs(stats["t"] - 2.0).max() <= 1e-13
+    assert np.abs(psi - ref["psi"]).max() <= 50 * rtol
+    assert abs(int(stats["accepted"].sum()) - int(ref["accepted"].sum())) <= 0.02 * ref["accepted"].sum() + 2
+
+
+def test_exp_error_behaviour(vo, ctx):
+    B0, B1, gp, psi0 = _system(vo, 16, 4)
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    s = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1).no_adaptive()
+    with pytest.raises(vo.VecOdeError) as e:
+        s.step_adaptive()
+    assert e.value.code == vo._cabi.VO_ERR_NOT_ADAPTIVE
+    with pytest.raises(vo.VecOdeError):
+        vo.MagnusExpLinearSolver(sp, gp, 0.0, 1.0, psi0, 0.1)  # no Commutator supplied
+    with pytest.raises(vo.VecOdeError):
+        s.with_tolerance(0.0, 1.0)
+    first = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1).step()
+    assert first.counts["Chkpt"] == 4 and first.counts["Step"] == 0  # first call is the checkpoint at t0

@@ -122,6 +122,7 @@ SIGNATURES = {
     "vo_exp_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
     "vo_exp_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _vp]),
     "vo_exp_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "vo_exp_reset": (_i32, [_vp, _vp]),
     "vo_exp_state_device_ptr": (_vp, [_vp]),
 }
 
