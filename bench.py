@@ -220,7 +220,70 @@ class HeatRK4:
         return float(st.counts["Step"]) * self.D, self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
-WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4)}
+class SchrodingerCFM4:
+    name = "schrodinger_cfm4"
+    label = ("config 5: commutator-free Magnus CFM4, 10^5 driven 64-level Schroedinger systems (complex f64) per GPU, h = 0.1, "
+             "fixed step, shared basis {-iH0, -iH1}")
+    unit_name = "trajectory-step"
+    bytes_per_unit = None  # compute-bound: the roofline is the FP64 tensor pipe
+    state_mb = 102
+    N_SYS = 100_000
+    NDIM = 64
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        self.vo, self.ctx = vo, ctx
+        H0, H1 = vo.workloads.schrodinger_system(self.NDIM)
+        self.basis = np.stack([-1j * H0, -1j * H1])
+        self.sp = vo.DenseBasisSplit(ctx, self.basis)
+        self.gp = vo.workloads.schrodinger_drive(self.N_SYS * world, self.N_SYS, rank * self.N_SYS)
+        self.psi0 = np.zeros((self.N_SYS, self.NDIM), dtype=np.complex128)
+        self.psi0[:, 0] = 1.0
+        self.solver = vo.ExpCFMSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1).no_adaptive()
+        self.solver.step()  # Chkpt at t0
+        self.solvers = []
+        # algorithmic FLOPs per trajectory-step: E * m* * M * 8 n^2 with m* from theta = ||L h||_1 of this config
+        # with m* the Taylor degree at theta_i = ||L_i h||_1 (bounded with |cos| <= 1), averaged over the systems: the
+        # kernel plans per 16-system tile with the tile's largest theta, so it never executes fewer terms than this.
+        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
+        a = 0.53867513459481288225 + 0.038675134594812882255
+        theta = 0.1 * a * (norm1[0] + self.gp[:, 0, 0] * norm1[1])
+
+        def degree(th):
+            sq = max(1, int(np.ceil(th)))
+            x, term, k = th / sq, 1.0, 0
+            while k < 60:
+                k += 1
+                term = term * x / k
+                if term <= 1.1102230246251565e-16:
+                    break
+            return sq * k
+
+        degs = np.array([degree(t) for t in np.unique(np.round(theta, 3))])
+        cnt = np.array([np.sum(np.round(theta, 3) == t) for t in np.unique(np.round(theta, 3))])
+        self.m_star, self.theta = float((degs * cnt).sum() / cnt.sum()), float(theta.max())
+        self.flops_per_unit = 2 * self.m_star * 2 * 8 * self.NDIM ** 2
+        self.bytes_per_unit = None
+
+    def run_steps(self, k):
+        self.solver.run(max_calls=k)
+
+    def units(self, k):
+        return float(k) * self.N_SYS
+
+    def e2e_setup(self):
+        import torch
+        self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_solver = self.vo.ExpCFMSolver(self.sp, self.gp, 0.0, 10.0, self.psi0, 0.1).no_adaptive()
+
+    def e2e_step(self):
+        self.e_solver.reset(self.pin_in.numpy().view(np.complex128))  # H2D of the initial states
+        st = self.e_solver.run()
+        self.e_solver.current(out=self.pin_out.numpy().view(np.complex128))  # D2H of the final states
+        return float(st.counts["Step"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
+
+
+WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, SchrodingerCFM4)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -245,6 +308,16 @@ def cpu_run(workload, n_traj, n_steps, threads):
                            max_calls=n_steps + 1)
         dt = time.perf_counter() - t0
         return float(r["accepted"].sum() + r["rejected"].sum()), dt
+    if workload == "schrodinger_cfm4":
+        H0, H1 = vo.workloads.schrodinger_system(64)
+        basis = np.stack([-1j * H0, -1j * H1])
+        gp = vo.workloads.schrodinger_drive(SchrodingerCFM4.N_SYS)[:n_traj]
+        psi0 = np.zeros((n_traj, 64), dtype=np.complex128)
+        psi0[:, 0] = 1.0
+        t0 = time.perf_counter()
+        r = ol.exp_ensemble("cfm4", basis, gp, psi0, 0.0, 1.0e9, 0.1, no_adaptive=True, max_calls=n_steps + 1, n_threads=threads)
+        dt = time.perf_counter() - t0
+        return float(r["accepted"].sum()), dt
     if workload == "heat_rk4":
         d = n_traj  # here: grid points
         u0 = vo.workloads.heat_u0(d)
@@ -260,6 +333,8 @@ def cpu_baseline(workload, budget_s=12.0):
     threads = ol.hardware_threads() if workload != "heat_rk4" else 1
     if workload == "heat_rk4":
         n, steps = 1 << 20, 2
+    elif workload == "schrodinger_cfm4":
+        n, steps = 4 * threads, 2
     else:
         n, steps = 64 * threads, 50
     units, dt = cpu_run(workload, n, steps, threads)  # calibration
@@ -267,6 +342,9 @@ def cpu_baseline(workload, budget_s=12.0):
     target = budget_s * rate  # units of work that fill the budget
     if workload == "heat_rk4":
         steps = int(min(40, max(2, target / n)))
+    elif workload == "schrodinger_cfm4":
+        steps = 10
+        n = int(min(SchrodingerCFM4.N_SYS, max(n, target / steps)))
     else:
         steps = 1000
         n = int(min(N_TRAJ, max(n, target / steps)))
@@ -288,6 +366,8 @@ def run_reference(args, rank):
     per_step_budget = min(0.5, 90.0 / max(total, 1))
     if wl == "heat_rk4":
         n, inner = 1 << 18, 1
+    elif wl == "schrodinger_cfm4":
+        n, inner = 2 * threads, 1
     else:
         n, inner = 32 * threads, 20
     units, dt = cpu_run(wl, n, inner, threads)
@@ -354,9 +434,9 @@ def main():
     ctx = vo.Context.on_torch_stream(local, arith=args.arith)
     W = WORKLOADS[args.workload]
     state_mb = W.state_mb * N_TRAJ / 1.0e6 if W is not HeatRK4 else W.state_mb
-    n_batches = 1 if W is HeatRK4 else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
+    n_batches = 1 if W in (HeatRK4, SchrodingerCFM4) else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
     w = W(vo, ctx, rank, world, n_batches)
-    for s in w.solvers:
+    for s in getattr(w, "solvers", []):
         s.set_events_per_launch(args.events_per_launch)
 
     def timed(k):
@@ -391,11 +471,22 @@ def main():
     value = units_per_rank * world / (ms * 1e-3)
     peak, peak_src = peaks()
     launches_per_step = launches / max(args.steps, 1)
+    if W is SchrodingerCFM4:
+        p64 = os.path.join(ROOT, "profiles", "fp64_peaks.json")
+        peak_tf, src = (json.load(open(p64))["dmma_tflops"], "measured by profiles/microbench/peaks.cu (profiles/fp64_peaks.json: dmma_tflops)") \
+            if os.path.exists(p64) else (45.0, "nominal B200 FP64 tensor peak (no measured figure committed)")
+        kernel_ms = ms / max(launches, 1)
+        ach = w.flops_per_unit * (units_per_rank / max(launches, 1)) / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic(W.name),
+                    "peak_source": src, "algorithmic_flops_per_unit": w.flops_per_unit, "taylor_degree": w.m_star, "theta": w.theta,
+                    "kernel_us": kernel_ms * 1e3,
+                    "note": "FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"}
     # dominant kernel: the step kernel itself (lorenz/vdp: the only launch; heat: 4 stage launches share the step evenly)
     kernel_ms = ms / max(launches, 1)
-    bytes_per_launch = W.bytes_per_unit * (units_per_rank / max(launches, 1)) / args.events_per_launch
+    bytes_per_launch = (W.bytes_per_unit or 0.0) * (units_per_rank / max(launches, 1)) / args.events_per_launch
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
+    if W is not SchrodingerCFM4:
+      roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
                 "peak_source": peak_src, "algorithmic_bytes_per_unit": W.bytes_per_unit, "kernel_us": kernel_ms * 1e3,
                 "note": "achieved = algorithmic bytes per launch / mean launch duration (CUDA events over the timed region, kernels back to back)"}
 
@@ -422,6 +513,16 @@ def main():
     e2e = {"value": e_units / (e_ms * 1e-3), "unit": f"{W.unit_name}s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
            "what": "per e2e step: upload x0 from pinned host memory, one whole solve of the config through RK45Solver.run(), download the final state"}
+
+    gather_ms = None
+    if world > 1 and W in (LorenzRK4, VdpDopri5):
+        # the final gather of the sharded ensemble (NCCL all_gather over NVLink), once per solve, outside the timed steps
+        barrier()
+        g0 = time.perf_counter()
+        full = vo.group.gather_states(w.pin_out.numpy(), N_TRAJ * world, device=torch.device("cuda", local))
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        assert full.shape[0] == N_TRAJ * world
 
     also = None
     if rank == 0 and world == 1 and not args.no_also and args.workload == "lorenz_rk4":
@@ -453,12 +554,15 @@ def main():
         line = {"metric": "ensemble trajectory-steps/sec", "value": value, "unit": f"{W.unit_name}s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": N_TRAJ if W is not HeatRK4 else 1,
+                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W is HeatRK4 else SchrodingerCFM4.N_SYS if W is SchrodingerCFM4 else N_TRAJ),
                            "arith": args.arith, "events_per_launch": args.events_per_launch,
                            "l2": f"{n_batches} independent batches of {W.state_mb} MB rotated per GPU (> {L2_MB} MB L2), so each launch streams from HBM"
-                           if W is not HeatRK4 else "state 512 MB per buffer > 126 MB L2",
+                           if W not in (HeatRK4, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W is HeatRK4 else
+                                                                        "compute-bound: 102 MB of state per launch, streamed once"),
                            "parallelism": f"trajectory-sharded x{world}, no data-path collective"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
+        if gather_ms is not None:
+            line["final_gather_ms"] = gather_ms
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if also:

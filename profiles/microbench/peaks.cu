@@ -25,6 +25,23 @@ template <int MODE, int ILP> __global__ void __launch_bounds__(128) fp64_kernel(
     if (s == 1.2345) out[0] = s;
 }
 
+// FP64 tensor core: mma.sync m8n8k4, NACC independent accumulator pairs per warp
+template <int NACC> __global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) c[j][0] = c[j][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s += c[j][0] + c[j][1];
+    if (s == 1.2345) out[0] = s;
+}
+
 struct Big { double pad[340]; };
 __global__ void empty_small(int) {}
 __global__ void empty_big(const __grid_constant__ Big) {}
@@ -73,6 +90,13 @@ int main() {
         report("DADD", time_ms([&] { fp64_kernel<2, 8><<<grid, 128>>>(out, 1.0000001, 1e-9, iters); }, 5), 8, 1);
         report("DFMA ILP2", time_ms([&] { fp64_kernel<0, 2><<<grid, 128>>>(out, 1.0000001, 1e-9, iters); }, 5), 2, 1);
         report("DFMA ILP1", time_ms([&] { fp64_kernel<0, 1><<<grid, 128>>>(out, 1.0000001, 1e-9, iters); }, 5), 1, 1);
+    }
+    for (int bps : {1, 2, 4}) {
+        const int grid = sms * bps, it2 = 8192;
+        float m8 = time_ms([&] { dmma_kernel<8><<<grid, 256>>>(out, it2); }, 5);
+        float m2 = time_ms([&] { dmma_kernel<2><<<grid, 256>>>(out, it2); }, 5);
+        printf("DMMA m8n8k4  CTAs/SM %d (8 warps each): 8 chains %.2f TFLOP/s, 2 chains %.2f TFLOP/s\n", bps,
+               (double)grid * 8 * it2 * 8 * 512 / (m8 * 1e-3) / 1e12, (double)grid * 8 * it2 * 2 * 512 / (m2 * 1e-3) / 1e12);
     }
     printf("empty kernel, 4 B params, grid 1117x128: %.2f us/launch\n", 1e3 * time_ms([&] { empty_small<<<1117, 128>>>(0); }, 2000));
     Big big{};

@@ -3,11 +3,11 @@
 The directory is `vec-ode_b200/` (not an importable name); `import vecode_b200` works through the shim module
 `vecode_b200.py` at the repository root.
 """
-from . import _cabi, workloads
+from . import _cabi, group, workloads
 from ._cabi import SO_PATH, StepResult, VecOdeError, build
 from .exp import DenseBasisSplit, ExpCFMSolver, MagnusExpLinearSolver, MidpointExpLinearSolver, with_commutator_slot
 from .base import (ButcherTableu, Context, Ensemble, LinearCombination, ODEError, ODEState, RK45Solver, Rhs, step_many)
 
 __all__ = ["ButcherTableu", "Context", "Ensemble", "LinearCombination", "ODEError", "ODEState", "RK45Solver", "Rhs", "step_many", "DenseBasisSplit", "ExpCFMSolver", "MagnusExpLinearSolver", "MidpointExpLinearSolver",
            "with_commutator_slot",
-           "StepResult", "VecOdeError", "build", "workloads", "SO_PATH"]
+           "StepResult", "VecOdeError", "build", "workloads", "group", "SO_PATH"]
