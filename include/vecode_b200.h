@@ -166,7 +166,9 @@ int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n);  /* 
 int32_t vo_solver_set_order_alpha(vo_solver s, double order, double alpha);  /* ODEAdaptiveData::new / with_alpha, ode.rs:114-131 */
 int32_t vo_solver_set_norm(vo_solver s, int32_t norm_kind);                  /* the user `Normed` impl, rk.rs:302 */
 int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n); /* one initial step per trajectory */
-/* Events (calls of step()/step_adaptive()) fused per kernel launch by vo_run. 1 = one event per sweep. */
+/* Events (calls of step()/step_adaptive()) fused per kernel launch on the register-resident path. 0 (default) =
+ * automatic: one per launch for vo_step, vo_step_adaptive and vo_step_many, which expose every event; 16 (lock-step) or 8 (per-trajectory
+ * control) inside vo_run, which only promises the final state. k >= 1 forces k everywhere. */
 int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k);
 /* 0 = whole-attempt register-resident kernel when the RHS/tableau allow it (default), 1 = force the
  * stage-granular path (one fused kernel per RK stage over the K buffers). */

@@ -60,7 +60,7 @@ struct vo_solver_s {
     EvSlot* ev_host = nullptr;  // pinned
     EvSlot ev_seen{};           // counter totals at the last read (device counters are cumulative)
     int64_t n_done = 0;         // per-trajectory mode: trajectories that have emitted End
-    int k_events = 1;
+    int k_events = 0;  // 0 = automatic: 1 per step()/step_many launch, fused inside vo_run (see run_fusion)
     int stage_path = 0;
     int record_dx_norm = 1;
 };
@@ -70,6 +70,11 @@ namespace {
 bool rhs_is_small(const vo_rhs_s* r) { return r->kind != VO_RHS_HEAT1D && r->d <= 4; }
 bool use_small(const vo_solver_s* s) { return !s->stage_path && rhs_is_small(s->rhs); }
 bool use_err(const vo_solver_s* s) { return s->tab.has_err && s->has_x_err; }
+// Events fused per launch. step()/vo_step_many expose every event, so they advance one at a time unless the caller
+// asked for more; vo_run only promises the state at the end, so it keeps each trajectory in registers for several
+// events per launch (the FP64 pipe, not HBM, then bounds a sweep).
+int step_fusion(const vo_solver_s* s) { return s->k_events > 0 ? s->k_events : 1; }
+int run_fusion(const vo_solver_s* s) { return s->k_events > 0 ? s->k_events : (s->uniform ? 16 : 8); }
 
 TableauDev make_tableau_dev(const vo_tableau_s& t) {
     TableauDev d;
@@ -661,7 +666,7 @@ int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n) {
 }
 
 int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k) {
-    if (!s || k < 1 || k > (1 << 20)) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_events_per_launch: bad k");
+    if (!s || k < 0 || k > (1 << 20)) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_events_per_launch: bad k");
     s->k_events = k;
     return VO_OK;
 }
@@ -696,7 +701,7 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
     if (r != VO_OK) return r;
     // lock-step phase: no read-back is needed, the host knows every event
     while (s->uniform && !s->u_done && (max_calls <= 0 || calls < max_calls)) {
-        int k = use_small(s) ? s->k_events : 1;
+        int k = use_small(s) ? run_fusion(s) : 1;
         if (max_calls > 0) k = (int)std::min<int64_t>(k, max_calls - calls);
         int64_t done = 0;
         r = do_events(s, adp, k, &acc, &done, false);
@@ -709,7 +714,7 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
         int batch = 4;
         while (s->n_done < s->n && (max_calls <= 0 || calls < max_calls)) {
             for (int b = 0; b < batch && (max_calls <= 0 || calls < max_calls); ++b) {
-                int k = use_small(s) ? s->k_events : 1;
+                int k = use_small(s) ? run_fusion(s) : 1;
                 if (max_calls > 0) k = (int)std::min<int64_t>(k, max_calls - calls);
                 int64_t done = 0;
                 r = do_events(s, adp, k, &acc, &done, false);
@@ -748,7 +753,7 @@ int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int6
     for (int64_t rd = 0; rd < rounds; ++rd)
         for (int i = 0; i < n; ++i) {
             vo_solver s = solvers[i];
-            int32_t r = do_events(s, adaptive != 0, use_small(s) ? s->k_events : 1, nullptr, nullptr, false);
+            int32_t r = do_events(s, adaptive != 0, use_small(s) ? step_fusion(s) : 1, nullptr, nullptr, false);
             if (r != VO_OK) return r;
         }
     return VO_OK;
