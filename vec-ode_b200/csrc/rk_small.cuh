@@ -210,7 +210,8 @@ template <bool STRICT> __device__ __forceinline__ double step_size_mul(double al
 
 template <class RHS, int S, bool STRICT>
 __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
-                                                                  const __grid_constant__ RhsParams rp, const __grid_constant__ StepList sl) {
+                                                                  const __grid_constant__ RhsParams rp, const __grid_constant__ StepList sl,
+                                                                  const pipe::Chain ch) {
     constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE;
     extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T]
     __shared__ __align__(8) uint64_t full[VO_STAGES];
@@ -224,9 +225,7 @@ __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __rest
         for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
         pipe::fence_mbar_init();
     }
-    __syncthreads();
-    pipe::launch_dependents();
-    pipe::grid_wait();
+    pipe::chain_enter(ch);
     auto issue = [&](int64_t k) {  // thread 0: all rows of this CTA's k-th tile into stage k % VO_STAGES
         const int st = (int)(k % VO_STAGES);
         const int64_t base = (first + k * G) * T;
@@ -277,6 +276,7 @@ __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __rest
 #pragma unroll
         for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
     }
+    pipe::chain_exit(ch);
 }
 
 // One lane of the per-trajectory control kernel: k_events calls of step()/step_adaptive() on registers, then the
@@ -388,9 +388,9 @@ __device__ __forceinline__ void ctl_count_events(const CtlShared& cs, EvSlot* __
 template <class RHS, int S, bool STRICT>
 __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
                                                                 const __grid_constant__ RhsParams rp, const CtlArrays ca,
-                                                                const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev) {
+                                                                const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev, const pipe::Chain ch) {
     constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE;
-    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T] doubles, then [VO_STAGES][T] status words
+    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T] doubles, then [VO_STAGES][3][T] words
     __shared__ __align__(8) uint64_t full[VO_STAGES];
     int nrows = D + 2;  // state, t, h
 #pragma unroll
@@ -405,9 +405,7 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
         pipe::fence_mbar_init();
     }
-    __syncthreads();
-    pipe::launch_dependents();
-    pipe::grid_wait();
+    pipe::chain_enter(ch);
     auto issue = [&](int64_t k) {
         const int st = (int)(k % VO_STAGES);
         const int64_t base = (first + k * G) * T;
@@ -458,6 +456,7 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         }
     }
     ctl_count_events(cs, ev, c_step, c_chkpt, c_rej, c_end, c_stuck);
+    pipe::chain_exit(ch);
 }
 
 // Register-prefetch fallback of the control kernel (odd N: SoA rows are not 16-byte aligned for bulk copies).

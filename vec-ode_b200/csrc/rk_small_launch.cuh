@@ -18,7 +18,11 @@ struct SmallLaunch {
     const CtlShared* cs;   // per-trajectory control (sl == nullptr)
     const StepList* sl;    // lock-step fixed steps (cs == nullptr)
     EvSlot* ev;
+    pipe::Chain chain;     // generation flags of the owning solver; chain.chained = this launch may skip the grid-wide wait
 };
+
+// The staged kernels need 16-byte aligned SoA rows (N even) and at least one full tile.
+static inline bool small_path_is_staged(int64_t N) { return (N % 2 == 0) && N >= RK_SMALL_THREADS; }
 
 // Persistent grid: every CTA gets the same number of 128-trajectory tiles (no partial last wave), all CTAs resident.
 template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem) {
@@ -33,15 +37,17 @@ template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N
     return (unsigned)ceil_div(tiles, iters);
 }
 
-// Launch with programmatic stream serialisation: the kernel calls griddepcontrol.wait before touching global memory, so
-// its launch latency and prologue overlap the tail of the previous kernel of the stream.
-template <class... KArgs, class... Args> static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
+// A CHAINED launch (see pipe::Chain) is submitted with programmatic stream serialisation, so its CTAs are scheduled as
+// the previous grid's CTAs retire and each starts as soon as its own predecessor CTA has published its generation flag.
+// An unchained launch is an ordinary launch: it starts after everything before it in the stream has completed.
+template <class... KArgs, class... Args>
+static void launch_staged(bool pdl, void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(RK_SMALL_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -52,12 +58,12 @@ static inline int per_traj_rows(const RhsParams& rp, int np) {
 }
 
 template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunch& L) {
-    const bool staged = (L.N % 2 == 0) && L.N >= RK_SMALL_THREADS;  // SoA rows 16-byte aligned for bulk copies
+    const bool staged = small_path_is_staged(L.N);
     if (L.sl) {
         if (staged) {
             const size_t smem = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double);
             auto k = rk_fixed_staged_kernel<RHS, S, STRICT>;
-            launch_pdl(k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl);
+            launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl, L.chain);
         } else {
             auto k = rk_fixed_kernel<RHS, S, STRICT>;
             k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, *L.sl);
@@ -66,7 +72,8 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
         if (staged) {
             const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
             auto k = rk_ctl_staged_kernel<RHS, S, STRICT>;
-            launch_pdl(k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
+            launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev,
+                          L.chain);
         } else {
             auto k = rk_ctl_kernel<RHS, S, STRICT>;
             k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);

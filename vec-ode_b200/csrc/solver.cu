@@ -28,6 +28,7 @@ namespace {
 
 constexpr double F64_EPS = 2.220446049250313e-16;
 constexpr int PARTIAL_CAP = 1 << 14;
+constexpr int CHAIN_FLAGS = 1 << 14;  // >= resident CTAs of any persistent grid (148 SMs x <= 32 CTAs)
 
 }  // namespace
 
@@ -63,6 +64,11 @@ struct vo_solver_s {
     int k_events = 0;  // 0 = automatic: 1 per step()/step_many launch, fused inside vo_run (see run_fusion)
     int stage_path = 0;
     int record_dx_norm = 1;
+    // CTA-to-CTA chaining of consecutive launches (pipe::Chain): generation flags, one per CTA
+    uint32_t* chain_flags = nullptr;
+    uint32_t chain_gen = 0;
+    int chain_kernel = -1;    // which staged kernel wrote the flags last (0 fixed, 1 control): the tile -> CTA map must match
+    bool chain_live = false;  // the previous launch on the stream that touched this solver's state was ours, inside this API call
 };
 
 namespace {
@@ -281,7 +287,11 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     vo_ctx c = s->ctx;
     const TableauDev tb = make_tableau_dev(s->tab);
     const RhsParams rp = make_rhs_params(s->rhs);
-    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev};
+    const int kernel_id = sl ? 0 : 1;
+    const bool staged = small_path_is_staged(s->n);
+    pipe::Chain ch{s->chain_flags, ++s->chain_gen, (staged && s->chain_live && s->chain_kernel == kernel_id) ? 1 : 0};
+    s->chain_live = staged, s->chain_kernel = kernel_id;
+    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, ch};
     int32_t r = VO_ERR_UNSUPPORTED;
     switch (s->rhs->kind) {
         case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
@@ -559,6 +569,9 @@ int32_t vo_rk_create(vo_ctx c, vo_tableau tableau, vo_rhs rhs, double t0, double
     if (r == VO_OK && cudaMalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: counters");
     if (r == VO_OK && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: pinned counters");
     if (r == VO_OK && cudaMalloc(&s->norm_partial, sizeof(double) * PARTIAL_CAP) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: norm scratch");
+    if (r == VO_OK && (cudaMalloc(&s->chain_flags, sizeof(uint32_t) * CHAIN_FLAGS) != cudaSuccess ||
+                       cudaMemsetAsync(s->chain_flags, 0, sizeof(uint32_t) * CHAIN_FLAGS, c->stream) != cudaSuccess))
+        r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: chain flags");
     if (r == VO_OK) {
         cudaError_t e = cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, c->stream);
         if (e != cudaSuccess) r = vo_fail(c, VO_ERR_CUDA, cudaGetErrorString(e));
@@ -587,7 +600,7 @@ int32_t vo_solver_destroy(vo_solver s) {
     vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
     for (vo_ens k : s->K) vo_ens_destroy(k);
     free_ctl(s);
-    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev);
+    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->chain_flags);
     cudaFreeHost(s->ev_host);
     delete s;
     return VO_OK;
@@ -679,6 +692,7 @@ int32_t vo_solver_set_path(vo_solver s, int32_t stage_path) {
 
 static int32_t step_impl(vo_solver s, bool adaptive, vo_step_result* res) {
     if (!s) return VO_ERR_BAD_ARG;
+    s->chain_live = false;  // anything may have been enqueued on the stream since our last launch
     if (res) std::memset(res, 0, sizeof *res);
     int32_t r = do_events(s, adaptive, 1, res, nullptr, true);
     if (r != VO_OK) return r;
@@ -697,6 +711,7 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
     DeviceGuard g(c->device);
     int64_t calls = 0;
     const bool adp = adaptive != 0;
+    s->chain_live = false;
     int32_t r = prepare_mode(s, adp);
     if (r != VO_OK) return r;
     // lock-step phase: no read-back is needed, the host knows every event
@@ -747,6 +762,7 @@ int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int6
         if (!solvers[i] || solvers[i]->ctx != solvers[0]->ctx) return vo_fail(solvers[0] ? solvers[0]->ctx : nullptr, VO_ERR_BAD_ARG, "vo_step_many: solvers must share one ctx");
     DeviceGuard g(solvers[0]->ctx->device);
     for (int i = 0; i < n; ++i) {
+        solvers[i]->chain_live = false;
         int32_t r = prepare_mode(solvers[i], adaptive != 0);
         if (r != VO_OK) return r;
     }
@@ -827,7 +843,7 @@ int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
     if (r == VO_OK) r = vo_ens_copy(s->next_x, x0);
     if (r == VO_OK && s->x_err) r = vo_ens_copy(s->x_err, x0);
     if (r != VO_OK) return r;
-    s->uniform = true;
+    s->uniform = true, s->chain_live = false;
     s->u_t = s->t0, s->u_h = s->h_init, s->u_prev_h = s->h_init, s->u_tgt = 0, s->u_done = false;
     s->u_accept = s->u_reject = 0, s->u_dx_norm = 0.0, s->n_done = 0;
     VO_CUDA(s->ctx, cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, s->ctx->stream));

@@ -42,4 +42,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- CTA-to-CTA chaining across launches --------------------------------------------------------------------------
+// Consecutive launches of one solver use the same grid and the same tile -> CTA mapping, and trajectories are
+// independent, so CTA b of launch n+1 depends only on CTA b of launch n. Instead of waiting for the whole previous grid
+// (griddepcontrol.wait), a chained launch waits for its own predecessor's generation flag: the ramp of launch n+1
+// overlaps the tail of launch n. Safe with programmatic dependent launch because a dependent grid is only scheduled
+// after every CTA of the primary has started, i.e. the CTA being waited for is already resident and waits for nothing.
+// The spin is bounded: a time-out falls back to griddepcontrol.wait (correct, just slower), so a broken chain cannot hang.
+struct Chain {
+    uint32_t* flags;  // one generation counter per CTA
+    uint32_t gen;     // generation of this launch (> 0)
+    int chained;      // 1: wait for flags[b] >= gen-1; 0: wait for the previous grid
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Entry protocol; every thread calls it (contains a __syncthreads()).
+__device__ __forceinline__ void chain_enter(const Chain& ch) {
+    launch_dependents();
+    if (!ch.chained) {
+        grid_wait();
+    } else {
+        if (threadIdx.x == 0) {
+            bool ok = false;
+            for (int spin = 0; spin < (1 << 16); ++spin) {
+                if ((int32_t)(ld_acquire(ch.flags + blockIdx.x) - (ch.gen - 1)) >= 0) {
+                    ok = true;
+                    break;
+                }
+                __nanosleep(64);
+            }
+            if (!ok) grid_wait();
+            asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies that follow read what the predecessor stored
+        }
+    }
+    __syncthreads();
+}
+
+// Exit protocol; every thread calls it after its last global store.
+__device__ __forceinline__ void chain_exit(const Chain& ch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release(ch.flags + blockIdx.x, ch.gen);
+    }
+}
+
 }  // namespace pipe
