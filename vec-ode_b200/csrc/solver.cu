@@ -356,6 +356,53 @@ template <class RHS, bool TAIL> void launch_pointwise(vo_ctx c, const double* x0
     else stage_pointwise_kernel<RHS, false, TAIL><<<grid, 128, 0, c->stream>>>(x0, N, sa, rp, k_out, nx, xe);
 }
 
+// TMA-staged heat stage: compact the K's this launch reads (FAST non-tail stages drop zero coefficients; STRICT keeps
+// them, like the reference), pick the pipeline depth so that ~200 KB of tiles are in flight per SM, dispatch on NK.
+template <bool STRICT, bool TAIL, int NK>
+int32_t launch_heat_tma_nk(vo_solver_s* s, const HeatArgs& ha_in, double* k_out, double* nx, double* xe) {
+    vo_ctx c = s->ctx;
+    auto k = stage_heat_tma_kernel<STRICT, TAIL, NK>;
+    constexpr int bps = NK <= 3 ? 2 : 1;
+    const size_t row_bytes = (size_t)(NK + 1) * HT_ROW * sizeof(double);
+    HeatArgs ha = ha_in;
+    ha.nst = (int)std::max<size_t>(2, std::min<size_t>(HT_STAGES_MAX, (size_t)(208 * 1024 / bps) / row_bytes));
+    const size_t smem = (size_t)ha.nst * row_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VO_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        attr_set = true;
+    }
+    const int64_t tiles = ceil_div(s->d, HT_TILE);
+    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
+    k<<<(unsigned)ceil_div(tiles, iters), HT_THREADS, smem, c->stream>>>(s->x->p, s->d, ha, k_out, nx, xe);
+    return VO_OK;
+}
+
+template <bool TAIL> int32_t launch_heat_tma(vo_solver_s* s, const StageArgs& sa, double kappa, double* k_out, double* nx, double* xe) {
+    const bool strict = s->ctx->arith == VO_ARITH_STRICT;
+    HeatArgs ha;
+    std::memset(&ha, 0, sizeof ha);
+    ha.dt = sa.dt, ha.kappa = kappa, ha.use_err = sa.use_err;
+    const int S = sa.s, nload = TAIL ? S - 1 : sa.i;
+    int nk = 0;
+    for (int j = 0; j < nload; ++j) {
+        const bool in_stage = j < sa.i;
+        if (!(strict || TAIL || sa.a[j] != 0.0)) continue;
+        // STRICT / TAIL keep every term in order, so the first sa.i compacted rows are exactly the stage's terms
+        ha.K[nk] = sa.K[j], ha.a[nk] = in_stage ? sa.a[j] : 0.0, ha.b[nk] = sa.b[j], ha.b_err[nk] = sa.b_err[j];
+        ++nk;
+    }
+    ha.nterm = (strict || TAIL) ? sa.i : nk;
+    ha.b_last = sa.b[S - 1], ha.b_err_last = sa.b_err[S - 1];
+#define VO_HEAT_CASE(NK) \
+    case NK: return strict ? launch_heat_tma_nk<true, TAIL, NK>(s, ha, k_out, nx, xe) : launch_heat_tma_nk<false, TAIL, NK>(s, ha, k_out, nx, xe);
+    switch (nk) {
+        VO_HEAT_CASE(0) VO_HEAT_CASE(1) VO_HEAT_CASE(2) VO_HEAT_CASE(3) VO_HEAT_CASE(4) VO_HEAT_CASE(5) VO_HEAT_CASE(6) VO_HEAT_CASE(7)
+    }
+#undef VO_HEAT_CASE
+    return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "stage path: HEAT1D needs s <= 8");
+}
+
 template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs& sa, double* k_out, double* nx, double* xe) {
     vo_ctx c = s->ctx;
     const vo_rhs_s* r = s->rhs;
@@ -379,10 +426,15 @@ template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs
             const bool strict = c->arith == VO_ARITH_STRICT;
             if (s->n == 1) {
                 if (s->tab.s > 8) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: HEAT1D needs s <= 8");
-                const int64_t tiles = ceil_div(s->d, HEAT_TILE);
-                const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
-                if (strict) stage_heat_kernel<true, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
-                else stage_heat_kernel<false, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
+                if (s->d % 2 == 0 && s->d >= 4 * HT_TILE) {
+                    int32_t hr = launch_heat_tma<TAIL>(s, sa, kappa, k_out, nx, xe);
+                    if (hr != VO_OK) return hr;
+                } else {
+                    const int64_t tiles = ceil_div(s->d, HEAT_TILE);
+                    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
+                    if (strict) stage_heat_kernel<true, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
+                    else stage_heat_kernel<false, TAIL><<<grid, HEAT_THREADS, 0, c->stream>>>(x0, s->d, sa, kappa, k_out, nx, xe);
+                }
             } else {
                 const unsigned grid = (unsigned)ceil_div(s->d * s->n, 256);
                 if (strict) stage_heat_ens_kernel<true, TAIL><<<grid, 256, 0, c->stream>>>(x0, s->d, s->n, sa, kappa, k_out, nx, xe);
