@@ -39,7 +39,8 @@ def ncu_traffic(workload):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(workload)
+        v = json.load(open(p)).get(workload)
+        return float(v) if isinstance(v, (int, float)) else None
     return None
 
 
