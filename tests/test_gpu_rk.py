@@ -366,3 +366,52 @@ def test_full_size_properties_lorenz(vo, ctx):
     half = n // 2
     assert np.array_equal(np.concatenate([run(x0[:half]), run(x0[half:])]), full)
     assert np.array_equal(run(x0[:2048]), full[:2048])
+
+
+def test_step_many_and_chained_launches_bit_exact(vo, ctx, oracle):
+    """vo_step_many round-robins several ensembles with no read-back; from the second round on every launch is CHAINED
+    (CTA b waits only for CTA b of the solver's previous launch, not for the whole grid). Results must equal the oracle
+    bit for bit — a missed dependency would show up as a torn state."""
+    n, rounds = 20000, 40
+    params = np.tile(vo.workloads.LORENZ_PARAMS, (n, 1))
+    tableau = vo.ButcherTableu.builtin("RK4")
+    rhs = vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+    x0s = [vo.workloads.lorenz_x0(n, first=q * n) for q in range(3)]
+    solvers = [vo.RK45Solver(rhs, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, x), 1e-3, tableau=tableau) for x in x0s]
+    vo.step_many(solvers, False, 1)        # the Chkpt at t0
+    vo.step_many(solvers, False, rounds)   # `rounds` steps each, interleaved
+    for x, s in zip(x0s, solvers):
+        ref = oracle.rk_ensemble("LORENZ63", params, oracle.builtin_tableau(1), 0.0, 1.0e9, x, 1e-3, n_threads=8, max_calls=rounds + 1)
+        assert np.array_equal(s.current()[1].to_host(), ref["x"])
+        assert s.stats()["accepted"][0] == rounds
+    # adaptive ensembles through the same entry point
+    mu = vo.workloads.vdp_mu(n)
+    rhs2 = vo.Rhs(ctx, "VDP", 2, [mu])
+    a = [vo.RK45Solver(rhs2, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, vo.workloads.vdp_x0(n)), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+         .with_tolerance(1e-6, 1e-6) for _ in range(2)]
+    vo.step_many(a, True, 31)
+    b = vo.RK45Solver(rhs2, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, vo.workloads.vdp_x0(n)), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+    b.with_tolerance(1e-6, 1e-6)
+    for _ in range(31):
+        b.step_adaptive()              # one unchained launch per call
+    for s in a:
+        assert np.array_equal(s.current()[1].to_host(), b.current()[1].to_host())
+        for k in ("accepted", "rejected", "t", "h"):
+            assert np.array_equal(s.stats()[k], b.stats()[k]), k
+
+
+def test_fast_mode_full_config2_within_1e12(vo, oracle):
+    """Config 2's whole interval t in [0,1] (1000 steps + remainder) in FMA arithmetic: <= 1e-12 relative (north_star)."""
+    n = 2048
+    x0 = vo.workloads.lorenz_x0(n)
+    params = np.tile(vo.workloads.LORENZ_PARAMS, (n, 1))
+    ref = oracle.rk_ensemble("LORENZ63", params, oracle.builtin_tableau(1), 0.0, 1.0, x0, 1e-3, n_threads=8)
+    c = vo.Context(0, arith="fast")
+    rhs = vo.Rhs(c, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(c, x0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    st = s.run()
+    assert st.counts["Step"] == int(ref["accepted"].sum())
+    x = s.current()[1].to_host()
+    rel = np.abs(x - ref["x"]).max() / np.abs(ref["x"]).max()
+    print("fast-mode max relative deviation at t = 1:", rel)
+    assert rel <= 1e-12

@@ -192,8 +192,11 @@ __global__ void __launch_bounds__(128) rk_fixed_kernel(double* __restrict__ x, i
 }
 
 // ---- per-trajectory control kernel ---------------------------------------------------------------------------
-// alpha * f^pw (ode.rs:133-135). STRICT keeps the general pow of the reference's `powf`; FAST takes the cube root
-// directly when pw is exactly 1/3 (the order RK45Solver hard-wires, rk.rs:258-260) — a few ulp apart, 4x fewer FP64 ops.
+// alpha * f^pw (ode.rs:133-135). STRICT keeps the general pow of the reference's `powf` (accepted / rejected counts
+// then match the CPU restatement step for step). FAST takes the cube root directly when pw is exactly 1.0/3.0 — the
+// order RK45Solver hard-wires (rk.rs:258-260): cbrt(f) and powf(f, 0.333...) agree to within an ulp
+// (f^(1/3 - fl(1/3)) - 1 < 1e-15 for any finite f), about how far two libm implementations of `powf` differ from each
+// other, at a quarter of the FP64 instructions.
 template <bool STRICT> __device__ __forceinline__ double step_size_mul(double alpha, double f, double pw, int pw_is_third) {
     if (!STRICT && pw_is_third) return alpha * cbrt(f);
     return alpha * pow(f, pw);
@@ -281,7 +284,9 @@ __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __rest
 
 // One lane of the per-trajectory control kernel: k_events calls of step()/step_adaptive() on registers, then the
 // masked write-back. Shared by the staged kernel body and its ragged tail.
-template <class RHS, int S, bool STRICT>
+// CFG 1 = the common adaptive configuration (step_adaptive with an error estimate and the L2 norm) resolved at compile
+// time; CFG 0 = everything decided from CtlShared at run time.
+template <class RHS, int S, bool STRICT, int CFG>
 __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int64_t i, const TableauDev& tb, const CtlArrays& ca, const CtlShared& cs,
                                          const double* __restrict__ tl, uint32_t word, double (&xc)[RHS::D], const double (&p)[RHS::NP], double t, double h,
                                          uint32_t n_acc, uint32_t n_rej, unsigned& c_step, unsigned& c_chkpt, unsigned& c_rej, unsigned& c_end, unsigned& c_stuck) {
@@ -305,9 +310,9 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
         }
         if (evk == VO_EV_STEP) {
             double xf[D], xe[D];
-            rk_attempt<RHS, S, STRICT>(tb, cs.use_err != 0, t, dt, xc, p, xf, xe);
-            if (cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
-                dxn = err_norm<STRICT, D>(xe, cs.norm_kind), dxn_set = true;
+            rk_attempt<RHS, S, STRICT>(tb, CFG == 1 ? true : cs.use_err != 0, t, dt, xc, p, xf, xe);
+            if (CFG == 1 || cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
+                dxn = err_norm<STRICT, D>(xe, CFG == 1 ? VO_NORM_L2 : cs.norm_kind), dxn_set = true;
                 const double f = cs.rtol / dxn;
                 const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
                 const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
@@ -385,7 +390,7 @@ __device__ __forceinline__ void ctl_count_events(const CtlShared& cs, EvSlot* __
 #ifndef VO_CTL_MIN_BLOCKS
 #define VO_CTL_MIN_BLOCKS 6
 #endif
-template <class RHS, int S, bool STRICT>
+template <class RHS, int S, bool STRICT, int CFG>
 __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
                                                                 const __grid_constant__ RhsParams rp, const CtlArrays ca,
                                                                 const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev, const pipe::Chain ch) {
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         __syncthreads();
         if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
         if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE))
-            ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, n_acc, n_rej, c_step, c_chkpt, c_rej, c_end, c_stuck);
+            ctl_lane<RHS, S, STRICT, CFG>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, n_acc, n_rej, c_step, c_chkpt, c_rej, c_end, c_stuck);
     }
     const int64_t i = n_full * T + threadIdx.x;  // ragged tail: plain loads, last CTA
     if (blockIdx.x == G - 1 && i < N) {
@@ -451,8 +456,8 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
             double xc[D], p[NP];
             lane_load<RHS>(x, N, rp, i, xc, p);
-            ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
-                                     c_stuck);
+            ctl_lane<RHS, S, STRICT, 0>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej,
+                                        c_end, c_stuck);
         }
     }
     ctl_count_events(cs, ev, c_step, c_chkpt, c_rej, c_end, c_stuck);
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int
             live_n = !((word_n >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
             if (live_n) lane_load<RHS>(x, N, rp, j, xn, pn), t_n = ca.t[j], h_n = ca.h[j], na_n = ca.n_accept[j], nr_n = ca.n_reject[j];
         }
-        if (live) ctl_lane<RHS, S, STRICT>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, na, nr, c_step, c_chkpt, c_rej, c_end, c_stuck);
+        if (live) ctl_lane<RHS, S, STRICT, 0>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, na, nr, c_step, c_chkpt, c_rej, c_end, c_stuck);
         word = word_n, live = (j < N) && live_n, t = t_n, h = h_n, na = na_n, nr = nr_n;
 #pragma unroll
         for (int c = 0; c < D; ++c) xc[c] = xn[c];

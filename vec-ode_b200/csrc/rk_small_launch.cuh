@@ -71,7 +71,8 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
     } else {
         if (staged) {
             const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
-            auto k = rk_ctl_staged_kernel<RHS, S, STRICT>;
+            const bool common = L.cs->adaptive && L.cs->use_err && L.cs->norm_kind == VO_NORM_L2;
+            auto k = common ? rk_ctl_staged_kernel<RHS, S, STRICT, 1> : rk_ctl_staged_kernel<RHS, S, STRICT, 0>;
             launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev,
                           L.chain);
         } else {

@@ -186,7 +186,7 @@ __global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restri
                 }
                 const double h = ca.h[i];
                 const double f = cs.rtol / acc;
-                const double fp_lim = fmin(fmax(cs.alpha * pow(f, cs.pw), 0.3), 2.0);
+                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
                 const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
                 if (!(acc == acc)) status |= VO_TRAJ_NONFINITE;
                 if (f <= 1.0) {
