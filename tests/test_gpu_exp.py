@@ -126,3 +126,25 @@ def test_exp_error_behaviour(vo, ctx):
         s.with_tolerance(0.0, 1.0)
     first = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1).step()
     assert first.counts["Chkpt"] == 4 and first.counts["Step"] == 0  # first call is the checkpoint at t0
+
+
+def test_full_size_properties_schrodinger(vo, ctx):
+    """Config 5 at full size (N = 1e5, n = 64, CFM4, h = 0.1): unitarity of every system after 10 steps, shard equivalence
+    (two halves == whole, bit for bit), and agreement of a 16-system prefix with a standalone 16-system run."""
+    N, n = 100_000, 64
+    H0, H1 = vo.workloads.schrodinger_system(n)
+    sp = vo.DenseBasisSplit(ctx, np.stack([-1j * H0, -1j * H1]))
+    gp = vo.workloads.schrodinger_drive(N)
+    psi0 = np.zeros((N, n), dtype=np.complex128)
+    psi0[:, 0] = 1.0
+
+    def run(lo, hi):
+        s = vo.ExpCFMSolver(sp, gp[lo:hi], 0.0, 1.0, psi0[lo:hi], 0.1).no_adaptive()
+        assert s.run().kind == "Done"
+        return s.current()[1]
+
+    full = run(0, N)
+    assert np.abs(np.linalg.norm(full, axis=1) - 1.0).max() <= 1e-13
+    half = 50_000
+    assert np.array_equal(np.concatenate([run(0, half), run(half, N)]), full)
+    assert np.array_equal(run(0, 16), full[:16])

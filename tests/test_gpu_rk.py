@@ -187,17 +187,18 @@ def test_config3_vdp_adaptive_ensemble(vo, ctx, oracle, tab, stage_path):
     assert np.quantile(err, 0.99) <= 200 * rtol, np.quantile(err, [0.5, 0.9, 0.99, 1.0])
 
 
-def test_small_and_stage_paths_agree_bitwise_adaptive(vo, ctx):
+@pytest.mark.parametrize("n", [300, 2500])
+def test_small_and_stage_paths_agree_bitwise_adaptive(vo, ctx, n):
     """Same device libm on both paths, so the register-resident and the stage-granular kernels must agree bit for bit,
-    step sequence included."""
-    n = 300
+    step sequence included. n = 300 runs the one-trajectory-per-thread control kernel, n = 2500 the two-per-thread one
+    (with a ragged tail of 2500 % 256 trajectories)."""
     mu = vo.workloads.vdp_mu(n)
     x0 = vo.workloads.vdp_x0(n)
     out = []
     for stage_path in (False, True):
         rhs = vo.Rhs(ctx, "VDP", 2, [mu])
         s = vo.RK45Solver(rhs, 0.0, 5.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
-        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path).set_events_per_launch(1 if stage_path else 5)
+        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path).set_events_per_launch(1 if (stage_path or n > 1000) else 5)
         s.run(adaptive=True)
         out.append((s.current()[1].to_host(), s.stats()))
     assert np.array_equal(out[0][0], out[1][0])
@@ -415,3 +416,60 @@ def test_fast_mode_full_config2_within_1e12(vo, oracle):
     rel = np.abs(x - ref["x"]).max() / np.abs(ref["x"]).max()
     print("fast-mode max relative deviation at t = 1:", rel)
     assert rel <= 1e-12
+
+
+def test_full_size_properties_vdp_adaptive(vo, ctx, oracle):
+    """Config 3 at full size (N = 1e6, t in [0, 20], per-trajectory control): size-independent properties —
+    (i) every trajectory reaches t_end and is flagged done, none stuck / non-finite; (ii) the ensemble split into two
+    shards (the multi-GPU decomposition, mu indexed by global trajectory number) gives the same bits; (iii) a strided
+    sample of 256 trajectories agrees with the oracle within rtol-scale error and its step counts within 1 %."""
+    n, tf, rtol = 1_000_000, 20.0, 1e-6
+    mu = vo.workloads.vdp_mu(n)
+    tableau = vo.ButcherTableu.builtin("DOPRI5")
+
+    def run(mu_part):
+        rhs = vo.Rhs(ctx, "VDP", 2, [mu_part])
+        s = vo.RK45Solver(rhs, 0.0, tf, vo.Ensemble.from_host(ctx, vo.workloads.vdp_x0(len(mu_part))), 1e-3, tableau=tableau).with_tolerance(rtol, rtol)
+        st = s.run(adaptive=True)
+        assert st.kind == "Done" and st.counts["End"] == len(mu_part)
+        return s.current()[1].to_host(), s.stats()
+
+    x, stats = run(mu)
+    assert np.all(stats["status"] == vo._cabi.TRAJ_DONE) and np.all(np.abs(stats["t"] - tf) <= 1e-12) and np.all(np.isfinite(x))
+    half = 499_968  # not a multiple of the tile sizes
+    xa, sa = run(mu[:half])
+    xb, sb = run(mu[half:])
+    assert np.array_equal(np.concatenate([xa, xb]), x)
+    assert np.array_equal(np.concatenate([sa["accepted"], sb["accepted"]]), stats["accepted"])
+    idx = np.arange(0, n, n // 256)[:256]
+    ref = oracle.rk_ensemble("VDP", mu[idx, None], oracle.builtin_tableau(2), 0.0, tf, vo.workloads.vdp_x0(len(idx)), 1e-3, n_threads=8, adaptive=True,
+                             rtol=rtol)
+    assert np.quantile(np.abs(x[idx] - ref["x"]).max(axis=1), 0.99) <= 200 * rtol
+    assert abs(int(stats["accepted"][idx].sum()) - int(ref["accepted"].sum())) <= 0.01 * ref["accepted"].sum()
+    print("config 3 full size: attempts", int(stats["accepted"].sum() + stats["rejected"].sum()), "rejected fraction",
+          float(stats["rejected"].sum() / (stats["accepted"].sum() + stats["rejected"].sum())))
+
+
+def test_full_size_properties_heat(vo, ctx):
+    """Config 4 at full size (d = 2^26): (i) the periodic stencil conserves the sum of u to rounding; (ii) linearity:
+    solve(a*u0) == a*solve(u0) bit for bit when a is a power of two; (iii) the two analytic modes of u0 decay by the RK4
+    amplification factor R(h*lambda_k) per step."""
+    d, steps, h = 1 << 26, 8, 0.25
+    u0 = vo.workloads.heat_u0(d)
+
+    def run(u):
+        rhs = vo.Rhs(ctx, "HEAT1D", d, [1.0])
+        s = vo.RK45Solver(rhs, 0.0, h * steps, vo.Ensemble.from_host(ctx, u[None, :]), h, tableau=vo.ButcherTableu.builtin("RK4"))
+        assert s.run().kind == "Done"
+        return s.current()[1].to_host()[0]
+
+    u = run(u0)
+    assert abs(u.sum() - u0.sum()) <= 1e-6
+    assert np.array_equal(run(4.0 * u0), 4.0 * u)
+    j = np.arange(d, dtype=np.float64)
+    expect = np.zeros(d)
+    for kmode, amp in ((1, 1.0), (7, 0.5)):
+        z = h * (2.0 * np.cos(2.0 * np.pi * kmode / d) - 2.0)
+        R = 1.0 + z + z * z / 2.0 + z ** 3 / 6.0 + z ** 4 / 24.0
+        expect += amp * (R ** steps) * np.sin(2.0 * np.pi * kmode * j / d)
+    assert np.abs(u - expect).max() <= 1e-12

@@ -1,0 +1,172 @@
+// rk_small2.cuh — the per-trajectory control kernel with TWO trajectories per thread.
+//
+// rk_ctl_staged_kernel (rk_small.cuh) is bound by the FP64 pipe and by instruction issue, not by HBM: an adaptive
+// DoPri5 attempt of a 2-component system is one long dependent chain with ILP 2. Giving every thread two independent
+// trajectories doubles the ILP, and everything that is per-thread rather than per-trajectory — tableau coefficient
+// loads into uniform registers, loop and barrier overhead, address arithmetic shared by the pair — is paid once per two
+// attempts. Arithmetic per trajectory is unchanged (same operations, same order), so results are bit-identical to the
+// one-trajectory kernel. Tile = 256 trajectories per CTA iteration (thread t owns trajectories t and t + 128 of the tile).
+// Compiled for the common adaptive configuration (step_adaptive, error estimate present, L2 norm); everything else, and
+// the ragged tail of the ensemble, goes through ctl_lane of rk_small.cuh.
+#pragma once
+#include "rk_small.cuh"
+
+#define VO_TILE2 256
+
+// rk_step (rk.rs:90-155) for U independent trajectories, interleaved statement by statement.
+template <class RHS, int S, bool STRICT, int U>
+__device__ __forceinline__ void rk_attempt_n(const TableauDev& tb, const double (&t)[U], const double (&dt)[U], const double (&x0)[U][RHS::D],
+                                             const double (&p)[U][RHS::NP], double (&xf)[U][RHS::D], double (&xe)[U][RHS::D]) {
+    using A = Ar<STRICT>;
+    constexpr int D = RHS::D;
+    double K[U][S][D];
+#pragma unroll
+    for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(t[u], x0[u], K[u][0], p[u]);  // rk.rs:111
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+        const double* row = &tb.ac[i * S];
+        double xs[U][D];
+#pragma unroll
+        for (int u = 0; u < U; ++u) combine<STRICT, D, S>(row, i, K[u], dt[u], x0[u], xs[u]);  // rk.rs:121-124
+#pragma unroll
+        for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(A::add(t[u], A::mul(row[i], dt[u])), xs[u], K[u][i], p[u]);  // rk.rs:119, 127
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        combine<STRICT, D, S>(tb.b, S, K[u], dt[u], x0[u], xe[u]);      // X_b (rk.rs:131-133), held in xe for the swap of rk.rs:142
+        combine<STRICT, D, S>(tb.b_err, S, K[u], dt[u], x0[u], xf[u]);  // X_berr: the propagated solution
+#pragma unroll
+        for (int c = 0; c < D; ++c) xe[u][c] = A::sub(xe[u][c], xf[u][c]);  // x_err = X_b - X_berr (rk.rs:147)
+    }
+}
+
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(128, 3) rk_ctl2_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                                const __grid_constant__ RhsParams rp, const CtlArrays ca,
+                                                                const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev, const pipe::Chain ch) {
+    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE2, U = 2;
+    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T] doubles, then [VO_STAGES][3][T] words
+    __shared__ __align__(8) uint64_t full[VO_STAGES];
+    int nrows = D + 2;  // state, t, h
+#pragma unroll
+    for (int q = 0; q < NP; ++q) nrows += rp.per_traj[q] ? 1 : 0;
+    uint32_t* wbuf = reinterpret_cast<uint32_t*>(sbuf + (size_t)VO_STAGES * nrows * T);
+    const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
+    const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
+    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
+        pipe::fence_mbar_init();
+    }
+    pipe::chain_enter(ch);
+    auto issue = [&](int64_t k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t base = (first + k * G) * T;
+        double* dst = sbuf + (size_t)st * nrows * T;
+        pipe::mbar_expect_tx(&full[st], (uint32_t)(nrows * T * sizeof(double) + 3 * T * sizeof(uint32_t)));
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) pipe::bulk_g2s(dst + (r++) * T, x + c * N + base, T * sizeof(double), &full[st]);
+        pipe::bulk_g2s(dst + (r++) * T, ca.t + base, T * sizeof(double), &full[st]);
+        pipe::bulk_g2s(dst + (r++) * T, ca.h + base, T * sizeof(double), &full[st]);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (rp.per_traj[q]) pipe::bulk_g2s(dst + (r++) * T, rp.per_traj[q] + base, T * sizeof(double), &full[st]);
+        uint32_t* wdst = wbuf + (size_t)st * 3 * T;  // status word, accepted, rejected
+        pipe::bulk_g2s(wdst, ca.word + base, T * sizeof(uint32_t), &full[st]);
+        pipe::bulk_g2s(wdst + T, ca.n_accept + base, T * sizeof(uint32_t), &full[st]);
+        pipe::bulk_g2s(wdst + 2 * T, ca.n_reject + base, T * sizeof(uint32_t), &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < my_count && k < VO_STAGES; ++k) issue(k);
+    for (int64_t k = 0; k < my_count; ++k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t base = (first + k * G) * T;
+        pipe::mbar_wait(&full[st], (uint32_t)((k / VO_STAGES) & 1));
+        double xc[U][D], p[U][NP], t[U], h[U];
+        uint32_t word[U], n_acc[U], n_rej[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double* src = sbuf + (size_t)st * nrows * T + threadIdx.x + 128 * u;
+            int r = 0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) xc[u][c] = src[(r++) * T];
+            t[u] = src[(r++) * T], h[u] = src[(r++) * T];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) p[u][q] = rp.per_traj[q] ? src[(r++) * T] : rp.shared[q];
+            const uint32_t* wsrc = wbuf + (size_t)st * 3 * T + threadIdx.x + 128 * u;
+            word[u] = wsrc[0], n_acc[u] = wsrc[T], n_rej[u] = wsrc[2 * T];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
+        const bool live0 = !((word[0] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE), live1 = !((word[1] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
+        // fast path: one event per launch and both trajectories take a Step (the steady state of an adaptive sweep)
+        bool pair = cs.k_events == 1 && live0 && live1;
+        double dt[U] = {0.0, 0.0};
+        if (pair) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int tgt = (int)(word[u] & VO_WORD_TGT_MASK);
+                if (tgt >= cs.n_tlist) {
+                    pair = false;
+                } else {
+                    const double rem = tl[tgt] - t[u];  // step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
+                    if (fabs(rem) <= 2.220446049250313e-16) pair = false;
+                    dt[u] = rem < h[u] ? rem : h[u];
+                }
+            }
+        }
+        if (pair) {
+            double xf[U][D], xe[U][D];
+            rk_attempt_n<RHS, S, STRICT, U>(tb, t, dt, xc, p, xf, xe);
+            double dxn[U], new_h[U];
+            bool rej[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // handle_step_adaptive, ode.rs:311-334
+                dxn[u] = err_norm<STRICT, D>(xe[u], VO_NORM_L2);
+                const double f = cs.rtol / dxn[u];
+                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
+                new_h[u] = fmin(fmax(fp_lim * h[u], cs.min_dt), cs.max_dt);
+                rej[u] = f <= 1.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // apply_step (ode.rs:402-428) + masked write-back
+                const int64_t i = base + threadIdx.x + 128 * u;
+                uint32_t status = word[u] >> VO_WORD_STATUS_SHIFT;
+                if (!(dxn[u] == dxn[u])) status |= VO_TRAJ_NONFINITE;
+                if (rej[u]) {
+                    if (h[u] <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
+                    ca.n_reject[i] = n_rej[u] + 1, ++c_rej;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) x[c * N + i] = xf[u][c];
+                    ca.t[i] = t[u] + dt[u];  // advance, ode.rs:184-188
+                    ca.n_accept[i] = n_acc[u] + 1, ++c_step;
+                }
+                ca.h[i] = new_h[u], ca.prev_h[i] = h[u];  // update_step_size, ode.rs:202-205
+                if (cs.record_dx_norm) ca.dx_norm[i] = dxn[u];
+                const uint32_t nw = (word[u] & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
+                if (nw != word[u]) ca.word[i] = nw;
+            }
+        } else {
+            if (live0) ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x, tb, ca, cs, tl, word[0], xc[0], p[0], t[0], h[0], n_acc[0], n_rej[0], c_step, c_chkpt, c_rej, c_end, c_stuck);
+            if (live1) ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x + 128, tb, ca, cs, tl, word[1], xc[1], p[1], t[1], h[1], n_acc[1], n_rej[1], c_step, c_chkpt, c_rej, c_end, c_stuck);
+        }
+    }
+    // ragged tail (N % 256 trajectories): plain loads, last CTA, up to two lanes per thread one after the other
+    if (blockIdx.x == G - 1) {
+        for (int64_t i = n_full * T + threadIdx.x; i < N; i += 128) {
+            const uint32_t word = ca.word[i];
+            if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
+                double xc[D], p[NP];
+                lane_load<RHS>(x, N, rp, i, xc, p);
+                ctl_lane<RHS, S, STRICT, 1>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
+                                            c_stuck);
+            }
+        }
+    }
+    ctl_count_events(cs, ev, c_step, c_chkpt, c_rej, c_end, c_stuck);
+    pipe::chain_exit(ch);
+}

@@ -4,7 +4,7 @@
 #include <unordered_map>
 #include <utility>
 
-#include "rk_small.cuh"
+#include "rk_small2.cuh"
 
 constexpr int RK_SMALL_THREADS = 128;
 
@@ -25,14 +25,14 @@ struct SmallLaunch {
 static inline bool small_path_is_staged(int64_t N) { return (N % 2 == 0) && N >= RK_SMALL_THREADS; }
 
 // Persistent grid: every CTA gets the same number of 128-trajectory tiles (no partial last wave), all CTAs resident.
-template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem) {
+template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem, int tile = RK_SMALL_THREADS) {
     static std::unordered_map<const void*, int> cache;  // resident CTAs per SM of each kernel instantiation
     int& bps = cache[(const void*)kernel];
     if (bps == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, RK_SMALL_THREADS, smem) != cudaSuccess || bps < 1) bps = 1;
     }
-    const int64_t tiles = ceil_div(N, RK_SMALL_THREADS);
+    const int64_t tiles = ceil_div(N, tile);
     const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
     return (unsigned)ceil_div(tiles, iters);
 }
@@ -72,6 +72,15 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
         if (staged) {
             const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
             const bool common = L.cs->adaptive && L.cs->use_err && L.cs->norm_kind == VO_NORM_L2;
+            if constexpr (S > 0) {
+                if (common && L.cs->k_events == 1 && L.N >= 4 * VO_TILE2) {  // two trajectories per thread (rk_small2.cuh)
+                    const size_t smem2 = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE2 * sizeof(double) + 3 * VO_TILE2 * sizeof(uint32_t));
+                    auto k2 = rk_ctl2_staged_kernel<RHS, S, STRICT>;
+                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
+                                  *L.cs, L.ev, L.chain);
+                    return;
+                }
+            }
             auto k = common ? rk_ctl_staged_kernel<RHS, S, STRICT, 1> : rk_ctl_staged_kernel<RHS, S, STRICT, 0>;
             launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev,
                           L.chain);
