@@ -187,6 +187,13 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
 int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int64_t rounds);
 /* ODESolver::current (ode.rs:216-218): borrowed view of x (valid until the next step) and the time range. */
 int32_t vo_current(vo_solver s, double* t_min, double* t_max, vo_ens* x);
+/* Checkpoint output (pub field ODEData.t_list + the Chkpt / End events, ode.rs:89-90, 165-176, 192-195): keep, for every
+ * entry k of t_list, the state each trajectory shows through current() at its Chkpt / End event for t_list[k]. With
+ * per-trajectory control the trajectories pass a checkpoint in different calls; the snapshot is complete once every
+ * trajectory has passed it (vo_solver_stats' status / t tell). vo_solver_snapshot returns a non-owning ensemble view
+ * (destroy it with vo_ens_destroy; the storage belongs to the solver). */
+int32_t vo_solver_enable_snapshots(vo_solver s);
+int32_t vo_solver_snapshot(vo_solver s, int32_t k, vo_ens* out);
 /* Per-trajectory controller state; any pointer may be NULL. Host arrays of length N. */
 int32_t vo_solver_stats(vo_solver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm,
                         int32_t* status);
@@ -210,6 +217,11 @@ int32_t vo_split_set_commutator(vo_split sp, const double* cs /* [M][M][M] */);
 int32_t vo_split_set_taylor_degree(vo_split sp, int32_t deg); /* 0 = automatic from theta = ||L||_1 bound */
 /* map_exp(&exp(L), &x) (exp/mod.rs:23-25) for every system: coef [N][M] complex (host), psi device [N][n] complex. */
 int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in_dev, void* psi_out_dev);
+
+/* NormedExponentialSplit::norm (exp/mod.rs:37-45): 2-norm of each of the N states psi_dev [N][n] complex -> out_host[N]. */
+int32_t vo_split_norm(vo_split sp, const void* psi_dev, int64_t N, double* out_host);
+/* Commutator::commutator (exp/mod.rs:47-54) on operators given as coefficient vectors la, lb, out: [N][M] complex (host). */
+int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int64_t N, double* out);
 
 /* Generator family replacing the closures of exp/magnus.rs:12,32 and exp/cfm.rs:54:
  *   L_i(t) = B_0 + sum_{m=1}^{M_gen-1} amp_im * cos(omega_im * t + phase_im) * B_m ,  gp = [N][M_gen-1][3]. */

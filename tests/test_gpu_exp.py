@@ -148,3 +148,23 @@ def test_full_size_properties_schrodinger(vo, ctx):
     half = 50_000
     assert np.array_equal(np.concatenate([run(0, half), run(half, N)]), full)
     assert np.array_equal(run(0, 16), full[:16])
+
+
+def test_split_norm_and_commutator(vo, ctx):
+    """NormedExponentialSplit::norm and Commutator::commutator of the shipped split (exp/mod.rs:37-54)."""
+    n, N = 16, 50
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    basis, cs = vo.with_commutator_slot(B0, B1)
+    sp = vo.DenseBasisSplit(ctx, basis, commutator_structure=cs)
+    s = vo.MagnusExpLinearSolver(sp, gp, 0.0, 0.5, 1.7 * psi0, 0.1, M_gen=2).no_adaptive()
+    np.testing.assert_allclose(sp.norm(s.state_device_ptr, N), 1.7, rtol=1e-14)
+    rng = np.random.default_rng(0)
+    la = np.zeros((N, 3), complex); lb = np.zeros((N, 3), complex)
+    la[:, :2] = rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))
+    lb[:, :2] = rng.standard_normal((N, 2))
+    c = sp.commutator(la, lb)
+    for i in range(N):
+        La, Lb = la[i, 0] * B0 + la[i, 1] * B1, lb[i, 0] * B0 + lb[i, 1] * B1
+        ref = La @ Lb - Lb @ La
+        got = c[i, 0] * basis[0] + c[i, 1] * basis[1] + c[i, 2] * basis[2]
+        assert np.abs(got - ref).max() <= 1e-13

@@ -473,3 +473,26 @@ def test_full_size_properties_heat(vo, ctx):
         R = 1.0 + z + z * z / 2.0 + z ** 3 / 6.0 + z ** 4 / 24.0
         expect += amp * (R ** steps) * np.sin(2.0 * np.pi * kmode * j / d)
     assert np.abs(u - expect).max() <= 1e-12
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+@pytest.mark.parametrize("stage_path", [False, True])
+def test_checkpoint_snapshots(vo, ctx, oracle, adaptive, stage_path):
+    """Checkpoint output (ODEData.t_list + Chkpt events, ode.rs:165-176, 192-195): the snapshot of entry k is the state
+    current() shows at that event = the final state of an oracle solve whose t_list stops at entry k."""
+    n = 96
+    kind, d, params, x0 = _case(vo, "HARMONIC2D", n, seed=11)
+    t_list = [0.0, 0.3, 0.55, 1.0]
+    rhs = _make_rhs(vo, ctx, kind, d, params)
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 0.01).with_tolerance(1e-7, 1e-7).set_t_list(t_list)
+    s.set_stage_path(stage_path).enable_snapshots()
+    assert s.run(adaptive=adaptive).kind == "Done"
+    otab = oracle.builtin_tableau(0)
+    for k in range(len(t_list)):
+        ref = oracle.rk_ensemble(kind, params, otab, 0.0, t_list[k], x0, 0.01, n_threads=2, adaptive=adaptive, rtol=1e-7, t_list=t_list[:k + 1])
+        got = s.snapshot(k).to_host()
+        if adaptive:
+            np.testing.assert_allclose(got, ref["x"], atol=1e-6)
+        else:
+            assert np.array_equal(got, ref["x"]), k
+    assert np.array_equal(s.snapshot(len(t_list) - 1).to_host(), s.current()[1].to_host())

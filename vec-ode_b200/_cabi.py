@@ -104,6 +104,8 @@ SIGNATURES = {
     "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
     "vo_step_many": (_i32, [_pvp, _i32, _i32, _i64]),
     "vo_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _pvp]),
+    "vo_solver_enable_snapshots": (_i32, [_vp]),
+    "vo_solver_snapshot": (_i32, [_vp, _i32, _pvp]),
     "vo_solver_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vo_solver_reset": (_i32, [_vp, _vp]),
     "vo_rk_try_step": (_i32, [_vp, _f64, _f64, _vp, _vp, _pvp]),
@@ -111,6 +113,8 @@ SIGNATURES = {
     "vo_split_destroy": (_i32, [_vp]),
     "vo_split_set_commutator": (_i32, [_vp, _vp]),
     "vo_split_set_taylor_degree": (_i32, [_vp, _i32]),
+    "vo_split_norm": (_i32, [_vp, _vp, _i64, _vp]),
+    "vo_split_commutator": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "vo_map_exp": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "vo_exp_create": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f64, _f64, _vp, _f64, _pvp]),
     "vo_exp_destroy": (_i32, [_vp]),

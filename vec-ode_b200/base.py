@@ -375,6 +375,16 @@ class RK45Solver:
         check(lib().vo_solver_stats(self._h, _np_ptr(acc), _np_ptr(rej), _np_ptr(t), _np_ptr(h), _np_ptr(dxn), _np_ptr(st)), self.ctx._h)
         return dict(accepted=acc, rejected=rej, t=t, h=h, dx_norm=dxn, status=st)
 
+    def enable_snapshots(self):
+        """Keep the state of every trajectory at each entry of t_list (its Chkpt / End events, ode.rs:165-176)."""
+        check(lib().vo_solver_enable_snapshots(self._h), self.ctx._h)
+        return self
+
+    def snapshot(self, k: int) -> Ensemble:
+        h = _vp()
+        check(lib().vo_solver_snapshot(self._h, k, C.byref(h)), self.ctx._h)
+        return Ensemble(self.ctx, self.d, self.n, _handle=h, _owner=_TensorOwner(self))  # view handle is ours, storage is the solver's
+
     def reset(self, x0: Ensemble):
         check(lib().vo_solver_reset(self._h, x0._h), self.ctx._h)
 

@@ -446,6 +446,19 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     }
 }
 
+// NormedExponentialSplit::norm (exp/mod.rs:37-45): 2-norm of every state, one warp per system
+__global__ void exp_norm_kernel(const double2* __restrict__ psi, int n, int64_t N, double* __restrict__ out) {
+    const int64_t sys = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (sys >= N) return;
+    double acc = 0.0;
+    for (int r = threadIdx.x & 31; r < n; r += 32) {
+        const double2 v = psi[sys * n + r];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) out[sys] = sqrt(acc);
+}
+
 __global__ void exp_ctl_fill_kernel(CtlArrays ca, int64_t N, double t, double h) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -595,6 +608,40 @@ int32_t vo_split_set_commutator(vo_split sp, const double* cs) {
 int32_t vo_split_set_taylor_degree(vo_split sp, int32_t deg) {
     if (!sp || deg < 0 || deg > 60) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_split_set_taylor_degree: 0 <= deg <= 60");
     sp->taylor_deg = deg;
+    return VO_OK;
+}
+
+int32_t vo_split_norm(vo_split sp, const void* psi_dev, int64_t N, double* out_host) {
+    if (!sp || !psi_dev || !out_host || N < 1) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_split_norm: bad argument");
+    vo_ctx c = sp->ctx;
+    DeviceGuard g(c->device);
+    double* out_dev = nullptr;
+    VO_CUDA(c, cudaMallocAsync(&out_dev, sizeof(double) * N, c->stream));
+    exp_norm_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, c->stream>>>((const double2*)psi_dev, sp->n, N, out_dev);
+    VO_CHECK_LAUNCH(c);
+    VO_CUDA(c, cudaMemcpyAsync(out_host, out_dev, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    cudaFreeAsync(out_dev, c->stream);
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VO_OK;
+}
+
+// Commutator::commutator (exp/mod.rs:47-54) on coefficient vectors: out_c = sum_ab la_a lb_b cs[a][b][c]. Operators of this
+// split ARE their M coefficients, so this is host-side bookkeeping on N*M complex numbers, not a device computation.
+int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int64_t N, double* out) {
+    if (!sp || !la || !lb || !out || N < 1) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_split_commutator: bad argument");
+    if (!sp->has_cs) return vo_fail(sp->ctx, VO_ERR_STATE, "vo_split_commutator: no structure tensor (vo_split_set_commutator)");
+    const int M = sp->M;
+    for (int64_t i = 0; i < N; ++i)
+        for (int cc = 0; cc < M; ++cc) {
+            std::complex<double> acc(0.0, 0.0);
+            for (int a = 0; a < M; ++a)
+                for (int b = 0; b < M; ++b) {
+                    const double sc = sp->cs[(a * M + b) * M + cc];
+                    if (sc != 0.0)
+                        acc += std::complex<double>(la[(i * M + a) * 2], la[(i * M + a) * 2 + 1]) * std::complex<double>(lb[(i * M + b) * 2], lb[(i * M + b) * 2 + 1]) * sc;
+                }
+            out[(i * M + cc) * 2] = acc.real(), out[(i * M + cc) * 2 + 1] = acc.imag();
+        }
     return VO_OK;
 }
 

@@ -46,6 +46,7 @@ struct CtlShared {
     int count_events;  // accumulate vo_step_result counters
     int pw_is_third;   // pw == 1.0/3.0 exactly (the order RK45Solver hard-wires, rk.rs:258-260)
     int record_dx_norm;  // keep ODEAdaptiveData.dx_norm (ode.rs:104) per trajectory
+    double* snap;        // optional [n_tlist][d][N]: the state each trajectory shows at its Chkpt / End events, else NULL
 };
 
 // Event counters, VO_EV_SLOTS copies 128 bytes apart to spread the atomics (host sums the slots).
@@ -332,6 +333,10 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
                 ++l_rej;
             }
         } else {  // Chkpt / End -> checkpoint_update, ode.rs:192-195
+            if (cs.snap && tgt < cs.n_tlist) {  // what current() shows the caller at this event
+#pragma unroll
+                for (int c = 0; c < D; ++c) cs.snap[((int64_t)tgt * D + c) * N + i] = xc[c];
+            }
             if (!prev_h_loaded) prev_h = ca.prev_h[i], prev_h_loaded = true;
             tgt += 1, h = prev_h, ctl_dirty = true;
             if (evk == VO_EV_END) {

@@ -64,6 +64,7 @@ struct vo_solver_s {
     int k_events = 0;  // 0 = automatic: 1 per step()/step_many launch, fused inside vo_run (see run_fusion)
     int stage_path = 0;
     int record_dx_norm = 1;
+    double* snap = nullptr;  // [n_tlist][d][N] checkpoint snapshots (vo_solver_enable_snapshots)
     // CTA-to-CTA chaining of consecutive launches (pipe::Chain): generation flags, one per CTA
     uint32_t* chain_flags = nullptr;
     uint32_t chain_gen = 0;
@@ -103,6 +104,7 @@ CtlShared make_ctl_shared(const vo_solver_s* s, int adaptive, int k_events) {
     cs.count_events = 1;
     cs.pw_is_third = s->pw == 1.0 / 3.0 ? 1 : 0;
     cs.record_dx_norm = s->record_dx_norm;
+    cs.snap = s->snap;
     return cs;
 }
 
@@ -115,6 +117,8 @@ int uni_step_size(const vo_solver_s* s, double* dt) {
     return VO_EV_STEP;
 }
 void uni_checkpoint(vo_solver_s* s, bool end) {
+    if (s->snap && s->u_tgt < (int)s->t_list.size())  // lock-step: the whole ensemble is at the checkpoint, copy it (stream-ordered)
+        cudaMemcpyAsync(s->snap + (size_t)s->u_tgt * s->d * s->n, s->x->p, sizeof(double) * s->d * s->n, cudaMemcpyDeviceToDevice, s->ctx->stream);
     s->u_tgt += 1, s->u_h = s->u_prev_h;
     if (end) s->u_done = true;
 }
@@ -203,6 +207,8 @@ __global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restri
                 ca.n_reject[i] += 1, ++c_rej;
             }
         } else {
+            if (cs.snap && tgt < cs.n_tlist)
+                for (int64_t c = 0; c < d; ++c) cs.snap[((int64_t)tgt * d + c) * N + i] = x[c * N + i];
             tgt += 1, ca.h[i] = ca.prev_h[i];
             if (evk == VO_EV_END) status |= VO_TRAJ_DONE, ++c_end;
             else ++c_chkpt;
@@ -330,6 +336,11 @@ int32_t small_uniform_events(vo_solver_s* s, int k, vo_step_result* res, int64_t
                 if (r != VO_OK) return r;
             }
         } else {
+            if (s->snap) {  // the steps queued so far must have run before the checkpoint copy
+                int32_t r = flush();
+                if (r != VO_OK) return r;
+                s->chain_live = false;  // the copy is not part of the CTA chain
+            }
             uni_checkpoint(s, ev == VO_EV_END);
             res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
         }
@@ -602,6 +613,17 @@ void finish_result(vo_solver_s* s, vo_step_result* res) {
 
 }  // namespace
 
+static int32_t alloc_snapshots(vo_solver s) {
+    vo_ctx c = s->ctx;
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(s->snap), s->snap = nullptr;
+    const size_t bytes = sizeof(double) * s->t_list.size() * (size_t)s->d * (size_t)s->n;
+    if (cudaMalloc(&s->snap, bytes) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_enable_snapshots: cudaMalloc failed");
+    VO_CUDA(c, cudaMemsetAsync(s->snap, 0, bytes, c->stream));
+    return VO_OK;
+}
+
+
 extern "C" {
 
 int32_t vo_rk_create(vo_ctx c, vo_tableau tableau, vo_rhs rhs, double t0, double tf, vo_ens x0, double h, vo_solver* out) {
@@ -652,7 +674,7 @@ int32_t vo_solver_destroy(vo_solver s) {
     vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
     for (vo_ens k : s->K) vo_ens_destroy(k);
     free_ctl(s);
-    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->chain_flags);
+    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->chain_flags), cudaFree(s->snap);
     cudaFreeHost(s->ev_host);
     delete s;
     return VO_OK;
@@ -703,6 +725,7 @@ int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n) {
         if (cudaMalloc(&s->t_list_dev, sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_set_t_list: cudaMalloc");
         VO_CUDA(c, cudaMemcpy(s->t_list_dev, t_list, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
+    if (s->snap) return alloc_snapshots(s);
     return VO_OK;
 }
 
@@ -806,6 +829,19 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
     finish_result(s, &acc);
     if (res) *res = acc;
     return VO_OK;
+}
+
+int32_t vo_solver_enable_snapshots(vo_solver s) {
+    if (!s) return VO_ERR_BAD_ARG;
+    DeviceGuard g(s->ctx->device);
+    return alloc_snapshots(s);
+}
+
+int32_t vo_solver_snapshot(vo_solver s, int32_t k, vo_ens* out) {
+    if (!s || !out) return VO_ERR_BAD_ARG;
+    if (!s->snap) return vo_fail(s->ctx, VO_ERR_STATE, "vo_solver_snapshot: snapshots are not enabled");
+    if (k < 0 || k >= (int32_t)s->t_list.size()) return vo_fail(s->ctx, VO_ERR_BAD_ARG, "vo_solver_snapshot: index outside t_list");
+    return vo_ens_wrap(s->ctx, s->snap + (size_t)k * s->d * s->n, s->d, s->n, out);
 }
 
 int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int64_t rounds) {

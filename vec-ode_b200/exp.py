@@ -58,7 +58,17 @@ class DenseBasisSplit:
 
     # Commutator (exp/mod.rs:47-54) on coefficient vectors ---------------------------------------------------------------
     def commutator(self, la: np.ndarray, lb: np.ndarray) -> np.ndarray:
-        return np.einsum("ia,ib,abc->ic", la, lb, self.cs)
+        la, lb = np.ascontiguousarray(la, dtype=np.complex128), np.ascontiguousarray(lb, dtype=np.complex128)
+        out = np.empty_like(la)
+        check(lib().vo_split_commutator(self._h, _np_ptr(la.view(np.float64)), _np_ptr(lb.view(np.float64)), la.shape[0], _np_ptr(out.view(np.float64))),
+              self.ctx._h)
+        return out
+
+    # NormedExponentialSplit::norm (exp/mod.rs:37-45) -------------------------------------------------------------------
+    def norm(self, psi_dev: int, n_systems: int) -> np.ndarray:
+        out = np.empty(n_systems)
+        check(lib().vo_split_norm(self._h, _vp(psi_dev), n_systems, _np_ptr(out)), self.ctx._h)
+        return out
 
     def __del__(self):
         try:
