@@ -217,6 +217,11 @@ int32_t vo_split_set_commutator(vo_split sp, const double* cs /* [M][M][M] */);
 int32_t vo_split_set_taylor_degree(vo_split sp, int32_t deg); /* 0 = automatic from theta = ||L||_1 bound */
 /* map_exp(&exp(L), &x) (exp/mod.rs:23-25) for every system: coef [N][M] complex (host), psi device [N][n] complex. */
 int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in_dev, void* psi_out_dev);
+/* Compositions of exponentials — what the split combinators of exp/split_exp.rs:24-517 (CommutativeExpSplit, StrangSplit,
+ * SemiComplexO4ExpSplit, TripleJumpExpSplit, RKNR4ExpSplit) reduce to once the two user splits A and B are disjoint index
+ * sets of one basis: psi <- map_exp(exp(L_K-1), ... map_exp(exp(L_0), psi)) with K coefficient sets coef [K][N][M],
+ * in ONE launch (the state never leaves registers between the K exponentials). */
+int32_t vo_map_exp_seq(vo_split sp, const double* coef_host, int32_t K, int64_t N, void* psi_in_dev, void* psi_out_dev);
 
 /* NormedExponentialSplit::norm (exp/mod.rs:37-45): 2-norm of each of the N states psi_dev [N][n] complex -> out_host[N]. */
 int32_t vo_split_norm(vo_split sp, const void* psi_dev, int64_t N, double* out_host);
@@ -228,9 +233,12 @@ int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int
 #define VO_EXP_MIDPOINT 0 /* MidpointExpLinearSolver, exp/magnus.rs:85-148 */
 #define VO_EXP_CFM4 1     /* ExpCFMSolver, exp/cfm.rs:102-224 */
 #define VO_EXP_MAGNUS42 2 /* MagnusExpLinearSolver, exp/magnus.rs:151-285 */
+#define VO_EXP_SPLIT_MIDPOINT 3 /* ExpSplitMidpointSolver, exp/split_exp.rs:520-562, 613-685 (literal: f at t, both splits by dt/2) */
 int32_t vo_exp_create(vo_ctx ctx, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N,
                       double t0, double tf, const double* psi0_host /* [N][n] (re,im) */, double h, vo_expsolver* out);
 int32_t vo_exp_destroy(vo_expsolver s);
+/* VO_EXP_SPLIT_MIDPOINT: bit m of a_mask set <=> basis matrix m belongs to split A (the rest form split B). */
+int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */
 int32_t vo_exp_with_tolerance(vo_expsolver s, double atol, double rtol);
 int32_t vo_exp_with_step_range(vo_expsolver s, double dt_min, double dt_max);

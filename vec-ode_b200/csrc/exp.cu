@@ -51,6 +51,7 @@ struct vo_expsolver_s {
     EvSlot ev_seen{};
     int64_t n_done = 0;
     bool want_err = true;  // alph_err / x_err present (exp/cfm.rs:157-161)
+    unsigned split_mask = 1u;  // VO_EXP_SPLIT_MIDPOINT: which basis matrices form split A (default: B_0)
     double atol = 1.0e-6, rtol = 1.0e-4, alpha = 0.9, pw = 1.0 / 3.0, min_dt = 1.0e-6, max_dt = 1.0;
 };
 
@@ -59,6 +60,8 @@ namespace {
 struct ExpKP {
     int n, M, M_gen, scheme, adaptive, want_err, taylor_deg, mode;  // mode 0: solver event, 1: bare map_exp
     int pw_is_third, count_events;
+    int nseq;             // mode 1: exponentials applied one after the other, coefficient sets [nseq][N][M]
+    unsigned split_mask;  // VO_EXP_SPLIT_MIDPOINT: bit m set <=> basis matrix m belongs to split A
     double t_end, t_start;
     double rtol, alpha, pw, min_dt, max_dt;
     double norm1[VO_EXP_MAX_M];
@@ -234,7 +237,9 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TB;
-        const int nexp = kp.mode == 1 ? 1 : (kp.scheme == VO_EXP_MIDPOINT ? 1 : (kp.scheme == VO_EXP_CFM4 ? 2 : 1)) + (kp.mode == 0 && kp.want_err && kp.scheme != VO_EXP_MIDPOINT ? 1 : 0);
+        const bool embedded = kp.mode == 0 && kp.want_err && (kp.scheme == VO_EXP_CFM4 || kp.scheme == VO_EXP_MAGNUS42);
+        const int nbase = kp.mode == 1 ? 1 : (kp.scheme == VO_EXP_CFM4 ? 2 : (kp.scheme == VO_EXP_SPLIT_MIDPOINT ? 3 : 1));
+        const int nexp = nbase + (embedded ? 1 : 0);
         // ---- phase A: per-system control and exponent coefficients (one thread per system)
         if (threadIdx.x < TB) {
             const int s = threadIdx.x;
@@ -280,6 +285,19 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                                     ce[0][m].x = (CFM_R4[0] * v0[m] + (CFM_R4[1] * v1[m])) * dt;
                                     ce[1][m].x = (CFM_R4[2] * v0[m] + (CFM_R4[3] * v1[m])) * dt;
                                     ce[2][m].x = (CFM_R2[0] * v0[m] + (CFM_R2[1] * v1[m])) * dt;  // error scheme, :83-97
+                                }
+                            } else if (kp.scheme == VO_EXP_SPLIT_MIDPOINT) {  // split_exp_midpoint, exp/split_exp.rs:520-562
+                                // literal: the generator is sampled at t (not t + dt/2) and BOTH splits are scaled by dt/2
+                                // (KA[0] and KB[0] by dt0, :540-548), applied as A, B, A (:556-559)
+                                double l[M];
+                                gen_coef<M>(g, kp.M_gen, t, l);
+                                const double dt0 = dt * 0.5;
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    const bool in_a = (kp.split_mask >> m) & 1u;
+                                    ce[0][m].x = in_a ? l[m] * dt0 : 0.0;
+                                    ce[1][m].x = in_a ? 0.0 : l[m] * dt0;
+                                    ce[2][m].x = ce[0][m].x;
                                 }
                             } else {  // magnus_42, exp/magnus.rs:28-83
                                 const double c_mid = 0.288675134594812882254574390251;
@@ -351,8 +369,31 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                     xer[j][q] = xei[j][q] = 0.0;
                 }
             map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
-            if (kp.mode == 0 && kp.scheme == VO_EXP_CFM4) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + M * TB, sPlan[2], sPlan[3], xfr, xfi, buf);
-            if (nexp > (kp.scheme == VO_EXP_CFM4 ? 2 : 1)) {  // embedded lower-order solution from x0, then x_err = that - xf
+            if (kp.mode == 0 && nbase >= 2) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + M * TB, sPlan[2], sPlan[3], xfr, xfi, buf);
+            if (kp.mode == 0 && nbase >= 3) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + 2 * M * TB, sPlan[4], sPlan[5], xfr, xfi, buf);
+            for (int q = 1; kp.mode == 1 && q < kp.nseq; ++q) {  // vo_map_exp_seq: the next exponential of the composition
+                __syncthreads();
+                if (threadIdx.x < TB) {
+                    const int64_t sys = base + threadIdx.x;
+                    double th = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const double2 c = sys < kp.N ? coef_in[((int64_t)q * kp.N + sys) * M + m] : make_double2(0.0, 0.0);
+                        sCoef[m * TB + threadIdx.x] = c;
+                        th += hypot(c.x, c.y) * kp.norm1[m];
+                    }
+                    sTheta[threadIdx.x] = th;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double th = 0.0;
+                    for (int s = 0; s < TB; ++s) th = fmax(th, sTheta[s]);
+                    taylor_plan(th, kp.taylor_deg, &sPlan[0], &sPlan[1]);
+                }
+                __syncthreads();
+                map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
+            }
+            if (embedded) {  // embedded lower-order solution from x0, then x_err = that - xf
                 const int e = nexp - 1;
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
@@ -522,13 +563,15 @@ int32_t exp_ev_read(vo_expsolver_s* s, EvSlot* out) {
 int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     vo_ctx c = s->ctx;
     if (adaptive && !s->want_err) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // ode.rs:312
-    if (adaptive && s->scheme == VO_EXP_MIDPOINT) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "MidpointExpLinearSolver has no error estimate");
+    if (adaptive && (s->scheme == VO_EXP_MIDPOINT || s->scheme == VO_EXP_SPLIT_MIDPOINT))
+        return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "this solver has no error estimate (it only implements ODESolver)");
     ExpKP kp = make_kp(s->sp, 0);
     kp.M_gen = s->M_gen, kp.scheme = s->scheme, kp.adaptive = adaptive ? 1 : 0;
     kp.want_err = (s->want_err && adaptive) ? 1 : 0;  // the embedded solution only feeds the controller
     kp.t_start = s->t0, kp.t_end = s->tf, kp.N = s->N, kp.count_events = 1;
     kp.rtol = s->rtol, kp.alpha = s->alpha, kp.pw = s->pw, kp.min_dt = s->min_dt, kp.max_dt = s->max_dt;
     kp.pw_is_third = s->pw == 1.0 / 3.0;
+    kp.split_mask = s->split_mask;
     return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev);
 }
 
@@ -645,15 +688,16 @@ int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int
     return VO_OK;
 }
 
-int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in_dev, void* psi_out_dev) {
-    if (!sp || !coef_host || N < 1 || !psi_in_dev || !psi_out_dev) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_map_exp: bad argument");
+int32_t vo_map_exp_seq(vo_split sp, const double* coef_host, int32_t K, int64_t N, void* psi_in_dev, void* psi_out_dev) {
+    if (!sp || !coef_host || N < 1 || K < 1 || !psi_in_dev || !psi_out_dev) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_map_exp_seq: bad argument");
     vo_ctx c = sp->ctx;
     DeviceGuard g(c->device);
     double2* coef_dev = nullptr;
-    VO_CUDA(c, cudaMallocAsync(&coef_dev, sizeof(double2) * N * sp->M, c->stream));
-    VO_CUDA(c, cudaMemcpyAsync(coef_dev, coef_host, sizeof(double2) * N * sp->M, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = sizeof(double2) * (size_t)K * N * sp->M;
+    VO_CUDA(c, cudaMallocAsync(&coef_dev, bytes, c->stream));
+    VO_CUDA(c, cudaMemcpyAsync(coef_dev, coef_host, bytes, cudaMemcpyHostToDevice, c->stream));
     ExpKP kp = make_kp(sp, 1);
-    kp.N = N;
+    kp.N = N, kp.nseq = K;
     CtlArrays none{};
     int32_t r = dispatch_exp(sp, kp, (double2*)psi_in_dev, (double2*)psi_out_dev, nullptr, coef_dev, none, nullptr);
     cudaFreeAsync(coef_dev, c->stream);
@@ -661,9 +705,19 @@ int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in
     return r;
 }
 
+int32_t vo_map_exp(vo_split sp, const double* coef_host, int64_t N, void* psi_in_dev, void* psi_out_dev) {
+    return vo_map_exp_seq(sp, coef_host, 1, N, psi_in_dev, psi_out_dev);
+}
+
+int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->split_mask = a_mask;
+    return VO_OK;
+}
+
 int32_t vo_exp_create(vo_ctx c, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N, double t0, double tf,
                       const double* psi0_host, double h, vo_expsolver* out) {
-    if (!c || !sp || !out || !psi0_host || N < 1 || scheme < 0 || scheme > VO_EXP_MAGNUS42 || M_gen < 1 || M_gen > sp->M || (M_gen > 1 && !gp_host))
+    if (!c || !sp || !out || !psi0_host || N < 1 || scheme < 0 || scheme > VO_EXP_SPLIT_MIDPOINT || M_gen < 1 || M_gen > sp->M || (M_gen > 1 && !gp_host))
         return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: bad argument");
     if (scheme == VO_EXP_MAGNUS42 && !sp->has_cs) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: Magnus needs vo_split_set_commutator (Commutator trait, exp/mod.rs:47-54)");
     DeviceGuard g(c->device);

@@ -40,8 +40,11 @@ __device__ __forceinline__ void rk_attempt_n(const TableauDev& tb, const double 
     }
 }
 
+#ifndef VO_CTL2_MIN_BLOCKS
+#define VO_CTL2_MIN_BLOCKS 3
+#endif
 template <class RHS, int S, bool STRICT>
-__global__ void __launch_bounds__(128, 3) rk_ctl2_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+__global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
                                                                 const __grid_constant__ RhsParams rp, const CtlArrays ca,
                                                                 const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev, const pipe::Chain ch) {
     constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE2, U = 2;
