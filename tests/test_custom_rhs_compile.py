@@ -1,0 +1,18 @@
+"""User RHS source -> sm_100a cubin with NVRTC (vo_rhs_custom_check): needs no GPU, so the run-time compilation path of
+vo_rhs_create_custom (the closure replacement, src/base/rk.rs:97) is checked on CPU too. No kernel is launched here."""
+import pytest
+
+BODY = "dx[0] = p[0] * x[0] - p[1] * x[0] * x[1];\ndx[1] = p[3] * x[0] * x[1] - p[2] * x[1];"
+
+
+@pytest.mark.parametrize("stages,arith", [(-1, "strict"), (7, "fast"), (5, "strict")])
+def test_user_rhs_compiles_into_the_kernel_templates(vo, stages, arith):
+    assert vo.Rhs.check_source(BODY, 2, 4, stages, arith) > 10_000  # bytes of cubin
+
+
+def test_user_rhs_compile_error_carries_the_log(vo):
+    with pytest.raises(vo.VecOdeError) as ei:
+        vo.Rhs.check_source("dx[0] = nope;", 1, 0)
+    assert "rhs_body(1)" in str(ei.value) and "nope" in str(ei.value)
+    with pytest.raises(vo.VecOdeError):
+        vo.Rhs.check_source("dx[0] = x[0];", 9, 0)

@@ -239,14 +239,33 @@ class Rhs:
     """Replaces the closure `FnMut(T, &V, &mut V) -> Result<(),()>` (src/base/rk.rs:97): a compiled-in device functor
     chosen by name, with parameters that are shared scalars or per-trajectory arrays."""
 
-    def __init__(self, ctx: Context, kind: str, d: int, params=None):
+    def __init__(self, ctx: Context, kind: str, d: int, params=None, body: str | None = None):
         self.ctx, self.kind, self.d = ctx, kind, d
         self._h = _vp()
-        check(lib().vo_rhs_create(ctx._h, _cabi.RHS[kind], d, C.byref(self._h)), ctx._h)
+        if kind == "CUSTOM":
+            n_params = 0 if params is None else len(params)
+            check(lib().vo_rhs_create_custom(ctx._h, body.encode(), d, n_params, C.byref(self._h)), ctx._h)
+        else:
+            check(lib().vo_rhs_create(ctx._h, _cabi.RHS[kind], d, C.byref(self._h)), ctx._h)
         self.num_params = int(lib().vo_rhs_num_params(self._h))
         if params is not None:
             for i, p in enumerate(params):
                 self.set_param(i, p)
+
+    @classmethod
+    def custom(cls, ctx: Context, body: str, d: int, params=()):
+        """The closure itself: `body` is CUDA C++ for the statements of `f(t, &x, &mut dx)` over `t`, `x[D]`, `dx[D]`, `p[NP]`;
+        it is compiled at run time into the same fused kernels as the built-in families (vo_rhs_create_custom)."""
+        return cls(ctx, "CUSTOM", d, list(params), body=body)
+
+    @staticmethod
+    def check_source(body: str, d: int, n_params: int, stages: int = -1, arith: str = "strict") -> int:
+        """Compile `body` without a GPU; returns the cubin size or raises VecOdeError carrying the compiler log."""
+        log = C.create_string_buffer(1 << 16)
+        rc = lib().vo_rhs_custom_check(body.encode(), d, n_params, stages, _cabi.ARITH_STRICT if arith == "strict" else _cabi.ARITH_FAST, log, len(log))
+        if rc < 0:
+            raise VecOdeError(rc, log.value.decode("utf-8", "replace"))
+        return rc
 
     def set_param(self, idx: int, value):
         if np.ndim(value) == 0:

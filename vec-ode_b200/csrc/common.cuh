@@ -1,14 +1,28 @@
 // common.cuh — handle definitions, error plumbing and arithmetic-mode helpers shared by all kernels.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of a user RHS (nvrtc_rhs.cu): device-side definitions only, no host headers
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
+#endif
 
 #include "../../include/vecode_b200.h"
 
+#define VO_MAX_PARAMS 8
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------------
 // Handles
 // ------------------------------------------------------------------------------------------------
@@ -41,14 +55,18 @@ struct vo_tableau_s {
     double b_err[VO_MAX_STAGES];
 };
 
-#define VO_MAX_PARAMS 8
 struct vo_rhs_s {
     vo_ctx ctx = nullptr;
     int kind = 0, d = 0, np = 0;
     double shared[VO_MAX_PARAMS];      // shared value of each parameter
     double* per_traj[VO_MAX_PARAMS];   // device array or nullptr
     int64_t per_traj_n[VO_MAX_PARAMS];
+    std::string body;                  // VO_RHS_CUSTOM: source of the RHS statements
+    std::map<int, void*> modules;      // VO_RHS_CUSTOM: compiled modules keyed by (stage count, arithmetic mode)
 };
+void custom_rhs_release(vo_rhs_s* r);  // nvrtc_rhs.cu
+
+#endif  // !__CUDACC_RTC__
 
 // Device-side view of the RHS parameters, passed by value to kernels.
 struct RhsParams {
@@ -65,6 +83,7 @@ struct TableauDev {
     int has_err;
 };
 
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------------
 // Errors
 // ------------------------------------------------------------------------------------------------
@@ -103,6 +122,8 @@ struct DeviceGuard {
     }
 };
 
+#endif  // !__CUDACC_RTC__
+
 // ------------------------------------------------------------------------------------------------
 // Arithmetic modes. STRICT: explicit round-to-nearest multiply and add (never contracted by nvcc), the
 // reference's operation order. FAST: ordinary operators, nvcc is free to emit DFMA.
@@ -117,4 +138,6 @@ template <bool STRICT> struct Ar {
     }
 };
 
+#ifndef __CUDACC_RTC__
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+#endif

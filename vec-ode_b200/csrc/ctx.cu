@@ -332,6 +332,7 @@ int32_t vo_rhs_destroy(vo_rhs r) {
     cudaStreamSynchronize(r->ctx->stream);
     for (int i = 0; i < VO_MAX_PARAMS; ++i)
         if (r->per_traj[i]) cudaFree(r->per_traj[i]);
+    if (r->kind == VO_RHS_CUSTOM) custom_rhs_release(r);
     delete r;
     return VO_OK;
 }

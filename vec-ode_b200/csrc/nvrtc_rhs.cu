@@ -1,0 +1,401 @@
+// nvrtc_rhs.cu — user-defined right-hand sides: the C-ABI replacement of the reference's RHS closure
+// `f: FnMut(T, &V, &mut V) -> Result<(),()>` (src/base/rk.rs:97; called at rk.rs:111 and :127).
+//
+// A closure cannot cross a C ABI into device code, so the caller hands over the SOURCE of its statements. It is wrapped
+// into a functor with the same shape as the compiled-in families of rhs.cuh and compiled at run time (NVRTC, sm_100a)
+// together with the very kernel templates the built-in families use — the headers are embedded in this shared object —
+// so a user RHS runs fused inside the register-resident whole-attempt kernels (rk_small.cuh, rk_small2.cuh) and inside
+// the stage-path kernel (rk_stage_pointwise.cuh) exactly like a built-in one. One module per (stage count, arithmetic
+// mode), compiled on first use and cached on the vo_rhs. VO_ARITH_STRICT modules are compiled with --fmad=false, so a
+// plain `a*b + c` in the body stays a separate multiply and add like the reference's Rust.
+//
+// libnvrtc is dlopen'ed on first use and the CUDA driver entry points are taken from the runtime
+// (cudaGetDriverEntryPoint), so the library still loads — and every other path still works — on a machine without them.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "rk_small_launch.cuh"
+#include "rk_stage_pointwise.cuh"
+
+namespace {
+
+struct Header {
+    const char* name;
+    const char* text;
+};
+const Header RTC_HEADERS[] = {
+#include "rtc_headers.inc"
+};
+constexpr int N_HEADERS = (int)(sizeof(RTC_HEADERS) / sizeof(RTC_HEADERS[0]));
+
+// ---- libnvrtc, loaded lazily -------------------------------------------------------------------------------------
+struct Nvrtc {
+    void* so = nullptr;
+    decltype(&nvrtcCreateProgram) createProgram = nullptr;
+    decltype(&nvrtcDestroyProgram) destroyProgram = nullptr;
+    decltype(&nvrtcCompileProgram) compileProgram = nullptr;
+    decltype(&nvrtcAddNameExpression) addNameExpression = nullptr;
+    decltype(&nvrtcGetLoweredName) getLoweredName = nullptr;
+    decltype(&nvrtcGetCUBINSize) getCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) getCUBIN = nullptr;
+    decltype(&nvrtcGetProgramLogSize) getProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) getProgramLog = nullptr;
+    decltype(&nvrtcGetErrorString) getErrorString = nullptr;
+};
+
+bool nvrtc_load(Nvrtc** out, std::string& err) {
+    static Nvrtc nv;
+    static std::once_flag once;
+    static std::string load_err;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("VECODE_NVRTC"), "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            nv.so = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (nv.so) break;
+        }
+        if (!nv.so) {
+            load_err = "user RHS: libnvrtc could not be loaded (set VECODE_NVRTC to its path)";
+            return;
+        }
+#define VO_NVRTC_SYM(field, sym)                                            \
+    nv.field = reinterpret_cast<decltype(nv.field)>(dlsym(nv.so, #sym));    \
+    if (!nv.field) load_err = std::string("user RHS: libnvrtc lacks ") + #sym;
+        VO_NVRTC_SYM(createProgram, nvrtcCreateProgram)
+        VO_NVRTC_SYM(destroyProgram, nvrtcDestroyProgram)
+        VO_NVRTC_SYM(compileProgram, nvrtcCompileProgram)
+        VO_NVRTC_SYM(addNameExpression, nvrtcAddNameExpression)
+        VO_NVRTC_SYM(getLoweredName, nvrtcGetLoweredName)
+        VO_NVRTC_SYM(getCUBINSize, nvrtcGetCUBINSize)
+        VO_NVRTC_SYM(getCUBIN, nvrtcGetCUBIN)
+        VO_NVRTC_SYM(getProgramLogSize, nvrtcGetProgramLogSize)
+        VO_NVRTC_SYM(getProgramLog, nvrtcGetProgramLog)
+        VO_NVRTC_SYM(getErrorString, nvrtcGetErrorString)
+#undef VO_NVRTC_SYM
+    });
+    if (!load_err.empty()) {
+        err = load_err;
+        return false;
+    }
+    *out = &nv;
+    return true;
+}
+
+// ---- driver entry points through the runtime ---------------------------------------------------------------------
+struct Driver {
+    decltype(&cuModuleLoadData) moduleLoadData = nullptr;
+    decltype(&cuModuleUnload) moduleUnload = nullptr;
+    decltype(&cuModuleGetFunction) moduleGetFunction = nullptr;
+    decltype(&cuLaunchKernelEx) launchKernelEx = nullptr;
+    decltype(&cuFuncSetAttribute) funcSetAttribute = nullptr;
+    decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) occupancy = nullptr;
+    decltype(&cuGetErrorString) getErrorString = nullptr;
+};
+
+bool driver_load(Driver** out, std::string& err) {
+    static Driver dr;
+    static std::once_flag once;
+    static std::string load_err;
+    std::call_once(once, [] {
+        auto get = [&](const char* sym, void** fn) {
+            cudaDriverEntryPointQueryResult st;
+            if (cudaGetDriverEntryPoint(sym, fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !*fn)
+                load_err = std::string("user RHS: CUDA driver entry point not available: ") + sym;
+        };
+        get("cuModuleLoadData", (void**)&dr.moduleLoadData);
+        get("cuModuleUnload", (void**)&dr.moduleUnload);
+        get("cuModuleGetFunction", (void**)&dr.moduleGetFunction);
+        get("cuLaunchKernelEx", (void**)&dr.launchKernelEx);
+        get("cuFuncSetAttribute", (void**)&dr.funcSetAttribute);
+        get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&dr.occupancy);
+        get("cuGetErrorString", (void**)&dr.getErrorString);
+        cudaGetLastError();
+    });
+    if (!load_err.empty()) {
+        err = load_err;
+        return false;
+    }
+    *out = &dr;
+    return true;
+}
+
+std::string cu_msg(Driver* dr, CUresult e) {
+    const char* s = nullptr;
+    if (dr->getErrorString(e, &s) != CUDA_SUCCESS || !s) return "CUDA driver error " + std::to_string((int)e);
+    return s;
+}
+
+// ---- one compiled module -----------------------------------------------------------------------------------------
+enum { K_FIXED_STAGED, K_FIXED, K_CTL_STAGED_GEN, K_CTL_STAGED_L2, K_CTL2_STAGED, K_CTL, K_SMALL_COUNT };
+enum { K_STAGE, K_STAGE_TAIL, K_STAGE_COUNT };
+constexpr int STAGE_MODULE = -1;  // `S` key of the stage-path module (it does not depend on the stage count)
+
+struct CustomModule {
+    CUmodule mod = nullptr;
+    CUfunction fn[K_SMALL_COUNT] = {};
+    int bps[K_SMALL_COUNT] = {};  // resident CTAs per SM at the shared-memory size last queried
+    size_t bps_smem[K_SMALL_COUNT] = {};
+};
+
+std::string rtc_source(const std::string& body, int d, int np, bool stage_module) {
+    std::string s = stage_module ? "#include \"rk_stage_pointwise.cuh\"\n" : "#include \"rk_small2.cuh\"\n";
+    s += "struct RhsCustom {\n    static constexpr int D = " + std::to_string(d) + ", NP = " + std::to_string(np > 0 ? np : 1) + ";\n";
+    s += "    template <bool STRICT> static __device__ __forceinline__ void eval(const double t, const double (&x)[D], double (&dx)[D], const double (&p)[NP]) {\n";
+    s += "#line 1 \"rhs_body\"\n" + body + "\n    }\n};\n";
+    return s;
+}
+
+std::vector<std::string> kernel_names(int S, bool strict, bool stage_module) {
+    const std::string st = strict ? "true" : "false", ss = std::to_string(S);
+    if (stage_module) return {"stage_pointwise_kernel<RhsCustom, " + st + ", false>", "stage_pointwise_kernel<RhsCustom, " + st + ", true>"};
+    std::vector<std::string> v(K_SMALL_COUNT);
+    v[K_FIXED_STAGED] = "rk_fixed_staged_kernel<RhsCustom, " + ss + ", " + st + ">";
+    v[K_FIXED] = "rk_fixed_kernel<RhsCustom, " + ss + ", " + st + ">";
+    v[K_CTL_STAGED_GEN] = "rk_ctl_staged_kernel<RhsCustom, " + ss + ", " + st + ", 0>";
+    v[K_CTL_STAGED_L2] = "rk_ctl_staged_kernel<RhsCustom, " + ss + ", " + st + ", 1>";
+    v[K_CTL2_STAGED] = S > 0 ? "rk_ctl2_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";
+    v[K_CTL] = "rk_ctl_kernel<RhsCustom, " + ss + ", " + st + ">";
+    return v;
+}
+
+// Source -> cubin. Needs no GPU. `lowered[i]` is the mangled name of names[i] ("" where names[i] is "").
+int32_t compile_custom(const std::string& body, int d, int np, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered,
+                       std::string& log) {
+    Nvrtc* nv = nullptr;
+    if (!nvrtc_load(&nv, log)) return VO_ERR_UNSUPPORTED;
+    const bool stage_module = S == STAGE_MODULE;
+    const std::string src = rtc_source(body, d, np, stage_module);
+    const char* hdr_text[N_HEADERS];
+    const char* hdr_name[N_HEADERS];
+    for (int i = 0; i < N_HEADERS; ++i) hdr_text[i] = RTC_HEADERS[i].text, hdr_name[i] = RTC_HEADERS[i].name;
+    nvrtcProgram prog;
+    nvrtcResult r = nv->createProgram(&prog, src.c_str(), "vo_user_rhs.cu", N_HEADERS, hdr_text, hdr_name);
+    if (r != NVRTC_SUCCESS) {
+        log = std::string("nvrtcCreateProgram: ") + nv->getErrorString(r);
+        return VO_ERR_CUDA;
+    }
+    const std::vector<std::string> names = kernel_names(S, strict, stage_module);
+    for (const std::string& n : names)
+        if (!n.empty()) nv->addNameExpression(prog, n.c_str());
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+                                      "-default-device"};  // the C-ABI prototypes in vecode_b200.h are declarations only; JIT mode rejects host functions
+    if (strict) opts.push_back("--fmad=false");
+    r = nv->compileProgram(prog, (int)opts.size(), opts.data());
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nv->getProgramLogSize(prog, &n);
+        std::string l(n, '\0');
+        if (n) nv->getProgramLog(prog, &l[0]);
+        if (l.size() > 4000) l.resize(4000), l += "\n[...]";
+        log = std::string("user RHS does not compile (") + nv->getErrorString(r) + "):\n" + l.c_str();
+        nv->destroyProgram(&prog);
+        return VO_ERR_BAD_ARG;
+    }
+    size_t n = 0;
+    nv->getCUBINSize(prog, &n);
+    cubin.resize(n);
+    nv->getCUBIN(prog, cubin.data());
+    lowered.assign(names.size(), "");
+    for (size_t i = 0; i < names.size(); ++i) {
+        if (names[i].empty()) continue;
+        const char* low = nullptr;
+        if (nv->getLoweredName(prog, names[i].c_str(), &low) != NVRTC_SUCCESS || !low) {
+            log = "user RHS: no lowered name for " + names[i];
+            nv->destroyProgram(&prog);
+            return VO_ERR_CUDA;
+        }
+        lowered[i] = low;
+    }
+    nv->destroyProgram(&prog);
+    return VO_OK;
+}
+
+int module_key(int S, bool strict) { return (S + 1) * 2 + (strict ? 1 : 0); }
+
+int32_t get_module(vo_rhs_s* r, int S, bool strict, Driver** drv, CustomModule** out) {
+    vo_ctx c = r->ctx;
+    std::string err;
+    if (!driver_load(drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
+    auto it = r->modules.find(module_key(S, strict));
+    if (it != r->modules.end()) {
+        *out = static_cast<CustomModule*>(it->second);
+        return VO_OK;
+    }
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    int32_t rc = compile_custom(r->body, r->d, r->np, S, strict, cubin, lowered, err);
+    if (rc != VO_OK) return vo_fail(c, rc, err);
+    cudaFree(0);  // make sure the primary context the runtime uses is current before the first driver call
+    CustomModule* m = new CustomModule();
+    CUresult e = (*drv)->moduleLoadData(&m->mod, cubin.data());
+    if (e != CUDA_SUCCESS) {
+        delete m;
+        return vo_fail(c, VO_ERR_CUDA, "user RHS: cuModuleLoadData: " + cu_msg(*drv, e));
+    }
+    for (size_t i = 0; i < lowered.size(); ++i) {
+        if (lowered[i].empty()) continue;
+        e = (*drv)->moduleGetFunction(&m->fn[i], m->mod, lowered[i].c_str());
+        if (e != CUDA_SUCCESS) {
+            (*drv)->moduleUnload(m->mod);
+            delete m;
+            return vo_fail(c, VO_ERR_CUDA, "user RHS: cuModuleGetFunction(" + lowered[i] + "): " + cu_msg(*drv, e));
+        }
+    }
+    r->modules[module_key(S, strict)] = m;
+    *out = m;
+    return VO_OK;
+}
+
+// Persistent grid of rk_small_launch.cuh::persistent_grid for a driver-API function.
+int32_t custom_grid(vo_ctx c, Driver* drv, CustomModule* m, int k, int64_t N, size_t smem, int tile, unsigned* grid) {
+    if (m->bps[k] == 0 || m->bps_smem[k] != smem) {
+        if (smem > 48 * 1024) {
+            CUresult e = drv->funcSetAttribute(m->fn[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+            if (e != CUDA_SUCCESS) return vo_fail(c, VO_ERR_CUDA, "user RHS: shared-memory attribute: " + cu_msg(drv, e));
+        }
+        int bps = 0;
+        if (drv->occupancy(&bps, m->fn[k], RK_SMALL_THREADS, smem) != CUDA_SUCCESS || bps < 1) bps = 1;
+        m->bps[k] = bps, m->bps_smem[k] = smem;
+    }
+    const int64_t tiles = ceil_div(N, tile);
+    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * m->bps[k]);
+    *grid = (unsigned)ceil_div(tiles, iters);
+    return VO_OK;
+}
+
+int32_t custom_launch(vo_ctx c, Driver* drv, CUfunction fn, unsigned grid, unsigned block, size_t smem, bool pdl, void** args) {
+    CUlaunchConfig cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDimX = grid, cfg.gridDimY = 1, cfg.gridDimZ = 1, cfg.blockDimX = block, cfg.blockDimY = 1, cfg.blockDimZ = 1;
+    cfg.sharedMemBytes = (unsigned)smem, cfg.hStream = (CUstream)c->stream;
+    CUlaunchAttribute at[1];
+    std::memset(at, 0, sizeof at);
+    at[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    at[0].value.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
+    CUresult e = drv->launchKernelEx(&cfg, fn, args, nullptr);
+    if (e != CUDA_SUCCESS) return vo_fail(c, VO_ERR_CUDA, "user RHS: kernel launch: " + cu_msg(drv, e));
+    return VO_OK;
+}
+
+int stage_count_key(int s) { return (s == 4 || s == 6 || s == 7) ? s : 0; }  // the unrolled instantiations of launch_family
+
+}  // namespace
+
+// The register-resident path for a user RHS: same kernel choice as launch_one (rk_small_launch.cuh).
+int32_t launch_small_custom(const SmallLaunch& L, vo_rhs_s* r) {
+    vo_ctx c = L.ctx;
+    const bool strict = c->arith == VO_ARITH_STRICT;
+    const int S = stage_count_key(L.tb->s);
+    Driver* drv = nullptr;
+    CustomModule* m = nullptr;
+    int32_t rc = get_module(r, S, strict, &drv, &m);
+    if (rc != VO_OK) return rc;
+    double* x = L.x;
+    int64_t N = L.N;
+    TableauDev tb = *L.tb;
+    RhsParams rp = *L.rp;
+    CtlArrays ca = L.ca;
+    EvSlot* ev = L.ev;
+    pipe::Chain ch = L.chain;
+    const int rows = r->d + per_traj_rows(rp, r->np);
+    const bool staged = small_path_is_staged(N), pdl = L.chain.chained != 0;
+    unsigned grid = 0;
+    if (L.sl) {
+        StepList sl = *L.sl;
+        if (staged) {
+            const size_t smem = (size_t)VO_STAGES * rows * VO_TILE * sizeof(double);
+            void* args[] = {&x, &N, &tb, &rp, &sl, &ch};
+            rc = custom_grid(c, drv, m, K_FIXED_STAGED, N, smem, VO_TILE, &grid);
+            return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED_STAGED], grid, RK_SMALL_THREADS, smem, pdl, args);
+        }
+        void* args[] = {&x, &N, &tb, &rp, &sl};
+        rc = custom_grid(c, drv, m, K_FIXED, N, 0, VO_TILE, &grid);
+        return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED], grid, RK_SMALL_THREADS, 0, false, args);
+    }
+    CtlShared cs = *L.cs;
+    if (staged) {
+        const bool common = cs.adaptive && cs.use_err && cs.norm_kind == VO_NORM_L2;
+        void* args[] = {&x, &N, &tb, &rp, &ca, &cs, &ev, &ch};
+        if (S > 0 && common && cs.k_events == 1 && N >= 4 * VO_TILE2) {
+            const size_t smem2 = (size_t)VO_STAGES * ((rows + 2) * VO_TILE2 * sizeof(double) + 3 * VO_TILE2 * sizeof(uint32_t));
+            rc = custom_grid(c, drv, m, K_CTL2_STAGED, N, smem2, VO_TILE2, &grid);
+            return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_CTL2_STAGED], grid, RK_SMALL_THREADS, smem2, pdl, args);
+        }
+        const size_t smem = (size_t)VO_STAGES * ((rows + 2) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
+        const int k = common ? K_CTL_STAGED_L2 : K_CTL_STAGED_GEN;
+        rc = custom_grid(c, drv, m, k, N, smem, VO_TILE, &grid);
+        return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[k], grid, RK_SMALL_THREADS, smem, pdl, args);
+    }
+    void* args[] = {&x, &N, &tb, &rp, &ca, &cs, &ev};
+    rc = custom_grid(c, drv, m, K_CTL, N, 0, VO_TILE, &grid);
+    return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_CTL], grid, RK_SMALL_THREADS, 0, false, args);
+}
+
+// The stage path for a user RHS (vo_rk_try_step, vo_rhs_eval, vo_solver_set_path(1)).
+int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t N, const StageArgs& sa_in, const RhsParams& rp_in, double* k_out,
+                            double* nx, double* xe) {
+    Driver* drv = nullptr;
+    CustomModule* m = nullptr;
+    int32_t rc = get_module(r, STAGE_MODULE, c->arith == VO_ARITH_STRICT, &drv, &m);
+    if (rc != VO_OK) return rc;
+    StageArgs sa = sa_in;
+    RhsParams rp = rp_in;
+    void* args[] = {&x0, &N, &sa, &rp, &k_out, &nx, &xe};
+    return custom_launch(c, drv, m->fn[tail ? K_STAGE_TAIL : K_STAGE], (unsigned)ceil_div(N, 128), 128, 0, false, args);
+}
+
+void custom_rhs_release(vo_rhs_s* r) {
+    std::string err;
+    Driver* drv = nullptr;
+    const bool have = driver_load(&drv, err);
+    for (auto& kv : r->modules) {
+        CustomModule* m = static_cast<CustomModule*>(kv.second);
+        if (have && m->mod) drv->moduleUnload(m->mod);
+        delete m;
+    }
+    r->modules.clear();
+}
+
+extern "C" {
+
+int32_t vo_rhs_create_custom(vo_ctx c, const char* body, int32_t d, int32_t n_params, vo_rhs* out) {
+    if (!c || !body || !out) return vo_fail(c, VO_ERR_BAD_ARG, "vo_rhs_create_custom: NULL argument");
+    if (d < 1 || d > 8 || n_params < 0 || n_params > VO_MAX_PARAMS) return vo_fail(c, VO_ERR_SHAPE, "vo_rhs_create_custom: needs 1 <= d <= 8 and 0 <= n_params <= 8");
+    DeviceGuard g(c->device);
+    vo_rhs r = new vo_rhs_s();
+    r->ctx = c, r->kind = VO_RHS_CUSTOM, r->d = d, r->np = n_params, r->body = body;
+    for (int i = 0; i < VO_MAX_PARAMS; ++i) r->shared[i] = 0.0, r->per_traj[i] = nullptr, r->per_traj_n[i] = 0;
+    // compile the stage-path module now, so that a source error is reported here rather than at the first step
+    Driver* drv = nullptr;
+    CustomModule* m = nullptr;
+    int32_t rc = get_module(r, STAGE_MODULE, c->arith == VO_ARITH_STRICT, &drv, &m);
+    if (rc != VO_OK) {
+        custom_rhs_release(r);
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return VO_OK;
+}
+
+int32_t vo_rhs_custom_check(const char* body, int32_t d, int32_t n_params, int32_t stages, int32_t arith, char* log, int64_t log_cap) {
+    if (log && log_cap > 0) log[0] = '\0';
+    if (!body || d < 1 || d > 8 || n_params < 0 || n_params > VO_MAX_PARAMS || stages < -1 || stages > VO_MAX_STAGES)
+        return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_rhs_custom_check: bad argument");
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    std::string msg;
+    const int32_t rc = compile_custom(body, d, n_params, stages < 0 ? STAGE_MODULE : stage_count_key(stages), arith == VO_ARITH_STRICT, cubin, lowered, msg);
+    if (rc != VO_OK) {
+        if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
+        return vo_fail(nullptr, rc, msg);
+    }
+    return (int32_t)std::min<size_t>(cubin.size(), 0x7fffffff);
+}
+
+}  // extern "C"

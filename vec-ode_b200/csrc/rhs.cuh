@@ -49,8 +49,10 @@ template <int NP> static __device__ __forceinline__ void load_params(const RhsPa
     for (int q = 0; q < NP; ++q) p[q] = rp.per_traj[q] ? __ldg(rp.per_traj[q] + i) : rp.shared[q];
 }
 
+#ifndef __CUDACC_RTC__
 static inline RhsParams make_rhs_params(const vo_rhs_s* r) {
     RhsParams rp;
     for (int q = 0; q < VO_MAX_PARAMS; ++q) rp.shared[q] = r->shared[q], rp.per_traj[q] = r->per_traj[q];
     return rp;
 }
+#endif

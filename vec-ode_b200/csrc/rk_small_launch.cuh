@@ -113,3 +113,5 @@ int32_t launch_small_diag(const SmallLaunch& L, int d);
 int32_t launch_small_harmonic(const SmallLaunch& L);
 int32_t launch_small_lorenz(const SmallLaunch& L);
 int32_t launch_small_vdp(const SmallLaunch& L);
+// user RHS compiled at run time (nvrtc_rhs.cu)
+int32_t launch_small_custom(const SmallLaunch& L, vo_rhs_s* r);

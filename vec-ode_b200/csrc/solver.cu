@@ -23,6 +23,8 @@
 #include "rk_stage.cuh"
 
 int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap);
+int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t N, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
+                            double* xe);  // nvrtc_rhs.cu
 
 namespace {
 
@@ -74,7 +76,7 @@ struct vo_solver_s {
 
 namespace {
 
-bool rhs_is_small(const vo_rhs_s* r) { return r->kind != VO_RHS_HEAT1D && r->d <= 4; }
+bool rhs_is_small(const vo_rhs_s* r) { return r->kind == VO_RHS_CUSTOM || (r->kind != VO_RHS_HEAT1D && r->d <= 4); }
 bool use_small(const vo_solver_s* s) { return !s->stage_path && rhs_is_small(s->rhs); }
 bool use_err(const vo_solver_s* s) { return s->tab.has_err && s->has_x_err; }
 // Events fused per launch. step()/vo_step_many expose every event, so they advance one at a time unless the caller
@@ -304,6 +306,10 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
         case VO_RHS_HARMONIC2D: r = launch_small_harmonic(L); break;
         case VO_RHS_LORENZ63: r = launch_small_lorenz(L); break;
         case VO_RHS_VDP: r = launch_small_vdp(L); break;
+        case VO_RHS_CUSTOM:
+            r = launch_small_custom(L, s->rhs);
+            if (r != VO_OK) return r;  // message already set (compile log, driver error)
+            break;
     }
     if (r != VO_OK) return vo_fail(c, r, "solver: no register-resident kernel for this RHS");
     VO_CHECK_LAUNCH(c);
@@ -432,6 +438,10 @@ template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs
         case VO_RHS_HARMONIC2D: launch_pointwise<RhsF<VO_RHS_HARMONIC2D, 2>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
         case VO_RHS_LORENZ63: launch_pointwise<RhsF<VO_RHS_LORENZ63, 3>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
         case VO_RHS_VDP: launch_pointwise<RhsF<VO_RHS_VDP, 2>, TAIL>(c, x0, s->n, sa, rp, k_out, nx, xe); break;
+        case VO_RHS_CUSTOM: {
+            int32_t cr = launch_stage_custom(c, s->rhs, TAIL, x0, s->n, sa, rp, k_out, nx, xe);
+            if (cr != VO_OK) return cr;
+        } break;
         case VO_RHS_HEAT1D: {
             const double kappa = r->shared[0];
             const bool strict = c->arith == VO_ARITH_STRICT;

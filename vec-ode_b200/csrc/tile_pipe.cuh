@@ -3,7 +3,9 @@
 // reads in flight per CTA, so the bytes in flight per SM are set by shared memory (tens of KB), not by how many loads
 // the register file can hold — which is what an HBM-latency-bound stream of small per-thread loads runs out of.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 namespace pipe {
 
