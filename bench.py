@@ -148,6 +148,9 @@ class VdpDopri5:
         self.x0 = vo.Ensemble.from_host(ctx, self.x0_host)
         self.solvers = [vo.RK45Solver(self.rhs, 0.0, 1.0e9, self.x0, 1e-3, tableau=self.tableau).with_tolerance(1e-6, 1e-6)
                         for _ in range(n_batches)]
+        if os.environ.get("VECODE_BENCH_NO_DX_NORM"):  # experiment switch: drop the per-attempt ODEAdaptiveData.dx_norm record (8 B)
+            for s_ in self.solvers:
+                s_.set_record_dx_norm(False)
         vo.step_many(self.solvers, True, 1)
         self._attempts0 = None
 
@@ -438,6 +441,8 @@ def main():
     W = WORKLOADS[args.workload]
     state_mb = W.state_mb * N_TRAJ / 1.0e6 if W is not HeatRK4 else W.state_mb
     n_batches = 1 if W in (HeatRK4, SchrodingerCFM4) else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
+    if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
+        n_batches = int(os.environ["VECODE_BENCH_BATCHES"])
     w = W(vo, ctx, rank, world, n_batches)
     for s in getattr(w, "solvers", []):
         s.set_events_per_launch(args.events_per_launch)

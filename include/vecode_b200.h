@@ -188,6 +188,9 @@ int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k);
 /* 0 = whole-attempt register-resident kernel when the RHS/tableau allow it (default), 1 = force the
  * stage-granular path (one fused kernel per RK stage over the K buffers). */
 int32_t vo_solver_set_path(vo_solver s, int32_t stage_path);
+/* ODEAdaptiveData.dx_norm (ode.rs:104, written at ode.rs:319 and read by nothing in the crate): 1 (default) keeps the error
+ * norm of every trajectory's latest attempt for vo_solver_stats; 0 drops that 8-byte store per attempted trajectory-step. */
+int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on);
 
 /* ODESolver::step (ode.rs:249-253) / AdaptiveODESolver::step_adaptive (ode.rs:337-341) applied to every
  * trajectory: ONE state-machine event per trajectory per call. res may be NULL. */

@@ -496,3 +496,59 @@ def test_checkpoint_snapshots(vo, ctx, oracle, adaptive, stage_path):
         else:
             assert np.array_equal(got, ref["x"]), k
     assert np.array_equal(s.snapshot(len(t_list) - 1).to_host(), s.current()[1].to_host())
+
+
+@pytest.mark.parametrize("n", [4096, 512])  # two-trajectory kernel / one-trajectory staged kernel
+def test_fast_controller_agrees_with_reference_chain_within_ulps(vo, n):
+    """FAST arithmetic evaluates handle_step_adaptive (ode.rs:311-334) as clamp(alpha * g^(-1/6)) with g = (dx_norm/rtol)^2
+    instead of sqrt -> div -> powf. Feed both modes a bit-identical error estimate and compare the controller alone: a
+    constant derivative dx = p, x0 = 0 and weights b = e_0, b_err = 0 make x_err = p*dt with one rounding in either mode."""
+    s_ = 4
+    ac = np.zeros((s_, s_))
+    for i in range(1, s_):
+        ac[i, i], ac[i, i - 1] = 0.5, 0.5
+    tab = lambda: vo.ButcherTableu.from_slices(ac.ravel(), [1.0, 0, 0, 0], [0.0, 0, 0, 0], s_)
+    rtol, h0 = 1e-6, 1e-3
+    p = np.concatenate([10.0 ** np.linspace(-9.0, 3.0, n - 6), [0.0, 1e-200, 1e160, 1e300, np.nan, rtol / h0]])
+    out = {}
+    for arith in ("strict", "fast"):
+        c = vo.Context(0, arith=arith)
+        rhs = vo.Rhs.custom(c, "dx[0] = p[0];", 1, [p])
+        s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(c, np.zeros((n, 1))), h0, tableau=tab()).with_tolerance(rtol, rtol)
+        s.step_adaptive()  # Chkpt at t0
+        s.step_adaptive()  # one attempt per trajectory
+        out[arith] = s.stats()
+        c.close()
+    a, b = out["strict"], out["fast"]
+    fin = np.isfinite(p) & (p < 1e150)
+    ulp = np.abs(a["h"] - b["h"]) / np.spacing(np.abs(a["h"]))
+    print("controller: max ulp distance of new h", ulp[fin].max(), "of dx_norm", (np.abs(a["dx_norm"] - b["dx_norm"]) / np.spacing(a["dx_norm"]))[fin & (p > 0)].max())
+    assert ulp[fin].max() <= 8
+    assert np.array_equal(a["h"][~fin], b["h"][~fin])  # clamped to 0.3 h either way (inf and NaN norms)
+    f = rtol / (p * h0)
+    sure = fin & (np.abs(f - 1.0) > 1e-12)
+    assert np.array_equal(a["rejected"][sure], b["rejected"][sure]) and np.array_equal(a["accepted"][sure], b["accepted"][sure])
+    nz = fin & (p > 1e-150)
+    assert np.all(np.abs(a["dx_norm"][nz] - b["dx_norm"][nz]) <= 8 * np.spacing(a["dx_norm"][nz]))
+    assert b["dx_norm"][p == 0.0][0] == 0.0 and np.isnan(b["dx_norm"][np.isnan(p)][0]) and np.isinf(b["dx_norm"][p == 1e300][0])
+    assert (a["status"] == b["status"]).all()
+
+
+def test_fast_mode_adaptive_config3_within_rtol(vo, oracle):
+    """Config 3 in FAST arithmetic (FMA, lean controller): within the requested tolerance of the oracle at t_end, and
+    the step sequences stay together (the controller differs from the reference chain by ulps only)."""
+    n, rtol, tf = 2048, 1e-6, 20.0
+    mu, x0 = vo.workloads.vdp_mu(n), vo.workloads.vdp_x0(n)
+    ref = oracle.rk_ensemble("VDP", mu[:, None], oracle.builtin_tableau(2), 0.0, tf, x0, 1e-3, n_threads=8, adaptive=True, rtol=rtol, atol=rtol)
+    c = vo.Context(0, arith="fast")
+    s = vo.RK45Solver(vo.Rhs(c, "VDP", 2, [mu]), 0.0, tf, vo.Ensemble.from_host(c, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+    s.with_tolerance(rtol, rtol).set_events_per_launch(1)
+    assert s.run(adaptive=True).kind == "Done"
+    x, st = s.current()[1].to_host(), s.stats()
+    same = np.mean((st["accepted"] == ref["accepted"]) & (st["rejected"] == ref["rejected"]))
+    err = np.abs(x - ref["x"]).max(axis=1)
+    print(f"fast adaptive: identical (accepted, rejected) on {same:.3f} of trajectories; accepted {st['accepted'].sum()}/{ref['accepted'].sum()}, "
+          f"err quantiles {np.quantile(err, [0.5, 0.99, 1.0])}")
+    assert abs(int(st["accepted"].sum()) - int(ref["accepted"].sum())) <= 0.01 * ref["accepted"].sum()
+    assert np.quantile(err, 0.99) <= 200 * rtol and same >= 0.5
+    c.close()

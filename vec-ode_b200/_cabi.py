@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libvecode_b200.so")
+SO_PATH = os.environ.get("VECODE_B200_SO") or os.path.join(_HERE, "libvecode_b200.so")  # the override selects an experimental build (tools/build_variant.sh)
 
 # status codes (include/vecode_b200.h)
 VO_OK = 0
@@ -101,6 +101,7 @@ SIGNATURES = {
     "vo_solver_set_h_array": (_i32, [_vp, _vp, _i64]),
     "vo_solver_set_events_per_launch": (_i32, [_vp, _i32]),
     "vo_solver_set_path": (_i32, [_vp, _i32]),
+    "vo_solver_set_record_dx_norm": (_i32, [_vp, _i32]),
     "vo_step": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),

@@ -361,6 +361,11 @@ class RK45Solver:
         check(lib().vo_solver_set_events_per_launch(self._h, k), self.ctx._h)
         return self
 
+    def set_record_dx_norm(self, on: bool = True):
+        """Keep ODEAdaptiveData.dx_norm (ode.rs:104) of each trajectory's latest attempt (default) or skip that store."""
+        check(lib().vo_solver_set_record_dx_norm(self._h, 1 if on else 0), self.ctx._h)
+        return self
+
     def set_stage_path(self, on: bool = True):
         check(lib().vo_solver_set_path(self._h, 1 if on else 0), self.ctx._h)
         return self

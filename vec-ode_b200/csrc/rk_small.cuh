@@ -36,6 +36,7 @@ struct CtlArrays {
 // Controller constants shared by the ensemble (ODEAdaptiveData, ode.rs:98-110) + launch options.
 struct CtlShared {
     double rtol, alpha, pw, min_dt, max_dt;
+    double inv_rtol, inv_rtol2;  // 1/rtol, 1/rtol^2 (host-computed; the FAST controller works on (dx_norm/rtol)^2)
     double t_list_inline[VO_INLINE_TLIST];
     const double* t_list;  // device copy when n_tlist > VO_INLINE_TLIST
     int n_tlist;
@@ -54,6 +55,26 @@ struct EvSlot {
     unsigned long long n_step, n_chkpt, n_reject, n_end, n_stuck;
     unsigned long long pad[11];
 };
+
+// t_list lookups (ode.rs:165-176 reads t_list[tgt_t] at the head of every call). The list is a kernel parameter (or a
+// global array when it is long); indexing it with a per-lane tgt would be a generic load with L1/L2 latency at the head
+// of every attempt's dependency chain (14 % of the stall samples of the DoPri5 kernel). The kernels copy the inline list
+// into shared memory once per CTA and read it with ld.shared.
+struct TList {
+    const double* glob;  // non-NULL: long list in global memory
+    uint32_t smem;       // shared-window address of the CTA's copy of the inline list
+    __device__ __forceinline__ double at(int k) const {
+        if (glob) return __ldg(glob + k);
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem + 8u * (uint32_t)k) : "memory");
+        return v;
+    }
+};
+// Every thread calls it before the first __syncthreads() of the kernel.
+__device__ __forceinline__ TList tlist_stage(const CtlShared& cs, double* s_tl) {
+    if (threadIdx.x < VO_INLINE_TLIST) s_tl[threadIdx.x] = cs.t_list_inline[threadIdx.x];
+    return TList{cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : nullptr, (uint32_t)__cvta_generic_to_shared(s_tl)};
+}
 
 template <bool STRICT, int D> __device__ __forceinline__ double err_norm(const double (&e)[D], int kind) {
     using A = Ar<STRICT>;
@@ -81,6 +102,13 @@ template <bool STRICT, int D> __device__ __forceinline__ double err_norm(const d
         acc = A::add(acc, A::mul(m, m));
     }
     return sqrt(acc);
+}
+
+template <bool STRICT, int D> __device__ __forceinline__ double err_sumsq(const double (&e)[D]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc = Ar<STRICT>::add(acc, Ar<STRICT>::mul(e[c], e[c]));
+    return acc;
 }
 
 // v[c] = (sum_{j<n} k[j]*K[j][c]) * dt + x0[c]  in the reference's order (lc.rs:20-54, rk.rs:123-124).
@@ -203,6 +231,77 @@ template <bool STRICT> __device__ __forceinline__ double step_size_mul(double al
     return alpha * pow(f, pw);
 }
 
+// handle_step_adaptive (ode.rs:311-334) from the error norm, literally: f = rtol / dx_norm, factor = clamp(alpha f^pw, 0.3, 2),
+// new h from the nominal h, reject iff f <= 1.
+template <bool STRICT>
+__device__ __forceinline__ void controller_ref(double dxn, double h, const CtlShared& cs, double& new_h, bool& reject) {
+    const double f = cs.rtol / dxn;
+    const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
+    new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+    reject = f <= 1.0;
+}
+// cold path of the FAST kernels (an order other than the 3 that RK45Solver hard-wires): kept out of line
+struct CtlRes {
+    double new_h;
+    int reject;
+};
+static __device__ __noinline__ CtlRes controller_ref_cold_call(double dxn, double h, double rtol, double alpha, double pw, double min_dt, double max_dt) {
+    const double f = rtol / dxn;
+    const double fp_lim = fmin(fmax(alpha * pow(f, pw), 0.3), 2.0);
+    return CtlRes{fmin(fmax(fp_lim * h, min_dt), max_dt), f <= 1.0 ? 1 : 0};
+}
+__device__ __forceinline__ void controller_ref_cold(double dxn, double h, const CtlShared& cs, double& new_h, bool& reject) {
+    const CtlRes r = controller_ref_cold_call(dxn, h, cs.rtol, cs.alpha, cs.pw, cs.min_dt, cs.max_dt);  // scalars in registers: no stack frame
+    new_h = r.new_h, reject = r.reject != 0;
+}
+
+// The same controller for the L2 norm in FAST arithmetic, from acc = sum_c e_c^2 without the square root, the division and
+// the cube root (which, not the Runge-Kutta stages, were a quarter of the DoPri5 sweep: 150 of 360 instructions per
+// attempt). With g = acc / rtol^2 = f^-2:   f^(1/3) = g^(-1/6),   f <= 1  <=>  g >= 1,   dx_norm = acc * f / rtol.
+// g^(-1/6) starts from the SFU (lg2/ex2 in f32: within 2^-20 for the g in [0.008, 729] where the factor is not clamped) and
+// takes ONE third-order step in f64: with r = 1 - g y^6, g^(-1/6) = y (1 - r)^(-1/6) = y (1 + r/6 + 7 r^2/72 + O(r^3)), and
+// the dropped term is 0.07 r^3 < 2^-57 for |r| <= 6 * 2^-20 — below the rounding of the result, so the factor is good to
+// ~1 ulp: the accuracy of the reference's own chain sqrt -> div -> powf.
+// Out-of-range g (0, inf, NaN, beyond f32) needs no branch: the seed is clamped to [1e-30, 1e30], where the factor is far
+// outside [0.3, 2] on the right side, a NaN ends as 0.3 like Rust's NaN.max(0.3), and only dx_norm takes the slow road.
+__device__ __forceinline__ void controller_l2_fast(double acc, double h, const CtlShared& cs, bool want_dxn, double& dxn, double& new_h, bool& reject) {
+    const double g = acc * cs.inv_rtol2;
+    const float gf = fminf(fmaxf(__double2float_rn(g), 1.0e-30f), 1.0e30f);
+    float lg, y0;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(gf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * -0.16666667f));
+    double y = (double)y0;
+    {
+        const double y2 = y * y;
+        const double r = fma(-g, (y2 * y2) * y2, 1.0);
+        y = fma(y * r, fma(r, 7.0 / 72.0, 1.0 / 6.0), y);
+    }
+    const double fp_lim = fmin(fmax(cs.alpha * y, 0.3), 2.0);
+    new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+    reject = g >= 1.0;
+    if (want_dxn) {
+        if (g > 1.0e-30 && g < 1.0e30) dxn = acc * (((y * y) * y) * cs.inv_rtol);
+        else dxn = sqrt(acc);
+    }
+}
+
+// L2-norm controller of the common adaptive configuration, dispatching on the arithmetic mode. `want_dxn`: the caller keeps
+// ODEAdaptiveData.dx_norm; `nonfinite` reports a NaN norm.
+template <bool STRICT>
+__device__ __forceinline__ void controller_l2(double acc, double h, const CtlShared& cs, bool want_dxn, double& dxn, double& new_h, bool& reject,
+                                              bool& nonfinite) {
+    nonfinite = !(acc == acc);
+    if (STRICT) {
+        dxn = sqrt(acc);
+        controller_ref<true>(dxn, h, cs, new_h, reject);
+    } else if (cs.pw_is_third) {
+        controller_l2_fast(acc, h, cs, want_dxn, dxn, new_h, reject);
+    } else {
+        dxn = sqrt(acc);
+        controller_ref_cold(dxn, h, cs, new_h, reject);
+    }
+}
+
 // ---- staged (TMA bulk-copy) variants ---------------------------------------------------------------------------
 // Same arithmetic as the two kernels above; the difference is how state reaches the registers. One CTA = 128 lanes =
 // one tile of 128 consecutive trajectories; thread 0 keeps VO_STAGES tiles (every SoA row the kernel reads: the d state
@@ -289,7 +388,7 @@ __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __rest
 // time; CFG 0 = everything decided from CtlShared at run time.
 template <class RHS, int S, bool STRICT, int CFG>
 __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int64_t i, const TableauDev& tb, const CtlArrays& ca, const CtlShared& cs,
-                                         const double* __restrict__ tl, uint32_t word, double (&xc)[RHS::D], const double (&p)[RHS::NP], double t, double h,
+                                         const TList& tl, uint32_t word, double (&xc)[RHS::D], const double (&p)[RHS::NP], double t, double h,
                                          uint32_t n_acc, uint32_t n_rej, unsigned& c_step, unsigned& c_chkpt, unsigned& c_rej, unsigned& c_end, unsigned& c_stuck) {
     constexpr int D = RHS::D;
     double prev_h = 0.0;
@@ -305,7 +404,7 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
         if (tgt >= cs.n_tlist) {
             evk = VO_EV_END;
         } else {
-            const double rem = tl[tgt] - t;
+            const double rem = tl.at(tgt) - t;
             if (fabs(rem) <= 2.220446049250313e-16) evk = (tgt >= cs.n_tlist - 1) ? VO_EV_END : VO_EV_CHKPT;
             else dt = rem < h ? rem : h, evk = VO_EV_STEP;
         }
@@ -313,12 +412,18 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
             double xf[D], xe[D];
             rk_attempt<RHS, S, STRICT>(tb, CFG == 1 ? true : cs.use_err != 0, t, dt, xc, p, xf, xe);
             if (CFG == 1 || cs.adaptive) {  // handle_step_adaptive, ode.rs:311-334
-                dxn = err_norm<STRICT, D>(xe, CFG == 1 ? VO_NORM_L2 : cs.norm_kind), dxn_set = true;
-                const double f = cs.rtol / dxn;
-                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
-                const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
-                if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
-                if (f <= 1.0) {
+                double new_h;
+                bool rejected, nonfinite;
+                if (CFG == 1) {
+                    controller_l2<STRICT>(err_sumsq<STRICT, D>(xe), h, cs, cs.record_dx_norm != 0, dxn, new_h, rejected, nonfinite);
+                } else {
+                    dxn = err_norm<STRICT, D>(xe, cs.norm_kind), nonfinite = !(dxn == dxn);
+                    if (STRICT) controller_ref<true>(dxn, h, cs, new_h, rejected);
+                    else controller_ref_cold(dxn, h, cs, new_h, rejected);
+                }
+                dxn_set = true;
+                if (nonfinite) status |= VO_TRAJ_NONFINITE;
+                if (rejected) {
                     evk = VO_EV_REJECT;
                     if (h <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
                 }
@@ -408,7 +513,8 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
     uint32_t* wbuf = reinterpret_cast<uint32_t*>(sbuf + (size_t)VO_STAGES * nrows * T);
     const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
     const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
-    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    __shared__ double s_tl[VO_INLINE_TLIST];
+    const TList tl = tlist_stage(cs, s_tl);
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -478,7 +584,9 @@ __global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
-    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    __shared__ double s_tl[VO_INLINE_TLIST];
+    const TList tl = tlist_stage(cs, s_tl);
+    __syncthreads();
     uint32_t word = 0, word_n = 0, na = 0, nr = 0, na_n = 0, nr_n = 0;
     double xc[D], p[RHS::NP], t = 0.0, h = 0.0, xn[D], pn[RHS::NP], t_n = 0.0, h_n = 0.0;
     bool live = false, live_n = false;

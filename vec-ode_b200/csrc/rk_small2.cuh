@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
     uint32_t* wbuf = reinterpret_cast<uint32_t*>(sbuf + (size_t)VO_STAGES * nrows * T);
     const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
     const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
-    const double* tl = cs.n_tlist > VO_INLINE_TLIST ? cs.t_list : cs.t_list_inline;
+    __shared__ double s_tl[VO_INLINE_TLIST];
+    const TList tl = tlist_stage(cs, s_tl);
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
         const bool live0 = !((word[0] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE), live1 = !((word[1] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
         // fast path: one event per launch and both trajectories take a Step (the steady state of an adaptive sweep)
         bool pair = cs.k_events == 1 && live0 && live1;
-        double dt[U] = {0.0, 0.0};
+        double dt[U] = {0.0, 0.0}, t_tgt[U] = {0.0, 0.0};
         if (pair) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
                 if (tgt >= cs.n_tlist) {
                     pair = false;
                 } else {
-                    const double rem = tl[tgt] - t[u];  // step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
+                    t_tgt[u] = tl.at(tgt);
+                    const double rem = t_tgt[u] - t[u];  // step_size_of (ode.rs:165-176) + check_step (ode.rs:389-399)
                     if (fabs(rem) <= 2.220446049250313e-16) pair = false;
                     dt[u] = rem < h[u] ? rem : h[u];
                 }
@@ -124,31 +126,38 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
         if (pair) {
             double xf[U][D], xe[U][D];
             rk_attempt_n<RHS, S, STRICT, U>(tb, t, dt, xc, p, xf, xe);
-            double dxn[U], new_h[U];
-            bool rej[U];
+            double dxn[U] = {0.0, 0.0}, new_h[U];
+            bool rej[U], nonfin[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {  // handle_step_adaptive, ode.rs:311-334
-                dxn[u] = err_norm<STRICT, D>(xe[u], VO_NORM_L2);
-                const double f = cs.rtol / dxn[u];
-                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
-                new_h[u] = fmin(fmax(fp_lim * h[u], cs.min_dt), cs.max_dt);
-                rej[u] = f <= 1.0;
+#ifdef VO_DIAG_NO_CTL  // diagnostic build only (tools/build_variant.sh): what the controller arithmetic costs
+                dxn[u] = xe[u][0], new_h[u] = h[u], rej[u] = xe[u][1] > 1.0e30, nonfin[u] = false;
+                continue;
+#endif
+                controller_l2<STRICT>(err_sumsq<STRICT, D>(xe[u]), h[u], cs, cs.record_dx_norm != 0, dxn[u], new_h[u], rej[u], nonfin[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {  // apply_step (ode.rs:402-428) + masked write-back
                 const int64_t i = base + threadIdx.x + 128 * u;
                 uint32_t status = word[u] >> VO_WORD_STATUS_SHIFT;
-                if (!(dxn[u] == dxn[u])) status |= VO_TRAJ_NONFINITE;
+                if (nonfin[u]) status |= VO_TRAJ_NONFINITE;
                 if (rej[u]) {
                     if (h[u] <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
                     ca.n_reject[i] = n_rej[u] + 1, ++c_rej;
                 } else {
 #pragma unroll
                     for (int c = 0; c < D; ++c) x[c * N + i] = xf[u][c];
-                    ca.t[i] = t[u] + dt[u];  // advance, ode.rs:184-188
+                    const double t_new = t[u] + dt[u];  // advance, ode.rs:184-188
+                    ca.t[i] = t_new;
                     ca.n_accept[i] = n_acc[u] + 1, ++c_step;
+                    // update_step_size (ode.rs:202-205) sets prev_h = h, and the only reader of prev_h is the Chkpt / End
+                    // branch (checkpoint_update, ode.rs:192-195). This trajectory's next event is one of those iff the test
+                    // of ode.rs:391 holds at t_new — evaluated here exactly as the next call will — so prev_h only has to
+                    // reach memory then: 8 bytes per attempt less on the HBM-bound sweep. (A rejected attempt leaves t where
+                    // this Step event found it, so its next event is a Step again.)
+                    if (fabs(t_tgt[u] - t_new) <= 2.220446049250313e-16) ca.prev_h[i] = h[u];
                 }
-                ca.h[i] = new_h[u], ca.prev_h[i] = h[u];  // update_step_size, ode.rs:202-205
+                ca.h[i] = new_h[u];
                 if (cs.record_dx_norm) ca.dx_norm[i] = dxn[u];
                 const uint32_t nw = (word[u] & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
                 if (nw != word[u]) ca.word[i] = nw;

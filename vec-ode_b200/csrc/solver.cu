@@ -96,6 +96,7 @@ CtlShared make_ctl_shared(const vo_solver_s* s, int adaptive, int k_events) {
     CtlShared cs;
     std::memset(&cs, 0, sizeof cs);
     cs.rtol = s->rtol, cs.alpha = s->alpha, cs.pw = s->pw, cs.min_dt = s->min_dt, cs.max_dt = s->max_dt;
+    cs.inv_rtol = 1.0 / s->rtol, cs.inv_rtol2 = 1.0 / (s->rtol * s->rtol);
     cs.n_tlist = (int)s->t_list.size();
     for (int i = 0; i < VO_INLINE_TLIST && i < cs.n_tlist; ++i) cs.t_list_inline[i] = s->t_list[i];
     cs.t_list = s->t_list_dev;
@@ -191,11 +192,11 @@ __global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restri
                     if (cs.norm_kind == VO_NORM_L2) acc = sqrt(acc);
                 }
                 const double h = ca.h[i];
-                const double f = cs.rtol / acc;
-                const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
-                const double new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+                double new_h;
+                bool rejected;
+                controller_ref<STRICT>(acc, h, cs, new_h, rejected);
                 if (!(acc == acc)) status |= VO_TRAJ_NONFINITE;
-                if (f <= 1.0) {
+                if (rejected) {
                     evk = VO_EV_REJECT;
                     if (h <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
                 }
@@ -726,6 +727,7 @@ int32_t vo_solver_with_init_step(vo_solver s, double h) {
 int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n) {
     if (!s || !t_list || n < 1) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_t_list: bad argument");
     if (n > (int32_t)VO_WORD_TGT_MASK) return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "vo_solver_set_t_list: list too long");
+    if (!s->uniform) return vo_fail(s->ctx, VO_ERR_STATE, "set_t_list: builder called after per-trajectory stepping began");
     vo_ctx c = s->ctx;
     DeviceGuard g(c->device);
     s->t_list.assign(t_list, t_list + n);
@@ -766,6 +768,12 @@ int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n) {
 int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k) {
     if (!s || k < 0 || k > (1 << 20)) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_events_per_launch: bad k");
     s->k_events = k;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->record_dx_norm = on ? 1 : 0;
     return VO_OK;
 }
 
