@@ -509,7 +509,7 @@ def test_fast_controller_agrees_with_reference_chain_within_ulps(vo, n):
         ac[i, i], ac[i, i - 1] = 0.5, 0.5
     tab = lambda: vo.ButcherTableu.from_slices(ac.ravel(), [1.0, 0, 0, 0], [0.0, 0, 0, 0], s_)
     rtol, h0 = 1e-6, 1e-3
-    p = np.concatenate([10.0 ** np.linspace(-9.0, 3.0, n - 6), [0.0, 1e-200, 1e160, 1e300, np.nan, rtol / h0]])
+    p = np.concatenate([10.0 ** np.linspace(-9.0, 3.0, n - 8), [0.0, 1e-200, 1e-14, 1e14, 1e160, 1e300, np.nan, rtol / h0]])
     out = {}
     for arith in ("strict", "fast"):
         c = vo.Context(0, arith=arith)

@@ -130,7 +130,7 @@ std::string cu_msg(Driver* dr, CUresult e) {
 }
 
 // ---- one compiled module -----------------------------------------------------------------------------------------
-enum { K_FIXED_STAGED, K_FIXED, K_CTL_STAGED_GEN, K_CTL_STAGED_L2, K_CTL2_STAGED, K_CTL, K_SMALL_COUNT };
+enum { K_FIXED_STAGED, K_FIXED, K_CTL_STAGED_GEN, K_CTL_STAGED_L2, K_CTL2_STAGED, K_CTL, K_FIXED2_STAGED, K_SMALL_COUNT };
 enum { K_STAGE, K_STAGE_TAIL, K_STAGE_COUNT };
 constexpr int STAGE_MODULE = -1;  // `S` key of the stage-path module (it does not depend on the stage count)
 
@@ -159,6 +159,7 @@ std::vector<std::string> kernel_names(int S, bool strict, bool stage_module) {
     v[K_CTL_STAGED_L2] = "rk_ctl_staged_kernel<RhsCustom, " + ss + ", " + st + ", 1>";
     v[K_CTL2_STAGED] = S > 0 ? "rk_ctl2_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";
     v[K_CTL] = "rk_ctl_kernel<RhsCustom, " + ss + ", " + st + ">";
+    v[K_FIXED2_STAGED] = S > 0 ? "rk_fixed2_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";
     return v;
 }
 
@@ -308,8 +309,13 @@ int32_t launch_small_custom(const SmallLaunch& L, vo_rhs_s* r) {
     if (L.sl) {
         StepList sl = *L.sl;
         if (staged) {
-            const size_t smem = (size_t)VO_STAGES * rows * VO_TILE * sizeof(double);
             void* args[] = {&x, &N, &tb, &rp, &sl, &ch};
+            if (S > 0 && N >= 4 * VO_TILE2) {
+                const size_t smem2 = (size_t)VO_STAGES * rows * VO_TILE2 * sizeof(double);
+                rc = custom_grid(c, drv, m, K_FIXED2_STAGED, N, smem2, VO_TILE2, &grid);
+                return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED2_STAGED], grid, RK_SMALL_THREADS, smem2, pdl, args);
+            }
+            const size_t smem = (size_t)VO_STAGES * rows * VO_TILE * sizeof(double);
             rc = custom_grid(c, drv, m, K_FIXED_STAGED, N, smem, VO_TILE, &grid);
             return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED_STAGED], grid, RK_SMALL_THREADS, smem, pdl, args);
         }

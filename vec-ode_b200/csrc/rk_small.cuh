@@ -262,18 +262,19 @@ __device__ __forceinline__ void controller_ref_cold(double dxn, double h, const 
 // takes ONE third-order step in f64: with r = 1 - g y^6, g^(-1/6) = y (1 - r)^(-1/6) = y (1 + r/6 + 7 r^2/72 + O(r^3)), and
 // the dropped term is 0.07 r^3 < 2^-57 for |r| <= 6 * 2^-20 — below the rounding of the result, so the factor is good to
 // ~1 ulp: the accuracy of the reference's own chain sqrt -> div -> powf.
-// Out-of-range g (0, inf, NaN, beyond f32) needs no branch: the seed is clamped to [1e-30, 1e30], where the factor is far
-// outside [0.3, 2] on the right side, a NaN ends as 0.3 like Rust's NaN.max(0.3), and only dx_norm takes the slow road.
+// Out-of-range g (0, inf, NaN, beyond f32) needs no branch: the seed is clamped to [1e-30, 1e30] and the residual to >= -1,
+// which leaves the factor far outside [0.3, 2] on the right side; a NaN ends as 0.3 like Rust's NaN.max(0.3).min(2.0); only
+// dx_norm takes the slow road.
 __device__ __forceinline__ void controller_l2_fast(double acc, double h, const CtlShared& cs, bool want_dxn, double& dxn, double& new_h, bool& reject) {
     const double g = acc * cs.inv_rtol2;
-    const float gf = fminf(fmaxf(__double2float_rn(g), 1.0e-30f), 1.0e30f);
+    const float gf = fmaxf(fminf(__double2float_rn(g), 1.0e30f), 1.0e-30f);  // a NaN lands on the 1e30 side
     float lg, y0;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(gf));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * -0.16666667f));
     double y = (double)y0;
     {
         const double y2 = y * y;
-        const double r = fma(-g, (y2 * y2) * y2, 1.0);
+        const double r = fmax(fma(-g, (y2 * y2) * y2, 1.0), -1.0);  // -1 only for g > 1e30, inf or NaN, where the seed is 1e-5
         y = fma(y * r, fma(r, 7.0 / 72.0, 1.0 / 6.0), y);
     }
     const double fp_lim = fmin(fmax(cs.alpha * y, 0.3), 2.0);

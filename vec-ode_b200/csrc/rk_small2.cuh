@@ -1,4 +1,4 @@
-// rk_small2.cuh — the per-trajectory control kernel with TWO trajectories per thread.
+// rk_small2.cuh — the register-resident kernels with TWO trajectories per thread (control kernel; fixed-step kernel below).
 //
 // rk_ctl_staged_kernel (rk_small.cuh) is bound by the FP64 pipe and by instruction issue, not by HBM: an adaptive
 // DoPri5 attempt of a 2-component system is one long dependent chain with ILP 2. Giving every thread two independent
@@ -38,6 +38,113 @@ __device__ __forceinline__ void rk_attempt_n(const TableauDev& tb, const double 
 #pragma unroll
         for (int c = 0; c < D; ++c) xe[u][c] = A::sub(xe[u][c], xf[u][c]);  // x_err = X_b - X_berr (rk.rs:147)
     }
+}
+
+// ---- lock-step fixed-step kernel, two trajectories per thread ------------------------------------------------------
+// rk_fixed_staged_kernel spends more issue slots on what is per THREAD (tableau coefficients into uniform registers, tile
+// addressing, barrier, loop) than on the ~70-100 FP64 operations of an RK4 step of a 3-component system, and at 10^6
+// trajectories per launch that — not HBM — sets its time (an L2-resident ensemble runs no faster). Two trajectories per
+// thread halve that overhead per trajectory and double the ILP; per-trajectory arithmetic is unchanged, so the bits are too.
+template <class RHS, int S, bool STRICT, int U>
+__device__ __forceinline__ void rk_attempt_fixed_n(const TableauDev& tb, bool use_err, double t, double dt, const double (&x0)[U][RHS::D],
+                                                   const double (&p)[U][RHS::NP], double (&xf)[U][RHS::D]) {
+    using A = Ar<STRICT>;
+    constexpr int D = RHS::D;
+    double K[U][S][D];
+#pragma unroll
+    for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(t, x0[u], K[u][0], p[u]);  // rk.rs:111
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+        const double* row = &tb.ac[i * S];
+        const double ti = A::add(t, A::mul(row[i], dt));  // rk.rs:119
+        double xs[U][D];
+#pragma unroll
+        for (int u = 0; u < U; ++u) combine<STRICT, D, S>(row, i, K[u], dt, x0[u], xs[u]);  // rk.rs:121-124
+#pragma unroll
+        for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(ti, xs[u], K[u][i], p[u]);  // rk.rs:127
+    }
+    // the propagated state: X_berr when the error branch runs (rk.rs:136-146), else X_b (rk.rs:131-133)
+#pragma unroll
+    for (int u = 0; u < U; ++u) combine<STRICT, D, S>(use_err ? tb.b_err : tb.b, S, K[u], dt, x0[u], xf[u]);
+}
+
+template <class RHS, int S, bool STRICT>
+__global__ void __launch_bounds__(128) rk_fixed2_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
+                                                               const __grid_constant__ RhsParams rp, const __grid_constant__ StepList sl,
+                                                               const pipe::Chain ch) {
+    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE2, U = 2;
+    extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T]
+    __shared__ __align__(8) uint64_t full[VO_STAGES];
+    int nrows = D;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) nrows += rp.per_traj[q] ? 1 : 0;
+    const int64_t n_full = N / T, G = gridDim.x, first = blockIdx.x;
+    const int64_t my_count = first < n_full ? (n_full - first + G - 1) / G : 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < VO_STAGES; ++s) pipe::mbar_init(&full[s], 1);
+        pipe::fence_mbar_init();
+    }
+    pipe::chain_enter(ch);
+    auto issue = [&](int64_t k) {  // thread 0: all rows of this CTA's k-th tile into stage k % VO_STAGES
+        const int st = (int)(k % VO_STAGES);
+        const int64_t base = (first + k * G) * T;
+        double* dst = sbuf + (size_t)st * nrows * T;
+        pipe::mbar_expect_tx(&full[st], (uint32_t)(nrows * T * sizeof(double)));
+        int r = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) pipe::bulk_g2s(dst + (r++) * T, x + c * N + base, T * sizeof(double), &full[st]);
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (rp.per_traj[q]) pipe::bulk_g2s(dst + (r++) * T, rp.per_traj[q] + base, T * sizeof(double), &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t k = 0; k < my_count && k < VO_STAGES; ++k) issue(k);
+    for (int64_t k = 0; k < my_count; ++k) {
+        const int st = (int)(k % VO_STAGES);
+        const int64_t i0 = (first + k * G) * T + threadIdx.x;
+        pipe::mbar_wait(&full[st], (uint32_t)((k / VO_STAGES) & 1));
+        double xc[U][D], p[U][NP];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double* src = sbuf + (size_t)st * nrows * T + threadIdx.x + 128 * u;
+            int r = 0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) xc[u][c] = src[(r++) * T];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) p[u][q] = rp.per_traj[q] ? src[(r++) * T] : rp.shared[q];
+        }
+        __syncthreads();  // every lane has taken its elements: the stage may be refilled
+        if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
+        for (int e = 0; e < sl.n; ++e) {
+            double xf[U][D];
+            rk_attempt_fixed_n<RHS, S, STRICT, U>(tb, sl.use_err != 0, sl.t[e], sl.dt[e], xc, p, xf);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < D; ++c) xc[u][c] = xf[u][c];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < D; ++c) x[c * N + i0 + 128 * u] = xc[u][c];
+    }
+    // ragged tail (N % 256 trajectories): plain loads, last CTA, one trajectory at a time
+    if (blockIdx.x == G - 1) {
+        for (int64_t i = n_full * T + threadIdx.x; i < N; i += 128) {
+            double xc[D], p[NP];
+            lane_load<RHS>(x, N, rp, i, xc, p);
+            for (int e = 0; e < sl.n; ++e) {
+                double xf[D], xe[D];
+                rk_attempt<RHS, S, STRICT>(tb, sl.use_err != 0, sl.t[e], sl.dt[e], xc, p, xf, xe);
+#pragma unroll
+                for (int c = 0; c < D; ++c) xc[c] = xf[c];
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
+        }
+    }
+    pipe::chain_exit(ch);
 }
 
 #ifndef VO_CTL2_MIN_BLOCKS

@@ -61,6 +61,15 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
     const bool staged = small_path_is_staged(L.N);
     if (L.sl) {
         if (staged) {
+            if constexpr (S > 0) {
+                if (L.N >= 4 * VO_TILE2) {  // two trajectories per thread (rk_small2.cuh)
+                    const size_t smem2 = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE2 * sizeof(double);
+                    auto k2 = rk_fixed2_staged_kernel<RHS, S, STRICT>;
+                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl,
+                                  L.chain);
+                    return;
+                }
+            }
             const size_t smem = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double);
             auto k = rk_fixed_staged_kernel<RHS, S, STRICT>;
             launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl, L.chain);
