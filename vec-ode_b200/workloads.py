@@ -48,6 +48,12 @@ def heat_u0(d: int) -> np.ndarray:
     return np.sin(2.0 * np.pi * j / d) + 0.5 * np.sin(14.0 * np.pi * j / d)
 
 
+def heat_u0_at(j, d: int) -> np.ndarray:
+    """Config 4's initial state at the grid indices `j` of a d-point grid (a slab of a domain-decomposed state)."""
+    j = np.asarray(j, dtype=np.float64)
+    return np.sin(2.0 * np.pi * j / d) + 0.5 * np.sin(14.0 * np.pi * j / d)
+
+
 def schrodinger_system(n: int = 64, seed_h1: int = 7):
     """Config 5: H0 real symmetric tridiagonal (diag (k-31.5)*0.05, off-diag 0.5), H1 = (G+G^dagger)/(2 sqrt n)."""
     k = np.arange(n, dtype=np.float64)
