@@ -226,8 +226,37 @@ __global__ void __launch_bounds__(128) rk_fixed_kernel(double* __restrict__ x, i
 // order RK45Solver hard-wires (rk.rs:258-260): cbrt(f) and powf(f, 0.333...) agree to within an ulp
 // (f^(1/3 - fl(1/3)) - 1 < 1e-15 for any finite f), about how far two libm implementations of `powf` differ from each
 // other, at a quarter of the FP64 instructions.
+// powf(f, 1/3) as the reference evaluates it (`f.powf(order.recip())`, ode.rs:120, 133-135): the exponent is the DOUBLE
+// nearest to 1/3, p = 1/3 + d with d = -1.85e-17, and Rust's powf is the C library's pow, which rounds correctly except for
+// about one argument in a thousand. So STRICT computes the correctly rounded f^p — cheaper than CUDA's general pow (which is
+// a 1-2 ulp function and differs from glibc far more often) and the closest one can get to the reference's bits:
+//   z ~ f^(-1/3) from the SFU (2^-20) and one third-order step;  y = f z^2 ~ f^(1/3) to 2^-50;
+//   one Newton step on y^3 = f with the residual f - y^3 carried in double-double (error 2^-100);
+//   f^p = f^(1/3) (1 + d ln f), added to the correction; the final y + c is the only rounding.
+// Explicit _rn intrinsics and fma throughout, so nvcc and NVRTC (--fmad=false) builds agree bit for bit.
+// Valid for f in [2^-90, 2^90]; the caller falls back to pow() outside.
+__device__ __forceinline__ double pow_third_cr(double f) {
+    float lg, z0;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(__double2float_rn(f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(z0) : "f"(__fmul_rn(lg, -0.33333334f)));
+    double z = (double)z0;
+    const double r = fma(-f, __dmul_rn(__dmul_rn(z, z), z), 1.0);                  // 1 - f z^3
+    z = fma(__dmul_rn(z, r), fma(r, 2.0 / 9.0, 1.0 / 3.0), z);                     // z (1 - r)^(-1/3) to third order
+    const double zz = __dmul_rn(z, z);
+    const double y = __dmul_rn(f, zz);
+    const double y2 = __dmul_rn(y, y), y2l = fma(y, y, -y2);
+    const double y3 = __dmul_rn(y2, y), y3l = __dadd_rn(fma(y2, y, -y3), __dmul_rn(y2l, y));
+    const double res = __dadd_rn(__dadd_rn(f, -y3), -y3l);                          // f - y^3 (the first difference is exact)
+    double c = __dmul_rn(res, __dmul_rn(zz, 1.0 / 3.0));                            // res / (3 y^2)
+    c = fma(__dmul_rn(y, -1.850371707708594e-17), __dmul_rn((double)lg, 0.6931471805599453), c);
+    return __dadd_rn(y, c);
+}
+
 template <bool STRICT> __device__ __forceinline__ double step_size_mul(double alpha, double f, double pw, int pw_is_third) {
-    if (!STRICT && pw_is_third) return alpha * cbrt(f);
+    if (pw_is_third) {
+        if (!STRICT) return alpha * cbrt(f);
+        if (f > 8.0e-28 && f < 1.2e27) return __dmul_rn(alpha, pow_third_cr(f));
+    }
     return alpha * pow(f, pw);
 }
 
