@@ -224,6 +224,22 @@ class HeatRK4:
         return float(st.counts["Step"]) * self.D, self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
+class HeatRK4Fused(HeatRK4):
+    """Config 4 through the whole-step kernel (rk_heat_fused.cuh): every stage of an RK4 step inside one kernel, the state read
+    once and written once. Not the stage path BASELINE.json names for config 4 — reported beside it."""
+    name = "heat_rk4_fused"
+    label = "config 4, whole-step kernel: RK4 on the 1-D heat equation, one state of 2^26 points, all four stages in one launch"
+    bytes_per_unit = 16.0  # read x, write next_x
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        super().__init__(vo, ctx, rank, world, n_batches)
+        self.solvers[0].set_fused_step()
+
+    def e2e_setup(self):
+        super().e2e_setup()
+        self.e_solver.set_fused_step()
+
+
 class HeatRK4DD:
     """Row N4: config 4's single state of 2^26 points split into one slab per GPU with ghost zones
     (vec-ode_b200/domain.py). STRONG scaling: the whole job is always 2^26 points."""
@@ -329,7 +345,7 @@ class SchrodingerCFM4:
         return float(st.counts["Step"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
-WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4DD, SchrodingerCFM4)}
+WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -377,7 +393,7 @@ def cpu_run(workload, n_traj, n_steps, threads):
 def cpu_baseline(workload, budget_s=12.0):
     from oracle import oracle_lib as ol
     name = workload
-    workload = "heat_rk4" if workload == "heat_rk4_dd" else workload  # the reference's path is the same single-state solve
+    workload = "heat_rk4" if workload.startswith("heat_rk4") else workload  # the reference's path is the same single-state solve
     threads = ol.hardware_threads() if workload != "heat_rk4" else 1
     if workload == "heat_rk4":
         n, steps = 1 << 20, 2
@@ -408,7 +424,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from oracle import oracle_lib as ol
-    wl = "heat_rk4" if args.workload == "heat_rk4_dd" else args.workload
+    wl = "heat_rk4" if args.workload.startswith("heat_rk4") else args.workload
     threads = ol.hardware_threads() if wl != "heat_rk4" else 1
     total = args.steps + args.warmup
     per_step_budget = min(0.5, 90.0 / max(total, 1))
@@ -483,8 +499,8 @@ def main():
 
     ctx = vo.Context.on_torch_stream(local, arith=args.arith)
     W = WORKLOADS[args.workload]
-    state_mb = W.state_mb * N_TRAJ / 1.0e6 if W not in (HeatRK4, HeatRK4DD) else W.state_mb
-    n_batches = 1 if W in (HeatRK4, HeatRK4DD, SchrodingerCFM4) else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
+    state_mb = W.state_mb * N_TRAJ / 1.0e6 if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD) else W.state_mb
+    n_batches = 1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
     if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
         n_batches = int(os.environ["VECODE_BENCH_BATCHES"])
     w = W(vo, ctx, rank, world, n_batches)
@@ -623,10 +639,10 @@ def main():
         line = {"metric": "ensemble trajectory-steps/sec", "value": value, "unit": f"{W.unit_name}s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if W is HeatRK4DD else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4DD) else SchrodingerCFM4.N_SYS if W is SchrodingerCFM4 else N_TRAJ),
+                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD) else SchrodingerCFM4.N_SYS if W is SchrodingerCFM4 else N_TRAJ),
                            "arith": args.arith, "events_per_launch": args.events_per_launch,
                            "l2": f"{n_batches} independent batches of {W.state_mb} MB rotated per GPU (> {L2_MB} MB L2), so each launch streams from HBM"
-                           if W not in (HeatRK4, HeatRK4DD, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W is HeatRK4 else
+                           if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
                            "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of 32 doubles per rank) every 4 steps" if W is HeatRK4DD

@@ -186,8 +186,10 @@ int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n); /* 
  * control) inside vo_run, which only promises the final state. k >= 1 forces k everywhere. */
 int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k);
 /* 0 = whole-attempt register-resident kernel when the RHS/tableau allow it (default), 1 = force the
- * stage-granular path (one fused kernel per RK stage over the K buffers). */
-int32_t vo_solver_set_path(vo_solver s, int32_t stage_path);
+ * stage-granular path (one fused kernel per RK stage over the K buffers), 2 = whole-step path for a single HEAT1D state
+ * (N = 1; 4, 6 or 7 stages): all stages of a step in one kernel, the state read and written once (16 B per grid point instead
+ * of 104 B for RK4); the same per-point operations in the same order as the stage path. */
+int32_t vo_solver_set_path(vo_solver s, int32_t path);
 /* ODEAdaptiveData.dx_norm (ode.rs:104, written at ode.rs:319 and read by nothing in the crate): 1 (default) keeps the error
  * norm of every trajectory's latest attempt for vo_solver_stats; 0 drops that 8-byte store per attempted trajectory-step. */
 int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on);

@@ -567,3 +567,46 @@ def test_fast_mode_adaptive_config3_within_rtol(vo, oracle):
     assert abs(int(st["accepted"].sum()) - int(ref["accepted"].sum())) <= 0.01 * ref["accepted"].sum()
     assert np.quantile(err, 0.99) <= 200 * rtol and same >= 0.5
     c.close()
+
+
+@pytest.mark.parametrize("d", [2048, 4099, (1 << 18) + 3])
+@pytest.mark.parametrize("tab", ["RK4", "RKF45_REF", "DOPRI5"])
+def test_heat_whole_step_kernel_bit_exact(vo, ctx, oracle, d, tab):
+    """All stages of a step in one kernel (rk_heat_fused.cuh): same per-point operations in the same order as the stage
+    path, so STRICT results are bit-identical to the oracle (fixed step, with and without the error estimate)."""
+    u0 = vo.workloads.heat_u0(d)
+    otab = oracle.builtin_tableau(oracle.TABLEAU_ID[tab])
+    n_steps = 6
+    rx, _, _ = oracle.rk_solve("HEAT1D", [1.0], otab, 0.0, 1.0e9, u0, 0.2, max_calls=n_steps + 1)
+    s = vo.RK45Solver(vo.Rhs(ctx, "HEAT1D", d, [1.0]), 0.0, 1.0e9, vo.Ensemble.from_host(ctx, u0[None, :]), 0.2, tableau=vo.ButcherTableu.builtin(tab))
+    s.set_fused_step()
+    launches = 0
+    for _ in range(n_steps + 1):
+        launches += s.step().counts["launches"]
+    assert launches == n_steps  # one kernel per step
+    assert np.array_equal(s.current()[1].to_host()[0], rx)
+
+
+def test_heat_whole_step_kernel_adaptive_and_fast(vo, ctx, oracle):
+    d = 1 << 16
+    u0 = vo.workloads.heat_u0(d)
+    out = []
+    for fused in (False, True):  # adaptive single state: x_err from the whole-step kernel feeds the same host controller
+        s = vo.RK45Solver(vo.Rhs(ctx, "HEAT1D", d, [1.0]), 0.0, 2.0, vo.Ensemble.from_host(ctx, u0[None, :]), 0.01).with_tolerance(1e-6, 1e-6)
+        s.with_step_range(1e-6, 0.3).with_init_step(0.01)
+        if fused:
+            s.set_fused_step()
+        s.run(adaptive=True)
+        out.append((s.current()[1].to_host()[0], s.stats()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("accepted", "rejected", "t", "h", "dx_norm"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    cf = vo.Context(0, arith="fast")
+    s = vo.RK45Solver(vo.Rhs(cf, "HEAT1D", d, [1.0]), 0.0, 1.0, vo.Ensemble.from_host(cf, u0[None, :]), 0.2, tableau=vo.ButcherTableu.builtin("RK4"))
+    s.no_adaptive().set_fused_step()
+    s.run()
+    rx, _, _ = oracle.rk_solve("HEAT1D", [1.0], oracle.builtin_tableau(1), 0.0, 1.0, u0, 0.2, no_adaptive=True)
+    assert np.abs(s.current()[1].to_host()[0] - rx).max() <= 1e-12 * np.abs(rx).max()
+    with pytest.raises(vo.VecOdeError):
+        vo.RK45Solver(vo.Rhs(ctx, "LORENZ63", 3), 0.0, 1.0, vo.Ensemble.from_host(ctx, vo.workloads.lorenz_x0(8)), 0.1).set_fused_step()
+    cf.close()

@@ -366,6 +366,11 @@ class RK45Solver:
         check(lib().vo_solver_set_record_dx_norm(self._h, 1 if on else 0), self.ctx._h)
         return self
 
+    def set_fused_step(self, on: bool = True):
+        """Whole-step path for a single HEAT1D state: every stage of a step in one kernel (vo_solver_set_path(s, 2))."""
+        check(lib().vo_solver_set_path(self._h, 2 if on else 0), self.ctx._h)
+        return self
+
     def set_stage_path(self, on: bool = True):
         check(lib().vo_solver_set_path(self._h, 1 if on else 0), self.ctx._h)
         return self

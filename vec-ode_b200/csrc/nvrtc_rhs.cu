@@ -327,9 +327,9 @@ int32_t launch_small_custom(const SmallLaunch& L, vo_rhs_s* r) {
     if (staged) {
         const bool common = cs.adaptive && cs.use_err && cs.norm_kind == VO_NORM_L2;
         void* args[] = {&x, &N, &tb, &rp, &ca, &cs, &ev, &ch};
-        if (S > 0 && common && cs.k_events == 1 && N >= 4 * VO_TILE2) {
-            const size_t smem2 = (size_t)VO_STAGES * ((rows + 2) * VO_TILE2 * sizeof(double) + 3 * VO_TILE2 * sizeof(uint32_t));
-            rc = custom_grid(c, drv, m, K_CTL2_STAGED, N, smem2, VO_TILE2, &grid);
+        if (S > 0 && common && cs.k_events == 1 && N >= 4 * VO_TILE_CTL) {
+            const size_t smem2 = (size_t)VO_STAGES * ((rows + 2) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t));
+            rc = custom_grid(c, drv, m, K_CTL2_STAGED, N, smem2, VO_TILE_CTL, &grid);
             return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_CTL2_STAGED], grid, RK_SMALL_THREADS, smem2, pdl, args);
         }
         const size_t smem = (size_t)VO_STAGES * ((rows + 2) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));

@@ -12,6 +12,10 @@
 #include "rk_small.cuh"
 
 #define VO_TILE2 256
+#ifndef VO_CTL_U
+#define VO_CTL_U 2  // trajectories per thread of the control kernel
+#endif
+#define VO_TILE_CTL (128 * VO_CTL_U)
 
 // rk_step (rk.rs:90-155) for U independent trajectories, interleaved statement by statement.
 template <class RHS, int S, bool STRICT, int U>
@@ -154,7 +158,7 @@ template <class RHS, int S, bool STRICT>
 __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel(double* __restrict__ x, int64_t N, const __grid_constant__ TableauDev tb,
                                                                 const __grid_constant__ RhsParams rp, const CtlArrays ca,
                                                                 const __grid_constant__ CtlShared cs, EvSlot* __restrict__ ev, const pipe::Chain ch) {
-    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE2, U = 2;
+    constexpr int D = RHS::D, NP = RHS::NP, T = VO_TILE_CTL, U = VO_CTL_U;
     extern __shared__ __align__(128) double sbuf[];  // [VO_STAGES][nrows][T] doubles, then [VO_STAGES][3][T] words
     __shared__ __align__(8) uint64_t full[VO_STAGES];
     int nrows = D + 2;  // state, t, h
@@ -212,10 +216,14 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
         }
         __syncthreads();
         if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
-        const bool live0 = !((word[0] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE), live1 = !((word[1] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
-        // fast path: one event per launch and both trajectories take a Step (the steady state of an adaptive sweep)
-        bool pair = cs.k_events == 1 && live0 && live1;
-        double dt[U] = {0.0, 0.0}, t_tgt[U] = {0.0, 0.0};
+        bool live[U];
+        // fast path: one event per launch and all of the thread's trajectories take a Step (the steady state of an adaptive sweep)
+        bool pair = cs.k_events == 1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) live[u] = !((word[u] >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE), pair = pair && live[u];
+        double dt[U], t_tgt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) dt[u] = 0.0, t_tgt[u] = 0.0;
         if (pair) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -233,7 +241,9 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
         if (pair) {
             double xf[U][D], xe[U][D];
             rk_attempt_n<RHS, S, STRICT, U>(tb, t, dt, xc, p, xf, xe);
-            double dxn[U] = {0.0, 0.0}, new_h[U];
+            double dxn[U], new_h[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) dxn[u] = 0.0;
             bool rej[U], nonfin[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {  // handle_step_adaptive, ode.rs:311-334
@@ -270,11 +280,14 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
                 if (nw != word[u]) ca.word[i] = nw;
             }
         } else {
-            if (live0) ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x, tb, ca, cs, tl, word[0], xc[0], p[0], t[0], h[0], n_acc[0], n_rej[0], c_step, c_chkpt, c_rej, c_end, c_stuck);
-            if (live1) ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x + 128, tb, ca, cs, tl, word[1], xc[1], p[1], t[1], h[1], n_acc[1], n_rej[1], c_step, c_chkpt, c_rej, c_end, c_stuck);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (live[u])
+                    ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x + 128 * u, tb, ca, cs, tl, word[u], xc[u], p[u], t[u], h[u], n_acc[u], n_rej[u], c_step,
+                                                c_chkpt, c_rej, c_end, c_stuck);
         }
     }
-    // ragged tail (N % 256 trajectories): plain loads, last CTA, up to two lanes per thread one after the other
+    // ragged tail (N % tile trajectories): plain loads, last CTA, one trajectory at a time
     if (blockIdx.x == G - 1) {
         for (int64_t i = n_full * T + threadIdx.x; i < N; i += 128) {
             const uint32_t word = ca.word[i];

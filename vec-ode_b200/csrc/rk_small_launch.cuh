@@ -82,10 +82,10 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
             const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
             const bool common = L.cs->adaptive && L.cs->use_err && L.cs->norm_kind == VO_NORM_L2;
             if constexpr (S > 0) {
-                if (common && L.cs->k_events == 1 && L.N >= 4 * VO_TILE2) {  // two trajectories per thread (rk_small2.cuh)
-                    const size_t smem2 = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE2 * sizeof(double) + 3 * VO_TILE2 * sizeof(uint32_t));
+                if (common && L.cs->k_events == 1 && L.N >= 4 * VO_TILE_CTL) {  // several trajectories per thread (rk_small2.cuh)
+                    const size_t smem2 = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t));
                     auto k2 = rk_ctl2_staged_kernel<RHS, S, STRICT>;
-                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
+                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE_CTL), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
                                   *L.cs, L.ev, L.chain);
                     return;
                 }

@@ -21,6 +21,7 @@
 
 #include "rk_small_launch.cuh"
 #include "rk_stage.cuh"
+#include "rk_heat_fused.cuh"
 
 int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap);
 int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t N, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
@@ -503,6 +504,43 @@ int32_t stage_rk_step(vo_solver_s* s, double t, double dt, bool per_traj, double
     return VO_OK;
 }
 
+// ---- whole-step path for the heat equation (rk_heat_fused.cuh) ------------------------------------------------
+template <int S> int32_t launch_heat_fused(vo_solver_s* s, const TableauDev& tb, const StageArgs& sa, double kappa, double* nx, double* xe) {
+    vo_ctx c = s->ctx;
+    constexpr int PPT = S <= 4 ? 8 : 4, L = HF_THREADS * PPT, T = L - 2 * S, BPS = S <= 4 ? 2 : 1;
+    if (s->d < L) return vo_fail(c, VO_ERR_UNSUPPORTED, "fused heat step: the state is shorter than one tile");
+    const int64_t tiles = ceil_div(s->d, T);
+    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * BPS);
+    const unsigned grid = (unsigned)ceil_div(tiles, iters);
+    if (c->arith == VO_ARITH_STRICT) heat_fused_step_kernel<S, true, PPT><<<grid, HF_THREADS, 0, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
+    else heat_fused_step_kernel<S, false, PPT><<<grid, HF_THREADS, 0, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+bool heat_fused_ok(const vo_solver_s* s) {
+    return s->stage_path == 2 && s->rhs->kind == VO_RHS_HEAT1D && s->n == 1 && (s->tab.s == 4 || s->tab.s == 6 || s->tab.s == 7);
+}
+
+// One rk_step (rk.rs:90-155) of the single heat state in ONE launch.
+int32_t heat_fused_rk_step(vo_solver_s* s, double dt, double* nx, double* xe, int* launches) {
+    const vo_tableau_s& t = s->tab;
+    const TableauDev tb = make_tableau_dev(t);
+    StageArgs sa;
+    std::memset(&sa, 0, sizeof sa);
+    sa.s = t.s, sa.dt = dt, sa.use_err = (t.has_err && xe) ? 1 : 0;
+    for (int j = 0; j < t.s; ++j) sa.b[j] = t.b[j], sa.b_err[j] = t.b_err[j];
+    const double kappa = s->rhs->shared[0];
+    int32_t r = VO_ERR_UNSUPPORTED;
+    switch (t.s) {
+        case 4: r = launch_heat_fused<4>(s, tb, sa, kappa, nx, xe); break;
+        case 6: r = launch_heat_fused<6>(s, tb, sa, kappa, nx, xe); break;
+        case 7: r = launch_heat_fused<7>(s, tb, sa, kappa, nx, xe); break;
+    }
+    if (r == VO_OK && launches) ++*launches;
+    return r;
+}
+
 // Lock-step stage path: one event, controller on the host (the norm is read back for adaptive steps).
 int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) {
     vo_ctx c = s->ctx;
@@ -511,7 +549,9 @@ int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) 
     int launches = 0;
     if (ev == VO_EV_STEP) {
         const double h = s->u_h;  // ode.rs:314
-        int32_t r = stage_rk_step(s, s->u_t, dt, false, s->next_x->p, use_err(s) ? s->x_err->p : nullptr, nullptr, &launches);
+        double* xe_p = use_err(s) ? s->x_err->p : nullptr;
+        int32_t r = heat_fused_ok(s) ? heat_fused_rk_step(s, dt, s->next_x->p, xe_p, &launches)
+                                     : stage_rk_step(s, s->u_t, dt, false, s->next_x->p, xe_p, nullptr, &launches);
         if (r != VO_OK) return r;
         if (adaptive) {
             double* out = (double*)c->dscratch;
@@ -777,9 +817,11 @@ int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on) {
     return VO_OK;
 }
 
-int32_t vo_solver_set_path(vo_solver s, int32_t stage_path) {
-    if (!s) return VO_ERR_BAD_ARG;
-    s->stage_path = stage_path ? 1 : 0;
+int32_t vo_solver_set_path(vo_solver s, int32_t path) {
+    if (!s || path < 0 || path > 2) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_path: path must be 0, 1 or 2");
+    if (path == 2 && !(s->rhs->kind == VO_RHS_HEAT1D && s->n == 1 && (s->tab.s == 4 || s->tab.s == 6 || s->tab.s == 7)))
+        return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "vo_solver_set_path: the whole-step path needs HEAT1D, one state (N = 1) and 4, 6 or 7 stages");
+    s->stage_path = path;
     return VO_OK;
 }
 
