@@ -21,10 +21,11 @@ def _reference(vo, ctx, d_total):
     return s.current()[1].to_host()[0]
 
 
+@pytest.mark.parametrize("fused", [False, True])  # stage path / whole-step kernel on the slab
 @pytest.mark.parametrize("d_total,k", [(4099, 1), (1 << 16, 4), ((1 << 18) + 2, 3)])  # plain stage kernel / TMA-staged stage kernel
-def test_single_rank_slab_with_periodic_ghosts_bitwise(vo, ctx, d_total, k):
+def test_single_rank_slab_with_periodic_ghosts_bitwise(vo, ctx, d_total, k, fused):
     ref = _reference(vo, ctx, d_total)
-    ds = vo.domain.HeatSlabSolver(ctx, d_total, lambda j: vo.workloads.heat_u0_at(j, d_total), 1.0, 0.0, 1.0e9, H_STEP, steps_per_exchange=k)
+    ds = vo.domain.HeatSlabSolver(ctx, d_total, lambda j: vo.workloads.heat_u0_at(j, d_total), 1.0, 0.0, 1.0e9, H_STEP, steps_per_exchange=k, fused=fused)
     for _ in range(N_STEPS + 1):
         ds.step()
     assert ds.exchanges == (N_STEPS - 1) // k

@@ -505,17 +505,25 @@ int32_t stage_rk_step(vo_solver_s* s, double t, double dt, bool per_traj, double
 }
 
 // ---- whole-step path for the heat equation (rk_heat_fused.cuh) ------------------------------------------------
-template <int S> int32_t launch_heat_fused(vo_solver_s* s, const TableauDev& tb, const StageArgs& sa, double kappa, double* nx, double* xe) {
+template <int S, bool STRICT> int32_t launch_heat_fused_a(vo_solver_s* s, const TableauDev& tb, const StageArgs& sa, double kappa, double* nx, double* xe) {
     vo_ctx c = s->ctx;
-    constexpr int PPT = S <= 4 ? 8 : 4, L = HF_THREADS * PPT, T = L - 2 * S, BPS = S <= 4 ? 2 : 1;
-    if (s->d < L) return vo_fail(c, VO_ERR_UNSUPPORTED, "fused heat step: the state is shorter than one tile");
+    constexpr int PPT = S <= 4 ? 8 : 4, L = HF_THREADS * PPT, HS = (S + 1) & ~1, T = L - 2 * HS, BPS = 2;
+    if (s->d < L) return vo_fail(c, VO_ERR_UNSUPPORTED, "whole-step heat kernel: the state is shorter than one tile");
+    auto k = heat_fused_step_kernel<S, STRICT, PPT>;
+    const size_t smem = (size_t)HF_NST * L * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VO_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     const int64_t tiles = ceil_div(s->d, T);
     const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * BPS);
-    const unsigned grid = (unsigned)ceil_div(tiles, iters);
-    if (c->arith == VO_ARITH_STRICT) heat_fused_step_kernel<S, true, PPT><<<grid, HF_THREADS, 0, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
-    else heat_fused_step_kernel<S, false, PPT><<<grid, HF_THREADS, 0, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
+    k<<<(unsigned)ceil_div(tiles, iters), HF_THREADS, smem, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
     VO_CHECK_LAUNCH(c);
     return VO_OK;
+}
+template <int S> int32_t launch_heat_fused(vo_solver_s* s, const TableauDev& tb, const StageArgs& sa, double kappa, double* nx, double* xe) {
+    return s->ctx->arith == VO_ARITH_STRICT ? launch_heat_fused_a<S, true>(s, tb, sa, kappa, nx, xe) : launch_heat_fused_a<S, false>(s, tb, sa, kappa, nx, xe);
 }
 
 bool heat_fused_ok(const vo_solver_s* s) {

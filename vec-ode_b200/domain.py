@@ -76,7 +76,7 @@ class HeatSlabSolver:
     the process group. Same stepping semantics as `RK45Solver.step()` for a single large state (N = 1, lock-step control on
     the host); every rank runs the same (t, dt) sequence, so the only data-path exchange is the ghost refresh."""
 
-    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4):
+    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4, fused: bool = False):
         from . import base
         rank, world = rank_world()
         self.ctx = ctx
@@ -87,6 +87,9 @@ class HeatSlabSolver:
         self.rhs = base.Rhs(ctx, "HEAT1D", self.slab.local_len, [kappa])
         self.solver = base.RK45Solver(self.rhs, t0, tf, base.Ensemble.from_host(ctx, u0[None, :]), h, tableau=self.tableau)
         self.solver.no_adaptive()
+        if fused:  # whole-step kernel (rk_heat_fused.cuh): its periodic wrap corrupts the same s points per step at the slab ends
+            self.solver.set_fused_step()
+        self._fused = fused
         self._views = {}
         self._since_exchange = 0  # ghosts are fresh at construction
         self.exchanges = 0
@@ -128,6 +131,8 @@ class HeatSlabSolver:
         """Restart from the local state `x0` (an Ensemble of the slab's length, ghosts included and fresh)."""
         self.solver.reset(x0)
         self.solver.no_adaptive()
+        if self._fused:
+            self.solver.set_fused_step()
         self._since_exchange = 0
 
     def local_interior(self) -> np.ndarray:
