@@ -187,18 +187,19 @@ def test_config3_vdp_adaptive_ensemble(vo, ctx, oracle, tab, stage_path):
     assert np.quantile(err, 0.99) <= 200 * rtol, np.quantile(err, [0.5, 0.9, 0.99, 1.0])
 
 
-@pytest.mark.parametrize("n", [300, 2500])
-def test_small_and_stage_paths_agree_bitwise_adaptive(vo, ctx, n):
+@pytest.mark.parametrize("n,k_small", [(300, 5), (2500, 1), (2500, 5), (2500, 0)])
+def test_small_and_stage_paths_agree_bitwise_adaptive(vo, ctx, n, k_small):
     """Same device libm on both paths, so the register-resident and the stage-granular kernels must agree bit for bit,
     step sequence included. n = 300 runs the one-trajectory-per-thread control kernel, n = 2500 the two-per-thread one
-    (with a ragged tail of 2500 % 256 trajectories)."""
+    (with a ragged tail of 2500 % 256 trajectories): one event per launch, five (the joint multi-event loop) and the
+    automatic eight of vo_run."""
     mu = vo.workloads.vdp_mu(n)
     x0 = vo.workloads.vdp_x0(n)
     out = []
     for stage_path in (False, True):
         rhs = vo.Rhs(ctx, "VDP", 2, [mu])
         s = vo.RK45Solver(rhs, 0.0, 5.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
-        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path).set_events_per_launch(1 if (stage_path or n > 1000) else 5)
+        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path).set_events_per_launch(1 if stage_path else k_small)
         s.run(adaptive=True)
         out.append((s.current()[1].to_host(), s.stats()))
     assert np.array_equal(out[0][0], out[1][0])
