@@ -507,18 +507,19 @@ int32_t stage_rk_step(vo_solver_s* s, double t, double dt, bool per_traj, double
 // ---- whole-step path for the heat equation (rk_heat_fused.cuh) ------------------------------------------------
 template <int S, bool STRICT> int32_t launch_heat_fused_a(vo_solver_s* s, const TableauDev& tb, const StageArgs& sa, double kappa, double* nx, double* xe) {
     vo_ctx c = s->ctx;
-    constexpr int PPT = S <= 4 ? 8 : 4, L = HF_THREADS * PPT, HS = (S + 1) & ~1, T = L - 2 * HS, BPS = 2;
-    if (s->d < L) return vo_fail(c, VO_ERR_UNSUPPORTED, "whole-step heat kernel: the state is shorter than one tile");
-    auto k = heat_fused_step_kernel<S, STRICT, PPT>;
-    const size_t smem = (size_t)HF_NST * L * sizeof(double);
+    constexpr int HS = (S + 1) & ~1, T = HF_WL - 2 * HS, WPB = HF_THREADS / 32, BPS = S <= 4 ? 2 : 1;
+    if (s->d < 4 * HF_WL) return vo_fail(c, VO_ERR_UNSUPPORTED, "whole-step heat kernel: the state is shorter than four warp tiles");
+    auto k = heat_fused_step_kernel<S, STRICT>;
+    const size_t smem = (size_t)WPB * HF_NST * HF_WL * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         VO_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int64_t tiles = ceil_div(s->d, T);
-    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * BPS);
-    k<<<(unsigned)ceil_div(tiles, iters), HF_THREADS, smem, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
+    const int64_t tiles = ceil_div(s->d, T);                                    // warp tiles
+    const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * BPS * WPB);    // per warp, all CTAs resident
+    const int64_t warps = ceil_div(tiles, iters);
+    k<<<(unsigned)ceil_div(warps, WPB), HF_THREADS, smem, c->stream>>>(s->x->p, s->d, tb, sa, kappa, nx, xe);
     VO_CHECK_LAUNCH(c);
     return VO_OK;
 }
