@@ -587,10 +587,10 @@ def main():
         # the final gather of the sharded ensemble (NCCL all_gather over NVLink), once per solve, outside the timed steps
         barrier()
         g0 = time.perf_counter()
-        full = vo.group.gather_states(w.pin_out.numpy(), N_TRAJ * world, device=torch.device("cuda", local))
+        full = vo.group.gather_states(w.pin_out.numpy(), N_TRAJ * world, device=torch.device("cuda", local), root=0)
         torch.cuda.synchronize()
         gather_ms = (time.perf_counter() - g0) * 1e3
-        assert full.shape[0] == N_TRAJ * world
+        assert (full is None) == (rank != 0) and (full is None or full.shape[0] == N_TRAJ * world)
 
     also = None
     if rank == 0 and world == 1 and not args.no_also and args.workload == "lorenz_rk4":

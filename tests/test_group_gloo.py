@@ -23,6 +23,8 @@ def _worker(rank, world, port, n_total, out_dir):
     x0 = vo.workloads.vdp_x0(hi - lo)
     r = ol.rk_ensemble("VDP", mu[:, None], ol.builtin_tableau(2), 0.0, 2.0, x0, 1e-3, adaptive=True, rtol=1e-6)
     full = vo.group.gather_states(r["x"], n_total)
+    rooted = vo.group.gather_states(r["x"], n_total, root=1)  # only rank 1 receives the ensemble
+    assert (rooted is None) == (rank != 1) and (rooted is None or np.array_equal(rooted, full))
     red = vo.group.reduce_stats(dict(accepted=r["accepted"], rejected=r["rejected"], t=r["t"], status=np.ones(hi - lo, np.int32)))
     if rank == 0:
         np.save(os.path.join(out_dir, "full.npy"), full)

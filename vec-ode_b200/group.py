@@ -27,9 +27,11 @@ def my_range(n_total: int):
     return shard_range(n_total, r, w)
 
 
-def gather_states(local, n_total: int, device=None) -> np.ndarray:
-    """all_gather of per-rank final states [n_local][d] into the whole ensemble [n_total][d] (on every rank). Ranks may
-    hold ragged shard sizes (ceil(N/G) ranges): shards are padded to the largest one for the collective."""
+def gather_states(local, n_total: int, device=None, root=None):
+    """Gather of per-rank final states [n_local][d] into the whole ensemble [n_total][d]. Ranks may hold ragged shard sizes
+    (ceil(N/G) ranges): shards are padded to the largest one for the collective. `root=None`: all_gather, every rank gets the
+    ensemble. `root=r`: only rank r receives it (the others return None) — one device-to-host copy of the whole ensemble
+    instead of one per rank, which is what dominates an 8-GPU gather."""
     import torch
     import torch.distributed as dist
     local = np.ascontiguousarray(local)
@@ -43,12 +45,19 @@ def gather_states(local, n_total: int, device=None) -> np.ndarray:
     t = torch.from_numpy(as_real.copy())
     if device is not None:
         t = t.to(device)
-    out = [torch.empty_like(t) for _ in range(w)]
-    dist.all_gather(out, t)
+    if root is None:
+        out = [torch.empty_like(t) for _ in range(w)]
+        dist.all_gather(out, t)
+    else:
+        out = [torch.empty_like(t) for _ in range(w)] if r == root else None
+        dist.gather(t, out, dst=root)
+        if r != root:
+            return None
+    whole = torch.stack(out).cpu().numpy()  # one device-to-host copy
     parts = []
-    for q, o in enumerate(out):
+    for q in range(w):
         lo, hi = shard_range(n_total, q, w)
-        a = o.cpu().numpy()
+        a = whole[q]
         if np.iscomplexobj(local):
             a = a.view(np.complex128)
         parts.append(a[: hi - lo])
