@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TRAJ = 1_000_000
+E2E_PARTS = int(os.environ.get("VECODE_BENCH_E2E_PARTS", "4"))  # chunks of the e2e solve (vec-ode_b200/pipeline.py); 1 = one solver
 L2_MB = 126
 
 
@@ -118,17 +119,19 @@ class LorenzRK4:
 
     def e2e_setup(self):
         import torch
+        vo = self.vo
         self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
-        self.e_x0 = self.vo.Ensemble(self.ctx, 3, N_TRAJ)
-        self.e_solver = self.vo.RK45Solver(self.rhs, 0.0, 1.0, self.e_x0, 1e-3, tableau=self.tableau)
+        tab = self.tableau
+
+        def make(ctx, lo, hi, x0):
+            return vo.RK45Solver(vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS)), 0.0, 1.0, x0, 1e-3, tableau=tab)
+        # the ensemble in E2E_PARTS chunks, each on its own stream and host thread: copies overlap the integration
+        self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 3, make, parts=E2E_PARTS)
 
     def e2e_step(self):
-        self.e_x0.upload(self.pin_in.numpy(), "aos")       # H2D from pinned memory (+ AoS->SoA on the device)
-        self.e_solver.reset(self.e_x0)
-        st = self.e_solver.run()
-        self.e_solver.current()[1].to_host("aos", out=self.pin_out.numpy())  # D2H of the result
-        return float(st.counts["Step"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
+        sts = self.e_chunked.solve(self.pin_in.numpy(), self.pin_out.numpy())  # H2D from pinned memory, whole solve, D2H of the result
+        return float(sum(st.counts["Step"] for st in sts)), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
 class VdpDopri5:
@@ -173,17 +176,18 @@ class VdpDopri5:
 
     def e2e_setup(self):
         import torch
+        vo = self.vo
         self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
-        self.e_x0 = self.vo.Ensemble(self.ctx, 2, N_TRAJ)
-        self.e_solver = self.vo.RK45Solver(self.rhs, 0.0, 20.0, self.e_x0, 1e-3, tableau=self.tableau).with_tolerance(1e-6, 1e-6)
+        tab, mu = self.tableau, self.mu
+
+        def make(ctx, lo, hi, x0):
+            return vo.RK45Solver(vo.Rhs(ctx, "VDP", 2, [mu[lo:hi].copy()]), 0.0, 20.0, x0, 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
+        self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 2, make, parts=E2E_PARTS)
 
     def e2e_step(self):
-        self.e_x0.upload(self.pin_in.numpy(), "aos")
-        self.e_solver.reset(self.e_x0)
-        st = self.e_solver.run(adaptive=True)
-        self.e_solver.current()[1].to_host("aos", out=self.pin_out.numpy())
-        return float(st.counts["Step"] + st.counts["Reject"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
+        sts = self.e_chunked.solve(self.pin_in.numpy(), self.pin_out.numpy(), adaptive=True)
+        return float(sum(st.counts["Step"] + st.counts["Reject"] for st in sts)), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
 class HeatRK4:
@@ -580,7 +584,9 @@ def main():
         e_units = float(u.item())
     e2e = {"value": e_units / (e_ms * 1e-3), "unit": f"{W.unit_name}s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
-           "what": "per e2e step: upload x0 from pinned host memory, one whole solve of the config through RK45Solver.run(), download the final state"}
+           "what": "per e2e step: upload x0 from pinned host memory, one whole solve of the config through RK45Solver.run(), download the final state"
+                   + (f"; the ensemble in {E2E_PARTS} chunks on their own streams and host threads (pipeline.ChunkedSolve), copies overlapping the integration"
+                      if W in (LorenzRK4, VdpDopri5) and E2E_PARTS > 1 else "")}
 
     gather_ms = None
     if world > 1 and W in (LorenzRK4, VdpDopri5):

@@ -3,7 +3,7 @@
 The directory is `vec-ode_b200/` (not an importable name); `import vecode_b200` works through the shim module
 `vecode_b200.py` at the repository root.
 """
-from . import _cabi, domain, group, workloads
+from . import _cabi, domain, group, pipeline, workloads
 from ._cabi import SO_PATH, StepResult, VecOdeError, build
 from .exp import DenseBasisSplit, ExpCFMSolver, MagnusExpLinearSolver, MidpointExpLinearSolver, with_commutator_slot
 from .split_exp import (CommutativeExpSplit, DirectSumL, ExpSplitMidpointSolver, RKNR4ExpSplit, SemiComplexO4ExpSplit, StrangSplit,
@@ -13,4 +13,4 @@ from .base import (ButcherTableu, Context, Ensemble, LinearCombination, ODEError
 __all__ = ["ButcherTableu", "Context", "Ensemble", "LinearCombination", "ODEError", "ODEState", "RK45Solver", "Rhs", "step_many", "DenseBasisSplit", "ExpCFMSolver", "MagnusExpLinearSolver", "MidpointExpLinearSolver",
            "with_commutator_slot", "CommutativeExpSplit", "DirectSumL", "ExpSplitMidpointSolver", "RKNR4ExpSplit",
            "SemiComplexO4ExpSplit", "StrangSplit", "TripleJumpExpSplit",
-           "StepResult", "VecOdeError", "build", "workloads", "group", "domain", "SO_PATH"]
+           "StepResult", "VecOdeError", "build", "workloads", "group", "domain", "pipeline", "SO_PATH"]

@@ -1,6 +1,7 @@
 // rk_small_launch.cuh — host-side dispatch of rk_small_kernel over (stage count, arithmetic mode, control mode).
 // Each RHS family is instantiated in its own translation unit (rk_small_<family>.cu) so they compile in parallel.
 #pragma once
+#include <mutex>
 #include <unordered_map>
 #include <utility>
 
@@ -27,6 +28,8 @@ static inline bool small_path_is_staged(int64_t N) { return (N % 2 == 0) && N >=
 // Persistent grid: every CTA gets the same number of 128-trajectory tiles (no partial last wave), all CTAs resident.
 template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem, int tile = RK_SMALL_THREADS) {
     static std::unordered_map<const void*, int> cache;  // resident CTAs per SM of each kernel instantiation
+    static std::mutex mu;                               // contexts may be driven from different host threads
+    std::lock_guard<std::mutex> lock(mu);
     int& bps = cache[(const void*)kernel];
     if (bps == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
