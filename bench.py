@@ -591,6 +591,7 @@ def main():
     gather_ms = None
     if world > 1 and W in (LorenzRK4, VdpDopri5):
         # the final gather of the sharded ensemble (NCCL all_gather over NVLink), once per solve, outside the timed steps
+        vo.group.gather_states(w.pin_out.numpy()[:1024], 1024 * world, device=torch.device("cuda", local), root=0)  # NCCL sets up its send/recv channels on first use
         barrier()
         g0 = time.perf_counter()
         full = vo.group.gather_states(w.pin_out.numpy(), N_TRAJ * world, device=torch.device("cuda", local), root=0)
