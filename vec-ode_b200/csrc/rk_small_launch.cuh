@@ -67,7 +67,11 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
             if constexpr (S > 0) {
                 if (L.N >= 4 * VO_TILE2) {  // two trajectories per thread (rk_small2.cuh)
                     const size_t smem2 = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE2 * sizeof(double);
+#ifdef VO_FIXED2_CTA  // A/B switch (tools/build_variant.sh): the CTA-staged version of the kernel
                     auto k2 = rk_fixed2_staged_kernel<RHS, S, STRICT>;
+#else
+                    auto k2 = rk_fixed2w_staged_kernel<RHS, S, STRICT>;
+#endif
                     launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl,
                                   L.chain);
                     return;
@@ -87,7 +91,11 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
             if constexpr (S > 0) {
                 if (common && L.cs->k_events == 1 && L.N >= 4 * VO_TILE_CTL) {  // several trajectories per thread (rk_small2.cuh)
                     const size_t smem2 = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t));
+#ifdef VO_CTL2_CTA  // A/B switch (tools/build_variant.sh): the CTA-staged version of the kernel
                     auto k2 = rk_ctl2_staged_kernel<RHS, S, STRICT>;
+#else
+                    auto k2 = rk_ctl2w_staged_kernel<RHS, S, STRICT>;  // warp-autonomous staging: 15.9 against 16.9 us on the VdP sweep
+#endif
                     launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE_CTL), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
                                   *L.cs, L.ev, L.chain);
                     return;
