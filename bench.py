@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TRAJ = 1_000_000
+DD_K = int(os.environ.get("VECODE_BENCH_DD_K", "4"))  # heat_rk4_dd: RK steps between ghost refreshes (ghost zone = 4 * DD_K points per side)
 E2E_PARTS = int(os.environ.get("VECODE_BENCH_E2E_PARTS", "4"))  # chunks of the e2e solve (vec-ode_b200/pipeline.py); 1 = one solver
 L2_MB = 126
 
@@ -249,7 +250,7 @@ class HeatRK4DD:
     (vec-ode_b200/domain.py). STRONG scaling: the whole job is always 2^26 points."""
     name = "heat_rk4_dd"
     label = ("config 4 domain-decomposed: RK4 on the 1-D heat equation, ONE state of 2^26 points split into one slab per GPU, "
-             "ghost zones of 16 points refreshed every 4 steps (one all-gather of 32 doubles per rank)")
+             f"ghost zones of {4 * DD_K} points refreshed every {DD_K} steps (one all-gather of {8 * DD_K} doubles per rank)")
     bytes_per_unit = 104.0
     unit_name = "grid-point-step"
     state_mb = 512
@@ -257,7 +258,7 @@ class HeatRK4DD:
 
     def __init__(self, vo, ctx, rank, world, n_batches):
         self.vo, self.ctx = vo, ctx
-        self.ds = vo.domain.HeatSlabSolver(ctx, self.D, lambda j: vo.workloads.heat_u0_at(j, self.D), 1.0, 0.0, 1.0e9, 0.25, steps_per_exchange=4)
+        self.ds = vo.domain.HeatSlabSolver(ctx, self.D, lambda j: vo.workloads.heat_u0_at(j, self.D), 1.0, 0.0, 1.0e9, 0.25, steps_per_exchange=DD_K)
         self.ds.step()  # Chkpt at t0
         self.solvers = []
 
@@ -275,7 +276,7 @@ class HeatRK4DD:
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
         self.e_x0 = self.vo.Ensemble(self.ctx, slab.local_len, 1)
         self.e_ds = self.vo.domain.HeatSlabSolver(self.ctx, self.D, lambda j: self.vo.workloads.heat_u0_at(j, self.D), 1.0, 0.0, 25.0, 0.25,
-                                                  steps_per_exchange=4)
+                                                  steps_per_exchange=DD_K)
 
     def e2e_step(self):
         self.e_x0.upload(self.pin_in.numpy(), "soa")
@@ -652,7 +653,7 @@ def main():
                            if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
-                           "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of 32 doubles per rank) every 4 steps" if W is HeatRK4DD
+                           "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of {8 * DD_K} doubles per rank) every {DD_K} steps" if W is HeatRK4DD
                                            else f"trajectory-sharded x{world}, no data-path collective")},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
         if gather_ms is not None:
