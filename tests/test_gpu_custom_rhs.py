@@ -135,3 +135,29 @@ def test_custom_rhs_compile_error_is_reported(vo, ctx):
     assert "rhs_body(1)" in str(ei.value) and "undefined_symbol" in str(ei.value)
     with pytest.raises(vo.VecOdeError):
         vo.Rhs.custom(ctx, "dx[0] = x[0];", 9, [])  # d > 8
+
+
+def test_custom_rhs_largest_shape_eight_components_eight_per_trajectory_parameters(vo, ctx):
+    """d = 8 with 8 per-trajectory parameters: the widest tiles (18 staged rows, > 48 KB of shared memory per CTA) and the
+    highest register pressure the run-time compiled kernels see. dx_c = p_c x_c has the closed form x_c(0) exp(p_c t); the
+    fixed-step run must also agree bit for bit between the register-resident kernel and the stage-path kernel of the same body."""
+    n, d = 4096, 8
+    rng = np.random.default_rng(11)
+    p = -2.0 * rng.random((n, d))
+    x0 = 0.5 + rng.random((n, d))
+    body = "\n".join(f"dx[{c}] = p[{c}] * x[{c}];" for c in range(d))
+    custom = vo.Rhs.custom(ctx, body, d, [p[:, c].copy() for c in range(d)])
+    # adaptive DoPri5 on the two-trajectory control kernel
+    s = vo.RK45Solver(custom, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5")).with_tolerance(1e-8, 1e-8)
+    assert s.run(adaptive=True).kind == "Done"
+    got = s.current()[1].to_host()
+    assert np.abs(got - x0 * np.exp(p * 1.0)).max() <= 1e-6
+    assert np.all(s.stats()["status"] == 1)
+    # fixed-step RKF45 (the reference's literal tableau): register-resident kernel == stage-path kernel
+    out = []
+    for stage in (False, True):
+        s = vo.RK45Solver(custom, 0.0, 0.2, vo.Ensemble.from_host(ctx, x0), 0.01)
+        s.set_stage_path(stage)
+        assert s.run().kind == "Done"
+        out.append(s.current()[1].to_host())
+    assert np.array_equal(out[0], out[1])
