@@ -257,6 +257,14 @@ int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int
 int32_t vo_exp_create(vo_ctx ctx, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N,
                       double t0, double tf, const double* psi0_host /* [N][n] (re,im) */, double h, vo_expsolver* out);
 int32_t vo_exp_destroy(vo_expsolver s);
+/* The generator closure itself (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32) in place of the compiled-in cosine family:
+ * `body` is CUDA C++ for statements that assign `g[1] .. g[M_gen-1]`, the real coefficients of L(t) = B_0 + sum_m g[m] B_m,
+ * from `const double t` and `const double* p` (this system's 3 (M_gen - 1) parameters as handed to vo_exp_create). It is
+ * compiled at run time (NVRTC, sm_100a) into the same tensor-core kernel the built-in family runs in; compile errors come
+ * back through vo_last_error. vo_exp_generator_check compiles without a ctx or a GPU (n in {16, 32, 64}, M basis matrices)
+ * and returns the cubin size (> 0) or a VO_ERR_* code with the compiler log in `log`. */
+int32_t vo_exp_set_generator(vo_expsolver s, const char* body);
+int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap);
 /* VO_EXP_SPLIT_MIDPOINT: bit m of a_mask set <=> basis matrix m belongs to split A (the rest form split B). */
 int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */

@@ -16,3 +16,11 @@ def test_user_rhs_compile_error_carries_the_log(vo):
     assert "rhs_body(1)" in str(ei.value) and "nope" in str(ei.value)
     with pytest.raises(vo.VecOdeError):
         vo.Rhs.check_source("dx[0] = x[0];", 9, 0)
+
+
+def test_user_generator_compiles_into_the_tensor_core_kernel(vo):
+    """vo_exp_generator_check: the generator closure of the exponential integrators -> exp_step_kernel, no GPU needed."""
+    assert vo.ExpCFMSolver.check_generator("g[1] = p[0] * cos(p[1] * t + p[2]);", 64, 2) > 10_000
+    with pytest.raises(vo.VecOdeError) as ei:
+        vo.ExpCFMSolver.check_generator("g[1] = nope;", 16, 2)
+    assert "generator_body(1)" in str(ei.value) and "nope" in str(ei.value)

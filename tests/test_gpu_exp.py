@@ -168,3 +168,56 @@ def test_split_norm_and_commutator(vo, ctx):
         ref = La @ Lb - Lb @ La
         got = c[i, 0] * basis[0] + c[i, 1] * basis[1] + c[i, 2] * basis[2]
         assert np.abs(got - ref).max() <= 1e-13
+
+
+COS_BODY = "g[1] = p[0] * cos(p[1] * t + p[2]);"
+
+
+@pytest.mark.parametrize("scheme,cls", [("cfm4", "ExpCFMSolver"), ("midpoint", "MidpointExpLinearSolver"), ("magnus42", "MagnusExpLinearSolver")])
+def test_user_generator_restating_the_cosine_family_gives_the_builtin_bits(vo, ctx, scheme, cls):
+    """vo_exp_set_generator: the generator closure (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32) compiled at run time
+    into the same tensor-core kernel. The cosine drive written as a body must reproduce the compiled-in family bit for bit."""
+    n, N = 64, 40
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    if scheme == "magnus42":
+        basis, cs = vo.with_commutator_slot(B0, B1)
+        sp = vo.DenseBasisSplit(ctx, basis, commutator_structure=cs)
+    else:
+        sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    out = []
+    for custom in (False, True):
+        s = getattr(vo, cls)(sp, gp, 0.0, 1.0, psi0, 0.1, M_gen=2).no_adaptive()
+        if custom:
+            s.set_generator(COS_BODY)
+        assert s.run().kind == "Done"
+        out.append(s.current()[1])
+    assert np.array_equal(out[0], out[1])
+
+
+def test_user_generator_against_dense_expm_restatement_of_cfm4(vo, ctx):
+    """A generator with no built-in counterpart, g(t) = a t exp(-b t) + c per system, against cfm_general (exp/cfm.rs:43-100)
+    restated with dense matrix exponentials: nodes C_GAUSS_LEGENDRE_4, weights CFM_R4_J2_GL (dat/mod.rs:4, 71-74)."""
+    from scipy.linalg import expm
+    n, N, h, steps = 16, 20, 0.1, 10
+    B0, B1, _, psi0 = _system(vo, n, N)
+    rng = np.random.default_rng(2)
+    gp = np.stack([rng.uniform(0.5, 2.0, N), rng.uniform(0.1, 1.0, N), rng.uniform(-0.5, 0.5, N)], axis=1)[:, None, :]
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    s = vo.ExpCFMSolver(sp, gp, 0.0, h * steps, psi0, h, M_gen=2).no_adaptive()
+    s.set_generator("g[1] = p[0] * t * exp(-p[1] * t) + p[2];")
+    assert s.run().kind == "Done"
+    got = s.current()[1]
+    c = (0.21132486540518711775, 0.78867513459481288225)
+    a = ((0.53867513459481288225, -0.038675134594812882255), (-0.038675134594812882255, 0.53867513459481288225))
+    for i in range(N):
+        g = lambda t: gp[i, 0, 0] * t * np.exp(-gp[i, 0, 1] * t) + gp[i, 0, 2]
+        x, t = psi0[i].copy(), 0.0
+        for _ in range(steps):
+            L = [B0 + g(t + cq * h) * B1 for cq in c]
+            for row in a:  # cfm_exp: x <- exp(dt * sum_j alpha_ij L_j) x, row after row
+                x = expm(h * (row[0] * L[0] + row[1] * L[1])) @ x
+            t += h
+        assert np.abs(got[i] - x).max() <= 1e-11, (i, np.abs(got[i] - x).max())
+    with pytest.raises(vo.VecOdeError) as ei:
+        s.set_generator("g[1] = undefined_symbol;")
+    assert "generator_body(1)" in str(ei.value)

@@ -65,6 +65,10 @@ struct vo_rhs_s {
     std::map<int, void*> modules;      // VO_RHS_CUSTOM: compiled modules keyed by (stage count, arithmetic mode)
 };
 void custom_rhs_release(vo_rhs_s* r);  // nvrtc_rhs.cu
+// run-time compiled generator of the exponential integrators (nvrtc_rhs.cu): module + kernel handle for exp_step_kernel<n, M, 16, user GEN>
+int32_t rtc_exp_module(vo_ctx c, const std::string& body, int ndim, int M, size_t smem, void** module_out, void** fn_out);
+int32_t rtc_exp_launch(vo_ctx c, void* fn, unsigned grid, unsigned block, size_t smem, void** args);
+void rtc_exp_unload(void* module);
 
 #endif  // !__CUDACC_RTC__
 

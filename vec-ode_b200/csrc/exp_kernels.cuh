@@ -1,0 +1,442 @@
+// exp_kernels.cuh — device side of the exponential integrators (see exp.cu for the design). Kept free of host headers so that
+// a user-defined generator (vo_exp_set_generator, nvrtc_rhs.cu) can be compiled at run time into the very same kernel.
+#pragma once
+#include "common.cuh"
+#include "rk_small.cuh"  // CtlArrays / EvSlot / status-word layout shared with the RK solver
+
+#define VO_EXP_MAX_M 4
+#define VO_EXP_MAX_E 3  // exponentials per step: CFM4 adaptive = 2 + 1, Magnus adaptive = 1 + 1
+
+struct ExpKP {
+    int n, M, M_gen, scheme, adaptive, want_err, taylor_deg, mode;  // mode 0: solver event, 1: bare map_exp
+    int pw_is_third, count_events;
+    int nseq;             // mode 1: exponentials applied one after the other, coefficient sets [nseq][N][M]
+    unsigned split_mask;  // VO_EXP_SPLIT_MIDPOINT: bit m set <=> basis matrix m belongs to split A
+    double t_end, t_start;
+    double rtol, alpha, pw, min_dt, max_dt;
+    double norm1[VO_EXP_MAX_M];
+    double cs[VO_EXP_MAX_M * VO_EXP_MAX_M * VO_EXP_MAX_M];
+    int64_t N;
+};
+
+// dat/mod.rs:4, 67-74 (same literals as the reference)
+__constant__ double C_GL4[2] = {0.21132486540518711775, 0.78867513459481288225};
+__constant__ double CFM_R4[4] = {0.53867513459481288225, -0.038675134594812882255, -0.038675134594812882255, 0.53867513459481288225};
+__constant__ double CFM_R2[2] = {0.5, 0.5};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Taylor plan of map_exp (same rule as the CPU restatement): sub-steps so that theta/sq <= 1, then the smallest degree
+// whose term falls below 2^-53.
+__device__ __forceinline__ void taylor_plan(double theta, int forced_deg, int* sq, int* deg) {
+    int s = theta > 1.0 ? (int)ceil(theta) : 1;
+    const double th = theta / s;
+    double term = 1.0;
+    int k = 0;
+    while (k < 60) {
+        ++k;
+        term = term * th / k;
+        if (term <= 1.1102230246251565e-16) break;
+    }
+    *sq = s, *deg = forced_deg > 0 ? forced_deg : k;
+}
+
+template <int NDIM, int M, int TB> struct Geo {
+    static constexpr int NW = NDIM / 8;      // row blocks of 8 (one warp each per column group)
+    static constexpr int NK = NDIM / 4;      // k-steps of 4
+    static constexpr int NCG = TB / 16;      // column groups of 16 systems
+    static constexpr int NT = 2;             // n-tiles of 8 columns per warp
+    static constexpr int LDT = NDIM + 4;     // padded row of the term buffer: conflict-free B-fragment loads
+    static constexpr int THREADS = NW * NCG * 32;
+    static constexpr int NBUF = (M * 2 * NDIM * NDIM * 8 + 2 * 2 * TB * LDT * 8 > 200 * 1024) ? 1 : 2;
+    static constexpr size_t SMEM_B = (size_t)M * 2 * NDIM * NDIM * sizeof(double);
+    static constexpr size_t SMEM_T = (size_t)NBUF * 2 * TB * LDT * sizeof(double);
+    static constexpr size_t SMEM_COEF = (size_t)VO_EXP_MAX_E * M * TB * sizeof(double2);
+    static constexpr size_t SMEM_MISC = (size_t)(NW * TB + 8 * TB) * sizeof(double) + 64 * sizeof(int);
+    static constexpr size_t SMEM = SMEM_B + SMEM_T + SMEM_COEF + SMEM_MISC;
+};
+
+// x <- exp(sum_m coef[m][s] B_m) x for the tile, state in C-fragment layout:
+// lane l of warp (w, cg) owns row 8w + l/4 and columns 16cg + 8j + 2(l%4) + q, j,q in {0,1}.
+template <int NDIM, int M, int TB>
+__device__ __forceinline__ void map_exp_tile(const double* __restrict__ sB, double* __restrict__ sT, const double2* __restrict__ sCoefE, int sq, int deg,
+                                             double (&xr)[2][2], double (&xi)[2][2], int& buf) {
+    using G = Geo<NDIM, M, TB>;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int w = wi % G::NW, cg = wi / G::NW;
+    const int row = 8 * w + (lane >> 2);
+    const double inv_sq = 1.0 / sq;
+    double cr[M][2][2], ci[M][2][2];  // coefficients / sq of this lane's four systems
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double2 c = sCoefE[m * TB + 16 * cg + 8 * j + 2 * (lane & 3) + q];
+                cr[m][j][q] = c.x * inv_sq, ci[m][j][q] = c.y * inv_sq;
+            }
+    for (int rep = 0; rep < sq; ++rep) {
+        double ar[2][2], ai[2][2], tr[2][2], ti[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) ar[j][q] = tr[j][q] = xr[j][q], ai[j][q] = ti[j][q] = xi[j][q];
+        for (int k = 1; k <= deg; ++k) {
+            // publish the current term: planar [plane][column][LDT], row fastest
+            if (G::NBUF == 1) __syncthreads();
+            double* Tr = sT + (size_t)buf * 2 * TB * G::LDT;
+            double* Ti = Tr + TB * G::LDT;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
+                    Tr[col * G::LDT + row] = tr[j][q], Ti[col * G::LDT + row] = ti[j][q];
+                }
+            __syncthreads();
+            double Wr[M][2][2], Wi[M][2][2];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) Wr[m][j][0] = Wr[m][j][1] = Wi[m][j][0] = Wi[m][j][1] = 0.0;
+            const double* bA = sB + ((size_t)w * G::NK) * 32 + lane;  // + ((m*2 + plane) * NW) * NK * 32 + kk * 32
+            const double* bX = Tr + (16 * cg + (lane >> 2)) * G::LDT + (lane & 3);
+#pragma unroll 4
+            for (int kk = 0; kk < G::NK; ++kk) {
+                double fr[2], fi[2], nfi[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    fr[j] = bX[8 * j * G::LDT + 4 * kk];
+                    fi[j] = bX[TB * G::LDT + 8 * j * G::LDT + 4 * kk];
+                    nfi[j] = -fi[j];
+                }
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const double a_re = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
+                    const double a_im = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        dmma(Wr[m][j][0], Wr[m][j][1], a_re, fr[j]);   // Re += Br Xr
+                        dmma(Wr[m][j][0], Wr[m][j][1], a_im, nfi[j]);  // Re -= Bi Xi
+                        dmma(Wi[m][j][0], Wi[m][j][1], a_im, fr[j]);   // Im += Bi Xr
+                        dmma(Wi[m][j][0], Wi[m][j][1], a_re, fi[j]);   // Im += Br Xi
+                    }
+                }
+            }
+            const double ik = 1.0 / k;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double sr = 0.0, si = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        sr += cr[m][j][q] * Wr[m][j][q] - ci[m][j][q] * Wi[m][j][q];
+                        si += cr[m][j][q] * Wi[m][j][q] + ci[m][j][q] * Wr[m][j][q];
+                    }
+                    tr[j][q] = sr * ik, ti[j][q] = si * ik;
+                    ar[j][q] += tr[j][q], ai[j][q] += ti[j][q];
+                }
+            if (G::NBUF == 2) buf ^= 1;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) xr[j][q] = ar[j][q], xi[j][q] = ai[j][q];
+    }
+}
+
+// generator family: L(t) = B_0 + sum_{m=1}^{M_gen-1} amp_m cos(omega_m t + phase_m) B_m ; coefficients beyond M_gen are 0.
+// The generator closures of the reference (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32) are a functor GEN with this
+// shape; GenCos is the compiled-in family, a user-defined one is compiled at run time (vo_exp_set_generator).
+struct GenCos {
+    template <int M> static __device__ __forceinline__ void coef(const double* __restrict__ gp, int M_gen, double t, double (&c)[M]) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) c[m] = 0.0;
+        c[0] = 1.0;
+#pragma unroll
+        for (int m = 1; m < M; ++m)
+            if (m < M_gen) c[m] = gp[(m - 1) * 3 + 0] * cos(gp[(m - 1) * 3 + 1] * t + gp[(m - 1) * 3 + 2]);
+    }
+};
+
+template <int NDIM, int M, int TB, class GEN>
+__global__ void __launch_bounds__(Geo<NDIM, M, TB>::THREADS, 1)
+exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ frag, double2* __restrict__ psi, double2* __restrict__ psi_out,
+                const double* __restrict__ gp, const double2* __restrict__ coef_in, const CtlArrays ca, EvSlot* __restrict__ ev) {
+    using G = Geo<NDIM, M, TB>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sB = reinterpret_cast<double*>(smem_raw);
+    double* sT = reinterpret_cast<double*>(smem_raw + G::SMEM_B);
+    double2* sCoef = reinterpret_cast<double2*>(smem_raw + G::SMEM_B + G::SMEM_T);               // [E][M][TB]
+    double* sNorm = reinterpret_cast<double*>(smem_raw + G::SMEM_B + G::SMEM_T + G::SMEM_COEF);  // [NW][TB]
+    double* sTheta = sNorm + G::NW * TB;                                                         // [E][TB]
+    double* sDt = sTheta + VO_EXP_MAX_E * TB;                                                    // [TB]
+    int* sEv = reinterpret_cast<int*>(sDt + TB + 4 * TB);                                        // [TB] event, then [8] plan, [1] any
+    int* sPlan = sEv + TB;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int w = wi % G::NW, cg = wi / G::NW;
+    const int row = 8 * w + (lane >> 2);
+
+    // the basis, already in A-fragment order, stays in shared memory for the life of the CTA
+    for (size_t i = threadIdx.x; i < G::SMEM_B / sizeof(double2); i += blockDim.x)
+        reinterpret_cast<double2*>(sB)[i] = reinterpret_cast<const double2*>(frag)[i];
+    __syncthreads();
+
+    const int64_t n_tiles = (kp.N + TB - 1) / TB;
+    int buf = 0;
+    unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TB;
+        const bool embedded = kp.mode == 0 && kp.want_err && (kp.scheme == VO_EXP_CFM4 || kp.scheme == VO_EXP_MAGNUS42);
+        const int nbase = kp.mode == 1 ? 1 : (kp.scheme == VO_EXP_CFM4 ? 2 : (kp.scheme == VO_EXP_SPLIT_MIDPOINT ? 3 : 1));
+        const int nexp = nbase + (embedded ? 1 : 0);
+        // ---- phase A: per-system control and exponent coefficients (one thread per system)
+        if (threadIdx.x < TB) {
+            const int s = threadIdx.x;
+            const int64_t sys = base + s;
+            int evk = 255;  // not live
+            double dt = 0.0;
+            double2 ce[VO_EXP_MAX_E][M];
+#pragma unroll
+            for (int e = 0; e < VO_EXP_MAX_E; ++e)
+#pragma unroll
+                for (int m = 0; m < M; ++m) ce[e][m] = make_double2(0.0, 0.0);
+            if (sys < kp.N) {
+                if (kp.mode == 1) {
+                    evk = VO_EV_STEP;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) ce[0][m] = coef_in[sys * M + m];
+                } else {
+                    const uint32_t word = ca.word[sys];
+                    if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
+                        const int tgt = (int)(word & VO_WORD_TGT_MASK);
+                        const double t = ca.t[sys], h = ca.h[sys];
+                        // step_size_of (ode.rs:165-176) with t_list = [t0, tf]
+                        if (tgt >= 2) {
+                            evk = VO_EV_END;
+                        } else {
+                            const double rem = (tgt == 0 ? kp.t_start : kp.t_end) - t;
+                            if (fabs(rem) <= 2.220446049250313e-16) evk = tgt >= 1 ? VO_EV_END : VO_EV_CHKPT;
+                            else dt = rem < h ? rem : h, evk = VO_EV_STEP;
+                        }
+                        if (evk == VO_EV_STEP) {
+                            const double* g = gp + sys * (kp.M_gen - 1) * 3;
+                            if (kp.scheme == VO_EXP_MIDPOINT) {  // exp/magnus.rs:10-26
+                                double l[M];
+                                GEN::template coef<M>(g, kp.M_gen, t + dt * 0.5, l);
+#pragma unroll
+                                for (int m = 0; m < M; ++m) ce[0][m].x = l[m] * dt;
+                            } else if (kp.scheme == VO_EXP_CFM4) {  // exp/cfm.rs:43-100, cfm_exp :20-40
+                                double v0[M], v1[M];
+                                GEN::template coef<M>(g, kp.M_gen, t + C_GL4[0] * dt, v0);
+                                GEN::template coef<M>(g, kp.M_gen, t + C_GL4[1] * dt, v1);
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    ce[0][m].x = (CFM_R4[0] * v0[m] + (CFM_R4[1] * v1[m])) * dt;
+                                    ce[1][m].x = (CFM_R4[2] * v0[m] + (CFM_R4[3] * v1[m])) * dt;
+                                    ce[2][m].x = (CFM_R2[0] * v0[m] + (CFM_R2[1] * v1[m])) * dt;  // error scheme, :83-97
+                                }
+                            } else if (kp.scheme == VO_EXP_SPLIT_MIDPOINT) {  // split_exp_midpoint, exp/split_exp.rs:520-562
+                                // literal: the generator is sampled at t (not t + dt/2) and BOTH splits are scaled by dt/2
+                                // (KA[0] and KB[0] by dt0, :540-548), applied as A, B, A (:556-559)
+                                double l[M];
+                                GEN::template coef<M>(g, kp.M_gen, t, l);
+                                const double dt0 = dt * 0.5;
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    const bool in_a = (kp.split_mask >> m) & 1u;
+                                    ce[0][m].x = in_a ? l[m] * dt0 : 0.0;
+                                    ce[1][m].x = in_a ? 0.0 : l[m] * dt0;
+                                    ce[2][m].x = ce[0][m].x;
+                                }
+                            } else {  // magnus_42, exp/magnus.rs:28-83
+                                const double c_mid = 0.288675134594812882254574390251;
+                                const double b1 = dt * 0.5, b2 = dt * dt * -0.144337567297406441127287195125;
+                                const double mid_t = t + b1;
+                                double l0[M], l1[M], w2[M];
+                                GEN::template coef<M>(g, kp.M_gen, mid_t - c_mid * dt, l0);
+                                GEN::template coef<M>(g, kp.M_gen, mid_t + c_mid * dt, l1);
+#pragma unroll
+                                for (int c = 0; c < M; ++c) w2[c] = 0.0;
+#pragma unroll
+                                for (int a = 0; a < M; ++a)
+#pragma unroll
+                                    for (int b = 0; b < M; ++b) {
+                                        const double ab = l0[a] * l1[b];
+#pragma unroll
+                                        for (int c = 0; c < M; ++c) {
+                                            const double sc = kp.cs[(a * M + b) * M + c];
+                                            if (sc != 0.0) w2[c] = w2[c] + ab * sc;
+                                        }
+                                    }
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    const double w1 = (l0[m] + l1[m]) * b1;
+                                    ce[0][m].x = w1 + w2[m] * b2;  // u = exp(w1 + w2)
+                                    ce[1][m].x = w1;               // u1 = exp(w1), the 2nd-order embedded solution
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            sEv[s] = evk, sDt[s] = dt;
+#pragma unroll
+            for (int e = 0; e < VO_EXP_MAX_E; ++e) {
+                double th = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    sCoef[(e * M + m) * TB + s] = ce[e][m];
+                    th += hypot(ce[e][m].x, ce[e][m].y) * kp.norm1[m];
+                }
+                sTheta[e * TB + s] = evk == VO_EV_STEP ? th : 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- phase B: tile-uniform Taylor plan per exponential
+        if (threadIdx.x == 0) {
+            int any = 0;
+            for (int s = 0; s < TB; ++s) any |= sEv[s] == VO_EV_STEP;
+            sPlan[2 * VO_EXP_MAX_E] = any;
+            for (int e = 0; e < VO_EXP_MAX_E; ++e) {
+                double th = 0.0;
+                for (int s = 0; s < TB; ++s) th = fmax(th, sTheta[e * TB + s]);
+                taylor_plan(th, kp.taylor_deg, &sPlan[2 * e], &sPlan[2 * e + 1]);
+            }
+        }
+        __syncthreads();
+        const bool any_step = sPlan[2 * VO_EXP_MAX_E] != 0;
+        // ---- phase C: the exponentials
+        double x0r[2][2], x0i[2][2], xfr[2][2], xfi[2][2], xer[2][2], xei[2][2];
+        if (any_step) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t sys = base + 16 * cg + 8 * j + 2 * (lane & 3) + q;
+                    const double2 v = sys < kp.N ? psi[sys * NDIM + row] : make_double2(0.0, 0.0);
+                    x0r[j][q] = xfr[j][q] = v.x, x0i[j][q] = xfi[j][q] = v.y;
+                    xer[j][q] = xei[j][q] = 0.0;
+                }
+            map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
+            if (kp.mode == 0 && nbase >= 2) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + M * TB, sPlan[2], sPlan[3], xfr, xfi, buf);
+            if (kp.mode == 0 && nbase >= 3) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + 2 * M * TB, sPlan[4], sPlan[5], xfr, xfi, buf);
+            for (int q = 1; kp.mode == 1 && q < kp.nseq; ++q) {  // vo_map_exp_seq: the next exponential of the composition
+                __syncthreads();
+                if (threadIdx.x < TB) {
+                    const int64_t sys = base + threadIdx.x;
+                    double th = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const double2 c = sys < kp.N ? coef_in[((int64_t)q * kp.N + sys) * M + m] : make_double2(0.0, 0.0);
+                        sCoef[m * TB + threadIdx.x] = c;
+                        th += hypot(c.x, c.y) * kp.norm1[m];
+                    }
+                    sTheta[threadIdx.x] = th;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double th = 0.0;
+                    for (int s = 0; s < TB; ++s) th = fmax(th, sTheta[s]);
+                    taylor_plan(th, kp.taylor_deg, &sPlan[0], &sPlan[1]);
+                }
+                __syncthreads();
+                map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
+            }
+            if (embedded) {  // embedded lower-order solution from x0, then x_err = that - xf
+                const int e = nexp - 1;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) xer[j][q] = x0r[j][q], xei[j][q] = x0i[j][q];
+                map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xer, xei, buf);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) xer[j][q] -= xfr[j][q], xei[j][q] -= xfi[j][q];
+            }
+        }
+        // ---- phase D: error norm (2-norm of x_err per system), controller, apply_step
+        if (kp.mode == 0) {
+            if (any_step && kp.adaptive) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        double v = xer[j][q] * xer[j][q] + xei[j][q] * xei[j][q];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4), v += __shfl_xor_sync(0xffffffffu, v, 8), v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if ((lane >> 2) == 0) sNorm[w * TB + 16 * cg + 8 * j + 2 * (lane & 3) + q] = v;
+                    }
+            }
+            __syncthreads();
+            if (threadIdx.x < TB) {
+                const int s = threadIdx.x;
+                const int64_t sys = base + s;
+                int evk = sEv[s];
+                if (evk != 255) {
+                    const uint32_t word = ca.word[sys];
+                    int tgt = (int)(word & VO_WORD_TGT_MASK);
+                    uint32_t status = word >> VO_WORD_STATUS_SHIFT;
+                    if (evk == VO_EV_STEP) {
+                        const double h = ca.h[sys];
+                        if (kp.adaptive) {  // handle_step_adaptive, ode.rs:311-334
+                            double nn = 0.0;
+                            for (int ww = 0; ww < G::NW; ++ww) nn += sNorm[ww * TB + s];
+                            const double dxn = sqrt(nn);
+                            const double f = kp.rtol / dxn;
+                            const double mul = kp.alpha * pow(f, kp.pw);  // step_size_mul, ode.rs:133-135
+                            const double fp_lim = fmin(fmax(mul, 0.3), 2.0);
+                            const double new_h = fmin(fmax(fp_lim * h, kp.min_dt), kp.max_dt);
+                            if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
+                            if (f <= 1.0) {
+                                evk = VO_EV_REJECT;
+                                if (h <= kp.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
+                            }
+                            ca.prev_h[sys] = h, ca.h[sys] = new_h, ca.dx_norm[sys] = dxn;
+                        }
+                        if (evk == VO_EV_STEP) ca.t[sys] += sDt[s], ca.n_accept[sys] += 1, ++c_step;
+                        else ca.n_reject[sys] += 1, ++c_rej;
+                    } else {  // Chkpt / End: checkpoint_update, ode.rs:192-195
+                        tgt += 1, ca.h[sys] = ca.prev_h[sys];
+                        if (evk == VO_EV_END) status |= VO_TRAJ_DONE, ++c_end;
+                        else ++c_chkpt;
+                    }
+                    const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
+                    if (nw != word) ca.word[sys] = nw;
+                    sEv[s] = evk;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase E: masked commit (accepted systems only)
+        if (any_step) {
+            double2* dst = kp.mode == 1 ? psi_out : psi;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
+                    const int64_t sys = base + col;
+                    if (sys < kp.N && sEv[col] == VO_EV_STEP) dst[sys * NDIM + row] = make_double2(xfr[j][q], xfi[j][q]);
+                }
+        }
+        __syncthreads();  // sEv / sCoef are rewritten by the next tile
+    }
+    if (kp.mode == 0 && kp.count_events && threadIdx.x < 32) {
+        c_step = __reduce_add_sync(0xffffffffu, c_step), c_chkpt = __reduce_add_sync(0xffffffffu, c_chkpt);
+        c_rej = __reduce_add_sync(0xffffffffu, c_rej), c_end = __reduce_add_sync(0xffffffffu, c_end);
+        c_stuck = __reduce_add_sync(0xffffffffu, c_stuck);
+        if (threadIdx.x == 0) {
+            EvSlot* slot = ev + (blockIdx.x % VO_EV_SLOTS);
+            if (c_step) atomicAdd(&slot->n_step, (unsigned long long)c_step);
+            if (c_chkpt) atomicAdd(&slot->n_chkpt, (unsigned long long)c_chkpt);
+            if (c_rej) atomicAdd(&slot->n_reject, (unsigned long long)c_rej);
+            if (c_end) atomicAdd(&slot->n_end, (unsigned long long)c_end);
+            if (c_stuck) atomicAdd(&slot->n_stuck, (unsigned long long)c_stuck);
+        }
+    }
+}

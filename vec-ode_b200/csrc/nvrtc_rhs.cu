@@ -164,12 +164,10 @@ std::vector<std::string> kernel_names(int S, bool strict, bool stage_module) {
 }
 
 // Source -> cubin. Needs no GPU. `lowered[i]` is the mangled name of names[i] ("" where names[i] is "").
-int32_t compile_custom(const std::string& body, int d, int np, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered,
-                       std::string& log) {
+int32_t rtc_compile(const std::string& src, const std::vector<std::string>& names, bool fmad_off, std::vector<char>& cubin,
+                    std::vector<std::string>& lowered, std::string& log) {
     Nvrtc* nv = nullptr;
     if (!nvrtc_load(&nv, log)) return VO_ERR_UNSUPPORTED;
-    const bool stage_module = S == STAGE_MODULE;
-    const std::string src = rtc_source(body, d, np, stage_module);
     const char* hdr_text[N_HEADERS];
     const char* hdr_name[N_HEADERS];
     for (int i = 0; i < N_HEADERS; ++i) hdr_text[i] = RTC_HEADERS[i].text, hdr_name[i] = RTC_HEADERS[i].name;
@@ -179,12 +177,11 @@ int32_t compile_custom(const std::string& body, int d, int np, int S, bool stric
         log = std::string("nvrtcCreateProgram: ") + nv->getErrorString(r);
         return VO_ERR_CUDA;
     }
-    const std::vector<std::string> names = kernel_names(S, strict, stage_module);
     for (const std::string& n : names)
         if (!n.empty()) nv->addNameExpression(prog, n.c_str());
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
                                       "-default-device"};  // the C-ABI prototypes in vecode_b200.h are declarations only; JIT mode rejects host functions
-    if (strict) opts.push_back("--fmad=false");
+    if (fmad_off) opts.push_back("--fmad=false");
     r = nv->compileProgram(prog, (int)opts.size(), opts.data());
     if (r != NVRTC_SUCCESS) {
         size_t n = 0;
@@ -192,7 +189,7 @@ int32_t compile_custom(const std::string& body, int d, int np, int S, bool stric
         std::string l(n, '\0');
         if (n) nv->getProgramLog(prog, &l[0]);
         if (l.size() > 4000) l.resize(4000), l += "\n[...]";
-        log = std::string("user RHS does not compile (") + nv->getErrorString(r) + "):\n" + l.c_str();
+        log = std::string("user source does not compile (") + nv->getErrorString(r) + "):\n" + l.c_str();
         nv->destroyProgram(&prog);
         return VO_ERR_BAD_ARG;
     }
@@ -213,6 +210,12 @@ int32_t compile_custom(const std::string& body, int d, int np, int S, bool stric
     }
     nv->destroyProgram(&prog);
     return VO_OK;
+}
+
+int32_t compile_custom(const std::string& body, int d, int np, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered,
+                       std::string& log) {
+    const bool stage_module = S == STAGE_MODULE;
+    return rtc_compile(rtc_source(body, d, np, stage_module), kernel_names(S, strict, stage_module), strict, cubin, lowered, log);
 }
 
 int module_key(int S, bool strict) { return (S + 1) * 2 + (strict ? 1 : 0); }
@@ -367,7 +370,69 @@ void custom_rhs_release(vo_rhs_s* r) {
     r->modules.clear();
 }
 
+// ---- the same machinery for the generator closure of the exponential integrators (exp.cu) -------------------------------
+// The functor wraps statements that assign g[1] .. g[M_gen-1], the real coefficients of L(t) = B_0 + sum_m g[m] B_m, from the
+// time `t` and this system's parameter row `p` (the 3 (M_gen - 1) doubles per system handed to vo_exp_create).
+int32_t rtc_exp_compile(const std::string& body, int ndim, int M, std::vector<char>& cubin, std::string& lowered, std::string& log) {
+    std::string src = "#include \"exp_kernels.cuh\"\nstruct GenCustom {\n"
+                      "    template <int M> static __device__ __forceinline__ void coef(const double* __restrict__ p, int M_gen, const double t, double (&c)[M]) {\n"
+                      "        double g[M];\n#pragma unroll\n        for (int m = 0; m < M; ++m) g[m] = 0.0;\n        {\n#line 1 \"generator_body\"\n" +
+                      body +
+                      "\n        }\n#pragma unroll\n        for (int m = 0; m < M; ++m) c[m] = (m >= 1 && m < M_gen) ? g[m] : 0.0;\n        c[0] = 1.0;\n    }\n};\n";
+    std::vector<std::string> names = {"exp_step_kernel<" + std::to_string(ndim) + ", " + std::to_string(M) + ", 16, GenCustom>"}, low;
+    const int32_t rc = rtc_compile(src, names, false, cubin, low, log);
+    if (rc == VO_OK) lowered = low[0];
+    return rc;
+}
+
+int32_t rtc_exp_module(vo_ctx c, const std::string& body, int ndim, int M, size_t smem, void** module_out, void** fn_out) {
+    std::string err, lowered;
+    Driver* drv = nullptr;
+    if (!driver_load(&drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
+    std::vector<char> cubin;
+    int32_t rc = rtc_exp_compile(body, ndim, M, cubin, lowered, err);
+    if (rc != VO_OK) return vo_fail(c, rc, err);
+    cudaFree(0);
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    CUresult e = drv->moduleLoadData(&mod, cubin.data());
+    if (e == CUDA_SUCCESS) e = drv->moduleGetFunction(&fn, mod, lowered.c_str());
+    if (e == CUDA_SUCCESS) e = drv->funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+    if (e != CUDA_SUCCESS) {
+        if (mod) drv->moduleUnload(mod);
+        return vo_fail(c, VO_ERR_CUDA, "user generator: module load: " + cu_msg(drv, e));
+    }
+    *module_out = mod, *fn_out = fn;
+    return VO_OK;
+}
+
+int32_t rtc_exp_launch(vo_ctx c, void* fn, unsigned grid, unsigned block, size_t smem, void** args) {
+    std::string err;
+    Driver* drv = nullptr;
+    if (!driver_load(&drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
+    return custom_launch(c, drv, (CUfunction)fn, grid, block, smem, false, args);
+}
+
+void rtc_exp_unload(void* module) {
+    std::string err;
+    Driver* drv = nullptr;
+    if (module && driver_load(&drv, err)) drv->moduleUnload((CUmodule)module);
+}
+
 extern "C" {
+
+int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap) {
+    if (log && log_cap > 0) log[0] = '\0';
+    if (!body || (n != 16 && n != 32 && n != 64) || M < 1 || M > 3) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_exp_generator_check: bad argument");
+    std::vector<char> cubin;
+    std::string lowered, msg;
+    const int32_t rc = rtc_exp_compile(body, n, M, cubin, lowered, msg);
+    if (rc != VO_OK) {
+        if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
+        return vo_fail(nullptr, rc, msg);
+    }
+    return (int32_t)std::min<size_t>(cubin.size(), 0x7fffffff);
+}
 
 int32_t vo_rhs_create_custom(vo_ctx c, const char* body, int32_t d, int32_t n_params, vo_rhs* out) {
     if (!c || !body || !out) return vo_fail(c, VO_ERR_BAD_ARG, "vo_rhs_create_custom: NULL argument");

@@ -100,6 +100,22 @@ class _ExpSolver:
         check(lib().vo_exp_create(self.ctx._h, sp._h, _cabi.EXP_SCHEME[self.SCHEME], self.M_gen, _np_ptr(gp), self.N, t0, tf,
                                   _np_ptr(psi0.view(np.float64)), h, C.byref(self._h)), self.ctx._h)
 
+    def set_generator(self, body: str):
+        """The generator closure itself (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32): CUDA C++ statements assigning
+        `g[1] .. g[M_gen-1]` of L(t) = B_0 + sum_m g[m] B_m from `t` and this system's parameter row `p` (the 3 (M_gen - 1)
+        doubles of `gp`); compiled at run time into the same tensor-core kernel (vo_exp_set_generator)."""
+        check(lib().vo_exp_set_generator(self._h, body.encode()), self.ctx._h)
+        return self
+
+    @staticmethod
+    def check_generator(body: str, n: int, M: int) -> int:
+        """Compile `body` without a GPU; returns the cubin size or raises VecOdeError carrying the compiler log."""
+        log = C.create_string_buffer(1 << 16)
+        rc = lib().vo_exp_generator_check(body.encode(), n, M, log, len(log))
+        if rc < 0:
+            raise _cabi.VecOdeError(rc, log.value.decode("utf-8", "replace"))
+        return rc
+
     def no_adaptive(self):  # exp/cfm.rs:157-161
         check(lib().vo_exp_no_adaptive(self._h), self.ctx._h)
         return self
