@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TRAJ = 1_000_000
+GROUP_SIMILAR = os.environ.get("VECODE_BENCH_GROUP", "1") != "0"  # schrodinger_cfm4: tiles of systems with similar drive amplitude
 DD_K = int(os.environ.get("VECODE_BENCH_DD_K", "4"))  # heat_rk4_dd: RK steps between ghost refreshes (ghost zone = 4 * DD_K points per side)
 E2E_PARTS = int(os.environ.get("VECODE_BENCH_E2E_PARTS", "4"))  # chunks of the e2e solve (vec-ode_b200/pipeline.py); 1 = one solver
 L2_MB = 126
@@ -305,7 +306,7 @@ class SchrodingerCFM4:
         self.gp = vo.workloads.schrodinger_drive(self.N_SYS * world, self.N_SYS, rank * self.N_SYS)
         self.psi0 = np.zeros((self.N_SYS, self.NDIM), dtype=np.complex128)
         self.psi0[:, 0] = 1.0
-        self.solver = vo.ExpCFMSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1).no_adaptive()
+        self.solver = vo.ExpCFMSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1, group_similar=GROUP_SIMILAR).no_adaptive()
         self.solver.step()  # Chkpt at t0
         self.solvers = []
         # algorithmic FLOPs per trajectory-step: E * m* * M * 8 n^2 with m* from theta = ||L h||_1 of this config
@@ -341,7 +342,7 @@ class SchrodingerCFM4:
         import torch
         self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
-        self.e_solver = self.vo.ExpCFMSolver(self.sp, self.gp, 0.0, 10.0, self.psi0, 0.1).no_adaptive()
+        self.e_solver = self.vo.ExpCFMSolver(self.sp, self.gp, 0.0, 10.0, self.psi0, 0.1).no_adaptive()  # caller order: the host-side reordering of 100 MB per solve would cost what the grouping gains
 
     def e2e_step(self):
         self.e_solver.reset(self.pin_in.numpy().view(np.complex128))  # H2D of the initial states

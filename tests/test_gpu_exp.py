@@ -221,3 +221,22 @@ def test_user_generator_against_dense_expm_restatement_of_cfm4(vo, ctx):
     with pytest.raises(vo.VecOdeError) as ei:
         s.set_generator("g[1] = undefined_symbol;")
     assert "generator_body(1)" in str(ei.value)
+
+
+def test_grouping_systems_by_drive_amplitude_keeps_the_callers_order(vo, ctx, oracle):
+    """group_similar=True reorders the systems on the device (tiles of similar ||L h|| share a Taylor plan with less waste);
+    results come back in the caller's order and stay within 1e-12 of the oracle."""
+    n, N = 16, 77
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    basis = np.stack([B0, B1])
+    sp = vo.DenseBasisSplit(ctx, basis)
+    ref = oracle.exp_ensemble("cfm4", basis, gp, psi0, 0.0, 1.0, 0.1, M_gen=2, no_adaptive=True, n_threads=4)
+    s = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1, M_gen=2, group_similar=True).no_adaptive()
+    assert s._perm is not None and not np.array_equal(s._perm, np.arange(N))
+    assert s.run().kind == "Done"
+    psi = s.current()[1]
+    assert np.abs(psi - ref["psi"]).max() <= 1e-12
+    st = s.stats()
+    assert np.array_equal(st["accepted"], ref["accepted"])
+    s.reset(psi0)
+    assert s.run().kind == "Done" and np.array_equal(s.current()[1], psi)
