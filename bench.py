@@ -291,7 +291,7 @@ class HeatRK4DD:
 class SchrodingerCFM4:
     name = "schrodinger_cfm4"
     label = ("config 5: commutator-free Magnus CFM4, 10^5 driven 64-level Schroedinger systems (complex f64) per GPU, h = 0.1, "
-             "fixed step, shared basis {-iH0, -iH1}")
+             "fixed step, shared basis {-iH0, -iH1}" + ("; device order grouped by drive amplitude (group_similar), e2e in the caller's order" if GROUP_SIMILAR else ""))
     unit_name = "trajectory-step"
     bytes_per_unit = None  # compute-bound: the roofline is the FP64 tensor pipe
     state_mb = 102
