@@ -264,6 +264,11 @@ int32_t vo_exp_destroy(vo_expsolver s);
  * back through vo_last_error. vo_exp_generator_check compiles without a ctx or a GPU (n in {16, 32, 64}, M basis matrices)
  * and returns the cubin size (> 0) or a VO_ERR_* code with the compiler log in `log`. */
 int32_t vo_exp_set_generator(vo_expsolver s, const char* body);
+/* The systems are independent, so their order on the device is free — and it matters: a tile of 16 systems runs the largest
+ * Taylor degree among them. After vo_exp_set_order(s, perm, N) the solver treats device slot j as the caller's system perm[j]:
+ * vo_exp_reset / vo_exp_current / vo_exp_stats speak the caller's order (the reordering runs on the device). The psi0 and gp
+ * handed to vo_exp_create are in device order; call this right after creating the solver. */
+int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n);
 int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap);
 /* VO_EXP_SPLIT_MIDPOINT: bit m of a_mask set <=> basis matrix m belongs to split A (the rest form split B). */
 int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);

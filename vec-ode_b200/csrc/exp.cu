@@ -18,6 +18,7 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "exp_kernels.cuh"
@@ -50,6 +51,9 @@ struct vo_expsolver_s {
     bool want_err = true;  // alph_err / x_err present (exp/cfm.rs:157-161)
     unsigned split_mask = 1u;  // VO_EXP_SPLIT_MIDPOINT: which basis matrices form split A (default: B_0)
     double atol = 1.0e-6, rtol = 1.0e-4, alpha = 0.9, pw = 1.0 / 3.0, min_dt = 1.0e-6, max_dt = 1.0;
+    int64_t* perm = nullptr;     // vo_exp_set_order: device slot j holds the caller's system perm[j] (device copy)
+    std::vector<int64_t> perm_host;
+    double2* stage = nullptr;    // [N][n] staging for the reordering copies
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
 };
@@ -68,6 +72,16 @@ __global__ void exp_norm_kernel(const double2* __restrict__ psi, int n, int64_t 
     }
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if ((threadIdx.x & 31) == 0) out[sys] = sqrt(acc);
+}
+
+// rows of n complex numbers: dst[j] = src[perm[j]] (gather) or dst[perm[j]] = src[j] (scatter); one warp per row
+__global__ void exp_reorder_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const int64_t* __restrict__ perm, int n, int64_t N, int scatter) {
+    const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= N) return;
+    const int64_t pj = perm[j];
+    const double2* s = src + (scatter ? j : pj) * n;
+    double2* d = dst + (scatter ? pj : j) * n;
+    for (int r = threadIdx.x & 31; r < n; r += 32) d[r] = s[r];
 }
 
 __global__ void exp_ctl_fill_kernel(CtlArrays ca, int64_t N, double t, double h) {
@@ -346,6 +360,7 @@ int32_t vo_exp_destroy(vo_expsolver s) {
     cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm), cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
     cudaFree(s->ev_dev), cudaFreeHost(s->ev_host);
     rtc_exp_unload(s->gen_module);
+    cudaFree(s->perm), cudaFree(s->stage);
     delete s;
     return VO_OK;
 }
@@ -439,7 +454,13 @@ int32_t vo_exp_current(vo_expsolver s, double* t_min, double* t_max, double* psi
         if (t_max) *t_max = *mm.second;
     }
     if (psi_host) {
-        VO_CUDA(c, cudaMemcpyAsync(psi_host, s->psi, sizeof(double2) * (size_t)s->N * s->sp->n, cudaMemcpyDeviceToHost, c->stream));
+        const double2* src = s->psi;
+        if (s->perm) {  // back to the caller's order on the device, then one copy
+            exp_reorder_kernel<<<(unsigned)ceil_div(s->N, 8), 256, 0, c->stream>>>(s->psi, s->stage, s->perm, s->sp->n, s->N, 1);
+            VO_CHECK_LAUNCH(c);
+            src = s->stage;
+        }
+        VO_CUDA(c, cudaMemcpyAsync(psi_host, src, sizeof(double2) * (size_t)s->N * s->sp->n, cudaMemcpyDeviceToHost, c->stream));
         VO_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     return VO_OK;
@@ -465,6 +486,14 @@ int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, doubl
     if (h) VO_CUDA(c, cudaMemcpyAsync(h, s->ca.h, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     if (dx_norm) VO_CUDA(c, cudaMemcpyAsync(dx_norm, s->ca.dx_norm, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!s->perm_host.empty()) {  // device order -> the caller's order (vo_exp_set_order)
+        auto unpermute = [&](auto* a) {
+            if (!a) return;
+            std::vector<typename std::remove_pointer<decltype(a)>::type> v(a, a + n);
+            for (size_t j = 0; j < n; ++j) a[(size_t)s->perm_host[j]] = v[j];
+        };
+        unpermute(accepted), unpermute(rejected), unpermute(t), unpermute(h), unpermute(dx_norm);
+    }
     return VO_OK;
 }
 
@@ -473,13 +502,36 @@ int32_t vo_exp_reset(vo_expsolver s, const double* psi0_host) {
     vo_ctx c = s->ctx;
     DeviceGuard g(c->device);
     const size_t nb = sizeof(double2) * (size_t)s->N * s->sp->n;
-    if (psi0_host) VO_CUDA(c, cudaMemcpyAsync(s->psi0, psi0_host, nb, cudaMemcpyHostToDevice, c->stream));
+    if (psi0_host && s->perm) {  // the caller's order on the host, the grouped order on the device
+        VO_CUDA(c, cudaMemcpyAsync(s->stage, psi0_host, nb, cudaMemcpyHostToDevice, c->stream));
+        exp_reorder_kernel<<<(unsigned)ceil_div(s->N, 8), 256, 0, c->stream>>>(s->stage, s->psi0, s->perm, s->sp->n, s->N, 0);
+        VO_CHECK_LAUNCH(c);
+    } else if (psi0_host) {
+        VO_CUDA(c, cudaMemcpyAsync(s->psi0, psi0_host, nb, cudaMemcpyHostToDevice, c->stream));
+    }
     VO_CUDA(c, cudaMemcpyAsync(s->psi, s->psi0, nb, cudaMemcpyDeviceToDevice, c->stream));
     VO_CUDA(c, cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, c->stream));
     std::memset(&s->ev_seen, 0, sizeof s->ev_seen);
     s->n_done = 0;
     exp_ctl_fill_kernel<<<(unsigned)ceil_div(s->N, 256), 256, 0, c->stream>>>(s->ca, s->N, s->t0, s->h_init);
     VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n) {
+    if (!s || !perm || n != s->N) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_exp_set_order: bad argument");
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    std::vector<char> seen((size_t)n, 0);
+    for (int64_t j = 0; j < n; ++j) {
+        if (perm[j] < 0 || perm[j] >= n || seen[(size_t)perm[j]]) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_set_order: not a permutation");
+        seen[(size_t)perm[j]] = 1;
+    }
+    if (!s->perm && (cudaMalloc(&s->perm, 8 * (size_t)n) != cudaSuccess || cudaMalloc(&s->stage, sizeof(double2) * (size_t)n * s->sp->n) != cudaSuccess))
+        return vo_fail(c, VO_ERR_ALLOC, "vo_exp_set_order: cudaMalloc failed");
+    s->perm_host.assign(perm, perm + n);
+    VO_CUDA(c, cudaMemcpyAsync(s->perm, perm, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
     return VO_OK;
 }
 

@@ -94,22 +94,23 @@ class _ExpSolver:
     def __init__(self, sp: DenseBasisSplit, gp, t0: float, tf: float, psi0, h: float, M_gen: Optional[int] = None, group_similar: bool = False):
         """`group_similar`: hand the systems to the device ordered by drive amplitude. A tile of 16 systems runs the largest
         Taylor degree among them (the plan is tile-uniform), so tiles of similar ||L h|| waste fewer terms: ~5 % on config 5.
-        The systems are independent, so the order is free; current() / stats() / reset() keep the caller's order (only
-        `state_device_ptr` shows the device order)."""
+        The systems are independent, so the order is free; current() / stats() / reset() keep the caller's order
+        (vo_exp_set_order: the reordering runs on the device; only `state_device_ptr` shows the device order)."""
         self.sp, self.ctx = sp, sp.ctx
         psi0 = np.ascontiguousarray(psi0, dtype=np.complex128)
         self.N, self.n = psi0.shape
         self.M_gen = sp.M if M_gen is None else M_gen
         gp = np.ascontiguousarray(gp, dtype=np.float64).reshape(self.N, max(self.M_gen - 1, 0), 3)
-        self._perm = self._inv = None
+        self._perm = None
         if group_similar and self.M_gen > 1:
             key = (np.abs(gp[:, :, 0]) * sp.norm1[1:self.M_gen][None, :]).sum(axis=1)
-            self._perm = np.argsort(key, kind="stable")
-            self._inv = np.argsort(self._perm, kind="stable")
-            gp, psi0 = np.ascontiguousarray(gp[self._perm]), np.ascontiguousarray(psi0[self._perm])
+            self._perm = np.ascontiguousarray(np.argsort(key, kind="stable"), dtype=np.int64)
+            gp, psi0 = np.ascontiguousarray(gp[self._perm]), np.ascontiguousarray(psi0[self._perm])  # once, at construction
         self._h = _vp()
         check(lib().vo_exp_create(self.ctx._h, sp._h, _cabi.EXP_SCHEME[self.SCHEME], self.M_gen, _np_ptr(gp), self.N, t0, tf,
                                   _np_ptr(psi0.view(np.float64)), h, C.byref(self._h)), self.ctx._h)
+        if self._perm is not None:  # from here on the C ABI speaks the caller's order (the reordering runs on the device)
+            check(lib().vo_exp_set_order(self._h, _np_ptr(self._perm), self.N), self.ctx._h)
 
     def set_generator(self, body: str):
         """The generator closure itself (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32): CUDA C++ statements assigning
@@ -158,21 +159,16 @@ class _ExpSolver:
         tmin, tmax = C.c_double(), C.c_double()
         psi = np.empty((self.N, self.n), dtype=np.complex128) if out is None else out
         check(lib().vo_exp_current(self._h, C.byref(tmin), C.byref(tmax), _np_ptr(psi.view(np.float64))), self.ctx._h)
-        if self._inv is not None:
-            psi[:] = psi[self._inv]
         return (tmin.value, tmax.value), psi
 
     def stats(self) -> dict:
         n = self.N
         acc, rej, t, h, dxn = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n), np.zeros(n), np.zeros(n)
         check(lib().vo_exp_stats(self._h, _np_ptr(acc), _np_ptr(rej), _np_ptr(t), _np_ptr(h), _np_ptr(dxn)), self.ctx._h)
-        d = dict(accepted=acc, rejected=rej, t=t, h=h, dx_norm=dxn)
-        return d if self._inv is None else {k: v[self._inv] for k, v in d.items()}
+        return dict(accepted=acc, rejected=rej, t=t, h=h, dx_norm=dxn)
 
     def reset(self, psi0: Optional[np.ndarray] = None):
         p = None if psi0 is None else np.ascontiguousarray(psi0, dtype=np.complex128)
-        if p is not None and self._perm is not None:
-            p = np.ascontiguousarray(p[self._perm])
         check(lib().vo_exp_reset(self._h, None if p is None else _np_ptr(p.view(np.float64))), self.ctx._h)
 
     @property
