@@ -44,11 +44,11 @@ def _worker(rank, world, port, d_total, k, n_steps, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("d_total,k", [(203, 2), (96, 1)])
-def test_two_rank_slabs_match_single_process_bitwise(tmp_path, oracle, vo, d_total, k):
+@pytest.mark.parametrize("world,d_total,k", [(2, 203, 2), (2, 96, 1), (3, 200, 2)])  # (3, 200): ragged slabs of 67, 67, 66 points
+def test_slabs_match_single_process_bitwise(tmp_path, oracle, vo, world, d_total, k):
     n_steps = 7
-    port = 31500 + (os.getpid() % 2000) + d_total
-    mp.spawn(_worker, args=(2, port, d_total, k, n_steps, str(tmp_path)), nprocs=2, join=True)
+    port = 31500 + (os.getpid() % 2000) + d_total + world
+    mp.spawn(_worker, args=(world, port, d_total, k, n_steps, str(tmp_path)), nprocs=world, join=True)
     ref = _steps(oracle, oracle.builtin_tableau(1), vo.workloads.heat_u0(d_total), n_steps)
     full = np.load(tmp_path / "full.npy")
     assert full.shape == (d_total,) and np.array_equal(full, ref)
