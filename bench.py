@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench.py — ensemble trajectory-steps/s of the time-stepping hot path on N B200s (BASELINE.json's metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lorenz_rk4|vdp_dopri5|heat_rk4] [--arith strict|fast]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vdp_dopri5|lorenz_rk4|heat_rk4|heat_rk4_fused|heat_rk4_dd|schrodinger_cfm4]
+                  [--arith strict|fast]
+The default workload is config 3 (adaptive DoPri5, 10^6 Van der Pol oscillators), the configuration the north-star target is
+quoted on; at N = 1 the other configs are measured in the same run and reported under `also`, each with its own roofline.
   python bench.py --impl reference ...      # the CPU restatement of the reference path on the host cores
 
 A "step" is ONE pass of the hot path over ONE batch: one kernel launch that advances every trajectory of a
@@ -156,6 +159,9 @@ class VdpDopri5:
         if os.environ.get("VECODE_BENCH_NO_DX_NORM"):  # experiment switch: drop the per-attempt ODEAdaptiveData.dx_norm record (8 B)
             for s_ in self.solvers:
                 s_.set_record_dx_norm(False)
+        if os.environ.get("VECODE_BENCH_MIXED"):  # experiment switch: store prev_h on every attempt (vo_solver_set_mixed_stepping)
+            for s_ in self.solvers:
+                s_.set_mixed_stepping(True)
         vo.step_many(self.solvers, True, 1)
         self._attempts0 = None
 
@@ -464,6 +470,39 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, peak_src):
+    """The `roofline` object of the dominant kernel from one timed region: algorithmic bytes (or FLOPs) per launch over the
+    mean launch duration (CUDA events around the region, kernels back to back on the launching stream)."""
+    kernel_ms = ms / max(launches, 1)
+    if W is SchrodingerCFM4:
+        p64 = os.path.join(ROOT, "profiles", "fp64_peaks.json")
+        peak_tf, src = (json.load(open(p64))["dmma_tflops"], "measured by profiles/microbench/peaks.cu (profiles/fp64_peaks.json: dmma_tflops)") \
+            if os.path.exists(p64) else (45.0, "nominal B200 FP64 tensor peak (no measured figure committed)")
+        ach = w.flops_per_unit * (units_per_rank / max(launches, 1)) / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic(W.name),
+                "peak_source": src, "algorithmic_flops_per_unit": w.flops_per_unit, "taylor_degree": w.m_star, "theta": w.theta,
+                "kernel_us": kernel_ms * 1e3,
+                "note": "FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"}
+    bytes_per_launch = W.bytes_per_unit * (units_per_rank / max(launches, 1)) / events_per_launch
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
+            "peak_source": peak_src, "algorithmic_bytes_per_unit": W.bytes_per_unit, "kernel_us": kernel_ms * 1e3,
+            "note": "achieved = algorithmic bytes per launch / mean launch duration (CUDA events over the timed region, kernels back to back)"}
+
+
+def n_batches_for(W, n_traj):
+    """Independent batches rotated per GPU so that the working set is >= 3x the L2 (each launch then streams from HBM)."""
+    if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4):
+        return 1
+    if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
+        return int(os.environ["VECODE_BENCH_BATCHES"])
+    state_mb = W.state_mb * n_traj / 1.0e6
+    return int(min(256, max(2, -(-3 * L2_MB // max(state_mb, 1e-9)))))
+
+
+SPIN_UP_MS = 40.0  # untimed load right before the timed region, whatever --warmup says: clocks and caches in their steady state
+
+
 def main():
     global N_TRAJ
     ap = argparse.ArgumentParser()
@@ -471,10 +510,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lorenz_rk4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="vdp_dopri5", choices=sorted(WORKLOADS),
+                    help="default: config 3, the configuration BASELINE.json's north-star target (>= 70 %% of HBM peak) is quoted on")
     ap.add_argument("--arith", default="fast", choices=["strict", "fast"],
-                    help="fast: FMA contraction (<= 2e-15 relative from the oracle on config 2, tests/test_gpu_rk.py); strict: the reference's "
-                         "un-fused operation order, bit-identical to the oracle")
+                    help="fast: FMA contraction and the reformulated controller (adaptive runs within rtol, fixed-step <= 1e-12 of the oracle, "
+                         "tests/test_gpu_rk.py); strict: the reference's un-fused operation order, bit-identical to the oracle")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--events-per-launch", type=int, default=1)
     ap.add_argument("--n-traj", type=int, default=N_TRAJ, help="trajectories per batch (experiments only; the named configs use 10^6)")
@@ -503,37 +543,61 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = vo.Context.on_torch_stream(local, arith=args.arith)
-    W = WORKLOADS[args.workload]
-    state_mb = W.state_mb * N_TRAJ / 1.0e6 if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD) else W.state_mb
-    n_batches = 1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else int(min(256, max(2, -(-3 * L2_MB // state_mb))))  # working set >= 3x L2
-    if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
-        n_batches = int(os.environ["VECODE_BENCH_BATCHES"])
-    w = W(vo, ctx, rank, world, n_batches)
-    for s in getattr(w, "solvers", []):
-        s.set_events_per_launch(args.events_per_launch)
-
-    def timed(k):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        l0 = ctx.launch_count
-        ev0.record()
-        w.run_steps(k)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ctx.launch_count - l0
+        return ms
 
+    peak, peak_src = peaks()
+
+    def device_leg(Wc, arith, steps, warmup, k_events=1, r=0, wsize=1, sync_ranks=False):
+        """W untimed warm-up steps (after one pass over EVERY batch and a spin-up), then exactly `steps` timed steps between
+        barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        c2 = vo.Context.on_torch_stream(local, arith=arith)
+        nb = n_batches_for(Wc, N_TRAJ)
+        w2 = Wc(vo, c2, r, wsize, nb)
+        for s_ in getattr(w2, "solvers", []):
+            s_.set_events_per_launch(k_events)
+        w2.run_steps(max(nb, 1))  # every batch has been through the kernel once (first-touch, module load, lazy allocations)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        w2.run_steps(max(nb, 4))
+        ev1.record()
+        torch.cuda.synchronize()
+        per_step_ms = max(ev0.elapsed_time(ev1) / max(nb, 4), 1e-4)
+        if sync_ranks:
+            per_step_ms = max_over_ranks(per_step_ms)  # every rank runs the same number of spin-up steps (heat_rk4_dd has a collective inside)
+        spin = int(min(max(SPIN_UP_MS / per_step_ms, 1), 100000))
+        w2.run_steps(spin)
+        w2.run_steps(warmup)
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        l0 = c2.launch_count
+        ev0.record()
+        w2.run_steps(steps)
+        ev1.record()
+        if sync_ranks:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        ms2 = ev0.elapsed_time(ev1)
+        if sync_ranks:
+            ms2 = max_over_ranks(ms2)
+        launches = c2.launch_count - l0
+        units = w2.units(steps) * k_events
+        return w2, c2, nb, ms2, launches, units
+
+    W = WORKLOADS[args.workload]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    timed(args.warmup)
     t_wall0 = time.time()
-    ms, launches = timed(args.steps)
+    w, ctx, n_batches, ms, launches, units_per_rank = device_leg(W, args.arith, args.steps, args.warmup, args.events_per_launch, rank, world, sync_ranks=True)
     # keep the same load up until the clock sampler has seen it (short timed regions are over before the first sample)
     while time.time() - t_wall0 < 0.6:
         w.run_steps(max(args.steps // 4, 16))
@@ -541,28 +605,9 @@ def main():
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    units_per_rank = w.units(args.steps) * args.events_per_launch
     value = units_per_rank * world / (ms * 1e-3)
-    peak, peak_src = peaks()
     launches_per_step = launches / max(args.steps, 1)
-    if W is SchrodingerCFM4:
-        p64 = os.path.join(ROOT, "profiles", "fp64_peaks.json")
-        peak_tf, src = (json.load(open(p64))["dmma_tflops"], "measured by profiles/microbench/peaks.cu (profiles/fp64_peaks.json: dmma_tflops)") \
-            if os.path.exists(p64) else (45.0, "nominal B200 FP64 tensor peak (no measured figure committed)")
-        kernel_ms = ms / max(launches, 1)
-        ach = w.flops_per_unit * (units_per_rank / max(launches, 1)) / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic(W.name),
-                    "peak_source": src, "algorithmic_flops_per_unit": w.flops_per_unit, "taylor_degree": w.m_star, "theta": w.theta,
-                    "kernel_us": kernel_ms * 1e3,
-                    "note": "FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"}
-    # dominant kernel: the step kernel itself (lorenz/vdp: the only launch; heat: 4 stage launches share the step evenly)
-    kernel_ms = ms / max(launches, 1)
-    bytes_per_launch = (W.bytes_per_unit or 0.0) * (units_per_rank / max(launches, 1)) / args.events_per_launch
-    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    if W is not SchrodingerCFM4:
-      roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
-                "peak_source": peak_src, "algorithmic_bytes_per_unit": W.bytes_per_unit, "kernel_us": kernel_ms * 1e3,
-                "note": "achieved = algorithmic bytes per launch / mean launch duration (CUDA events over the timed region, kernels back to back)"}
+    roofline = roofline_of(W, w, units_per_rank, ms, launches, args.events_per_launch, peak, peak_src)
 
     # ---- end to end through the public API with host buffers -----------------------------------------------------------
     w.e2e_setup()
@@ -576,11 +621,8 @@ def main():
         e_units += u
     e1.record()
     barrier()
-    e_ms = e0.elapsed_time(e1)
+    e_ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
-        t = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item())
         u = torch.tensor([e_units], device="cuda", dtype=torch.float64)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)  # the final reduction of the per-rank counters (NCCL over NVLink)
         e_units = float(u.item())
@@ -602,43 +644,36 @@ def main():
         assert (full is None) == (rank != 0) and (full is None or full.shape[0] == N_TRAJ * world)
 
     also = None
-    if rank == 0 and world == 1 and not args.no_also and args.workload == "lorenz_rk4":
-        # secondary figures, short runs: the other arithmetic mode, the fused (FP64-bound) mode and config 3
+    if rank == 0 and world == 1 and not args.no_also:
+        # The other configs and arithmetic modes, short runs, each a full roofline object measured the same way as the headline.
         del w
         also = {}
 
-        def quick(Wc, arith, steps, k_events=1):
-            c2 = vo.Context.on_torch_stream(local, arith=arith)
-            nb = int(min(256, max(2, -(-3 * L2_MB // Wc.state_mb))))
-            w2 = Wc(vo, c2, 0, 1, nb)
-            for s_ in w2.solvers:
-                s_.set_events_per_launch(k_events)
-            w2.run_steps(max(steps // 10, 2 * nb))
-            torch.cuda.synchronize()
-            a0 = w2.attempts() if hasattr(w2, "attempts") else None
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            w2.run_steps(steps)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms2 = ev0.elapsed_time(ev1)
-            units = (w2.attempts() - a0) if a0 is not None else w2.units(steps) * k_events
-            rate = units / (ms2 * 1e-3)
-            out = {"value": rate, "unit": f"{Wc.unit_name}s/s", "arith": arith, "events_per_launch": k_events, "us_per_launch": ms2 / steps * 1e3}
-            if k_events == 1:
-                out["hbm_gbs_algorithmic"] = Wc.bytes_per_unit * rate / 1e9
-                out["frac_of_hbm_peak"] = Wc.bytes_per_unit * rate / 1e9 / peak
-            del w2
-            return out
+        def leg(key, Wc, arith, steps, k_events=1):
+            try:
+                w2, c2, nb, ms2, l2, units = device_leg(Wc, arith, steps, 3, k_events)
+                out = {"value": units / (ms2 * 1e-3), "unit": f"{Wc.unit_name}s/s", "arith": arith, "events_per_launch": k_events, "steps": steps,
+                       "ms_per_step": ms2 / steps, "gpu_launches": int(l2), "batches": nb}
+                if k_events == 1:
+                    out["roofline"] = roofline_of(Wc, w2, units, ms2, l2, 1, peak, peak_src)
+                del w2
+                also[key] = out
+            except Exception as e:  # secondary figures only
+                also[key] = {"error": str(e)}
 
-        try:
-            other = "strict" if args.arith == "fast" else "fast"
-            also[f"lorenz_rk4_{other}"] = quick(LorenzRK4, other, 3200)
-            also["lorenz_rk4_fused16"] = quick(LorenzRK4, args.arith, 320, k_events=16)
-            also["vdp_dopri5_fast"] = quick(VdpDopri5, "fast", 1400)
-            also["vdp_dopri5_strict"] = quick(VdpDopri5, "strict", 1400)
-        except Exception as e:  # secondary figures only
-            also["error"] = str(e)
+        other = "strict" if args.arith == "fast" else "fast"
+        if W is not VdpDopri5:
+            leg("vdp_dopri5_fast", VdpDopri5, "fast", 1400)
+        leg(f"vdp_dopri5_{other}" if W is VdpDopri5 else "vdp_dopri5_strict", VdpDopri5, other if W is VdpDopri5 else "strict", 1400)
+        if W is not LorenzRK4:
+            leg("lorenz_rk4_fast", LorenzRK4, "fast", 3200)
+        leg(f"lorenz_rk4_{other}" if W is LorenzRK4 else "lorenz_rk4_strict", LorenzRK4, other if W is LorenzRK4 else "strict", 3200)
+        leg("lorenz_rk4_fused16", LorenzRK4, "fast", 320, k_events=16)
+        if W not in (HeatRK4, HeatRK4Fused):
+            leg("heat_rk4", HeatRK4, "fast", 40)
+            leg("heat_rk4_fused", HeatRK4Fused, "fast", 100)
+        if W is not SchrodingerCFM4:
+            leg("schrodinger_cfm4", SchrodingerCFM4, "fast", 10)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -654,6 +689,7 @@ def main():
                            if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
+                           "warmup_note": f"every batch touched once, then ~{SPIN_UP_MS:.0f} ms of the same launches and the {args.warmup} warm-up steps, all untimed, before the {args.steps} timed steps",
                            "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of {8 * DD_K} doubles per rank) every {DD_K} steps" if W is HeatRK4DD
                                            else f"trajectory-sharded x{world}, no data-path collective")},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}

@@ -52,6 +52,14 @@ int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out);
 int32_t vo_ctx_destroy(vo_ctx ctx);
 int32_t vo_ctx_sync(vo_ctx ctx);
 void* vo_ctx_stream(vo_ctx ctx);
+/* Consecutive launches of one solver are chained CTA to CTA (a launch starts working on a tile as soon as the previous
+ * launch has released that tile instead of waiting for the whole grid) — across API calls too, which is what makes the
+ * reference's driver loop `while let Ok(_) = solver.step() {}` (src/impls/nalgebra.rs:62) run at the rate of vo_run. The
+ * library knows about everything it enqueues itself. If the CALLER enqueues work on the ctx's stream that reads or writes a
+ * solver's state (a kernel of its own on a borrowed device pointer, a framework op on a wrapped tensor), it calls
+ * vo_ctx_fence afterwards: the next launch of every solver on the ctx then waits for the whole stream like an ordinary
+ * launch. */
+int32_t vo_ctx_fence(vo_ctx ctx);
 /* Message of the most recent failure on this ctx (NULL ctx: last failure of a create call on this thread).
  * Replaces ODEError.msg (src/base/ode.rs:13-30) and the reference's panic messages. */
 const char* vo_last_error(vo_ctx ctx);
@@ -193,6 +201,13 @@ int32_t vo_solver_set_path(vo_solver s, int32_t path);
 /* ODEAdaptiveData.dx_norm (ode.rs:104, written at ode.rs:319 and read by nothing in the crate): 1 (default) keeps the error
  * norm of every trajectory's latest attempt for vo_solver_stats; 0 drops that 8-byte store per attempted trajectory-step. */
 int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on);
+/* The reference sets prev_h = h on every adaptive attempt (update_step_size, ode.rs:202-205) and reads it in one place, the
+ * Chkpt / End branch (checkpoint_update, ode.rs:192-195). The one-event adaptive kernels therefore write prev_h only for a
+ * trajectory whose next event is a checkpoint (8 bytes per attempt less). That is invisible as long as a solver under
+ * per-trajectory control is only ever stepped adaptively; a non-adaptive step() after step_adaptive() could reach a
+ * checkpoint with a prev_h that was never written, so it returns VO_ERR_STATE unless mixed stepping was switched on (1)
+ * before the first adaptive step — the kernels then store prev_h on every attempt like the reference. Default 0. */
+int32_t vo_solver_set_mixed_stepping(vo_solver s, int32_t on);
 
 /* ODESolver::step (ode.rs:249-253) / AdaptiveODESolver::step_adaptive (ode.rs:337-341) applied to every
  * trajectory: ONE state-machine event per trajectory per call. res may be NULL. */

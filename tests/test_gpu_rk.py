@@ -611,3 +611,163 @@ def test_heat_whole_step_kernel_adaptive_and_fast(vo, ctx, oracle):
     with pytest.raises(vo.VecOdeError):
         vo.RK45Solver(vo.Rhs(ctx, "LORENZ63", 3), 0.0, 1.0, vo.Ensemble.from_host(ctx, vo.workloads.lorenz_x0(8)), 0.1).set_fused_step()
     cf.close()
+
+
+# ---- round 2: chains that survive API calls, kernels that must not chain, the bench's kernels against the oracle ----------
+def test_chain_survives_api_calls_bit_exact(vo, ctx, oracle):
+    """The reference's driver loop `while let Ok(_) = solver.step() {}` (src/impls/nalgebra.rs:62): one launch per call. The
+    CTA chain now stays alive from call to call (nothing else is enqueued on the ctx in between), so every launch after the
+    first skips the grid-wide wait. Library calls that touch the state (here an in-place scale by 1.0 of the borrowed
+    ensemble) and vo_ctx_fence break the chain for one launch. Bits must be the oracle's throughout."""
+    n, calls = 20000, 160
+    params = np.tile(vo.workloads.LORENZ_PARAMS, (n, 1))
+    x0 = vo.workloads.lorenz_x0(n)
+    rhs = vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+    s = vo.RK45Solver(rhs, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    other = vo.RK45Solver(rhs, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, x0[::-1].copy()), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    for k in range(calls + 1):  # the first call is the Chkpt at t0
+        st = s.step()
+        assert st.kind == "Ok"
+        other.step()  # a second solver interleaved on the same ctx: its launches touch only its own state
+        if k == 40:
+            vo.LinearCombination.scale(s.current()[1], 1.0)  # library op on the solver's state: chain broken for one launch
+        if k == 80:
+            ctx.fence()
+        if k == 120:
+            ctx.sync()
+    ref = oracle.rk_ensemble("LORENZ63", params, oracle.builtin_tableau(1), 0.0, 1.0e9, x0, 1e-3, n_threads=8, max_calls=calls + 1)
+    assert np.array_equal(s.current()[1].to_host(), ref["x"])
+    ref2 = oracle.rk_ensemble("LORENZ63", params, oracle.builtin_tableau(1), 0.0, 1.0e9, x0[::-1].copy(), 1e-3, n_threads=8, max_calls=calls + 1)
+    assert np.array_equal(other.current()[1].to_host(), ref2["x"])
+
+
+@pytest.mark.parametrize("max_calls", [9, 17, 41, 8 * 30 + 3])
+def test_run_tail_launch_on_another_kernel_is_not_chained(vo, ctx, max_calls):
+    """vo_run fuses 8 events per launch (one-trajectory kernel, 128-trajectory tiles) and ends a budget of 8 m + r calls with
+    a launch of r events; r = 1 selects the two-trajectory kernel (256-trajectory tiles, another grid): that launch must not
+    be chained to its predecessor, whose CTA b owned other trajectories. The stage path (no chaining at all) is the check."""
+    n = 6144
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n)
+    out = []
+    for stage_path in (False, True):
+        rhs = vo.Rhs(ctx, "VDP", 2, [mu])
+        s = vo.RK45Solver(rhs, 0.0, 50.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+        s.with_tolerance(1e-6, 1e-6).set_stage_path(stage_path)
+        s.run(adaptive=True, max_calls=max_calls)
+        s.run(adaptive=True, max_calls=max_calls)  # and again: 8-event launches follow the 1-event one
+        out.append((s.current()[1].to_host(), s.stats()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("accepted", "rejected", "t", "h", "dx_norm"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    assert int(out[0][1]["accepted"].sum() + out[0][1]["rejected"].sum()) == n * (2 * max_calls - 1)  # all but the Chkpt call
+
+
+@pytest.mark.parametrize("tab", ["DOPRI5", "RKF45_REF"])
+def test_strict_one_event_control_kernel_against_oracle(vo, ctx, oracle, tab):
+    """The kernel bench.py times for config 3 — rk_ctl2w_staged_kernel<.., STRICT>, ONE event per launch, N >= 1024 — straight
+    against the oracle: same accepted / rejected counts per trajectory and the state within rtol. (The controller's powf is
+    correctly rounded here and glibc's in the oracle, which rounds differently for about one argument in a thousand, so a
+    step size may differ in its last bit now and then: states are compared to 1e-9, not bitwise.)"""
+    n, rtol, tf = 2048, 1e-6, 4.0
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n)
+    ref = oracle.rk_ensemble("VDP", mu[:, None], oracle.builtin_tableau(oracle.TABLEAU_ID[tab]), 0.0, tf, x0, 1e-3, n_threads=8, adaptive=True, rtol=rtol)
+    rhs = vo.Rhs(ctx, "VDP", 2, [mu])
+    s = vo.RK45Solver(rhs, 0.0, tf, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin(tab)).with_tolerance(rtol, rtol)
+    s.set_events_per_launch(1)
+    l0 = ctx.launch_count
+    st = s.run(adaptive=True)
+    assert st.kind == "Done"
+    stats = s.stats()
+    calls = int((ref["accepted"] + ref["rejected"]).max()) + 2
+    assert ctx.launch_count - l0 >= calls  # one event per launch: at least as many launches as the slowest trajectory has events
+    same = (stats["accepted"] == ref["accepted"]) & (stats["rejected"] == ref["rejected"])
+    print(f"{tab}: per-trajectory counts equal for {same.mean() * 100:.2f} % of {n}; totals gpu {stats['accepted'].sum()}/{stats['rejected'].sum()}"
+          f" oracle {ref['accepted'].sum()}/{ref['rejected'].sum()}")
+    assert same.mean() >= 0.995
+    assert abs(int(stats["accepted"].sum()) - int(ref["accepted"].sum())) <= 4 and abs(int(stats["rejected"].sum()) - int(ref["rejected"].sum())) <= 4
+    x = s.current()[1].to_host()
+    assert np.abs(x[same] - ref["x"][same]).max() <= 1e-9
+    assert np.abs(x - ref["x"]).max() <= 50 * rtol
+
+
+def test_strict_full_config2_bit_exact(vo, ctx, oracle):
+    """Config 2's whole interval t in [0,1] (1000 steps + the remainder step) in strict arithmetic, through one launch per
+    step() call and through vo_run's fused launches: bit-identical to the oracle."""
+    n = 2048
+    x0 = vo.workloads.lorenz_x0(n)
+    params = np.tile(vo.workloads.LORENZ_PARAMS, (n, 1))
+    ref = oracle.rk_ensemble("LORENZ63", params, oracle.builtin_tableau(1), 0.0, 1.0, x0, 1e-3, n_threads=8)
+    rhs = vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+    a = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    calls = 0
+    while a.step().is_ok:
+        calls += 1
+    b = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4"))
+    st = b.run()
+    assert st.counts["Step"] == int(ref["accepted"].sum()) and calls == int(ref["accepted"][0]) + 1
+    assert np.array_equal(a.current()[1].to_host(), ref["x"])
+    assert np.array_equal(b.current()[1].to_host(), ref["x"])
+
+
+def test_shared_then_per_trajectory_parameters_same_kernel(vo, ctx, oracle):
+    """The shared-memory size of a staged kernel depends on how many RHS parameters are per-trajectory arrays. A solver with
+    shared parameters runs first, then one with per-trajectory parameters through the SAME kernel instantiation with a larger
+    tile: the large-shared-memory opt-in and the occupancy must follow (they are cached per (device, kernel, size))."""
+    n = 4096
+    tab = vo.ButcherTableu.builtin("DOPRI5")
+    x0 = vo.workloads.vdp_x0(n)
+    for per_traj in (False, True):
+        mu = vo.workloads.vdp_mu(n) if per_traj else np.full(n, 3.0)
+        rhs = vo.Rhs(ctx, "VDP", 2, [mu if per_traj else 3.0])
+        s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6).set_events_per_launch(1)
+        assert s.run(adaptive=True).kind == "Done"
+        ref = oracle.rk_ensemble("VDP", mu[:, None], oracle.builtin_tableau(2), 0.0, 1.0, x0, 1e-3, n_threads=8, adaptive=True, rtol=1e-6)
+        assert np.abs(s.current()[1].to_host() - ref["x"]).max() <= 1e-9
+    rng = np.random.default_rng(5)
+    lam, y0 = -rng.random((n, 4)) * 2.0, rng.standard_normal((n, 4))
+    for per_traj in (False, True):
+        p = lam if per_traj else np.tile(lam[0], (n, 1))
+        rhs = _make_rhs(vo, ctx, "DIAG_LINEAR", 4, p, per_traj=per_traj)
+        s = vo.RK45Solver(rhs, 0.0, 0.05, vo.Ensemble.from_host(ctx, y0), 1e-3, tableau=vo.ButcherTableu.builtin("RK4")).set_events_per_launch(1)
+        assert s.run().kind == "Done"
+        ref = oracle.rk_ensemble("DIAG_LINEAR", p, oracle.builtin_tableau(1), 0.0, 0.05, y0, 1e-3, n_threads=8)
+        assert np.array_equal(s.current()[1].to_host(), ref["x"])
+
+
+def test_mixed_step_and_step_adaptive(vo, ctx, oracle):
+    """step() after step_adaptive() under per-trajectory control. The one-event adaptive kernels keep prev_h — read only by the
+    Chkpt / End branch (ode.rs:192-195) — up to date only where a checkpoint comes next, so by default the mix is refused;
+    with mixed stepping switched on they store it on every attempt (ode.rs:202-205) and the mix follows the oracle's rule:
+    the step size a checkpoint restores is the one in force BEFORE the last adaptive attempt."""
+    n = 2048
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n)
+    tab = vo.ButcherTableu.builtin("DOPRI5")
+
+    def make():
+        rhs = vo.Rhs(ctx, "VDP", 2, [mu])
+        s = vo.RK45Solver(rhs, 0.0, 0.5, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
+        return s.set_events_per_launch(1).set_t_list([0.0, 0.05, 0.5])
+
+    s = make()
+    for _ in range(6):
+        s.step_adaptive()
+    with pytest.raises(vo.VecOdeError):
+        s.step()
+    s = make().set_mixed_stepping(True)
+    for _ in range(6):
+        s.step_adaptive()
+    t = make().set_mixed_stepping(True)
+    for _ in range(5):
+        t.step_adaptive()
+    h_before_last = t.stats()["h"].copy()
+    # non-adaptive steps up to the checkpoint at 0.05: every trajectory then restores prev_h = the h before its last adaptive attempt
+    passed = 0
+    for _ in range(3000):
+        passed += s.step().counts["Chkpt"]
+        if passed == n:
+            break
+    assert passed == n
+    assert np.array_equal(s.stats()["h"], h_before_last)

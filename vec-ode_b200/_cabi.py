@@ -53,6 +53,7 @@ SIGNATURES = {
     "vo_ctx_create": (_i32, [_i32, _vp, _pvp]),
     "vo_ctx_destroy": (_i32, [_vp]),
     "vo_ctx_sync": (_i32, [_vp]),
+    "vo_ctx_fence": (_i32, [_vp]),
     "vo_ctx_stream": (_vp, [_vp]),
     "vo_last_error": (C.c_char_p, [_vp]),
     "vo_version": (_i32, []),
@@ -102,6 +103,7 @@ SIGNATURES = {
     "vo_solver_set_events_per_launch": (_i32, [_vp, _i32]),
     "vo_solver_set_path": (_i32, [_vp, _i32]),
     "vo_solver_set_record_dx_norm": (_i32, [_vp, _i32]),
+    "vo_solver_set_mixed_stepping": (_i32, [_vp, _i32]),
     "vo_step": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),

@@ -54,6 +54,11 @@ class Context:
     def sync(self):
         check(lib().vo_ctx_sync(self._h), self._h)
 
+    def fence(self):
+        """Tell the library that the caller enqueued work of its own on this context's stream that touches solver state
+        (vo_ctx_fence): the next launch of every solver waits for the whole stream instead of chaining to its predecessor."""
+        check(lib().vo_ctx_fence(self._h), self._h)
+
     @property
     def launch_count(self) -> int:
         return int(lib().vo_ctx_launch_count(self._h))
@@ -364,6 +369,12 @@ class RK45Solver:
     def set_record_dx_norm(self, on: bool = True):
         """Keep ODEAdaptiveData.dx_norm (ode.rs:104) of each trajectory's latest attempt (default) or skip that store."""
         check(lib().vo_solver_set_record_dx_norm(self._h, 1 if on else 0), self.ctx._h)
+        return self
+
+    def set_mixed_stepping(self, on: bool = True):
+        """Allow step() after step_adaptive() under per-trajectory control: the adaptive kernels then store prev_h on every
+        attempt (update_step_size, ode.rs:202-205) instead of only where a checkpoint comes next (vo_solver_set_mixed_stepping)."""
+        check(lib().vo_solver_set_mixed_stepping(self._h, 1 if on else 0), self.ctx._h)
         return self
 
     def set_fused_step(self, on: bool = True):

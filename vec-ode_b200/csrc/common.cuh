@@ -33,6 +33,10 @@ struct vo_ctx_s {
     int arith = VO_ARITH_STRICT;
     int sm_count = 148;
     int64_t launches = 0;
+    // Bumped by every library call that enqueues work on the stream EXCEPT the chained register-resident launches of
+    // solver.cu (and by vo_ctx_fence, for work the caller enqueues on the stream behind the library's back). A solver may
+    // chain its next launch to its previous one only while the epoch has not moved in between (pipe::Chain).
+    uint64_t epoch = 1;
     std::string err;
     // small pinned scratch for result read-back and a device mirror
     void* pinned = nullptr;   // 4 KiB
@@ -99,8 +103,13 @@ static inline int32_t vo_fail(vo_ctx ctx, int32_t code, const std::string& msg) 
     return code;
 }
 
+static inline void vo_touch(vo_ctx ctx) {
+    if (ctx) ctx->epoch++;
+}
+
 #define VO_CUDA(ctx, call)                                                                              \
     do {                                                                                                \
+        vo_touch(ctx);                                                                                  \
         cudaError_t _e = (call);                                                                        \
         if (_e != cudaSuccess)                                                                          \
             return vo_fail((ctx), VO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));     \
@@ -112,7 +121,21 @@ static inline int32_t vo_fail(vo_ctx ctx, int32_t code, const std::string& msg) 
         if (_e != cudaSuccess)                                                                          \
             return vo_fail((ctx), VO_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
         (ctx)->launches++;                                                                              \
+        (ctx)->epoch++;                                                                                 \
     } while (0)
+
+// the chained register-resident launches themselves: they touch only their own solver's state, so they leave the epoch alone
+#define VO_CHECK_LAUNCH_CHAINED(ctx)                                                                    \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return vo_fail((ctx), VO_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+        (ctx)->launches++;                                                                              \
+    } while (0)
+
+// Opt a kernel into more than 48 KB of dynamic shared memory. The attribute is per device and per function, and contexts on
+// several devices may be driven from different host threads, so what has been set is remembered per (device, function).
+cudaError_t vo_ensure_smem_attr(int device, const void* func, size_t bytes);
 
 struct DeviceGuard {
     int prev = -1;

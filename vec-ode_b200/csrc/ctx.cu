@@ -1,10 +1,25 @@
 // ctx.cu — contexts, ensembles (SoA device buffers), tableaux and RHS handles.
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <tuple>
 
 #include "common.cuh"
 
 thread_local std::string g_vo_tls_err;
+
+cudaError_t vo_ensure_smem_attr(int device, const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;  // largest opt-in made so far per (device, function)
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[{device, func}];
+    if (have >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 
 extern "C" {
 
@@ -65,6 +80,12 @@ int32_t vo_ctx_sync(vo_ctx c) {
     if (!c) return VO_ERR_BAD_ARG;
     DeviceGuard g(c->device);
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VO_OK;
+}
+
+int32_t vo_ctx_fence(vo_ctx c) {
+    if (!c) return VO_ERR_BAD_ARG;
+    vo_touch(c);
     return VO_OK;
 }
 

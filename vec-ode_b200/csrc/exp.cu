@@ -96,12 +96,7 @@ int32_t launch_exp(vo_ctx c, const ExpKP& kp, const double* frag, double2* psi, 
                    const CtlArrays& ca, EvSlot* ev) {
     using G = Geo<NDIM, M, TB>;
     auto k = exp_step_kernel<NDIM, M, TB, GenCos>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess)
-            return vo_fail(c, VO_ERR_CUDA, "exp: shared-memory carve-out rejected");
-        configured = true;
-    }
+    if (vo_ensure_smem_attr(c->device, (const void*)k, G::SMEM) != cudaSuccess) return vo_fail(c, VO_ERR_CUDA, "exp: shared-memory carve-out rejected");
     const int64_t tiles = ceil_div(kp.N, TB);
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, c->sm_count);
     k<<<grid, G::THREADS, G::SMEM, c->stream>>>(kp, frag, psi, psi_out, gp, coef_in, ca, ev);

@@ -305,44 +305,38 @@ int32_t launch_small_custom(const SmallLaunch& L, vo_rhs_s* r) {
     RhsParams rp = *L.rp;
     CtlArrays ca = L.ca;
     EvSlot* ev = L.ev;
-    pipe::Chain ch = L.chain;
+    pipe::Chain ch{};
     const int rows = r->d + per_traj_rows(rp, r->np);
-    const bool staged = small_path_is_staged(N), pdl = L.chain.chained != 0;
-    unsigned grid = 0;
+    const bool staged = small_path_is_staged(N);
+    // grid, then the chain decision (same kernel and same grid as this solver's previous launch), then the launch
+    auto go = [&](int k, size_t smem, int tile, void** args) -> int32_t {
+        unsigned grid = 0;
+        int32_t rc2 = custom_grid(c, drv, m, k, N, smem, tile, &grid);
+        if (rc2 != VO_OK) return rc2;
+        ch = L.cst->next((const void*)m->fn[k], grid, staged);
+        return custom_launch(c, drv, m->fn[k], grid, RK_SMALL_THREADS, smem, ch.chained != 0, args);
+    };
     if (L.sl) {
         StepList sl = *L.sl;
         if (staged) {
             void* args[] = {&x, &N, &tb, &rp, &sl, &ch};
-            if (S > 0 && N >= 4 * VO_TILE2) {
-                const size_t smem2 = (size_t)VO_STAGES * rows * VO_TILE2 * sizeof(double);
-                rc = custom_grid(c, drv, m, K_FIXED2_STAGED, N, smem2, VO_TILE2, &grid);
-                return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED2_STAGED], grid, RK_SMALL_THREADS, smem2, pdl, args);
-            }
-            const size_t smem = (size_t)VO_STAGES * rows * VO_TILE * sizeof(double);
-            rc = custom_grid(c, drv, m, K_FIXED_STAGED, N, smem, VO_TILE, &grid);
-            return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED_STAGED], grid, RK_SMALL_THREADS, smem, pdl, args);
+            if (S > 0 && N >= 4 * VO_TILE2) return go(K_FIXED2_STAGED, (size_t)VO_STAGES * rows * VO_TILE2 * sizeof(double), VO_TILE2, args);
+            return go(K_FIXED_STAGED, (size_t)VO_STAGES * rows * VO_TILE * sizeof(double), VO_TILE, args);
         }
         void* args[] = {&x, &N, &tb, &rp, &sl};
-        rc = custom_grid(c, drv, m, K_FIXED, N, 0, VO_TILE, &grid);
-        return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_FIXED], grid, RK_SMALL_THREADS, 0, false, args);
+        return go(K_FIXED, 0, VO_TILE, args);
     }
     CtlShared cs = *L.cs;
     if (staged) {
         const bool common = cs.adaptive && cs.use_err && cs.norm_kind == VO_NORM_L2;
         void* args[] = {&x, &N, &tb, &rp, &ca, &cs, &ev, &ch};
-        if (S > 0 && common && cs.k_events == 1 && N >= 4 * VO_TILE_CTL) {
-            const size_t smem2 = (size_t)VO_STAGES * ((rows + 2) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t));
-            rc = custom_grid(c, drv, m, K_CTL2_STAGED, N, smem2, VO_TILE_CTL, &grid);
-            return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_CTL2_STAGED], grid, RK_SMALL_THREADS, smem2, pdl, args);
-        }
-        const size_t smem = (size_t)VO_STAGES * ((rows + 2) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
-        const int k = common ? K_CTL_STAGED_L2 : K_CTL_STAGED_GEN;
-        rc = custom_grid(c, drv, m, k, N, smem, VO_TILE, &grid);
-        return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[k], grid, RK_SMALL_THREADS, smem, pdl, args);
+        if (S > 0 && common && cs.k_events == 1 && N >= 4 * VO_TILE_CTL)
+            return go(K_CTL2_STAGED, (size_t)VO_STAGES * ((rows + 2) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t)), VO_TILE_CTL, args);
+        return go(common ? K_CTL_STAGED_L2 : K_CTL_STAGED_GEN, (size_t)VO_STAGES * ((rows + 2) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t)),
+                  VO_TILE, args);
     }
     void* args[] = {&x, &N, &tb, &rp, &ca, &cs, &ev};
-    rc = custom_grid(c, drv, m, K_CTL, N, 0, VO_TILE, &grid);
-    return rc != VO_OK ? rc : custom_launch(c, drv, m->fn[K_CTL], grid, RK_SMALL_THREADS, 0, false, args);
+    return go(K_CTL, 0, VO_TILE, args);
 }
 
 // The stage path for a user RHS (vo_rk_try_step, vo_rhs_eval, vo_solver_set_path(1)).

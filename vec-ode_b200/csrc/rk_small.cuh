@@ -47,6 +47,7 @@ struct CtlShared {
     int count_events;  // accumulate vo_step_result counters
     int pw_is_third;   // pw == 1.0/3.0 exactly (the order RK45Solver hard-wires, rk.rs:258-260)
     int record_dx_norm;  // keep ODEAdaptiveData.dx_norm (ode.rs:104) per trajectory
+    int lazy_prev_h;     // two-trajectory control kernels: write prev_h only when its one reader (the Chkpt / End branch) comes next
     double* snap;        // optional [n_tlist][d][N]: the state each trajectory shows at its Chkpt / End events, else NULL
 };
 

@@ -272,8 +272,9 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
                     // of ode.rs:391 holds at t_new — evaluated here exactly as the next call will — so prev_h only has to
                     // reach memory then: 8 bytes per attempt less on the HBM-bound sweep. (A rejected attempt leaves t where
                     // this Step event found it, so its next event is a Step again.)
-                    if (fabs(t_tgt[u] - t_new) <= 2.220446049250313e-16) ca.prev_h[i] = h[u];
+                    if (cs.lazy_prev_h && fabs(t_tgt[u] - t_new) <= 2.220446049250313e-16) ca.prev_h[i] = h[u];
                 }
+                if (!cs.lazy_prev_h) ca.prev_h[i] = h[u];  // update_step_size on every adaptive attempt, ode.rs:202-205
                 ca.h[i] = new_h[u];
                 if (cs.record_dx_norm) ca.dx_norm[i] = dxn[u];
                 const uint32_t nw = (word[u] & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
                 }
             }
             *reinterpret_cast<double2*>(ca.h + i0) = make_double2(new_h[0], new_h[1]);  // update_step_size, ode.rs:202-205
+            if (!cs.lazy_prev_h) *reinterpret_cast<double2*>(ca.prev_h + i0) = make_double2(h[0], h[1]);
             if (cs.record_dx_norm) *reinterpret_cast<double2*>(ca.dx_norm + i0) = make_double2(dxn[0], dxn[1]);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
                 if (nonfin[u]) status |= VO_TRAJ_NONFINITE;
                 if (rej[u] && h[u] <= cs.min_dt) status |= VO_TRAJ_STUCK, ++c_stuck;
                 // prev_h has one reader, the Chkpt / End branch (ode.rs:192-195): it reaches memory only if that is this trajectory's next event
-                if (!rej[u] && fabs(t_tgt[u] - (t[u] + dt[u])) <= 2.220446049250313e-16) ca.prev_h[i0 + u] = h[u];
+                if (cs.lazy_prev_h && !rej[u] && fabs(t_tgt[u] - (t[u] + dt[u])) <= 2.220446049250313e-16) ca.prev_h[i0 + u] = h[u];
                 const uint32_t nw = (word[u] & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
                 if (nw != word[u]) ca.word[i0 + u] = nw;
             }

@@ -1,13 +1,31 @@
 // rk_small_launch.cuh — host-side dispatch of rk_small_kernel over (stage count, arithmetic mode, control mode).
 // Each RHS family is instantiated in its own translation unit (rk_small_<family>.cu) so they compile in parallel.
 #pragma once
+#include <map>
 #include <mutex>
-#include <unordered_map>
+#include <tuple>
 #include <utility>
 
 #include "rk_small2.cuh"
 
 constexpr int RK_SMALL_THREADS = 128;
+
+// Host side of pipe::Chain for one solver: which staged kernel wrote the generation flags last, and with which grid. A launch
+// may skip the grid-wide wait only if the launch before it (of this solver) was the SAME kernel instantiation on the SAME
+// grid — then CTA b of both launches owns the same tiles (the tile -> CTA map is a function of the grid size) — and nothing
+// else has touched the solver's state in between (`live`, kept by solver.cu from the ctx's epoch).
+struct ChainState {
+    uint32_t* flags = nullptr;
+    uint32_t gen = 0;
+    const void* fn = nullptr;
+    unsigned grid = 0;
+    bool live = false;
+    pipe::Chain next(const void* kernel, unsigned g, bool staged) {
+        pipe::Chain ch{flags, ++gen, (staged && live && fn == kernel && grid == g) ? 1 : 0};
+        fn = kernel, grid = g, live = staged;
+        return ch;
+    }
+};
 
 struct SmallLaunch {
     vo_ctx ctx;
@@ -19,21 +37,27 @@ struct SmallLaunch {
     const CtlShared* cs;   // per-trajectory control (sl == nullptr)
     const StepList* sl;    // lock-step fixed steps (cs == nullptr)
     EvSlot* ev;
-    pipe::Chain chain;     // generation flags of the owning solver; chain.chained = this launch may skip the grid-wide wait
+    ChainState* cst;       // chaining state of the owning solver
 };
 
 // The staged kernels need 16-byte aligned SoA rows (N even) and at least one full tile.
 static inline bool small_path_is_staged(int64_t N) { return (N % 2 == 0) && N >= RK_SMALL_THREADS; }
 
 // Persistent grid: every CTA gets the same number of 128-trajectory tiles (no partial last wave), all CTAs resident.
+// The shared-memory size depends on run-time facts (how many RHS parameters are per-trajectory arrays), and both the large
+// shared-memory opt-in and the occupancy are per device, so resident CTAs per SM are cached per (device, kernel, smem).
 template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N, size_t smem, int tile = RK_SMALL_THREADS) {
-    static std::unordered_map<const void*, int> cache;  // resident CTAs per SM of each kernel instantiation
-    static std::mutex mu;                               // contexts may be driven from different host threads
-    std::lock_guard<std::mutex> lock(mu);
-    int& bps = cache[(const void*)kernel];
-    if (bps == 0) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, RK_SMALL_THREADS, smem) != cudaSuccess || bps < 1) bps = 1;
+    static std::map<std::tuple<int, const void*, size_t>, int> cache;
+    static std::mutex mu;  // contexts may be driven from different host threads
+    int bps;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int& slot = cache[std::make_tuple(c->device, (const void*)kernel, smem)];
+        if (slot == 0) {
+            vo_ensure_smem_attr(c->device, (const void*)kernel, smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slot, kernel, RK_SMALL_THREADS, smem) != cudaSuccess || slot < 1) slot = 1;
+        }
+        bps = slot;
     }
     const int64_t tiles = ceil_div(N, tile);
     const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
@@ -43,15 +67,17 @@ template <class K> static unsigned persistent_grid(vo_ctx c, K kernel, int64_t N
 // A CHAINED launch (see pipe::Chain) is submitted with programmatic stream serialisation, so its CTAs are scheduled as
 // the previous grid's CTAs retire and each starts as soon as its own predecessor CTA has published its generation flag.
 // An unchained launch is an ordinary launch: it starts after everything before it in the stream has completed.
+// The kernel's last parameter is the pipe::Chain, which is made here from the solver's ChainState once the grid is known.
 template <class... KArgs, class... Args>
-static void launch_staged(bool pdl, void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
+static void launch_staged(ChainState* cst, void (*kernel)(KArgs...), unsigned grid, size_t smem, cudaStream_t stream, Args&&... args) {
+    const pipe::Chain ch = cst->next((const void*)kernel, grid, true);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(RK_SMALL_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    cfg.attrs = at, cfg.numAttrs = ch.chained ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)..., ch);
 }
 
 static inline int per_traj_rows(const RhsParams& rp, int np) {
@@ -72,16 +98,16 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
 #else
                     auto k2 = rk_fixed2w_staged_kernel<RHS, S, STRICT>;
 #endif
-                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl,
-                                  L.chain);
+                    launch_staged(L.cst, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE2), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl);
                     return;
                 }
             }
             const size_t smem = (size_t)VO_STAGES * (RHS::D + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double);
             auto k = rk_fixed_staged_kernel<RHS, S, STRICT>;
-            launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl, L.chain);
+            launch_staged(L.cst, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, *L.sl);
         } else {
             auto k = rk_fixed_kernel<RHS, S, STRICT>;
+            L.cst->live = false;
             k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, *L.sl);
         }
     } else {
@@ -96,16 +122,16 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
 #else
                     auto k2 = rk_ctl2w_staged_kernel<RHS, S, STRICT>;  // warp-autonomous staging: 15.9 against 16.9 us on the VdP sweep
 #endif
-                    launch_staged(L.chain.chained != 0, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE_CTL), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
-                                  *L.cs, L.ev, L.chain);
+                    launch_staged(L.cst, k2, persistent_grid(L.ctx, k2, L.N, smem2, VO_TILE_CTL), smem2, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca,
+                                  *L.cs, L.ev);
                     return;
                 }
             }
             auto k = common ? rk_ctl_staged_kernel<RHS, S, STRICT, 1> : rk_ctl_staged_kernel<RHS, S, STRICT, 0>;
-            launch_staged(L.chain.chained != 0, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev,
-                          L.chain);
+            launch_staged(L.cst, k, persistent_grid(L.ctx, k, L.N, smem), smem, L.ctx->stream, L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
         } else {
             auto k = rk_ctl_kernel<RHS, S, STRICT>;
+            L.cst->live = false;
             k<<<persistent_grid(L.ctx, k, L.N, 0), RK_SMALL_THREADS, 0, L.ctx->stream>>>(L.x, L.N, *L.tb, *L.rp, L.ca, *L.cs, L.ev);
         }
     }

@@ -67,12 +67,15 @@ struct vo_solver_s {
     int k_events = 0;  // 0 = automatic: 1 per step()/step_many launch, fused inside vo_run (see run_fusion)
     int stage_path = 0;
     int record_dx_norm = 1;
+    int mixed_stepping = 0;     // vo_solver_set_mixed_stepping: step() may follow step_adaptive() on per-trajectory control
+    bool prev_h_stale = false;  // a lazy-prev_h adaptive launch has run: ca.prev_h is only valid where a checkpoint comes next
     double* snap = nullptr;  // [n_tlist][d][N] checkpoint snapshots (vo_solver_enable_snapshots)
-    // CTA-to-CTA chaining of consecutive launches (pipe::Chain): generation flags, one per CTA
-    uint32_t* chain_flags = nullptr;
-    uint32_t chain_gen = 0;
-    int chain_kernel = -1;    // which staged kernel wrote the flags last (0 fixed, 1 control): the tile -> CTA map must match
-    bool chain_live = false;  // the previous launch on the stream that touched this solver's state was ours, inside this API call
+    // CTA-to-CTA chaining of consecutive launches (pipe::Chain): generation flags, one per CTA, and which kernel / grid wrote
+    // them last (rk_small_launch.cuh). The chain survives across API calls: it is alive while the ctx's epoch still has the
+    // value it had right after this solver's previous register-resident launch, i.e. while nothing but such launches (of this
+    // or of other solvers, which touch only their own state) has been enqueued on the ctx since.
+    ChainState cst;
+    uint64_t chain_epoch = 0;
 };
 
 namespace {
@@ -108,6 +111,7 @@ CtlShared make_ctl_shared(const vo_solver_s* s, int adaptive, int k_events) {
     cs.count_events = 1;
     cs.pw_is_third = s->pw == 1.0 / 3.0 ? 1 : 0;
     cs.record_dx_norm = s->record_dx_norm;
+    cs.lazy_prev_h = s->mixed_stepping ? 0 : 1;
     cs.snap = s->snap;
     return cs;
 }
@@ -121,8 +125,10 @@ int uni_step_size(const vo_solver_s* s, double* dt) {
     return VO_EV_STEP;
 }
 void uni_checkpoint(vo_solver_s* s, bool end) {
-    if (s->snap && s->u_tgt < (int)s->t_list.size())  // lock-step: the whole ensemble is at the checkpoint, copy it (stream-ordered)
+    if (s->snap && s->u_tgt < (int)s->t_list.size()) {  // lock-step: the whole ensemble is at the checkpoint, copy it (stream-ordered)
+        vo_touch(s->ctx);                                // the copy is not part of the CTA chain
         cudaMemcpyAsync(s->snap + (size_t)s->u_tgt * s->d * s->n, s->x->p, sizeof(double) * s->d * s->n, cudaMemcpyDeviceToDevice, s->ctx->stream);
+    }
     s->u_tgt += 1, s->u_h = s->u_prev_h;
     if (end) s->u_done = true;
 }
@@ -276,8 +282,10 @@ void ev_sum(const EvSlot* h, EvSlot* out) {
 // read (synchronises the stream), so launches made without a read-back (vo_step_many) are never lost.
 int32_t ev_read(vo_solver_s* s, EvSlot* out) {
     vo_ctx c = s->ctx;
+    const uint64_t epoch = c->epoch;
     VO_CUDA(c, cudaMemcpyAsync(s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS, cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->epoch = epoch;  // reading the counters touches no solver state: the CTA chains stay alive
     EvSlot tot;
     ev_sum(s->ev_host, &tot);
     out->n_step = tot.n_step - s->ev_seen.n_step, out->n_chkpt = tot.n_chkpt - s->ev_seen.n_chkpt;
@@ -297,11 +305,8 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     vo_ctx c = s->ctx;
     const TableauDev tb = make_tableau_dev(s->tab);
     const RhsParams rp = make_rhs_params(s->rhs);
-    const int kernel_id = sl ? 0 : 1;
-    const bool staged = small_path_is_staged(s->n);
-    pipe::Chain ch{s->chain_flags, ++s->chain_gen, (staged && s->chain_live && s->chain_kernel == kernel_id) ? 1 : 0};
-    s->chain_live = staged, s->chain_kernel = kernel_id;
-    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, ch};
+    if (s->chain_epoch != c->epoch) s->cst.live = false;  // something else was enqueued on the ctx since our last launch
+    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, &s->cst};
     int32_t r = VO_ERR_UNSUPPORTED;
     switch (s->rhs->kind) {
         case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
@@ -314,7 +319,8 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
             break;
     }
     if (r != VO_OK) return vo_fail(c, r, "solver: no register-resident kernel for this RHS");
-    VO_CHECK_LAUNCH(c);
+    VO_CHECK_LAUNCH_CHAINED(c);
+    s->chain_epoch = c->epoch;
     return VO_OK;
 }
 
@@ -347,7 +353,6 @@ int32_t small_uniform_events(vo_solver_s* s, int k, vo_step_result* res, int64_t
             if (s->snap) {  // the steps queued so far must have run before the checkpoint copy
                 int32_t r = flush();
                 if (r != VO_OK) return r;
-                s->chain_live = false;  // the copy is not part of the CTA chain
             }
             uni_checkpoint(s, ev == VO_EV_END);
             res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
@@ -386,14 +391,11 @@ int32_t launch_heat_tma_nk(vo_solver_s* s, const HeatArgs& ha_in, double* k_out,
     HeatArgs ha = ha_in;
     ha.nst = (int)std::max<size_t>(2, std::min<size_t>(HT_STAGES_MAX, (size_t)(208 * 1024 / bps) / row_bytes));
     const size_t smem = (size_t)ha.nst * row_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VO_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-        attr_set = true;
-    }
+    VO_CUDA(c, vo_ensure_smem_attr(c->device, (const void*)k, 216 * 1024));
     const int64_t tiles = ceil_div(s->d, HT_TILE);
     const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
     k<<<(unsigned)ceil_div(tiles, iters), HT_THREADS, smem, c->stream>>>(s->x->p, s->d, ha, k_out, nx, xe);
+    VO_CHECK_LAUNCH(c);
     return VO_OK;
 }
 
@@ -450,8 +452,7 @@ template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs
             if (s->n == 1) {
                 if (s->tab.s > 8) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: HEAT1D needs s <= 8");
                 if (s->d % 2 == 0 && s->d >= 4 * HT_TILE) {
-                    int32_t hr = launch_heat_tma<TAIL>(s, sa, kappa, k_out, nx, xe);
-                    if (hr != VO_OK) return hr;
+                    return launch_heat_tma<TAIL>(s, sa, kappa, k_out, nx, xe);  // checks its own launch
                 } else {
                     const int64_t tiles = ceil_div(s->d, HEAT_TILE);
                     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
@@ -511,11 +512,7 @@ template <int S, bool STRICT> int32_t launch_heat_fused_a(vo_solver_s* s, const 
     if (s->d < 4 * HF_WL) return vo_fail(c, VO_ERR_UNSUPPORTED, "whole-step heat kernel: the state is shorter than four warp tiles");
     auto k = heat_fused_step_kernel<S, STRICT>;
     const size_t smem = (size_t)WPB * HF_NST * HF_WL * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        VO_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    VO_CUDA(c, vo_ensure_smem_attr(c->device, (const void*)k, smem));
     const int64_t tiles = ceil_div(s->d, T);                                    // warp tiles
     const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * BPS * WPB);    // per warp, all CTAs resident
     const int64_t warps = ceil_div(tiles, iters);
@@ -642,11 +639,19 @@ int32_t do_events(vo_solver_s* s, bool adaptive, int k, vo_step_result* res, int
         return stage_uniform_event(s, adaptive, res);
     }
     // per-trajectory control
+    if (!adaptive && s->prev_h_stale)
+        return vo_fail(c, VO_ERR_STATE,
+                       "step() after step_adaptive() on per-trajectory control: call vo_solver_set_mixed_stepping(s, 1) before the first step_adaptive() "
+                       "(by default the adaptive kernels keep prev_h, which only a checkpoint reads (ode.rs:192-195), up to date only where a checkpoint comes next)");
     int launches = 0;
     if (small) {
         const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, k);
         int32_t r = launch_small(s, &cs, nullptr);
         if (r != VO_OK) return r;
+        // the dispatch condition of the two-trajectory control kernels (launch_one, rk_small_launch.cuh), the only ones with a lazy prev_h
+        const bool unrolled = s->tab.s == 4 || s->tab.s == 6 || s->tab.s == 7;
+        if (adaptive && cs.lazy_prev_h && cs.use_err && cs.norm_kind == VO_NORM_L2 && k == 1 && unrolled && small_path_is_staged(s->n) && s->n >= 4 * VO_TILE_CTL)
+            s->prev_h_stale = true;
         launches = 1;
         if (calls_done) *calls_done = k;
     } else {
@@ -703,8 +708,8 @@ int32_t vo_rk_create(vo_ctx c, vo_tableau tableau, vo_rhs rhs, double t0, double
     if (r == VO_OK && cudaMalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: counters");
     if (r == VO_OK && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: pinned counters");
     if (r == VO_OK && cudaMalloc(&s->norm_partial, sizeof(double) * PARTIAL_CAP) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: norm scratch");
-    if (r == VO_OK && (cudaMalloc(&s->chain_flags, sizeof(uint32_t) * CHAIN_FLAGS) != cudaSuccess ||
-                       cudaMemsetAsync(s->chain_flags, 0, sizeof(uint32_t) * CHAIN_FLAGS, c->stream) != cudaSuccess))
+    if (r == VO_OK && (cudaMalloc(&s->cst.flags, sizeof(uint32_t) * CHAIN_FLAGS) != cudaSuccess ||
+                       cudaMemsetAsync(s->cst.flags, 0, sizeof(uint32_t) * CHAIN_FLAGS, c->stream) != cudaSuccess))
         r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: chain flags");
     if (r == VO_OK) {
         cudaError_t e = cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, c->stream);
@@ -734,7 +739,7 @@ int32_t vo_solver_destroy(vo_solver s) {
     vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
     for (vo_ens k : s->K) vo_ens_destroy(k);
     free_ctl(s);
-    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->chain_flags), cudaFree(s->snap);
+    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->cst.flags), cudaFree(s->snap);
     cudaFreeHost(s->ev_host);
     delete s;
     return VO_OK;
@@ -826,6 +831,13 @@ int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on) {
     return VO_OK;
 }
 
+int32_t vo_solver_set_mixed_stepping(vo_solver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (on && s->prev_h_stale) return vo_fail(s->ctx, VO_ERR_STATE, "vo_solver_set_mixed_stepping: adaptive steps have already run with the lazy prev_h");
+    s->mixed_stepping = on ? 1 : 0;
+    return VO_OK;
+}
+
 int32_t vo_solver_set_path(vo_solver s, int32_t path) {
     if (!s || path < 0 || path > 2) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_path: path must be 0, 1 or 2");
     if (path == 2 && !(s->rhs->kind == VO_RHS_HEAT1D && s->n == 1 && (s->tab.s == 4 || s->tab.s == 6 || s->tab.s == 7)))
@@ -836,7 +848,6 @@ int32_t vo_solver_set_path(vo_solver s, int32_t path) {
 
 static int32_t step_impl(vo_solver s, bool adaptive, vo_step_result* res) {
     if (!s) return VO_ERR_BAD_ARG;
-    s->chain_live = false;  // anything may have been enqueued on the stream since our last launch
     if (res) std::memset(res, 0, sizeof *res);
     int32_t r = do_events(s, adaptive, 1, res, nullptr, true);
     if (r != VO_OK) return r;
@@ -855,7 +866,6 @@ int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result*
     DeviceGuard g(c->device);
     int64_t calls = 0;
     const bool adp = adaptive != 0;
-    s->chain_live = false;
     int32_t r = prepare_mode(s, adp);
     if (r != VO_OK) return r;
     // lock-step phase: no read-back is needed, the host knows every event
@@ -919,7 +929,6 @@ int32_t vo_step_many(const vo_solver* solvers, int32_t n, int32_t adaptive, int6
         if (!solvers[i] || solvers[i]->ctx != solvers[0]->ctx) return vo_fail(solvers[0] ? solvers[0]->ctx : nullptr, VO_ERR_BAD_ARG, "vo_step_many: solvers must share one ctx");
     DeviceGuard g(solvers[0]->ctx->device);
     for (int i = 0; i < n; ++i) {
-        solvers[i]->chain_live = false;
         int32_t r = prepare_mode(solvers[i], adaptive != 0);
         if (r != VO_OK) return r;
     }
@@ -1000,7 +1009,7 @@ int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
     if (r == VO_OK) r = vo_ens_copy(s->next_x, x0);
     if (r == VO_OK && s->x_err) r = vo_ens_copy(s->x_err, x0);
     if (r != VO_OK) return r;
-    s->uniform = true, s->chain_live = false;
+    s->uniform = true, s->cst.live = false, s->prev_h_stale = false;
     s->u_t = s->t0, s->u_h = s->h_init, s->u_prev_h = s->h_init, s->u_tgt = 0, s->u_done = false;
     s->u_accept = s->u_reject = 0, s->u_dx_norm = 0.0, s->n_done = 0;
     VO_CUDA(s->ctx, cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, s->ctx->stream));
