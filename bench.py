@@ -122,7 +122,7 @@ class LorenzRK4:
     def units(self, k):
         return float(k) * N_TRAJ
 
-    def e2e_setup(self):
+    def e2e_setup(self, group=None):
         import torch
         vo = self.vo
         self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
@@ -132,9 +132,18 @@ class LorenzRK4:
         def make(ctx, lo, hi, x0):
             return vo.RK45Solver(vo.Rhs(ctx, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS)), 0.0, 1.0, x0, 1e-3, tableau=tab)
         # the ensemble in E2E_PARTS chunks, each on its own stream and host thread: copies overlap the integration
-        self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 3, make, parts=E2E_PARTS)
+        self.e_sharded = None
+        if group is not None and group.world > 1:  # N > 1: one ensemble of world x 10^6 trajectories, gathered to rank 0 chunk by chunk
+            self.n_total = N_TRAJ * group.world
+            self.pin_full = torch.empty((self.n_total, 3), dtype=torch.float64).pin_memory() if group.ranks[0] == 0 else None
+            self.e_sharded = vo.pipeline.ShardedChunkedSolve(group, self.n_total, 3, make, parts=E2E_PARTS, arith=self.ctx.arith)
+        else:
+            self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 3, make, parts=E2E_PARTS)
 
     def e2e_step(self):
+        if self.e_sharded is not None:  # H2D of this rank's shard, whole solve, NCCL gather + ONE D2H of the whole ensemble on rank 0
+            sts = self.e_sharded.solve(self.pin_in.numpy(), None if self.pin_full is None else self.pin_full.numpy())
+            return float(sum(st.counts["Step"] for st in sts)), self.pin_in.numel() * 8, 0 if self.pin_full is None else self.pin_full.numel() * 8
         sts = self.e_chunked.solve(self.pin_in.numpy(), self.pin_out.numpy())  # H2D from pinned memory, whole solve, D2H of the result
         return float(sum(st.counts["Step"] for st in sts)), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
@@ -182,7 +191,7 @@ class VdpDopri5:
     def units(self, k):
         return float(k) * N_TRAJ  # every lane is live (tf = 1e9): one attempt per trajectory per sweep
 
-    def e2e_setup(self):
+    def e2e_setup(self, group=None):
         import torch
         vo = self.vo
         self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
@@ -191,9 +200,19 @@ class VdpDopri5:
 
         def make(ctx, lo, hi, x0):
             return vo.RK45Solver(vo.Rhs(ctx, "VDP", 2, [mu[lo:hi].copy()]), 0.0, 20.0, x0, 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
-        self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 2, make, parts=E2E_PARTS)
+        self.e_sharded = None
+        if group is not None and group.world > 1:  # N > 1: one ensemble of world x 10^6 oscillators, gathered to rank 0 chunk by chunk
+            self.n_total = N_TRAJ * group.world
+            self.pin_full = torch.empty((self.n_total, 2), dtype=torch.float64).pin_memory() if group.ranks[0] == 0 else None
+            self.e_sharded = vo.pipeline.ShardedChunkedSolve(group, self.n_total, 2, make, parts=E2E_PARTS, arith=self.ctx.arith)
+        else:
+            self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 2, make, parts=E2E_PARTS)
 
     def e2e_step(self):
+        if self.e_sharded is not None:
+            sts = self.e_sharded.solve(self.pin_in.numpy(), None if self.pin_full is None else self.pin_full.numpy(), adaptive=True)
+            return (float(sum(st.counts["Step"] + st.counts["Reject"] for st in sts)), self.pin_in.numel() * 8,
+                    0 if self.pin_full is None else self.pin_full.numel() * 8)
         sts = self.e_chunked.solve(self.pin_in.numpy(), self.pin_out.numpy(), adaptive=True)
         return float(sum(st.counts["Step"] + st.counts["Reject"] for st in sts)), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
@@ -221,7 +240,7 @@ class HeatRK4:
     def units(self, k):
         return float(k) * self.D
 
-    def e2e_setup(self):
+    def e2e_setup(self, group=None):
         import torch
         self.pin_in = torch.from_numpy(self.x0_host.copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
@@ -247,8 +266,8 @@ class HeatRK4Fused(HeatRK4):
         super().__init__(vo, ctx, rank, world, n_batches)
         self.solvers[0].set_fused_step()
 
-    def e2e_setup(self):
-        super().e2e_setup()
+    def e2e_setup(self, group=None):
+        super().e2e_setup(group)
         self.e_solver.set_fused_step()
 
 
@@ -276,7 +295,7 @@ class HeatRK4DD:
     def units(self, k):
         return float(k) * self.ds.slab.m  # owned points only: the ghost points are redundant work
 
-    def e2e_setup(self):
+    def e2e_setup(self, group=None):
         import torch
         slab = self.ds.slab
         self.pin_in = torch.from_numpy(self.vo.workloads.heat_u0_at(slab.global_index(), self.D)[None, :].copy()).pin_memory()
@@ -344,7 +363,7 @@ class SchrodingerCFM4:
     def units(self, k):
         return float(k) * self.N_SYS
 
-    def e2e_setup(self):
+    def e2e_setup(self, group=None):
         import torch
         self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
@@ -500,6 +519,111 @@ def n_batches_for(W, n_traj):
     return int(min(256, max(2, -(-3 * L2_MB // max(state_mb, 1e-9)))))
 
 
+def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier, max_over_ranks, peak, peak_src):
+    """N > 1 only: (a) STRONG scaling — ONE ensemble of 10^6 trajectories sharded over the ranks, device-resident sweeps and
+    whole solves gathered to rank 0; (b) config 5 sharded — 10^5 Schroedinger systems in all, CFM4, gathered to rank 0."""
+    out = {}
+    n_total = 1_000_000
+    lo, hi = vo.workloads.shard_range(n_total, rank, world)
+    n_loc = hi - lo
+    try:
+        ctx = vo.Context.on_torch_stream(local, arith=args.arith)
+        adaptive = W is VdpDopri5
+        if adaptive:
+            tab, d = vo.ButcherTableu.builtin("DOPRI5"), 2
+            mu = vo.workloads.vdp_mu(n_total, n_loc, lo)
+            x0_host = vo.workloads.vdp_x0(n_loc)
+            mk_rhs = lambda c, a, b: vo.Rhs(c, "VDP", 2, [mu[a:b].copy()])
+            mk = lambda c, rhs, x0, tf: vo.RK45Solver(rhs, 0.0, tf, x0, 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
+            tf = 20.0
+        else:
+            tab, d = vo.ButcherTableu.builtin("RK4"), 3
+            x0_host = vo.workloads.lorenz_x0(n_loc, first=lo)
+            mk_rhs = lambda c, a, b: vo.Rhs(c, "LORENZ63", 3, list(vo.workloads.LORENZ_PARAMS))
+            mk = lambda c, rhs, x0, tf: vo.RK45Solver(rhs, 0.0, tf, x0, 1e-3, tableau=tab)
+            tf = 1.0
+        # device-resident sweeps: enough batches of this rank's shard to exceed the L2
+        nb = int(min(256, max(2, -(-3 * L2_MB // max(W.state_mb * n_loc / 1.0e6, 1e-9)))))
+        rhs = mk_rhs(ctx, 0, n_loc)
+        x0 = vo.Ensemble.from_host(ctx, x0_host)
+        solvers = [mk(ctx, rhs, x0, 1.0e9) for _ in range(nb)]
+        vo.step_many(solvers, adaptive, 1 + max(1, int(40.0e-3 / (nb * 4.0e-6))))  # Chkpt + ~40 ms of spin-up
+        steps = 2000
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        vo.step_many(solvers, adaptive, steps // nb)
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        done = (steps // nb) * nb
+        out["strong_scaling"] = {"what": f"ONE ensemble of {n_total} trajectories sharded over {world} GPUs ({n_loc} per GPU), device-resident sweeps, {nb} batches per GPU",
+                                 "value": done * float(n_total) / (ms * 1e-3), "unit": f"{W.unit_name}s/s", "ms_per_step": ms / done, "steps": done, "scaling": "strong"}
+        del solvers
+        # whole solves of the one ensemble through the sharded pipeline, gathered to rank 0
+        pin_in = torch.from_numpy(x0_host.copy()).pin_memory()
+        pin_full = torch.empty((n_total, d), dtype=torch.float64).pin_memory() if rank == 0 else None
+
+        def make(c, a, b, x0c):
+            return mk(c, mk_rhs(c, a, b), x0c, tf)
+        sh = vo.pipeline.ShardedChunkedSolve(group, n_total, d, make, parts=E2E_PARTS, arith=args.arith)
+        full = None if pin_full is None else pin_full.numpy()
+        sh.solve(pin_in.numpy(), full, adaptive=adaptive)
+        barrier()
+        g0 = time.perf_counter()
+        units = 0.0
+        for _ in range(3):
+            sts = sh.solve(pin_in.numpy(), full, adaptive=adaptive)
+            units += float(sum(st.counts["Step"] + st.counts["Reject"] for st in sts))
+        barrier()
+        e_ms = max_over_ranks((time.perf_counter() - g0) * 1e3)
+        u = torch.tensor([units], device="cuda", dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        out["strong_scaling"]["e2e"] = {"value": float(u.item()) / (e_ms * 1e-3), "unit": f"{W.unit_name}s/s", "ms_per_solve": e_ms / 3,
+                                        "what": "whole solves of the one ensemble: shard upload, integrate, chunk-wise NCCL gather + device-to-host copy on rank 0"}
+    except Exception as e:
+        out["strong_scaling_error"] = repr(e)
+    try:
+        n_sys = SchrodingerCFM4.N_SYS
+        lo, hi = vo.workloads.shard_range(n_sys, rank, world)
+        ctx5 = group.ctxs[0]
+        H0, H1 = vo.workloads.schrodinger_system(64)
+        sp = vo.DenseBasisSplit(ctx5, np.stack([-1j * H0, -1j * H1]))
+        gp = vo.workloads.schrodinger_drive(n_sys, hi - lo, lo)
+        psi0 = np.zeros((hi - lo, 64), dtype=np.complex128)
+        psi0[:, 0] = 1.0
+        solver = vo.ExpCFMSolver(sp, gp, 0.0, 10.0, psi0, 0.1, group_similar=GROUP_SIMILAR).no_adaptive()
+        pin_full = torch.empty((n_sys, 128), dtype=torch.float64).pin_memory() if rank == 0 else None
+        rows = [vo.workloads.shard_range(n_sys, r, world) for r in range(world)]
+
+        def solve_once():
+            solver.reset(psi0)
+            st = solver.run()
+            state = solver.state_ensemble()  # [n_loc][64] complex in the caller's order, as an ensemble of 128-component rows (AoS = SoA for the copy)
+            group.gather_placed([state], [(b - a) * 128 for a, b in rows], [a * 128 for a, _ in rows], None if pin_full is None else pin_full.numpy().reshape(1, -1),
+                                root=0, layout="soa")
+            group.sync()
+            return float(st.counts["Step"])
+        solve_once()
+        barrier()
+        g0 = time.perf_counter()
+        units = sum(solve_once() for _ in range(2))
+        barrier()
+        e_ms = max_over_ranks((time.perf_counter() - g0) * 1e3)
+        u = torch.tensor([units], device="cuda", dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        ok = None
+        if rank == 0:
+            nrm = np.linalg.norm(pin_full.numpy().view(np.complex128), axis=1)
+            ok = bool(np.all(np.abs(nrm - 1.0) < 1e-10))
+        out["schrodinger_cfm4_sharded"] = {"what": f"config 5: {n_sys} systems in all, CFM4, 100 steps, sharded over {world} GPUs, final states gathered to rank 0 (NCCL + one D2H)",
+                                           "value": float(u.item()) / (e_ms * 1e-3), "unit": "trajectory-steps/s", "ms_per_solve": e_ms / 2, "scaling": "strong",
+                                           "unitarity_ok": ok}
+    except Exception as e:
+        out["schrodinger_cfm4_sharded_error"] = repr(e)
+    return out
+
+
 SPIN_UP_MS = 40.0  # untimed load right before the timed region, whatever --warmup says: clocks and caches in their steady state
 
 
@@ -610,7 +734,12 @@ def main():
     roofline = roofline_of(W, w, units_per_rank, ms, launches, args.events_per_launch, peak, peak_src)
 
     # ---- end to end through the public API with host buffers -----------------------------------------------------------
-    w.e2e_setup()
+    # N > 1: the ranks form a vo_group (NCCL inside the library; torch.distributed only carries the 128-byte id) and every
+    # e2e step ends with the final gather of the whole ensemble into rank 0's pinned host array, inside the timed region.
+    group = None
+    if world > 1:
+        group = vo.group.Group.from_torch_distributed(vo.Context(local, arith=args.arith))
+    w.e2e_setup(group)
     w.e2e_step()  # warm
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -624,24 +753,36 @@ def main():
     e_ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
         u = torch.tensor([e_units], device="cuda", dtype=torch.float64)
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)  # the final reduction of the per-rank counters (NCCL over NVLink)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
         e_units = float(u.item())
+    sharded = world > 1 and getattr(w, "e_sharded", None) is not None
     e2e = {"value": e_units / (e_ms * 1e-3), "unit": f"{W.unit_name}s/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
            "what": "per e2e step: upload x0 from pinned host memory, one whole solve of the config through RK45Solver.run(), download the final state"
                    + (f"; the ensemble in {E2E_PARTS} chunks on their own streams and host threads (pipeline.ChunkedSolve), copies overlapping the integration"
-                      if W in (LorenzRK4, VdpDopri5) and E2E_PARTS > 1 else "")}
+                      if W in (LorenzRK4, VdpDopri5) and E2E_PARTS > 1 else "")
+                   + (f"; ONE ensemble of {world} x {N_TRAJ} trajectories: every rank uploads its shard, and each finished chunk is gathered to rank 0 with "
+                      "vo_group_gather_placed (NCCL over NVLink from device state, then one device-to-host copy into rank 0's pinned array of the WHOLE "
+                      "ensemble) inside the timed region; h2d bytes are per rank, d2h bytes are rank 0's" if sharded else "")}
 
     gather_ms = None
-    if world > 1 and W in (LorenzRK4, VdpDopri5):
-        # the final gather of the sharded ensemble (NCCL all_gather over NVLink), once per solve, outside the timed steps
-        vo.group.gather_states(w.pin_out.numpy()[:1024], 1024 * world, device=torch.device("cuda", local), root=0)  # NCCL sets up its send/recv channels on first use
+    if sharded:
+        # the final gather on its own, for reference: the rank's whole shard in one piece -> rank 0's pinned host array
+        shard_ens = vo.Ensemble.from_host(group.ctxs[0], w.x0_host)
+        full = w.pin_full.numpy() if rank == 0 else None
+        group.gather([shard_ens], N_TRAJ * world, root=0, out=full)  # NCCL sets up its channels on first use
         barrier()
         g0 = time.perf_counter()
-        full = vo.group.gather_states(w.pin_out.numpy(), N_TRAJ * world, device=torch.device("cuda", local), root=0)
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - g0) * 1e3
-        assert (full is None) == (rank != 0) and (full is None or full.shape[0] == N_TRAJ * world)
+        for _ in range(3):
+            group.gather([shard_ens], N_TRAJ * world, root=0, out=full)
+        barrier()
+        gather_ms = max_over_ranks((time.perf_counter() - g0) * 1e3 / 3)
+        if rank == 0:
+            assert np.array_equal(full[-N_TRAJ:], vo.workloads.lorenz_x0(N_TRAJ, first=(world - 1) * N_TRAJ) if W is LorenzRK4 else vo.workloads.vdp_x0(N_TRAJ))
+
+    multi = None
+    if world > 1 and not args.no_also and W in (LorenzRK4, VdpDopri5):
+        multi = multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier, max_over_ranks, peak, peak_src)
 
     also = None
     if rank == 0 and world == 1 and not args.no_also:
@@ -695,6 +836,10 @@ def main():
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
+            line["final_gather_note"] = (f"vo_group_gather of the whole ensemble ({world} x {W.state_mb if W is LorenzRK4 else 16} MB of state) on its own: NCCL into rank 0's "
+                                         "device buffer + one device-to-host copy into pinned memory; inside e2e the same transfer runs chunk by chunk")
+        if multi:
+            line["multi_gpu"] = multi
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if also:

@@ -36,6 +36,7 @@ extern "C" {
 #define VO_ERR_NOT_ADAPTIVE (-5) /* step_adaptive on a solver without x_err (ode.rs:312, rk.rs:317-319) */
 #define VO_ERR_UNSUPPORTED (-6)
 #define VO_ERR_STATE (-7)
+#define VO_ERR_NCCL (-8)
 
 typedef struct vo_ctx_s* vo_ctx;
 typedef struct vo_ens_s* vo_ens;
@@ -44,6 +45,7 @@ typedef struct vo_rhs_s* vo_rhs;
 typedef struct vo_solver_s* vo_solver;
 typedef struct vo_split_s* vo_split;
 typedef struct vo_expsolver_s* vo_expsolver;
+typedef struct vo_group_s* vo_group;
 
 /* ---- context ---------------------------------------------------------------------------------- */
 /* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
@@ -60,6 +62,8 @@ void* vo_ctx_stream(vo_ctx ctx);
  * vo_ctx_fence afterwards: the next launch of every solver on the ctx then waits for the whole stream like an ordinary
  * launch. */
 int32_t vo_ctx_fence(vo_ctx ctx);
+/* Order everything enqueued on `waiter` from now on after everything enqueued on `other` so far (device-side, no host wait). */
+int32_t vo_ctx_wait_for(vo_ctx waiter, vo_ctx other);
 /* Message of the most recent failure on this ctx (NULL ctx: last failure of a create call on this thread).
  * Replaces ODEError.msg (src/base/ode.rs:13-30) and the reference's panic messages. */
 const char* vo_last_error(vo_ctx ctx);
@@ -294,10 +298,67 @@ int32_t vo_exp_step(vo_expsolver s, vo_step_result* res);
 int32_t vo_exp_step_adaptive(vo_expsolver s, vo_step_result* res);
 int32_t vo_exp_run(vo_expsolver s, int32_t adaptive, int64_t max_calls, vo_step_result* res);
 int32_t vo_exp_current(vo_expsolver s, double* t_min, double* t_max, double* psi_host /* nullable */);
+/* The states in the caller's order as a non-owning device view (one row of 2 * n * N doubles, [N][n] complex interleaved;
+ * destroy it with vo_ens_destroy; valid until the next step) — what vo_group_gather_placed takes for a sharded ensemble. */
+int32_t vo_exp_current_device(vo_expsolver s, vo_ens* out);
 int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm);
 /* Back to (t0, psi0, h): psi0_host NULL re-uses the state given at creation, otherwise uploads a new one. */
 int32_t vo_exp_reset(vo_expsolver s, const double* psi0_host);
 void* vo_exp_state_device_ptr(vo_expsolver s);
+
+/* ---- multi-GPU: one ensemble sharded by trajectory over the GPUs of one box ------------------------------------------ */
+/* The reference has no parallelism of any kind; what replaces "one solver object per trajectory, run them in any order" is
+ * rank r of G integrating the contiguous range vo_group_shard_range(N, r, G) of the ensemble. Trajectories are independent
+ * (nothing in rk_step, handle_step_adaptive, cfm_general or magnus_42 couples them), so stepping needs NO collective; NCCL
+ * over NVLink / NVSwitch appears only at the ends of a solve: the gather of the final states, the reduction of the counters
+ * (and one scalar per attempt for a domain-decomposed adaptive state, vo_group_allreduce).
+ * Two ways to form a group:
+ *   one process per GPU   rank 0 calls vo_group_unique_id, the host program ships the VO_GROUP_ID_BYTES to the other ranks,
+ *                         every rank calls vo_group_create_rank(its ctx, id, rank, world) — the per-member arrays below then
+ *                         have ONE entry;
+ *   one process, G GPUs   vo_group_create_local(ctxs, G): one ctx per device, ncclCommInitAll; the per-member arrays have G
+ *                         entries (entry i belongs to ctxs[i] = rank i) and one host thread drives all GPUs. */
+#define VO_GROUP_ID_BYTES 128
+int32_t vo_group_unique_id(void* id_out /* VO_GROUP_ID_BYTES */);
+int32_t vo_group_create_rank(vo_ctx ctx, const void* id, int32_t rank, int32_t world, vo_group* out);
+int32_t vo_group_create_local(const vo_ctx* ctxs, int32_t n, vo_group* out);
+int32_t vo_group_destroy(vo_group g);
+int32_t vo_group_world(vo_group g);
+int32_t vo_group_local_members(vo_group g);
+int32_t vo_group_member_rank(vo_group g, int32_t member);
+const char* vo_group_last_error(vo_group g);
+int32_t vo_group_nccl_version(void);
+/* contiguous ceil(N/G) ranges */
+int32_t vo_group_shard_range(int64_t n_total, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+/* Upload the whole initial ensemble ([n_total][d] or [d][n_total] host array on the root) once and hand every member its
+ * shard over NVLink: local_out[i] is member i's ensemble of shape (d, shard length). Synchronous on return. */
+int32_t vo_group_scatter(vo_group g, const double* host_in, int32_t layout, int64_t d, int64_t n_total, int32_t root, const vo_ens* local_out);
+/* `while let Ok(_) = solver.step() {}` on every local shard (vo_run), then vo_group_reduce_stats if out != NULL. */
+typedef struct vo_group_stats {
+    int64_t accepted, rejected;                 /* sums over the whole ensemble */
+    int64_t n_traj, n_done, n_nonfinite, n_stuck; /* trajectories in all, and with each VO_TRAJ_* bit set */
+    double t_min, t_max;
+} vo_group_stats;
+int32_t vo_group_run(vo_group g, const vo_solver* local, int32_t adaptive, int64_t max_calls, vo_group_stats* out);
+/* The final gather: local[i] is member i's shard (for a solver: the ensemble vo_current returns). The root receives the whole
+ * ensemble — as a device ensemble [d][n_total] (vo_group_gather_device: a view into the group's gather buffer, valid until the
+ * next gather, destroy it with vo_ens_destroy; NULL on the other ranks), or in host_out through ONE device-to-host copy
+ * (vo_group_gather: synchronous on the root; pinned host memory makes the copy run at PCIe speed). Enqueued on each member's
+ * stream, i.e. after the solve. */
+int32_t vo_group_gather_device(vo_group g, const vo_ens* local, int64_t n_total, int32_t root, vo_ens* out);
+int32_t vo_group_gather(vo_group g, const vo_ens* local, int64_t n_total, int32_t root, double* host_out, int32_t layout);
+/* The general, asynchronous form: rank r holds rows[r] trajectories (any sizes; local[i]->n == rows[rank of member i]; the
+ * ensembles may live on other contexts of the member's device — order the group's ctx after them with vo_ctx_wait_for) and
+ * the root places them at row row_off[r] of a host array of host_n trajectories. One message per shard, one device-to-host
+ * copy per shard straight into its place, nothing synchronises: a pipelined solve gathers its chunks one by one while later
+ * chunks still integrate. vo_group_sync waits for everything enqueued on the group's streams. */
+int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, const int64_t* rows /* [world] */, const int64_t* row_off /* [world] */,
+                               double* host_out, int32_t layout, int64_t host_n);
+int32_t vo_group_sync(vo_group g);
+/* all-reduce of the per-shard counters; every rank receives the totals */
+int32_t vo_group_reduce_stats(vo_group g, const vo_solver* local, vo_group_stats* out);
+/* in-place all-reduce of n <= 32 doubles per member, host values in and out ([members][n]); op 0 sum, 1 max, 2 min */
+int32_t vo_group_allreduce(vo_group g, double* host_inout, int32_t n, int32_t op);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,8 @@ def _worker(rank, world, port, n_total, out_dir):
     full = vo.group.gather_states(r["x"], n_total)
     rooted = vo.group.gather_states(r["x"], n_total, root=1)  # only rank 1 receives the ensemble
     assert (rooted is None) == (rank != 1) and (rooted is None or np.array_equal(rooted, full))
-    red = vo.group.reduce_stats(dict(accepted=r["accepted"], rejected=r["rejected"], t=r["t"], status=np.ones(hi - lo, np.int32)))
+    # rank 0 reports DONE|STUCK (5), rank 1 DONE|NONFINITE (3): the reduction must return their union (7), not the maximum
+    red = vo.group.reduce_stats(dict(accepted=r["accepted"], rejected=r["rejected"], t=r["t"], status=np.full(hi - lo, 5 if rank == 0 else 3, np.int32)))
     if rank == 0:
         np.save(os.path.join(out_dir, "full.npy"), full)
         np.save(os.path.join(out_dir, "red.npy"), np.array([red["accepted"], red["rejected"], red["t_min"], red["t_max"], red["status"]]))
@@ -42,7 +43,7 @@ def test_two_rank_shard_gather_reduce(tmp_path, oracle, vo, n_total):
     full, red = np.load(tmp_path / "full.npy"), np.load(tmp_path / "red.npy")
     assert full.shape == (n_total, 2) and np.array_equal(full, ref["x"])
     assert int(red[0]) == int(ref["accepted"].sum()) and int(red[1]) == int(ref["rejected"].sum())
-    assert red[2] == ref["t"].min() and red[3] == ref["t"].max() and int(red[4]) == 1
+    assert red[2] == ref["t"].min() and red[3] == ref["t"].max() and int(red[4]) == 7
 
 
 def test_gather_complex_states_single_process(vo):

@@ -15,7 +15,8 @@ SO_PATH = os.environ.get("VECODE_B200_SO") or os.path.join(_HERE, "libvecode_b20
 # status codes (include/vecode_b200.h)
 VO_OK = 0
 VO_ERR_BAD_ARG, VO_ERR_SHAPE, VO_ERR_CUDA, VO_ERR_ALLOC = -1, -2, -3, -4
-VO_ERR_NOT_ADAPTIVE, VO_ERR_UNSUPPORTED, VO_ERR_STATE = -5, -6, -7
+VO_ERR_NOT_ADAPTIVE, VO_ERR_UNSUPPORTED, VO_ERR_STATE, VO_ERR_NCCL = -5, -6, -7, -8
+GROUP_ID_BYTES = 128
 ARITH_STRICT, ARITH_FAST = 0, 1
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 NORM = {"L2": 0, "LINF": 1, "L1": 2, "HYPOT": 3}
@@ -26,7 +27,7 @@ EV_STEP, EV_CHKPT, EV_REJECT, EV_END, EV_ERR = range(5)
 STATE_OK, STATE_DONE, STATE_ERR = range(3)
 TRAJ_DONE, TRAJ_NONFINITE, TRAJ_STUCK = 1, 2, 4
 
-_ERR_NAMES = {-1: "BAD_ARG", -2: "SHAPE", -3: "CUDA", -4: "ALLOC", -5: "NOT_ADAPTIVE", -6: "UNSUPPORTED", -7: "STATE"}
+_ERR_NAMES = {-1: "BAD_ARG", -2: "SHAPE", -3: "CUDA", -4: "ALLOC", -5: "NOT_ADAPTIVE", -6: "UNSUPPORTED", -7: "STATE", -8: "NCCL"}
 
 
 class VecOdeError(RuntimeError):
@@ -45,6 +46,14 @@ class StepResult(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GroupStats(C.Structure):
+    _fields_ = [("accepted", C.c_int64), ("rejected", C.c_int64), ("n_traj", C.c_int64), ("n_done", C.c_int64),
+                ("n_nonfinite", C.c_int64), ("n_stuck", C.c_int64), ("t_min", C.c_double), ("t_max", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 _pvp = C.POINTER(C.c_void_p)
 
@@ -54,6 +63,7 @@ SIGNATURES = {
     "vo_ctx_destroy": (_i32, [_vp]),
     "vo_ctx_sync": (_i32, [_vp]),
     "vo_ctx_fence": (_i32, [_vp]),
+    "vo_ctx_wait_for": (_i32, [_vp, _vp]),
     "vo_ctx_stream": (_vp, [_vp]),
     "vo_last_error": (C.c_char_p, [_vp]),
     "vo_version": (_i32, []),
@@ -135,9 +145,28 @@ SIGNATURES = {
     "vo_exp_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_exp_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
     "vo_exp_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _vp]),
+    "vo_exp_current_device": (_i32, [_vp, _pvp]),
     "vo_exp_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "vo_exp_reset": (_i32, [_vp, _vp]),
     "vo_exp_state_device_ptr": (_vp, [_vp]),
+    "vo_group_unique_id": (_i32, [_vp]),
+    "vo_group_create_rank": (_i32, [_vp, _vp, _i32, _i32, _pvp]),
+    "vo_group_create_local": (_i32, [_pvp, _i32, _pvp]),
+    "vo_group_destroy": (_i32, [_vp]),
+    "vo_group_world": (_i32, [_vp]),
+    "vo_group_local_members": (_i32, [_vp]),
+    "vo_group_member_rank": (_i32, [_vp, _i32]),
+    "vo_group_last_error": (C.c_char_p, [_vp]),
+    "vo_group_nccl_version": (_i32, []),
+    "vo_group_shard_range": (_i32, [_i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "vo_group_scatter": (_i32, [_vp, _vp, _i32, _i64, _i64, _i32, _pvp]),
+    "vo_group_run": (_i32, [_vp, _pvp, _i32, _i64, C.POINTER(GroupStats)]),
+    "vo_group_gather_device": (_i32, [_vp, _pvp, _i64, _i32, _pvp]),
+    "vo_group_gather": (_i32, [_vp, _pvp, _i64, _i32, _vp, _i32]),
+    "vo_group_gather_placed": (_i32, [_vp, _pvp, _i32, _vp, _vp, _vp, _i32, _i64]),
+    "vo_group_sync": (_i32, [_vp]),
+    "vo_group_reduce_stats": (_i32, [_vp, _pvp, C.POINTER(GroupStats)]),
+    "vo_group_allreduce": (_i32, [_vp, _vp, _i32, _i32]),
 }
 
 _lib = None

@@ -59,6 +59,10 @@ class Context:
         (vo_ctx_fence): the next launch of every solver waits for the whole stream instead of chaining to its predecessor."""
         check(lib().vo_ctx_fence(self._h), self._h)
 
+    def wait_for(self, other: "Context"):
+        """Order this context's stream after everything enqueued so far on `other` (vo_ctx_wait_for; no host wait)."""
+        check(lib().vo_ctx_wait_for(self._h, other._h), self._h)
+
     @property
     def launch_count(self) -> int:
         return int(lib().vo_ctx_launch_count(self._h))

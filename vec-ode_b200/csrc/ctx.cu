@@ -83,6 +83,29 @@ int32_t vo_ctx_sync(vo_ctx c) {
     return VO_OK;
 }
 
+// Stream-order `waiter` after everything enqueued so far on `other` (an event recorded on one stream, waited for on the other;
+// no host synchronisation). Both contexts may sit on different devices.
+int32_t vo_ctx_wait_for(vo_ctx waiter, vo_ctx other) {
+    if (!waiter || !other) return VO_ERR_BAD_ARG;
+    if (waiter == other || waiter->stream == other->stream) return VO_OK;
+    cudaEvent_t ev = nullptr;
+    {
+        DeviceGuard g(other->device);
+        VO_CUDA(other, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, other->stream);
+        if (e != cudaSuccess) {
+            cudaEventDestroy(ev);
+            return vo_fail(other, VO_ERR_CUDA, std::string("cudaEventRecord: ") + cudaGetErrorString(e));
+        }
+    }
+    DeviceGuard g(waiter->device);
+    cudaError_t e = cudaStreamWaitEvent(waiter->stream, ev, 0);
+    cudaEventDestroy(ev);  // released once the recorded work has completed
+    vo_touch(waiter);
+    if (e != cudaSuccess) return vo_fail(waiter, VO_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+    return VO_OK;
+}
+
 int32_t vo_ctx_fence(vo_ctx c) {
     if (!c) return VO_ERR_BAD_ARG;
     vo_touch(c);

@@ -461,6 +461,22 @@ int32_t vo_exp_current(vo_expsolver s, double* t_min, double* t_max, double* psi
     return VO_OK;
 }
 
+// The states in the caller's order as a device-side view for device-side consumers (vo_group_gather_*): one row of
+// 2 * n * N doubles ([N][n] complex, interleaved), valid until the next step. With vo_exp_set_order in force the view is the
+// solver's staging buffer after the device-side reordering, else the state itself.
+int32_t vo_exp_current_device(vo_expsolver s, vo_ens* out) {
+    if (!s || !out) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    const double2* src = s->psi;
+    if (s->perm) {
+        exp_reorder_kernel<<<(unsigned)ceil_div(s->N, 8), 256, 0, c->stream>>>(s->psi, s->stage, s->perm, s->sp->n, s->N, 1);
+        VO_CHECK_LAUNCH(c);
+        src = s->stage;
+    }
+    return vo_ens_wrap(c, const_cast<double2*>(src), 1, 2 * (int64_t)s->sp->n * s->N, out);
+}
+
 int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, double* t, double* h, double* dx_norm) {
     if (!s) return VO_ERR_BAD_ARG;
     vo_ctx c = s->ctx;

@@ -256,6 +256,41 @@ void free_ctl(vo_solver_s* s) {
     s->ca = CtlArrays{};
 }
 
+// Per-shard totals for vo_group_reduce_stats: sums[6] = accepted, rejected, trajectories, done, non-finite, stuck;
+// mm[2] = max t, max (-t). One block-reduced pass over the controller arrays, a handful of atomics per block.
+__global__ void ctl_stats_kernel(CtlArrays ca, int64_t N, unsigned long long* __restrict__ sums, double* __restrict__ mm) {
+    unsigned long long acc = 0, rej = 0, done = 0, nonfin = 0, stuck = 0;
+    double tmax = -1.0e308, tneg = -1.0e308;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        acc += ca.n_accept[i], rej += ca.n_reject[i];
+        const uint32_t st = ca.word[i] >> VO_WORD_STATUS_SHIFT;
+        done += (st & VO_TRAJ_DONE) ? 1 : 0, nonfin += (st & VO_TRAJ_NONFINITE) ? 1 : 0, stuck += (st & VO_TRAJ_STUCK) ? 1 : 0;
+        const double t = ca.t[i];
+        tmax = fmax(tmax, t), tneg = fmax(tneg, -t);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o), rej += __shfl_xor_sync(0xffffffffu, rej, o), done += __shfl_xor_sync(0xffffffffu, done, o);
+        nonfin += __shfl_xor_sync(0xffffffffu, nonfin, o), stuck += __shfl_xor_sync(0xffffffffu, stuck, o);
+        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o)), tneg = fmax(tneg, __shfl_xor_sync(0xffffffffu, tneg, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[0], acc), atomicAdd(&sums[1], rej), atomicAdd(&sums[3], done), atomicAdd(&sums[4], nonfin), atomicAdd(&sums[5], stuck);
+        // order-preserving integer image of a double, so that atomicMax on the bits is max on the values
+        auto key = [](double v) {
+            const long long b = __double_as_longlong(v);
+            return b >= 0 ? b : (long long)(0x8000000000000000ull - (unsigned long long)b);
+        };
+        atomicMax(reinterpret_cast<long long*>(&mm[0]), key(tmax)), atomicMax(reinterpret_cast<long long*>(&mm[1]), key(tneg));
+    }
+}
+__global__ void ctl_stats_finish_kernel(unsigned long long* sums, double* mm, unsigned long long n) {
+    sums[2] = n;
+    for (int q = 0; q < 2; ++q) {
+        const long long k = *reinterpret_cast<long long*>(&mm[q]);
+        mm[q] = __longlong_as_double(k >= 0 ? k : (long long)(0x8000000000000000ull - (unsigned long long)k));
+    }
+}
+
 // lock-step -> per-trajectory: every trajectory inherits the shared scalars.
 int32_t materialize(vo_solver_s* s) {
     if (!s->uniform) return VO_OK;
@@ -1016,6 +1051,37 @@ int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
     std::memset(&s->ev_seen, 0, sizeof s->ev_seen);
     return VO_OK;
 }
+
+}  // extern "C"
+
+// group.cu: this shard's totals into device memory, stream-ordered (no synchronisation)
+int32_t vo_solver_local_stats(vo_solver s, unsigned long long* sums_dev, double* mm_dev) {
+    if (!s || !sums_dev || !mm_dev) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    if (s->uniform) {
+        const unsigned long long n = (unsigned long long)s->n;
+        const unsigned long long h_sums[6] = {(unsigned long long)s->u_accept * n, (unsigned long long)s->u_reject * n, n, s->u_done ? n : 0ull, 0ull, 0ull};
+        const double h_mm[2] = {s->u_t, -s->u_t};
+        // small pageable sources are staged by the runtime before the call returns, so stack arrays are safe here
+        VO_CUDA(c, cudaMemcpyAsync(sums_dev, h_sums, sizeof h_sums, cudaMemcpyHostToDevice, c->stream));
+        VO_CUDA(c, cudaMemcpyAsync(mm_dev, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, c->stream));
+        return VO_OK;
+    }
+    const uint64_t epoch = c->epoch;
+    VO_CUDA(c, cudaMemsetAsync(sums_dev, 0, 6 * sizeof(unsigned long long), c->stream));
+    const long long lowest = (long long)0x8000000000000000ull;  // below the key of every double
+    const long long init[2] = {lowest, lowest};
+    VO_CUDA(c, cudaMemcpyAsync(mm_dev, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    ctl_stats_kernel<<<(unsigned)std::min<int64_t>(ceil_div(s->n, 256), (int64_t)c->sm_count * 4), 256, 0, c->stream>>>(s->ca, s->n, sums_dev, mm_dev);
+    VO_CHECK_LAUNCH(c);
+    ctl_stats_finish_kernel<<<1, 1, 0, c->stream>>>(sums_dev, mm_dev, (unsigned long long)s->n);
+    VO_CHECK_LAUNCH(c);
+    c->epoch = epoch;  // read-only with respect to the solver's state
+    return VO_OK;
+}
+
+extern "C" {
 
 int32_t vo_rk_try_step(vo_solver s, double t, double dt, vo_ens next_x, vo_ens x_err, vo_ens* K) {
     if (!s || !next_x) return VO_ERR_BAD_ARG;

@@ -161,6 +161,13 @@ class _ExpSolver:
         check(lib().vo_exp_current(self._h, C.byref(tmin), C.byref(tmax), _np_ptr(psi.view(np.float64))), self.ctx._h)
         return (tmin.value, tmax.value), psi
 
+    def state_ensemble(self):
+        """The states in the caller's order as a device-side Ensemble view (one row of 2 n N doubles), for `Group.gather_placed`."""
+        from .base import Ensemble, _TensorOwner
+        h = _vp()
+        check(lib().vo_exp_current_device(self._h, C.byref(h)), self.ctx._h)
+        return Ensemble(self.ctx, 1, 2 * self.n * self.N, _handle=h, _owner=_TensorOwner(self))
+
     def stats(self) -> dict:
         n = self.N
         acc, rej, t, h, dxn = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n), np.zeros(n), np.zeros(n)
