@@ -201,10 +201,17 @@ class VdpDopri5:
         def make(ctx, lo, hi, x0):
             return vo.RK45Solver(vo.Rhs(ctx, "VDP", 2, [mu[lo:hi].copy()]), 0.0, 20.0, x0, 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
         self.e_sharded = None
-        if group is not None and group.world > 1:  # N > 1: one ensemble of world x 10^6 oscillators, gathered to rank 0 chunk by chunk
-            self.n_total = N_TRAJ * group.world
-            self.pin_full = torch.empty((self.n_total, 2), dtype=torch.float64).pin_memory() if group.ranks[0] == 0 else None
-            self.e_sharded = vo.pipeline.ShardedChunkedSolve(group, self.n_total, 2, make, parts=E2E_PARTS, arith=self.ctx.arith)
+        if group is not None and group.world > 1:
+            # N > 1: ONE ensemble of world x 10^6 oscillators (mu swept over the whole of it), sharded round-robin so that every
+            # rank sees the whole mu range (the cost of a trajectory grows with mu), gathered to rank 0 chunk by chunk
+            G, r = group.world, group.ranks[0]
+            self.n_total = N_TRAJ * G
+            mu_il = vo.workloads.vdp_mu(self.n_total)[r::G].copy()
+
+            def make_il(ctx, lo, hi, x0):
+                return vo.RK45Solver(vo.Rhs(ctx, "VDP", 2, [mu_il[lo:hi].copy()]), 0.0, 20.0, x0, 1e-3, tableau=tab).with_tolerance(1e-6, 1e-6)
+            self.pin_full = torch.empty((self.n_total, 2), dtype=torch.float64).pin_memory() if r == 0 else None
+            self.e_sharded = vo.pipeline.ShardedChunkedSolve(group, self.n_total, 2, make_il, parts=E2E_PARTS, arith=self.ctx.arith, interleave=True)
         else:
             self.e_chunked = vo.pipeline.ChunkedSolve(self.ctx.device, self.ctx.arith, N_TRAJ, 2, make, parts=E2E_PARTS)
 
@@ -566,7 +573,15 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
 
         def make(c, a, b, x0c):
             return mk(c, mk_rhs(c, a, b), x0c, tf)
-        sh = vo.pipeline.ShardedChunkedSolve(group, n_total, d, make, parts=E2E_PARTS, arith=args.arith)
+        il = adaptive  # round-robin sharding balances the mu sweep
+        if il:
+            n_il = max(0, -(-(n_total - rank) // world))
+            mu_il = vo.workloads.vdp_mu(n_total)[rank::world].copy()
+            pin_in = torch.from_numpy(vo.workloads.vdp_x0(n_il)).pin_memory()
+
+            def make(c, a, b, x0c):  # noqa: F811
+                return mk(c, vo.Rhs(c, "VDP", 2, [mu_il[a:b].copy()]), x0c, tf)
+        sh = vo.pipeline.ShardedChunkedSolve(group, n_total, d, make, parts=E2E_PARTS, arith=args.arith, interleave=il)
         full = None if pin_full is None else pin_full.numpy()
         sh.solve(pin_in.numpy(), full, adaptive=adaptive)
         barrier()
@@ -624,6 +639,28 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
     return out
 
 
+def numa_bind(torch, local):
+    """Run this rank's host threads on the CPUs of its GPU's NUMA node, so that the pinned staging buffers it allocates
+    (first touch) and the threads that drive its copies are local to the GPU's PCIe root. Returns the node, or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        dev = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 SPIN_UP_MS = 40.0  # untimed load right before the timed region, whatever --warmup says: clocks and caches in their steady state
 
 
@@ -659,6 +696,7 @@ def main():
     import vecode_b200 as vo
 
     torch.cuda.set_device(local)
+    numa = numa_bind(torch, local) if world > 1 else None  # pinned buffers and copy threads next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -834,6 +872,8 @@ def main():
                            "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of {8 * DD_K} doubles per rank) every {DD_K} steps" if W is HeatRK4DD
                                            else f"trajectory-sharded x{world}, no data-path collective")},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
+        if numa is not None:
+            line["config"]["numa_node_rank0"] = numa
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
             line["final_gather_note"] = (f"vo_group_gather of the whole ensemble ({world} x {W.state_mb if W is LorenzRK4 else 16} MB of state) on its own: NCCL into rank 0's "

@@ -212,6 +212,12 @@ int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on);
  * checkpoint with a prev_h that was never written, so it returns VO_ERR_STATE unless mixed stepping was switched on (1)
  * before the first adaptive step — the kernels then store prev_h on every attempt like the reference. Default 0. */
 int32_t vo_solver_set_mixed_stepping(vo_solver s, int32_t on);
+/* The one-event adaptive sweep (vo_step_adaptive / vo_step_many on ensembles of >= 1024 trajectories with an unrolled stage
+ * count) runs on a tile-blocked private copy of the state — one contiguous block per 64 trajectories holding x, the
+ * per-trajectory parameters and every controller scalar — which is packed on entry to such a run and unpacked before anything
+ * else reads the state (vo_current, vo_solver_stats, other kernels). Same arithmetic, same bits; 0 keeps the sweep on the
+ * public layout. Default 1. */
+int32_t vo_solver_set_blocked(vo_solver s, int32_t on);
 
 /* ODESolver::step (ode.rs:249-253) / AdaptiveODESolver::step_adaptive (ode.rs:337-341) applied to every
  * trajectory: ONE state-machine event per trajectory per call. res may be NULL. */
@@ -354,6 +360,11 @@ int32_t vo_group_gather(vo_group g, const vo_ens* local, int64_t n_total, int32_
  * chunks still integrate. vo_group_sync waits for everything enqueued on the group's streams. */
 int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, const int64_t* rows /* [world] */, const int64_t* row_off /* [world] */,
                                double* host_out, int32_t layout, int64_t host_n);
+/* Round-robin sharding (rank r holds trajectories r, r + G, r + 2G, ... of a block of `tot` consecutive ones: the static
+ * interleave that balances an adaptive ensemble whose cost varies along the trajectory index): the root interleaves the
+ * shards on the device into the block's natural order and copies the block to rows [row0, row0 + tot) of the host array.
+ * local[i]->n == ceil((tot - rank) / G). Asynchronous like vo_group_gather_placed. */
+int32_t vo_group_gather_interleaved(vo_group g, const vo_ens* local, int32_t root, int64_t tot, int64_t row0, double* host_out, int32_t layout, int64_t host_n);
 int32_t vo_group_sync(vo_group g);
 /* all-reduce of the per-shard counters; every rank receives the totals */
 int32_t vo_group_reduce_stats(vo_group g, const vo_solver* local, vo_group_stats* out);

@@ -31,14 +31,23 @@ def main():
     sh = vo.pipeline.ShardedChunkedSolve(g, n, 2, make, parts=3, arith="strict")
     full = np.zeros((n, 2)) if rank == 0 else None
     sh.solve(vo.workloads.vdp_x0(hi - lo), full, adaptive=True)
+    # round-robin sharding (rank r holds trajectories r, r + G, ...), gathered back into natural order
+    mu_all = vo.workloads.vdp_mu(n)
+    mu_il = mu_all[rank::world].copy()
+
+    def make_il(c, a, b, x0):
+        return vo.RK45Solver(vo.Rhs(c, "VDP", 2, [mu_il[a:b].copy()]), 0.0, tf, x0, 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5")).with_tolerance(1e-6, 1e-6)
+    shi = vo.pipeline.ShardedChunkedSolve(g, n, 2, make_il, parts=3, arith="strict", interleave=True)
+    full_il = np.zeros((n, 2)) if rank == 0 else None
+    shi.solve(vo.workloads.vdp_x0(len(mu_il)), full_il, adaptive=True)
     if rank == 0:
-        mu_all = vo.workloads.vdp_mu(n)
         ref = vo.RK45Solver(vo.Rhs(ctx, "VDP", 2, [mu_all]), 0.0, tf, vo.Ensemble.from_host(ctx, vo.workloads.vdp_x0(n)), 1e-3,
                             tableau=vo.ButcherTableu.builtin("DOPRI5")).with_tolerance(1e-6, 1e-6)
         ref.run(adaptive=True)
         rx, rs = ref.current()[1].to_host(), ref.stats()
         assert np.array_equal(got, rx), "gathered ensemble differs from the single-GPU solve"
         assert np.array_equal(full, rx), "chunk-wise gathered ensemble differs from the single-GPU solve"
+        assert np.array_equal(full_il, rx), "round-robin sharded ensemble differs from the single-GPU solve"
         assert tot["accepted"] == int(rs["accepted"].sum()) and tot["rejected"] == int(rs["rejected"].sum()) and tot["n_done"] == n
     else:
         assert got is None

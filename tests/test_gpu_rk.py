@@ -663,9 +663,11 @@ def test_run_tail_launch_on_another_kernel_is_not_chained(vo, ctx, max_calls):
     assert int(out[0][1]["accepted"].sum() + out[0][1]["rejected"].sum()) == n * (2 * max_calls - 1)  # all but the Chkpt call
 
 
+@pytest.mark.parametrize("blocked", [True, False])
 @pytest.mark.parametrize("tab", ["DOPRI5", "RKF45_REF"])
-def test_strict_one_event_control_kernel_against_oracle(vo, ctx, oracle, tab):
-    """The kernel bench.py times for config 3 — rk_ctl2w_staged_kernel<.., STRICT>, ONE event per launch, N >= 1024 — straight
+def test_strict_one_event_control_kernel_against_oracle(vo, ctx, oracle, tab, blocked):
+    """The kernels bench.py times for config 3 — rk_ctl2b_kernel<.., STRICT> on the tile-blocked state (blocked) and
+    rk_ctl2w_staged_kernel<.., STRICT> on the public layout, ONE event per launch, N >= 1024 — straight
     against the oracle: same accepted / rejected counts per trajectory and the state within rtol. (The controller's powf is
     correctly rounded here and glibc's in the oracle, which rounds differently for about one argument in a thousand, so a
     step size may differ in its last bit now and then: states are compared to 1e-9, not bitwise.)"""
@@ -675,7 +677,7 @@ def test_strict_one_event_control_kernel_against_oracle(vo, ctx, oracle, tab):
     ref = oracle.rk_ensemble("VDP", mu[:, None], oracle.builtin_tableau(oracle.TABLEAU_ID[tab]), 0.0, tf, x0, 1e-3, n_threads=8, adaptive=True, rtol=rtol)
     rhs = vo.Rhs(ctx, "VDP", 2, [mu])
     s = vo.RK45Solver(rhs, 0.0, tf, vo.Ensemble.from_host(ctx, x0), 1e-3, tableau=vo.ButcherTableu.builtin(tab)).with_tolerance(rtol, rtol)
-    s.set_events_per_launch(1)
+    s.set_events_per_launch(1).set_blocked(blocked)
     l0 = ctx.launch_count
     st = s.run(adaptive=True)
     assert st.kind == "Done"
@@ -771,3 +773,46 @@ def test_mixed_step_and_step_adaptive(vo, ctx, oracle):
             break
     assert passed == n
     assert np.array_equal(s.stats()["h"], h_before_last)
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+@pytest.mark.parametrize("n", [1024, 2500, 40_000])
+def test_blocked_sweep_equals_public_layout_bitwise(vo, n, arith):
+    """The one-event adaptive sweep on the tile-blocked private copy of the state (rk_small_blk.cuh) against the same sweep on
+    the public layout (rk_ctl2w_staged_kernel): same arithmetic, so every bit of the state and of the controller arrays must
+    agree — through checkpoints (the slow path inside the blocked kernel), snapshots, ragged tails (n % 256 != 0: padded
+    tiles), reads in mid-run (vo_solver_stats / vo_current unpack, the next launch goes on from the tiles), a write to the
+    borrowed ensemble (the tiles are re-packed), a parameter change and a switch to the 8-event kernel and back."""
+    c = vo.Context(0, arith=arith)
+    mu = vo.workloads.vdp_mu(n)
+    x0 = vo.workloads.vdp_x0(n) + 1e-3 * np.sin(np.arange(2 * n)).reshape(n, 2)
+    out = []
+    for blocked in (True, False):
+        rhs = vo.Rhs(c, "VDP", 2, [mu])
+        s = vo.RK45Solver(rhs, 0.0, 1.5, vo.Ensemble.from_host(c, x0), 1e-3, tableau=vo.ButcherTableu.builtin("DOPRI5")).with_tolerance(1e-6, 1e-6)
+        s.set_blocked(blocked).set_events_per_launch(1).set_t_list([0.0, 0.4, 1.0, 1.5]).enable_snapshots()
+        for _ in range(25):
+            s.step_adaptive()
+        mid = s.stats()                                   # unpack; both layouts valid
+        for _ in range(10):
+            s.step_adaptive()
+        vo.LinearCombination.scale(s.current()[1], 1.0 + 2.0 ** -30)   # the caller writes the borrowed state: tiles must be re-packed
+        for _ in range(10):
+            s.step_adaptive()
+        rhs.set_param(0, mu * (1.0 + 2.0 ** -20))         # a parameter changes under the tiles
+        for _ in range(10):
+            s.step_adaptive()
+        s.set_events_per_launch(8)
+        s.run(adaptive=True, max_calls=24)                # the 8-event kernel on the public layout ...
+        s.set_events_per_launch(1)
+        st = s.run(adaptive=True)                         # ... and back to the one-event sweep until every trajectory is done
+        assert st.kind == "Done"
+        out.append((s.current()[1].to_host(), s.stats(), mid, [s.snapshot(k).to_host() for k in range(4)]))
+    (xa, sa, ma, snapa), (xb, sb, mb, snapb) = out
+    assert np.array_equal(xa, xb)
+    for k in ("accepted", "rejected", "t", "h", "dx_norm", "status"):
+        assert np.array_equal(sa[k], sb[k]), k
+        assert np.array_equal(ma[k], mb[k]), "mid-run " + k
+    for a, b in zip(snapa, snapb):
+        assert np.array_equal(a, b)
+    assert np.all(sa["status"] == 1) and np.all(sa["t"] == 1.5)

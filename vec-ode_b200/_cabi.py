@@ -114,6 +114,7 @@ SIGNATURES = {
     "vo_solver_set_path": (_i32, [_vp, _i32]),
     "vo_solver_set_record_dx_norm": (_i32, [_vp, _i32]),
     "vo_solver_set_mixed_stepping": (_i32, [_vp, _i32]),
+    "vo_solver_set_blocked": (_i32, [_vp, _i32]),
     "vo_step": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
@@ -164,6 +165,7 @@ SIGNATURES = {
     "vo_group_gather_device": (_i32, [_vp, _pvp, _i64, _i32, _pvp]),
     "vo_group_gather": (_i32, [_vp, _pvp, _i64, _i32, _vp, _i32]),
     "vo_group_gather_placed": (_i32, [_vp, _pvp, _i32, _vp, _vp, _vp, _i32, _i64]),
+    "vo_group_gather_interleaved": (_i32, [_vp, _pvp, _i32, _i64, _i64, _vp, _i32, _i64]),
     "vo_group_sync": (_i32, [_vp]),
     "vo_group_reduce_stats": (_i32, [_vp, _pvp, C.POINTER(GroupStats)]),
     "vo_group_allreduce": (_i32, [_vp, _vp, _i32, _i32]),

@@ -381,6 +381,11 @@ class RK45Solver:
         check(lib().vo_solver_set_mixed_stepping(self._h, 1 if on else 0), self.ctx._h)
         return self
 
+    def set_blocked(self, on: bool = True):
+        """Run the one-event adaptive sweep on the tile-blocked private copy of the state (default) or on the public layout."""
+        check(lib().vo_solver_set_blocked(self._h, 1 if on else 0), self.ctx._h)
+        return self
+
     def set_fused_step(self, on: bool = True):
         """Whole-step path for a single HEAT1D state: every stage of a step in one kernel (vo_solver_set_path(s, 2))."""
         check(lib().vo_solver_set_path(self._h, 2 if on else 0), self.ctx._h)

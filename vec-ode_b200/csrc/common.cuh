@@ -65,6 +65,7 @@ struct vo_rhs_s {
     double shared[VO_MAX_PARAMS];      // shared value of each parameter
     double* per_traj[VO_MAX_PARAMS];   // device array or nullptr
     int64_t per_traj_n[VO_MAX_PARAMS];
+    uint64_t version = 0;              // bumped whenever a parameter changes (solvers that keep a packed copy of per-trajectory parameters re-pack)
     std::string body;                  // VO_RHS_CUSTOM: source of the RHS statements
     std::map<int, void*> modules;      // VO_RHS_CUSTOM: compiled modules keyed by (stage count, arithmetic mode)
 };
@@ -89,6 +90,11 @@ struct TableauDev {
     double b_err[VO_MAX_STAGES];
     int s;
     int has_err;
+    // First-same-as-last structure, detected on the host bit for bit: bit 0 set <=> b_err[j] == ac[s-1][j] for every j < s-1,
+    // bit 1 the same for b. The first s-1 terms of that final combination are then the very operations that formed the last
+    // stage's argument, in the same order, so the kernels reuse that partial sum instead of recomputing it (Dormand-Prince:
+    // the propagated 5th-order solution is stage 7's argument plus the term b_err[6] * K_7 — kept, zero or not).
+    int reuse;
 };
 
 #ifndef __CUDACC_RTC__

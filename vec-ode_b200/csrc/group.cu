@@ -387,6 +387,81 @@ int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, co
     return VO_OK;
 }
 
+// Round-robin sharding: rank r holds the trajectories j = r, r + G, r + 2G, ... of a block of `tot` consecutive trajectories
+// (rows[r] = ceil((tot - r) / G) of them), the static interleave that balances an adaptive ensemble whose cost varies smoothly
+// along the trajectory index. The root receives every shard as one message, interleaves them on the device
+// into the block's natural order and moves the block to rows [row0, row0 + tot) of the host array with ONE copy. Asynchronous
+// like vo_group_gather_placed.
+struct InterleaveArgs {
+    int64_t start[16], rows[16];
+    int G;
+};
+__global__ void interleave_kernel(const double* __restrict__ gbuf, double* __restrict__ img, InterleaveArgs a, int64_t d, int64_t tot, int aos) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= tot) return;
+    const int r = (int)(j % a.G);
+    const int64_t i = j / a.G, n_r = a.rows[r];
+    const double* blk = gbuf + d * a.start[r];
+    for (int64_t c = 0; c < d; ++c) img[aos ? j * d + c : c * tot + j] = blk[c * n_r + i];
+}
+
+int32_t vo_group_gather_interleaved(vo_group g, const vo_ens* local, int32_t root, int64_t tot, int64_t row0, double* host_out, int32_t layout, int64_t host_n) {
+    if (!g || !local || root < 0 || root >= g->world || g->world > 16 || tot < 0 || row0 < 0 || row0 + tot > host_n || (layout != VO_LAYOUT_AOS && layout != VO_LAYOUT_SOA))
+        return g_fail(g, VO_ERR_BAD_ARG, "vo_group_gather_interleaved: bad argument");
+    const int G = g->world;
+    const int64_t d = local[0] ? local[0]->d : 0;
+    InterleaveArgs ia;
+    std::memset(&ia, 0, sizeof ia);
+    ia.G = G;
+    int64_t total = 0;
+    for (int r = 0; r < G; ++r) ia.rows[r] = tot > r ? (tot - r + G - 1) / G : 0, ia.start[r] = total, total += ia.rows[r];
+    for (size_t i = 0; i < g->m.size(); ++i)
+        if (!local[i] || local[i]->d != d || (ia.rows[g->m[i].rank] > 0 && local[i]->n != ia.rows[g->m[i].rank]) || local[i]->ctx->device != g->m[i].ctx->device)
+            return g_fail(g, VO_ERR_SHAPE, "vo_group_gather_interleaved: member " + std::to_string(i) + " must hand in ceil((tot - rank) / G) trajectories on its device");
+    Member* rm = find_member(g, root);
+    if (rm) {
+        if (!host_out) return g_fail(g, VO_ERR_BAD_ARG, "vo_group_gather_interleaved: the root needs a host buffer");
+        DeviceGuard dg(rm->ctx->device);
+        const size_t need = (size_t)(d * total) * 2;
+        if (rm->gbuf_elems < need) {
+            cudaStreamSynchronize(rm->ctx->stream);
+            cudaFree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
+            if (cudaMalloc(&rm->gbuf, sizeof(double) * need) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather_interleaved: gather buffer");
+            rm->gbuf_elems = need;
+        }
+    }
+    if (G > 1) VO_NCCL(g, g->nc->groupStart());
+    for (size_t i = 0; i < g->m.size(); ++i) {
+        Member& mb = g->m[i];
+        DeviceGuard dg(mb.ctx->device);
+        vo_touch(mb.ctx);
+        const int64_t n_i = ia.rows[mb.rank];
+        if (mb.rank == root) {
+            if (n_i > 0) {
+                cudaError_t e = cudaMemcpyAsync(mb.gbuf + d * ia.start[root], local[i]->p, sizeof(double) * d * n_i, cudaMemcpyDeviceToDevice, mb.ctx->stream);
+                if (e != cudaSuccess) return g_fail(g, VO_ERR_CUDA, std::string("vo_group_gather_interleaved: ") + cudaGetErrorString(e));
+            }
+            for (int r = 0; r < G; ++r)
+                if (r != root && ia.rows[r] > 0) VO_NCCL(g, g->nc->recv(mb.gbuf + d * ia.start[r], (size_t)(d * ia.rows[r]), ncclDouble, r, mb.comm, mb.ctx->stream));
+        } else if (n_i > 0) {
+            VO_NCCL(g, g->nc->send(local[i]->p, (size_t)(d * n_i), ncclDouble, root, mb.comm, mb.ctx->stream));
+        }
+    }
+    if (G > 1) VO_NCCL(g, g->nc->groupEnd());
+    if (rm && tot > 0) {
+        DeviceGuard dg(rm->ctx->device);
+        cudaStream_t st = rm->ctx->stream;
+        double* img = rm->gbuf + d * total;
+        const int aos = (layout == VO_LAYOUT_AOS) ? 1 : 0;
+        interleave_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(rm->gbuf, img, ia, d, tot, aos);
+        rm->ctx->launches++;
+        cudaError_t e = aos ? cudaMemcpyAsync(host_out + row0 * d, img, sizeof(double) * d * tot, cudaMemcpyDeviceToHost, st)
+                            : cudaMemcpy2DAsync(host_out + row0, sizeof(double) * host_n, img, sizeof(double) * tot, sizeof(double) * tot, (size_t)d, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return g_fail(g, VO_ERR_CUDA, std::string("vo_group_gather_interleaved: ") + cudaGetErrorString(e));
+    }
+    return VO_OK;
+}
+
 int32_t vo_group_sync(vo_group g) {
     if (!g) return VO_ERR_BAD_ARG;
     for (Member& mb : g->m) {

@@ -142,6 +142,38 @@ __device__ __forceinline__ void combine(const double* __restrict__ k, int n, con
     for (int c = 0; c < D; ++c) v[c] = A::add(A::mul(v[c], dt), x0[c]);
 }
 
+// The two halves of `combine`: the weighted sum of the stage derivatives, and `* dt + x0`. Splitting them lets a final
+// combination whose first s-1 weights equal the last row of the tableau (TableauDev::reuse) start from the last stage's sum.
+template <bool STRICT, int D, int SM>
+__device__ __forceinline__ void combine_sum(const double* __restrict__ k, int n, const double (&K)[SM][D], double (&v)[D]) {
+    using A = Ar<STRICT>;
+#pragma unroll
+    for (int c = 0; c < D; ++c) v[c] = A::mul(k[0], K[0][c]);
+#pragma unroll
+    for (int j = 1; j < SM; ++j)
+        if (j < n) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[c] = A::axpy(v[c], k[j], K[j][c]);
+        }
+}
+template <bool STRICT, int D> __device__ __forceinline__ void combine_finish(const double (&v)[D], double dt, const double (&x0)[D], double (&out)[D]) {
+    using A = Ar<STRICT>;
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = A::add(A::mul(v[c], dt), x0[c]);
+}
+// out = ((vsum + k_last * K_last) * dt) + x0: the tail of a final combination that shares its first s-1 terms with vsum
+template <bool STRICT, int D>
+__device__ __forceinline__ void combine_tail(const double (&vsum)[D], double k_last, const double (&K_last)[D], double dt, const double (&x0)[D], double (&out)[D]) {
+    using A = Ar<STRICT>;
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = A::add(A::mul(A::axpy(vsum[c], k_last, K_last[c]), dt), x0[c]);
+}
+
+// Rust's `v.max(lo)` / `v.min(hi)` for a bound that is not NaN: a NaN v yields the bound (ode.rs:321-324). A compare and two
+// selects; CUDA's fmax / fmin cost seven instructions each for the NaN cases of BOTH operands.
+__device__ __forceinline__ double at_least(double v, double lo) { return v > lo ? v : lo; }
+__device__ __forceinline__ double at_most(double v, double hi) { return v < hi ? v : hi; }
+
 // rk_step (src/base/rk.rs:90-155). On return xf is the state the reference propagates (X_berr when the error
 // branch runs, else X_b) and xe = X_b - X_berr.
 template <class RHS, int S, bool STRICT>
@@ -151,23 +183,33 @@ __device__ __forceinline__ void rk_attempt(const TableauDev& tb, bool use_err, d
     constexpr int D = RHS::D;
     constexpr int SM = S > 0 ? S : VO_MAX_STAGES;
     const int s = S > 0 ? S : tb.s;
-    double K[SM][D];
+    double K[SM][D], vlast[D];
     RHS::template eval<STRICT>(t, x0, K[0], p);  // rk.rs:111
+#pragma unroll
+    for (int c = 0; c < D; ++c) vlast[c] = 0.0;
 #pragma unroll
     for (int i = 1; i < SM; ++i) {
         if (i < s) {
             const double* row = &tb.ac[i * s];
             const double ti = A::add(t, A::mul(row[i], dt));  // rk.rs:119
-            double xs[D];
-            combine<STRICT, D, SM>(row, i, K, dt, x0, xs);    // rk.rs:121-124
+            double v[D], xs[D];
+            combine_sum<STRICT, D, SM>(row, i, K, v);         // rk.rs:121-122
+            combine_finish<STRICT, D>(v, dt, x0, xs);         // rk.rs:123-124
+            if (S > 0 && i == S - 1) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) vlast[c] = v[c];
+            }
             RHS::template eval<STRICT>(ti, xs, K[i], p);      // rk.rs:127
         }
     }
-    combine<STRICT, D, SM>(tb.b, s, K, dt, x0, xf);           // rk.rs:131-133
+    // the final combinations (rk.rs:131-133, 143-146); with the first-same-as-last structure their first s-1 terms are vlast
+    if (S > 1 && (tb.reuse & 2)) combine_tail<STRICT, D>(vlast, tb.b[S > 1 ? S - 1 : 0], K[S > 1 ? S - 1 : 0], dt, x0, xf);
+    else combine<STRICT, D, SM>(tb.b, s, K, dt, x0, xf);      // rk.rs:131-133
     if (use_err) {                                            // rk.rs:136-151
 #pragma unroll
         for (int c = 0; c < D; ++c) xe[c] = xf[c];            // swap: xe := X_b
-        combine<STRICT, D, SM>(tb.b_err, s, K, dt, x0, xf);   // xf := X_berr
+        if (S > 1 && (tb.reuse & 1)) combine_tail<STRICT, D>(vlast, tb.b_err[S > 1 ? S - 1 : 0], K[S > 1 ? S - 1 : 0], dt, x0, xf);
+        else combine<STRICT, D, SM>(tb.b_err, s, K, dt, x0, xf);   // xf := X_berr
 #pragma unroll
         for (int c = 0; c < D; ++c) xe[c] = A::sub(xe[c], xf[c]);
     }
@@ -253,12 +295,15 @@ __device__ __forceinline__ double pow_third_cr(double f) {
     return __dadd_rn(y, c);
 }
 
+// the general powf, out of line: inlined, its argument classification is hoisted into the hot path of every attempt
+static __device__ __noinline__ double pow_cold(double f, double pw) { return pow(f, pw); }
+
 template <bool STRICT> __device__ __forceinline__ double step_size_mul(double alpha, double f, double pw, int pw_is_third) {
     if (pw_is_third) {
         if (!STRICT) return alpha * cbrt(f);
         if (f > 8.0e-28 && f < 1.2e27) return __dmul_rn(alpha, pow_third_cr(f));
     }
-    return alpha * pow(f, pw);
+    return alpha * pow_cold(f, pw);
 }
 
 // handle_step_adaptive (ode.rs:311-334) from the error norm, literally: f = rtol / dx_norm, factor = clamp(alpha f^pw, 0.3, 2),
@@ -266,8 +311,8 @@ template <bool STRICT> __device__ __forceinline__ double step_size_mul(double al
 template <bool STRICT>
 __device__ __forceinline__ void controller_ref(double dxn, double h, const CtlShared& cs, double& new_h, bool& reject) {
     const double f = cs.rtol / dxn;
-    const double fp_lim = fmin(fmax(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
-    new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
+    const double fp_lim = at_most(at_least(step_size_mul<STRICT>(cs.alpha, f, cs.pw, cs.pw_is_third), 0.3), 2.0);
+    new_h = at_most(at_least(fp_lim * h, cs.min_dt), cs.max_dt);
     reject = f <= 1.0;
 }
 // cold path of the FAST kernels (an order other than the 3 that RK45Solver hard-wires): kept out of line
@@ -277,8 +322,8 @@ struct CtlRes {
 };
 static __device__ __noinline__ CtlRes controller_ref_cold_call(double dxn, double h, double rtol, double alpha, double pw, double min_dt, double max_dt) {
     const double f = rtol / dxn;
-    const double fp_lim = fmin(fmax(alpha * pow(f, pw), 0.3), 2.0);
-    return CtlRes{fmin(fmax(fp_lim * h, min_dt), max_dt), f <= 1.0 ? 1 : 0};
+    const double fp_lim = at_most(at_least(alpha * pow(f, pw), 0.3), 2.0);
+    return CtlRes{at_most(at_least(fp_lim * h, min_dt), max_dt), f <= 1.0 ? 1 : 0};
 }
 __device__ __forceinline__ void controller_ref_cold(double dxn, double h, const CtlShared& cs, double& new_h, bool& reject) {
     const CtlRes r = controller_ref_cold_call(dxn, h, cs.rtol, cs.alpha, cs.pw, cs.min_dt, cs.max_dt);  // scalars in registers: no stack frame
@@ -295,42 +340,87 @@ __device__ __forceinline__ void controller_ref_cold(double dxn, double h, const 
 // Out-of-range g (0, inf, NaN, beyond f32) needs no branch: the seed is clamped to [1e-30, 1e30] and the residual to >= -1,
 // which leaves the factor far outside [0.3, 2] on the right side; a NaN ends as 0.3 like Rust's NaN.max(0.3).min(2.0); only
 // dx_norm takes the slow road.
-__device__ __forceinline__ void controller_l2_fast(double acc, double h, const CtlShared& cs, bool want_dxn, double& dxn, double& new_h, bool& reject) {
-    const double g = acc * cs.inv_rtol2;
-    const float gf = fmaxf(fminf(__double2float_rn(g), 1.0e30f), 1.0e-30f);  // a NaN lands on the 1e30 side
-    float lg, y0;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(gf));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * -0.16666667f));
-    double y = (double)y0;
-    {
-        const double y2 = y * y;
-        const double r = fmax(fma(-g, (y2 * y2) * y2, 1.0), -1.0);  // -1 only for g > 1e30, inf or NaN, where the seed is 1e-5
-        y = fma(y * r, fma(r, 7.0 / 72.0, 1.0 / 6.0), y);
+// U trajectories at once, statement by statement, so that the U dependent chains (seed -> refinement -> clamps) overlap.
+template <int U>
+__device__ __forceinline__ void controller_l2_fast_n(const double (&acc)[U], const double (&h)[U], const CtlShared& cs, bool want_dxn, double (&dxn)[U],
+                                                     double (&new_h)[U], bool (&reject)[U]) {
+    double g[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = acc[u] * cs.inv_rtol2;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float gf = fmaxf(fminf(__double2float_rn(g[u]), 1.0e30f), 1.0e-30f);  // a NaN lands on the 1e30 side
+        float lg, y0;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(gf));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(lg * -0.16666667f));
+        y[u] = (double)y0;
     }
-    const double fp_lim = fmin(fmax(cs.alpha * y, 0.3), 2.0);
-    new_h = fmin(fmax(fp_lim * h, cs.min_dt), cs.max_dt);
-    reject = g >= 1.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double y2 = y[u] * y[u];
+        const double r = at_least(fma(-g[u], (y2 * y2) * y2, 1.0), -1.0);  // -1 only for g > 1e30, inf or NaN, where the seed is 1e-5
+        y[u] = fma(y[u] * r, fma(r, 7.0 / 72.0, 1.0 / 6.0), y[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const double fp_lim = at_most(at_least(cs.alpha * y[u], 0.3), 2.0);
+        new_h[u] = at_most(at_least(fp_lim * h[u], cs.min_dt), cs.max_dt);
+        reject[u] = g[u] >= 1.0;
+    }
     if (want_dxn) {
-        if (g > 1.0e-30 && g < 1.0e30) dxn = acc * (((y * y) * y) * cs.inv_rtol);
-        else dxn = sqrt(acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dxn[u] = acc[u] * (((y[u] * y[u]) * y[u]) * cs.inv_rtol);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (!(g[u] > 1.0e-30 && g[u] < 1.0e30)) dxn[u] = sqrt(acc[u]);  // 0, inf, NaN, beyond the seed's range: the slow road
     }
 }
 
-// L2-norm controller of the common adaptive configuration, dispatching on the arithmetic mode. `want_dxn`: the caller keeps
-// ODEAdaptiveData.dx_norm; `nonfinite` reports a NaN norm.
+// L2-norm controller of the common adaptive configuration, dispatching on the arithmetic mode, for U trajectories of one
+// thread. `want_dxn`: the caller keeps ODEAdaptiveData.dx_norm; `nonfinite` reports a NaN norm.
+template <bool STRICT, int U>
+__device__ __forceinline__ void controller_l2_n(const double (&acc)[U], const double (&h)[U], const CtlShared& cs, bool want_dxn, double (&dxn)[U],
+                                                double (&new_h)[U], bool (&reject)[U], bool (&nonfinite)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) nonfinite[u] = !(acc[u] == acc[u]);
+    if (STRICT) {  // handle_step_adaptive literally (ode.rs:311-334): sqrt and / are IEEE-exact, powf correctly rounded
+        double f[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) dxn[u] = sqrt(acc[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = cs.rtol / dxn[u];
+        bool third = cs.pw_is_third != 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) third = third && (f[u] > 8.0e-28 && f[u] < 1.2e27);
+        if (third) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) m[u] = __dmul_rn(cs.alpha, pow_third_cr(f[u]));
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) m[u] = step_size_mul<true>(cs.alpha, f[u], cs.pw, cs.pw_is_third);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double fp_lim = at_most(at_least(m[u], 0.3), 2.0);
+            new_h[u] = at_most(at_least(fp_lim * h[u], cs.min_dt), cs.max_dt);
+            reject[u] = f[u] <= 1.0;
+        }
+    } else if (cs.pw_is_third) {
+        controller_l2_fast_n<U>(acc, h, cs, want_dxn, dxn, new_h, reject);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) dxn[u] = sqrt(acc[u]), controller_ref_cold(dxn[u], h[u], cs, new_h[u], reject[u]);
+    }
+}
+
 template <bool STRICT>
 __device__ __forceinline__ void controller_l2(double acc, double h, const CtlShared& cs, bool want_dxn, double& dxn, double& new_h, bool& reject,
                                               bool& nonfinite) {
-    nonfinite = !(acc == acc);
-    if (STRICT) {
-        dxn = sqrt(acc);
-        controller_ref<true>(dxn, h, cs, new_h, reject);
-    } else if (cs.pw_is_third) {
-        controller_l2_fast(acc, h, cs, want_dxn, dxn, new_h, reject);
-    } else {
-        dxn = sqrt(acc);
-        controller_ref_cold(dxn, h, cs, new_h, reject);
-    }
+    const double a[1] = {acc}, hh[1] = {h};
+    double d[1] = {dxn}, nh[1];
+    bool rj[1], nf[1];
+    controller_l2_n<STRICT, 1>(a, hh, cs, want_dxn, d, nh, rj, nf);
+    dxn = d[0], new_h = nh[0], reject = rj[0], nonfinite = nf[0];
 }
 
 // ---- staged (TMA bulk-copy) variants ---------------------------------------------------------------------------
@@ -413,12 +503,32 @@ __global__ void __launch_bounds__(VO_TILE) rk_fixed_staged_kernel(double* __rest
     pipe::chain_exit(ch);
 }
 
+// Where one trajectory's state and controller scalars live in global memory. SoaAcc: the public layout (SoA ensemble + CtlArrays,
+// element i of every array). rk_small_blk.cuh adds the tile-blocked layout of the one-event sweep.
+struct SoaAcc {
+    double* x;
+    int64_t N;
+    CtlArrays ca;
+    int64_t i;
+    __device__ __forceinline__ int64_t gidx() const { return i; }  // trajectory number (snapshots are indexed by it)
+    __device__ __forceinline__ int64_t count() const { return N; }
+    __device__ __forceinline__ void st_x(int c, double v) const { x[c * N + i] = v; }
+    __device__ __forceinline__ void st_t(double v) const { ca.t[i] = v; }
+    __device__ __forceinline__ void st_h(double v) const { ca.h[i] = v; }
+    __device__ __forceinline__ double ld_prev_h() const { return ca.prev_h[i]; }
+    __device__ __forceinline__ void st_prev_h(double v) const { ca.prev_h[i] = v; }
+    __device__ __forceinline__ void st_dxn(double v) const { ca.dx_norm[i] = v; }
+    __device__ __forceinline__ void st_acc(uint32_t v) const { ca.n_accept[i] = v; }
+    __device__ __forceinline__ void st_rej(uint32_t v) const { ca.n_reject[i] = v; }
+    __device__ __forceinline__ void st_word(uint32_t v) const { ca.word[i] = v; }
+};
+
 // One lane of the per-trajectory control kernel: k_events calls of step()/step_adaptive() on registers, then the
 // masked write-back. Shared by the staged kernel body and its ragged tail.
 // CFG 1 = the common adaptive configuration (step_adaptive with an error estimate and the L2 norm) resolved at compile
 // time; CFG 0 = everything decided from CtlShared at run time.
-template <class RHS, int S, bool STRICT, int CFG>
-__device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int64_t i, const TableauDev& tb, const CtlArrays& ca, const CtlShared& cs,
+template <class RHS, int S, bool STRICT, int CFG, class ACC>
+__device__ __forceinline__ void ctl_lane(const ACC& a, const TableauDev& tb, const CtlShared& cs,
                                          const TList& tl, uint32_t word, double (&xc)[RHS::D], const double (&p)[RHS::NP], double t, double h,
                                          uint32_t n_acc, uint32_t n_rej, unsigned& c_step, unsigned& c_chkpt, unsigned& c_rej, unsigned& c_end, unsigned& c_stuck) {
     constexpr int D = RHS::D;
@@ -471,9 +581,9 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
         } else {  // Chkpt / End -> checkpoint_update, ode.rs:192-195
             if (cs.snap && tgt < cs.n_tlist) {  // what current() shows the caller at this event
 #pragma unroll
-                for (int c = 0; c < D; ++c) cs.snap[((int64_t)tgt * D + c) * N + i] = xc[c];
+                for (int c = 0; c < D; ++c) cs.snap[((int64_t)tgt * D + c) * a.count() + a.gidx()] = xc[c];
             }
-            if (!prev_h_loaded) prev_h = ca.prev_h[i], prev_h_loaded = true;
+            if (!prev_h_loaded) prev_h = a.ld_prev_h(), prev_h_loaded = true;
             tgt += 1, h = prev_h, ctl_dirty = true;
             if (evk == VO_EV_END) {
                 status |= VO_TRAJ_DONE, ++c_end;
@@ -484,18 +594,18 @@ __device__ __forceinline__ void ctl_lane(double* __restrict__ x, int64_t N, int6
     }
     if (moved) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) x[c * N + i] = xc[c];
-        ca.t[i] = t;
+        for (int c = 0; c < D; ++c) a.st_x(c, xc[c]);
+        a.st_t(t);
     }
     if (ctl_dirty) {
-        ca.h[i] = h;
-        ca.prev_h[i] = prev_h;
+        a.st_h(h);
+        a.st_prev_h(prev_h);
     }
-    if (dxn_set && cs.record_dx_norm) ca.dx_norm[i] = dxn;
-    if (l_step) ca.n_accept[i] = n_acc + l_step;  // counters came in with the tile: no read-modify-write round trip here
-    if (l_rej) ca.n_reject[i] = n_rej + l_rej;
+    if (dxn_set && cs.record_dx_norm) a.st_dxn(dxn);
+    if (l_step) a.st_acc(n_acc + l_step);  // counters came in with the tile: no read-modify-write round trip here
+    if (l_rej) a.st_rej(n_rej + l_rej);
     const uint32_t nw = ((uint32_t)tgt & VO_WORD_TGT_MASK) | (status << VO_WORD_STATUS_SHIFT);
-    if (nw != word) ca.word[i] = nw;
+    if (nw != word) a.st_word(nw);
     c_step += l_step, c_rej += l_rej;
 }
 
@@ -590,7 +700,7 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         __syncthreads();
         if (threadIdx.x == 0 && k + VO_STAGES < my_count) issue(k + VO_STAGES);
         if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE))
-            ctl_lane<RHS, S, STRICT, CFG>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, n_acc, n_rej, c_step, c_chkpt, c_rej, c_end, c_stuck);
+            ctl_lane<RHS, S, STRICT, CFG>(SoaAcc{x, N, ca, i}, tb, cs, tl, word, xc, p, t, h, n_acc, n_rej, c_step, c_chkpt, c_rej, c_end, c_stuck);
     }
     const int64_t i = n_full * T + threadIdx.x;  // ragged tail: plain loads, last CTA
     if (blockIdx.x == G - 1 && i < N) {
@@ -598,7 +708,7 @@ __global__ void __launch_bounds__(VO_TILE, VO_CTL_MIN_BLOCKS) rk_ctl_staged_kern
         if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
             double xc[D], p[NP];
             lane_load<RHS>(x, N, rp, i, xc, p);
-            ctl_lane<RHS, S, STRICT, 0>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej,
+            ctl_lane<RHS, S, STRICT, 0>(SoaAcc{x, N, ca, i}, tb, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej,
                                         c_end, c_stuck);
         }
     }
@@ -633,7 +743,7 @@ __global__ void __launch_bounds__(128) rk_ctl_kernel(double* __restrict__ x, int
             live_n = !((word_n >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE);
             if (live_n) lane_load<RHS>(x, N, rp, j, xn, pn), t_n = ca.t[j], h_n = ca.h[j], na_n = ca.n_accept[j], nr_n = ca.n_reject[j];
         }
-        if (live) ctl_lane<RHS, S, STRICT, 0>(x, N, i, tb, ca, cs, tl, word, xc, p, t, h, na, nr, c_step, c_chkpt, c_rej, c_end, c_stuck);
+        if (live) ctl_lane<RHS, S, STRICT, 0>(SoaAcc{x, N, ca, i}, tb, cs, tl, word, xc, p, t, h, na, nr, c_step, c_chkpt, c_rej, c_end, c_stuck);
         word = word_n, live = (j < N) && live_n, t = t_n, h = h_n, na = na_n, nr = nr_n;
 #pragma unroll
         for (int c = 0; c < D; ++c) xc[c] = xn[c];

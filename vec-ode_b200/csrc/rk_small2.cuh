@@ -23,7 +23,7 @@ __device__ __forceinline__ void rk_attempt_n(const TableauDev& tb, const double 
                                              const double (&p)[U][RHS::NP], double (&xf)[U][RHS::D], double (&xe)[U][RHS::D]) {
     using A = Ar<STRICT>;
     constexpr int D = RHS::D;
-    double K[U][S][D];
+    double K[U][S][D], vlast[U][D];
 #pragma unroll
     for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(t[u], x0[u], K[u][0], p[u]);  // rk.rs:111
 #pragma unroll
@@ -31,17 +31,34 @@ __device__ __forceinline__ void rk_attempt_n(const TableauDev& tb, const double 
         const double* row = &tb.ac[i * S];
         double xs[U][D];
 #pragma unroll
-        for (int u = 0; u < U; ++u) combine<STRICT, D, S>(row, i, K[u], dt[u], x0[u], xs[u]);  // rk.rs:121-124
+        for (int u = 0; u < U; ++u) {
+            double v[D];
+            combine_sum<STRICT, D, S>(row, i, K[u], v);              // rk.rs:121-122
+            combine_finish<STRICT, D>(v, dt[u], x0[u], xs[u]);       // rk.rs:123-124
+            if (i == S - 1) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) vlast[u][c] = v[c];
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(A::add(t[u], A::mul(row[i], dt[u])), xs[u], K[u][i], p[u]);  // rk.rs:119, 127
     }
+    // X_b (rk.rs:131-133, held in xe for the swap of rk.rs:142) and X_berr, the propagated solution. With the first-same-as-last
+    // structure (TableauDev::reuse) the first S-1 terms of a combination are the last stage's sum: same operations, same order.
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        combine<STRICT, D, S>(tb.b, S, K[u], dt[u], x0[u], xe[u]);      // X_b (rk.rs:131-133), held in xe for the swap of rk.rs:142
-        combine<STRICT, D, S>(tb.b_err, S, K[u], dt[u], x0[u], xf[u]);  // X_berr: the propagated solution
+        if (tb.reuse & 2) combine_tail<STRICT, D>(vlast[u], tb.b[S - 1], K[u][S - 1], dt[u], x0[u], xe[u]);
+        else combine<STRICT, D, S>(tb.b, S, K[u], dt[u], x0[u], xe[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (tb.reuse & 1) combine_tail<STRICT, D>(vlast[u], tb.b_err[S - 1], K[u][S - 1], dt[u], x0[u], xf[u]);
+        else combine<STRICT, D, S>(tb.b_err, S, K[u], dt[u], x0[u], xf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int c = 0; c < D; ++c) xe[u][c] = A::sub(xe[u][c], xf[u][c]);  // x_err = X_b - X_berr (rk.rs:147)
-    }
 }
 
 // ---- lock-step fixed-step kernel, two trajectories per thread ------------------------------------------------------
@@ -54,7 +71,7 @@ __device__ __forceinline__ void rk_attempt_fixed_n(const TableauDev& tb, bool us
                                                    const double (&p)[U][RHS::NP], double (&xf)[U][RHS::D]) {
     using A = Ar<STRICT>;
     constexpr int D = RHS::D;
-    double K[U][S][D];
+    double K[U][S][D], vlast[U][D];
 #pragma unroll
     for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(t, x0[u], K[u][0], p[u]);  // rk.rs:111
 #pragma unroll
@@ -63,13 +80,26 @@ __device__ __forceinline__ void rk_attempt_fixed_n(const TableauDev& tb, bool us
         const double ti = A::add(t, A::mul(row[i], dt));  // rk.rs:119
         double xs[U][D];
 #pragma unroll
-        for (int u = 0; u < U; ++u) combine<STRICT, D, S>(row, i, K[u], dt, x0[u], xs[u]);  // rk.rs:121-124
+        for (int u = 0; u < U; ++u) {
+            double v[D];
+            combine_sum<STRICT, D, S>(row, i, K[u], v);          // rk.rs:121-122
+            combine_finish<STRICT, D>(v, dt, x0[u], xs[u]);      // rk.rs:123-124
+            if (i == S - 1) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) vlast[u][c] = v[c];
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) RHS::template eval<STRICT>(ti, xs[u], K[u][i], p[u]);  // rk.rs:127
     }
     // the propagated state: X_berr when the error branch runs (rk.rs:136-146), else X_b (rk.rs:131-133)
+    const double* w = use_err ? tb.b_err : tb.b;
+    const bool reuse = (tb.reuse & (use_err ? 1 : 2)) != 0;  // first S-1 weights == the last row of the tableau: start from the last stage's sum
 #pragma unroll
-    for (int u = 0; u < U; ++u) combine<STRICT, D, S>(use_err ? tb.b_err : tb.b, S, K[u], dt, x0[u], xf[u]);
+    for (int u = 0; u < U; ++u) {
+        if (reuse) combine_tail<STRICT, D>(vlast[u], w[S - 1], K[u][S - 1], dt, x0[u], xf[u]);
+        else combine<STRICT, D, S>(w, S, K[u], dt, x0[u], xf[u]);
+    }
 }
 
 template <class RHS, int S, bool STRICT>
@@ -284,7 +314,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (live[u])
-                    ctl_lane<RHS, S, STRICT, 1>(x, N, base + threadIdx.x + 128 * u, tb, ca, cs, tl, word[u], xc[u], p[u], t[u], h[u], n_acc[u], n_rej[u], c_step,
+                    ctl_lane<RHS, S, STRICT, 1>(SoaAcc{x, N, ca, base + threadIdx.x + 128 * u}, tb, cs, tl, word[u], xc[u], p[u], t[u], h[u], n_acc[u], n_rej[u], c_step,
                                                 c_chkpt, c_rej, c_end, c_stuck);
         }
     }
@@ -295,7 +325,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS) rk_ctl2_staged_kernel
             if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
                 double xc[D], p[NP];
                 lane_load<RHS>(x, N, rp, i, xc, p);
-                ctl_lane<RHS, S, STRICT, 1>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
+                ctl_lane<RHS, S, STRICT, 1>(SoaAcc{x, N, ca, i}, tb, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
                                             c_stuck);
             }
         }
@@ -405,11 +435,11 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
         if (pair) {
             double xf[U][D], xe[U][D];
             rk_attempt_n<RHS, S, STRICT, U>(tb, t, dt, xc, p, xf, xe);
-            double dxn[U] = {0.0, 0.0}, new_h[U];
+            double dxn[U] = {0.0, 0.0}, new_h[U], acc[U];
             bool rej[U], nonfin[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)  // handle_step_adaptive, ode.rs:311-334
-                controller_l2<STRICT>(err_sumsq<STRICT, D>(xe[u]), h[u], cs, cs.record_dx_norm != 0, dxn[u], new_h[u], rej[u], nonfin[u]);
+            for (int u = 0; u < U; ++u) acc[u] = err_sumsq<STRICT, D>(xe[u]);
+            controller_l2_n<STRICT, U>(acc, h, cs, cs.record_dx_norm != 0, dxn, new_h, rej, nonfin);  // handle_step_adaptive, ode.rs:311-334
             // apply_step (ode.rs:402-428) + masked write-back: 128-bit stores where both trajectories commit the same way
             if (!rej[0] && !rej[1]) {
 #pragma unroll
@@ -450,7 +480,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (live[u])
-                    ctl_lane<RHS, S, STRICT, 1>(x, N, i0 + u, tb, ca, cs, tl, word[u], xc[u], p[u], t[u], h[u], n_acc[u], n_rej[u], c_step, c_chkpt, c_rej, c_end,
+                    ctl_lane<RHS, S, STRICT, 1>(SoaAcc{x, N, ca, i0 + u}, tb, cs, tl, word[u], xc[u], p[u], t[u], h[u], n_acc[u], n_rej[u], c_step, c_chkpt, c_rej, c_end,
                                                 c_stuck);
         }
     }
@@ -462,7 +492,7 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
             if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
                 double xc[D], p[NP];
                 lane_load<RHS>(x, N, rp, i, xc, p);
-                ctl_lane<RHS, S, STRICT, 1>(x, N, i, tb, ca, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
+                ctl_lane<RHS, S, STRICT, 1>(SoaAcc{x, N, ca, i}, tb, cs, tl, word, xc, p, ca.t[i], ca.h[i], ca.n_accept[i], ca.n_reject[i], c_step, c_chkpt, c_rej, c_end,
                                             c_stuck);
             }
         }

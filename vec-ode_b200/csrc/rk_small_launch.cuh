@@ -6,7 +6,7 @@
 #include <tuple>
 #include <utility>
 
-#include "rk_small2.cuh"
+#include "rk_small_blk.cuh"
 
 constexpr int RK_SMALL_THREADS = 128;
 
@@ -38,6 +38,7 @@ struct SmallLaunch {
     const StepList* sl;    // lock-step fixed steps (cs == nullptr)
     EvSlot* ev;
     ChainState* cst;       // chaining state of the owning solver
+    const BlkView* blk = nullptr;  // non-NULL: the state lives in the tile-blocked copy (rk_small_blk.cuh) and x / ca are stale
 };
 
 // The staged kernels need 16-byte aligned SoA rows (N even) and at least one full tile.
@@ -80,6 +81,13 @@ static void launch_staged(ChainState* cst, void (*kernel)(KArgs...), unsigned gr
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)..., ch);
 }
 
+// When the one-event adaptive sweep may run on the tile-blocked copy of the state: the dispatch condition of the
+// two-trajectory control kernels (below) for a compiled-in RHS family with an unrolled stage count.
+static inline bool small_path_blocked_ok(int64_t N, int stages, const CtlShared& cs) {
+    const bool unrolled = stages == 4 || stages == 6 || stages == 7;
+    return unrolled && small_path_is_staged(N) && N >= 4 * VO_TILE_CTL && cs.adaptive && cs.use_err && cs.norm_kind == VO_NORM_L2 && cs.k_events == 1;
+}
+
 static inline int per_traj_rows(const RhsParams& rp, int np) {
     int n = 0;
     for (int q = 0; q < np; ++q) n += rp.per_traj[q] ? 1 : 0;
@@ -115,6 +123,13 @@ template <class RHS, int S, bool STRICT> static void launch_one(const SmallLaunc
             const size_t smem = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE * sizeof(double) + 3 * VO_TILE * sizeof(uint32_t));
             const bool common = L.cs->adaptive && L.cs->use_err && L.cs->norm_kind == VO_NORM_L2;
             if constexpr (S > 0) {
+                if (L.blk) {  // the one-event sweep on the tile-blocked state (solver.cu decided with small_path_blocked_ok)
+                    const size_t smemb = (size_t)4 * VO_BLK_NST * L.blk->read_bytes;
+                    auto kb = rk_ctl2b_kernel<RHS, S, STRICT>;
+                    launch_staged(L.cst, kb, persistent_grid(L.ctx, kb, L.blk->n_wtiles * VO_BLK_WT, smemb, VO_TILE_CTL), smemb, L.ctx->stream, *L.blk, L.N, *L.tb, *L.rp,
+                                  *L.cs, L.ev);
+                    return;
+                }
                 if (common && L.cs->k_events == 1 && L.N >= 4 * VO_TILE_CTL) {  // several trajectories per thread (rk_small2.cuh)
                     const size_t smem2 = (size_t)VO_STAGES * ((RHS::D + 2 + per_traj_rows(*L.rp, RHS::NP)) * VO_TILE_CTL * sizeof(double) + 3 * VO_TILE_CTL * sizeof(uint32_t));
 #ifdef VO_CTL2_CTA  // A/B switch (tools/build_variant.sh): the CTA-staged version of the kernel

@@ -76,6 +76,14 @@ struct vo_solver_s {
     // or of other solvers, which touch only their own state) has been enqueued on the ctx since.
     ChainState cst;
     uint64_t chain_epoch = 0;
+    // Tile-blocked copy of (x, per-trajectory parameters, controller arrays) for the one-event adaptive sweep
+    // (rk_small_blk.cuh). Exactly one of the two layouts may be stale at any time: the blocked kernel leaves the public one
+    // (x, ca) stale, every other writer leaves the tiles stale; readers call ensure_soa first.
+    BlkView bv{};
+    bool blk_valid = false, soa_valid = true;
+    uint64_t blk_par_version = 0;  // rhs->version the tiles' parameter rows were packed from
+    uint64_t both_epoch = 0;       // ctx epoch when both layouts were last known equal (a library call on the ctx since then may have written x)
+    int use_blocked = 1;           // vo_solver_set_blocked: 0 keeps the sweep on the public layout (A/B and tests)
 };
 
 namespace {
@@ -93,6 +101,12 @@ TableauDev make_tableau_dev(const vo_tableau_s& t) {
     TableauDev d;
     std::memcpy(d.ac, t.ac, sizeof d.ac), std::memcpy(d.b, t.b, sizeof d.b), std::memcpy(d.b_err, t.b_err, sizeof d.b_err);
     d.s = t.s, d.has_err = t.has_err ? 1 : 0;
+    d.reuse = 0;
+    if (t.s >= 2) {
+        const double* last = &t.ac[(t.s - 1) * t.s];
+        if (t.has_err && std::memcmp(t.b_err, last, sizeof(double) * (t.s - 1)) == 0) d.reuse |= 1;
+        if (std::memcmp(t.b, last, sizeof(double) * (t.s - 1)) == 0) d.reuse |= 2;
+    }
     return d;
 }
 
@@ -291,6 +305,59 @@ __global__ void ctl_stats_finish_kernel(unsigned long long* sums, double* mm, un
     }
 }
 
+// ---- tile-blocked copy of the state (rk_small_blk.cuh) -------------------------------------------------------------------
+BlkPackArgs blk_args(const vo_solver_s* s) {
+    BlkPackArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.x = s->x->p, a.N = s->n, a.ca = s->ca, a.D = (int)s->d;
+    for (int q = 0; q < s->rhs->np; ++q)
+        if (s->rhs->per_traj[q]) a.par[a.npt++] = s->rhs->per_traj[q];
+    return a;
+}
+
+// public layout -> tiles, if the tiles are stale
+int32_t ensure_blk(vo_solver_s* s) {
+    vo_ctx c = s->ctx;
+    if (s->blk_valid && s->soa_valid && s->both_epoch != c->epoch) s->blk_valid = false;  // something on the ctx may have written x since
+    if (s->blk_valid && s->blk_par_version != s->rhs->version) {                           // a parameter changed under the tiles
+        if (!s->soa_valid) {
+            const BlkPackArgs a = blk_args(s);
+            blk_unpack_kernel<<<(unsigned)ceil_div(s->n, 256), 256, 0, c->stream>>>(s->bv, a, s->x->p);
+            VO_CHECK_LAUNCH(c);
+            s->soa_valid = true;
+        }
+        s->blk_valid = false;
+    }
+    if (s->blk_valid) return VO_OK;
+    const BlkPackArgs a = blk_args(s);
+    const int R = (int)s->d + 2 + a.npt;
+    const int64_t n_wtiles = ceil_div(s->n, VO_TILE_CTL) * (VO_TILE_CTL / VO_BLK_WT);
+    if (!s->bv.base || s->bv.R != R || s->bv.n_wtiles != n_wtiles) {
+        VO_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(s->bv.base), s->bv = BlkView{};
+        const uint32_t rb = blk_read_bytes(R);
+        if (cudaMalloc(&s->bv.base, (size_t)n_wtiles * (rb + 1024u)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "solver: tile-blocked state allocation failed");
+        s->bv.n_wtiles = n_wtiles, s->bv.read_bytes = rb, s->bv.stride = rb + 1024u, s->bv.R = R;
+    }
+    blk_pack_kernel<<<(unsigned)ceil_div(n_wtiles * VO_BLK_WT, 256), 256, 0, c->stream>>>(s->bv, a);
+    VO_CHECK_LAUNCH(c);
+    s->blk_valid = true, s->blk_par_version = s->rhs->version, s->both_epoch = c->epoch;
+    return VO_OK;
+}
+
+// tiles -> public layout, if the public layout is stale. `writing`: the caller is about to change x / ca, so the tiles go stale.
+int32_t ensure_soa(vo_solver_s* s, bool writing) {
+    vo_ctx c = s->ctx;
+    if (!s->soa_valid) {
+        const BlkPackArgs a = blk_args(s);
+        blk_unpack_kernel<<<(unsigned)ceil_div(s->n, 256), 256, 0, c->stream>>>(s->bv, a, s->x->p);
+        VO_CHECK_LAUNCH(c);
+        s->soa_valid = true, s->both_epoch = c->epoch;
+    }
+    if (writing) s->blk_valid = false;
+    return VO_OK;
+}
+
 // lock-step -> per-trajectory: every trajectory inherits the shared scalars.
 int32_t materialize(vo_solver_s* s) {
     if (!s->uniform) return VO_OK;
@@ -303,7 +370,7 @@ int32_t materialize(vo_solver_s* s) {
                                                                          (uint32_t)s->u_reject, word);
     VO_CHECK_LAUNCH(c);
     s->n_done = s->u_done ? s->n : 0;
-    s->uniform = false;
+    s->uniform = false, s->blk_valid = false, s->soa_valid = true;
     return VO_OK;
 }
 
@@ -340,8 +407,18 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     vo_ctx c = s->ctx;
     const TableauDev tb = make_tableau_dev(s->tab);
     const RhsParams rp = make_rhs_params(s->rhs);
+    // the one-event adaptive sweep of a compiled-in family runs on the tile-blocked copy of the state; everything else on the public layout
+    const bool blocked = cs && !s->uniform && s->use_blocked && s->rhs->kind != VO_RHS_CUSTOM && small_path_blocked_ok(s->n, s->tab.s, *cs);
+    if (blocked) {
+        int32_t br = ensure_blk(s);
+        if (br != VO_OK) return br;
+        s->soa_valid = false;
+    } else if (!s->uniform) {
+        int32_t br = ensure_soa(s, true);
+        if (br != VO_OK) return br;
+    }
     if (s->chain_epoch != c->epoch) s->cst.live = false;  // something else was enqueued on the ctx since our last launch
-    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, &s->cst};
+    SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, &s->cst, blocked ? &s->bv : nullptr};
     int32_t r = VO_ERR_UNSUPPORTED;
     switch (s->rhs->kind) {
         case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
@@ -637,6 +714,8 @@ int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
     }
     const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, 1);
     const unsigned grid = (unsigned)ceil_div(s->n, 256);
+    int32_t sr = ensure_soa(s, true);
+    if (sr != VO_OK) return sr;
     ctl_prepare_kernel<<<grid, 256, 0, c->stream>>>(s->ca, cs, s->n, s->evv, s->dtv);
     VO_CHECK_LAUNCH(c);
     ++*launches;
@@ -774,7 +853,7 @@ int32_t vo_solver_destroy(vo_solver s) {
     vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
     for (vo_ens k : s->K) vo_ens_destroy(k);
     free_ctl(s);
-    cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->cst.flags), cudaFree(s->snap);
+    cudaFree(s->bv.base), cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->cst.flags), cudaFree(s->snap);
     cudaFreeHost(s->ev_host);
     delete s;
     return VO_OK;
@@ -847,6 +926,7 @@ int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n) {
     vo_ctx c = s->ctx;
     DeviceGuard g(c->device);
     int32_t r = materialize(s);
+    if (r == VO_OK) r = ensure_soa(s, true);
     if (r != VO_OK) return r;
     VO_CUDA(c, cudaMemcpyAsync(s->ca.h, h_host, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VO_CUDA(c, cudaMemcpyAsync(s->ca.prev_h, h_host, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -863,6 +943,12 @@ int32_t vo_solver_set_events_per_launch(vo_solver s, int32_t k) {
 int32_t vo_solver_set_record_dx_norm(vo_solver s, int32_t on) {
     if (!s) return VO_ERR_BAD_ARG;
     s->record_dx_norm = on ? 1 : 0;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_blocked(vo_solver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->use_blocked = on ? 1 : 0;
     return VO_OK;
 }
 
@@ -980,6 +1066,10 @@ int32_t vo_current(vo_solver s, double* t_min, double* t_max, vo_ens* x) {
     if (!s) return VO_ERR_BAD_ARG;
     vo_ctx c = s->ctx;
     DeviceGuard g(c->device);
+    if (!s->uniform) {
+        int32_t er = ensure_soa(s, false);
+        if (er != VO_OK) return er;
+    }
     if (x) *x = s->x;
     if (t_min || t_max) {
         if (s->uniform) {
@@ -994,6 +1084,7 @@ int32_t vo_current(vo_solver s, double* t_min, double* t_max, vo_ens* x) {
             if (t_max) *t_max = *mm.second;
         }
     }
+    s->both_epoch = c->epoch;  // nothing above wrote the state; what the caller does with the borrowed ensemble moves the epoch on
     return VO_OK;
 }
 
@@ -1013,6 +1104,8 @@ int32_t vo_solver_stats(vo_solver s, int64_t* accepted, int64_t* rejected, doubl
         }
         return VO_OK;
     }
+    int32_t er = ensure_soa(s, false);
+    if (er != VO_OK) return er;
     std::vector<uint32_t> tmp(n);
     if (accepted) {
         VO_CUDA(c, cudaMemcpyAsync(tmp.data(), s->ca.n_accept, 4 * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1033,6 +1126,7 @@ int32_t vo_solver_stats(vo_solver s, int64_t* accepted, int64_t* rejected, doubl
     if (h) VO_CUDA(c, cudaMemcpyAsync(h, s->ca.h, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     if (dx_norm) VO_CUDA(c, cudaMemcpyAsync(dx_norm, s->ca.dx_norm, 8 * n, cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    s->both_epoch = c->epoch;  // read-only
     return VO_OK;
 }
 
@@ -1040,6 +1134,7 @@ int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
     if (!s || !x0) return VO_ERR_BAD_ARG;
     if (x0->d != s->d || x0->n != s->n) return vo_fail(s->ctx, VO_ERR_SHAPE, "vo_solver_reset: shape mismatch");
     DeviceGuard g(s->ctx->device);
+    s->blk_valid = false, s->soa_valid = true;  // everything is overwritten
     int32_t r = vo_ens_copy(s->x, x0);
     if (r == VO_OK) r = vo_ens_copy(s->next_x, x0);
     if (r == VO_OK && s->x_err) r = vo_ens_copy(s->x_err, x0);
@@ -1068,6 +1163,8 @@ int32_t vo_solver_local_stats(vo_solver s, unsigned long long* sums_dev, double*
         VO_CUDA(c, cudaMemcpyAsync(mm_dev, h_mm, sizeof h_mm, cudaMemcpyHostToDevice, c->stream));
         return VO_OK;
     }
+    int32_t er = ensure_soa(s, false);
+    if (er != VO_OK) return er;
     const uint64_t epoch = c->epoch;
     VO_CUDA(c, cudaMemsetAsync(sums_dev, 0, 6 * sizeof(unsigned long long), c->stream));
     const long long lowest = (long long)0x8000000000000000ull;  // below the key of every double
@@ -1089,6 +1186,10 @@ int32_t vo_rk_try_step(vo_solver s, double t, double dt, vo_ens next_x, vo_ens x
     DeviceGuard g(c->device);
     if (next_x->d != s->d || next_x->n != s->n || (x_err && (x_err->d != s->d || x_err->n != s->n)))
         return vo_fail(c, VO_ERR_SHAPE, "vo_rk_try_step: shape mismatch");
+    if (!s->uniform) {
+        int32_t er = ensure_soa(s, false);
+        if (er != VO_OK) return er;
+    }
     if (K)
         for (int j = 0; j < s->tab.s; ++j)
             if (!K[j] || K[j]->d != s->d || K[j]->n != s->n) return vo_fail(c, VO_ERR_SHAPE, "vo_rk_try_step: K must hold s ensembles of the solver's shape");

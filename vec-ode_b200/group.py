@@ -105,6 +105,13 @@ class Group:
         self._check(lib().vo_group_gather_placed(self._h, self._arr(ens_list), root, rows_a.ctypes.data_as(C.c_void_p), off_a.ctypes.data_as(C.c_void_p), ptr,
                                                  _cabi.LAYOUT_AOS if layout == "aos" else _cabi.LAYOUT_SOA, host_n))
 
+    def gather_interleaved(self, ens_list, tot: int, row0: int, out, host_n: int, root: int = 0, layout: str = "aos"):
+        """Asynchronous gather of a round-robin sharded block (vo_group_gather_interleaved): rank r holds trajectories
+        r, r + G, ... of the block's `tot`; the root places the block, in natural order, at rows [row0, row0 + tot) of `out`."""
+        ptr = out.ctypes.data_as(C.c_void_p) if (root in self.ranks and out is not None) else None
+        self._check(lib().vo_group_gather_interleaved(self._h, self._arr(ens_list), root, tot, row0, ptr,
+                                                      _cabi.LAYOUT_AOS if layout == "aos" else _cabi.LAYOUT_SOA, host_n))
+
     def sync(self):
         self._check(lib().vo_group_sync(self._h))
 

@@ -60,35 +60,57 @@ class ShardedChunkedSolve:
     """The same pipeline for ONE ensemble sharded by trajectory over the GPUs of a `Group` (one process per GPU): this rank
     uploads, integrates and hands over its shard in `parts` chunks, and every chunk is gathered to the root as soon as it is
     done — NCCL from the chunk's device state into the root's gather buffer, then one device-to-host copy straight into the
-    chunk's place in the root's host array (vo_group_gather_placed) — while the later chunks still integrate. The root's
-    host link carries the whole ensemble once; nothing else crosses PCIe on the way back.
+    chunk's place in the root's host array — while the later chunks still integrate. The root's host link carries the whole
+    ensemble once; nothing else crosses PCIe on the way back.
+
+    Sharding: contiguous ceil(N/G) ranges (`interleave=False`, vo_group_gather_placed), or round-robin (`interleave=True`:
+    rank r holds trajectories r, r + G, ...; vo_group_gather_interleaved) — the static interleave that balances an adaptive
+    ensemble whose cost varies along the trajectory index, e.g. config 3's mu sweep.
 
     `make_solver(ctx, lo, hi, x0)` as for ChunkedSolve, with [lo, hi) indices into THIS RANK's shard. All ranks issue the
     chunk gathers in the same order (chunk 0, 1, ...) on the group's own stream, which follows each chunk's stream through
     an event (vo_ctx_wait_for)."""
 
-    def __init__(self, group, n_total: int, d: int, make_solver, parts: int = 4, arith: str = "fast"):
+    def __init__(self, group, n_total: int, d: int, make_solver, parts: int = 4, arith: str = "fast", interleave: bool = False):
         import threading
-        self.group, self.n_total, self.d, self.parts = group, n_total, d, parts
+        self.group, self.n_total, self.d, self.parts, self.interleave = group, n_total, d, parts, interleave
         self.gctx = group.ctxs[0]
         self.rank, self.world = group.ranks[0], group.world
-        self.lo, self.hi = shard_range(n_total, self.rank, self.world)
-        n_local = self.hi - self.lo
-        self.local = ChunkedSolve(self.gctx.device, arith, n_local, d, make_solver, parts=parts)
-        # chunk q of rank r: rows and where they go in the whole ensemble
-        self.rows, self.off = [], []
-        for q in range(parts):
-            rows_q, off_q = [], []
-            for r in range(self.world):
-                slo, shi = shard_range(n_total, r, self.world)
-                lo, hi = shard_range(shi - slo, q, parts)
-                rows_q.append(max(hi - lo, 0)), off_q.append(slo + min(lo, shi - slo))
-            self.rows.append(rows_q), self.off.append(off_q)
+        G, r = self.world, self.rank
+        self.plan = []  # per chunk: (local lo, local hi, gather arguments)
+        if interleave:
+            self.n_local = max(0, -(-(n_total - r) // G))
+            n0 = -(-n_total // G)  # rank 0's count, the largest: chunk boundaries in units of G consecutive trajectories
+            for q in range(parts):
+                lo, hi = shard_range(n0, q, parts)
+                row0, tot = lo * G, max(0, min(hi * G, n_total) - lo * G)
+                mine = max(0, -(-(tot - r) // G))
+                self.plan.append((lo, lo + mine, (tot, row0)))
+        else:
+            slo, shi = shard_range(n_total, r, G)
+            self.n_local = shi - slo
+            for q in range(parts):
+                rows_q, off_q = [], []
+                for rr in range(G):
+                    a, b = shard_range(n_total, rr, G)
+                    lo, hi = shard_range(b - a, q, parts)
+                    rows_q.append(max(hi - lo, 0)), off_q.append(a + min(lo, b - a))
+                lo, hi = shard_range(self.n_local, q, parts)
+                self.plan.append((lo, max(lo, hi), (rows_q, off_q)))
+        self.chunks = []
+        for lo, hi, _ in self.plan:
+            if hi <= lo:
+                self.chunks.append(None)
+                continue
+            ctx = Context(self.gctx.device, arith=arith)
+            x0 = Ensemble(ctx, d, hi - lo)
+            self.chunks.append((lo, hi, ctx, x0, make_solver(ctx, lo, hi, x0)))
+        self.pool = ThreadPoolExecutor(max_workers=max(parts, 1))
         self._turn, self._cv = 0, threading.Condition()
-        self._placeholder = None  # a rank whose chunk q is empty still takes part in the gather with a 1-row dummy of 0 rows
+        self._placeholder = None  # a rank whose chunk is empty still takes part in the gather
 
-    def _one(self, q, chunk, host_in, host_out, adaptive, root):
-        st = None
+    def _one(self, q, host_in, host_out, adaptive, root):
+        chunk, st = self.chunks[q], None
         if chunk is not None:
             lo, hi, ctx, x0, solver = chunk
             x0.upload(host_in[lo:hi], "aos")
@@ -100,31 +122,28 @@ class ShardedChunkedSolve:
                 self.gctx.wait_for(chunk[2])
                 ens = chunk[4].current()[1]
             else:
-                ens = self._dummy()
-            self.group.gather_placed([ens], self.rows[q], self.off[q], host_out, root=root)
+                if self._placeholder is None:
+                    self._placeholder = Ensemble(self.gctx, self.d, 1)
+                ens = self._placeholder
+            args = self.plan[q][2]
+            if self.interleave:
+                self.group.gather_interleaved([ens], args[0], args[1], host_out, self.n_total, root=root)
+            else:
+                self.group.gather_placed([ens], args[0], args[1], host_out, root=root)
             self._turn += 1
             self._cv.notify_all()
         return st
 
-    def _dummy(self):
-        if self._placeholder is None:
-            self._placeholder = Ensemble(self.gctx, self.d, 1)
-        return self._placeholder
-
     def solve(self, host_in_local: np.ndarray, host_out_full, adaptive: bool = False, root: int = 0):
         """host_in_local: this rank's shard [n_local][d]; host_out_full: [n_total][d] on the root (ignored elsewhere).
         Returns this rank's per-chunk ODEState list; the whole ensemble is in host_out_full on the root on return."""
+        assert host_in_local.shape == (self.n_local, self.d)
         self._turn = 0
-        by_q = {q: None for q in range(self.parts)}
-        for q, c in enumerate(self.local.chunks):
-            by_q[q] = c
-        assert all(self.rows[q][self.rank] == (0 if by_q[q] is None else by_q[q][1] - by_q[q][0]) for q in range(self.parts))
-        pool = self.local.pool
-        futs = [pool.submit(self._one, q, by_q[q], host_in_local, host_out_full, adaptive, root) for q in range(self.parts)]
+        futs = [self.pool.submit(self._one, q, host_in_local, host_out_full, adaptive, root) for q in range(self.parts)]
         sts = [f.result() for f in futs]
         self.group.sync()
         return [s for s in sts if s is not None]
 
     @property
     def launch_count(self) -> int:
-        return self.local.launch_count
+        return sum(c[2].launch_count for c in self.chunks if c is not None)
