@@ -168,6 +168,9 @@ class VdpDopri5:
         if os.environ.get("VECODE_BENCH_NO_DX_NORM"):  # experiment switch: drop the per-attempt ODEAdaptiveData.dx_norm record (8 B)
             for s_ in self.solvers:
                 s_.set_record_dx_norm(False)
+        if os.environ.get("VECODE_BENCH_NO_BLOCKED"):  # experiment switch: keep the sweep on the public layout (rk_ctl2w_staged_kernel)
+            for s_ in self.solvers:
+                s_.set_blocked(False)
         if os.environ.get("VECODE_BENCH_MIXED"):  # experiment switch: store prev_h on every attempt (vo_solver_set_mixed_stepping)
             for s_ in self.solvers:
                 s_.set_mixed_stepping(True)

@@ -40,7 +40,9 @@ class ExpCfg(C.Structure):
                 ("no_adaptive", C.c_int32), ("taylor_deg", C.c_int32),
                 ("t0", C.c_double), ("tf", C.c_double), ("h0", C.c_double), ("rtol", C.c_double),
                 ("min_dt", C.c_double), ("max_dt", C.c_double), ("order", C.c_double), ("alpha", C.c_double),
-                ("max_calls", C.c_int64)]
+                ("max_calls", C.c_int64),
+                ("n_nodes", C.c_int32), ("n_rows", C.c_int32), ("n_rows_err", C.c_int32), ("pad_", C.c_int32),
+                ("c", C.c_void_p), ("alpha_tab", C.c_void_p), ("alpha_err_tab", C.c_void_p)]
 
 
 _lib = None
@@ -148,16 +150,26 @@ def rk_step(rhs, params, tableau, t, dt, x0, want_err=True):
 
 
 def exp_ensemble(scheme, basis, gp, psi0, t0, tf, h0, M_gen=None, cs=None, adaptive=False, no_adaptive=True,
-                 taylor_deg=0, rtol=1e-4, min_dt=1e-6, max_dt=1.0, order=3.0, alpha=0.9, max_calls=0, n_threads=1):
-    """basis: complex [M][n][n] (already -i*H_m); gp: [N][M_gen-1][3]; psi0: complex [N][n]."""
+                 taylor_deg=0, rtol=1e-4, min_dt=1e-6, max_dt=1.0, order=3.0, alpha=0.9, max_calls=0, n_threads=1, tables=None):
+    """basis: complex [M][n][n] (already -i*H_m); gp: [N][M_gen-1][3]; psi0: complex [N][n].
+    scheme "cfm_table": cfm_general (cfm.rs:43-100) with tables = (c[k], alpha[s][k], alpha_err[s_err][k] | None)."""
     basis = np.ascontiguousarray(basis, dtype=np.complex128)
     M, n, _ = basis.shape
     M_gen = M if M_gen is None else M_gen
     psi = np.ascontiguousarray(psi0, dtype=np.complex128).copy()
     N = psi.shape[0]
     gp = np.ascontiguousarray(gp, dtype=np.float64).reshape(N, max(M_gen - 1, 0), 3)
-    cfg = ExpCfg(n, M, {"midpoint": 0, "cfm4": 1, "magnus42": 2}[scheme], int(adaptive), int(no_adaptive), taylor_deg,
+    cfg = ExpCfg(n, M, {"midpoint": 0, "cfm4": 1, "magnus42": 2, "cfm_table": 3}[scheme], int(adaptive), int(no_adaptive), taylor_deg,
                  t0, tf, h0, rtol, min_dt, max_dt, order, alpha, max_calls)
+    keep = []
+    if scheme == "cfm_table":
+        c_t, a_t, e_t = tables
+        c_a = np.ascontiguousarray(c_t, dtype=np.float64)
+        a_a = np.ascontiguousarray(a_t, dtype=np.float64).reshape(-1, c_a.size)
+        e_a = None if e_t is None else np.ascontiguousarray(e_t, dtype=np.float64).reshape(-1, c_a.size)
+        keep = [c_a, a_a, e_a]
+        cfg.n_nodes, cfg.n_rows, cfg.n_rows_err = c_a.size, a_a.shape[0], 0 if e_a is None else e_a.shape[0]
+        cfg.c, cfg.alpha_tab, cfg.alpha_err_tab = c_a.ctypes.data, a_a.ctypes.data, None if e_a is None else e_a.ctypes.data
     t = np.zeros(N)
     h = np.zeros(N)
     acc = np.zeros(N, dtype=np.int64)

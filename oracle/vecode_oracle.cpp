@@ -647,9 +647,15 @@ void orc_lc_linear_combination(double* v, const double* const* v_arr, const doub
 // Generator family: L_i(t) = -i * (H_0 + sum_{m>=1} g_m(t; p_i) H_m), g_m(t) = amp_{i,m} * cos(omega_{i,m} t + phase_{i,m}).
 // Basis handed in as B_m = -i * H_m so coefficients are real; gp: [N][M-1][3] = (amp, omega, phase).
 struct ExpCfg {
-    int32_t n, M, scheme /*0 midpoint, 1 cfm4, 2 magnus42*/, adaptive, no_adaptive, taylor_deg;
+    int32_t n, M, scheme /*0 midpoint, 1 cfm4, 2 magnus42, 3 cfm_general with the tables below*/, adaptive, no_adaptive, taylor_deg;
     double t0, tf, h0, rtol, min_dt, max_dt, order, alpha;
     int64_t max_calls;
+    // scheme 3: cfm_general (cfm.rs:43-100) with caller-supplied nodes c[n_nodes], alpha[n_rows][n_nodes] and the optional
+    // lower-order alph_err[n_rows_err][n_nodes]
+    int32_t n_nodes, n_rows, n_rows_err, pad_;
+    const double* c;
+    const double* alpha_tab;
+    const double* alpha_err_tab;
 };
 
 static void gen_coef(const ExpCfg& c, const double* gp_i, double t, std::vector<cplx>& coef) {
@@ -703,6 +709,24 @@ void orc_exp_ensemble(const ExpCfg* cfg, const double* basis /*[M][n][n] complex
                     if (want_err) {                                                                // cfm.rs:83-97
                         cfm_exp(sp, dat.x.data(), dx.data(), dt, va, k, CFM_R2_J1_GL, 2);
                         for (int r = 0; r < n; ++r) dx[r] = dx[r] - dat.next_x[r];
+                    }
+                } else if (cfg->scheme == 3) {  // cfm_general with runtime tables, cfm.rs:43-100
+                    const int kn = cfg->n_nodes;
+                    va.resize((size_t)kn);
+                    for (int q = 0; q < kn; ++q) gen_coef(gc, gpi, t + cfg->c[q] * dt, va[q]), pad(va[q]);   // :70-72
+                    cfm_exp(sp, dat.x.data(), tmp.data(), dt, va, k, cfg->alpha_tab, kn);                      // :74-75
+                    for (int i = 1; i < cfg->n_rows; ++i) {                                                    // :76-80
+                        cfm_exp(sp, tmp.data(), tmp2.data(), dt, va, k, cfg->alpha_tab + (size_t)i * kn, kn);
+                        std::swap(tmp, tmp2);
+                    }
+                    dat.next_x = tmp;                                                                          // :81
+                    if (want_err && cfg->alpha_err_tab) {                                                      // :83-97
+                        cfm_exp(sp, dat.x.data(), tmp.data(), dt, va, k, cfg->alpha_err_tab, kn);
+                        for (int i = 1; i < cfg->n_rows_err; ++i) {
+                            cfm_exp(sp, tmp.data(), tmp2.data(), dt, va, k, cfg->alpha_err_tab + (size_t)i * kn, kn);
+                            std::swap(tmp, tmp2);
+                        }
+                        for (int r = 0; r < n; ++r) dx[r] = tmp[r] - dat.next_x[r];
                     }
                 } else {  // magnus_42, magnus.rs:28-83
                     const double c_mid = 0.288675134594812882254574390251;

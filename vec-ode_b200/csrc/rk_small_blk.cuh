@@ -16,6 +16,13 @@
 // before anything else looks at the state (vo_current, vo_solver_stats, another kernel, the stage path, ...). Arithmetic,
 // event logic and the tile -> CTA map (CTA b owns tiles 4b .. 4b+3 of every grid-stride round) are those of
 // rk_ctl2w_staged_kernel, so results are bit-identical to it (tests/test_gpu_rk.py) and the launches chain the same way.
+//
+// MEASURED (round 2, 10^6 Van der Pol oscillators, DoPri5, one attempt per launch; gpurun_out r2c): 10.24 M warp instructions per
+// launch against 10.67 M on the public layout (fast; 13.22 M against 13.74 M strict), the same 52 MB of DRAM reads — and 18.4 us
+// against 17.1 us per launch (fast), 21.2 against 20.5 (strict). The sweep is not bound by instruction issue after all: it moves
+// 92-96 B per attempt (52 read: state 16, t 8, h 8, mu 8, word + two counters 12; ~42 written), which at 17.1 us is 5.5 TB/s =
+// 85 % of the measured copy peak. Fewer instructions buy nothing there, and one 3.3 KB bulk copy per warp tile has a longer
+// latency than the seven 16-byte cp.async of the public-layout kernel. Kept as an option (vo_solver_set_blocked), off by default.
 #pragma once
 #include "rk_small2.cuh"
 

@@ -83,7 +83,7 @@ struct vo_solver_s {
     bool blk_valid = false, soa_valid = true;
     uint64_t blk_par_version = 0;  // rhs->version the tiles' parameter rows were packed from
     uint64_t both_epoch = 0;       // ctx epoch when both layouts were last known equal (a library call on the ctx since then may have written x)
-    int use_blocked = 1;           // vo_solver_set_blocked: 0 keeps the sweep on the public layout (A/B and tests)
+    int use_blocked = 0;           // vo_solver_set_blocked: 1 runs the one-event sweep on the tile-blocked copy (measured: no faster, see rk_small_blk.cuh)
 };
 
 namespace {
