@@ -280,6 +280,8 @@ int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int
 #define VO_EXP_CFM4 1     /* ExpCFMSolver, exp/cfm.rs:102-224 */
 #define VO_EXP_MAGNUS42 2 /* MagnusExpLinearSolver, exp/magnus.rs:151-285 */
 #define VO_EXP_SPLIT_MIDPOINT 3 /* ExpSplitMidpointSolver, exp/split_exp.rs:520-562, 613-685 (literal: f at t, both splits by dt/2) */
+#define VO_EXP_CFM_TABLE 4      /* cfm_general (exp/cfm.rs:43-100) with the caller's nodes and weights: vo_exp_set_cfm_tables */
+#define VO_EXP_SPLIT_CFM 5      /* split_cfm (exp/split_exp.rs:568-609), the BAB commutator-free split: vo_exp_set_split_cfm_tables */
 int32_t vo_exp_create(vo_ctx ctx, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N,
                       double t0, double tf, const double* psi0_host /* [N][n] (re,im) */, double h, vo_expsolver* out);
 int32_t vo_exp_destroy(vo_expsolver s);
@@ -296,6 +298,21 @@ int32_t vo_exp_set_generator(vo_expsolver s, const char* body);
  * handed to vo_exp_create are in device order; call this right after creating the solver. */
 int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n);
 int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap);
+/* The arguments `c`, `alpha`, `alph_err` of cfm_general (exp/cfm.rs:47-52): k <= 4 nodes, alpha [rows][k] with rows <= 8
+ * exponentials per step, alph_err [rows_err][k] (rows_err <= min(rows, 4)) or NULL for no embedded solution. A step is
+ *   x <- exp(dt sum_q alpha[rows-1][q] L(t + c_q dt)) ... exp(dt sum_q alpha[0][q] L(t + c_q dt)) x
+ * with every exponent formed by cfm_exp's operations in its order (cfm.rs:31-37). Mismatched shapes return VO_ERR_SHAPE with the
+ * reference's panic message. VO_EXP_CFM4 solvers are created with C_GAUSS_LEGENDRE_4 / CFM_R4_J2_GL / CFM_R2_J1_GL already set. */
+int32_t vo_exp_set_cfm_tables(vo_expsolver s, const double* c, int32_t k, const double* alpha, int32_t rows, const double* alpha_err, int32_t rows_err);
+/* split_cfm's `c`, `rho` [stages][k], `sigma` [stages + 1][k] (split_exp.rs:571-573): per step B(sigma_0) A(rho_0) B(sigma_1) ...
+ * A(rho_{stages-1}) B(sigma_stages), A and B being the two index sets of vo_exp_set_split_mask. 2 stages + 1 <= 8. */
+int32_t vo_exp_set_split_cfm_tables(vo_expsolver s, const double* c, int32_t k, const double* rho, const double* sigma, int32_t stages);
+/* The coefficient tables of src/dat/mod.rs:3-6, 66-81 (quad::C_GAUSS_LEGENDRE_4, cfqm::*) as the reference spells them. */
+#define VO_CFM_C_GAUSS_LEGENDRE_4 0
+#define VO_CFM_R2_J1_GL 1
+#define VO_CFM_R4_J2_GL 2
+#define VO_CFM_BLANES17_R4_J4 3
+int32_t vo_cfm_builtin_table(int32_t which, double* out /* [rows][cols], nullable */, int32_t* rows, int32_t* cols);
 /* VO_EXP_SPLIT_MIDPOINT: bit m of a_mask set <=> basis matrix m belongs to split A (the rest form split B). */
 int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */

@@ -201,3 +201,21 @@ def solve_fixed(scheme, sp, gp_i, M_gen, psi0, t0, h, n_steps, cs=None, tables=N
             x, _ = magnus_42(sp, g, t, x, h, cs, want_err=False)
         t += h
     return x
+
+
+def split_cfm(sp, a_idx, f, t, x0, dt, c, rho, sigma):
+    """src/exp/split_exp.rs:568-609 with the two user splits SpA, SpB as the index sets `a_idx` / the rest of ONE shared basis:
+    an operator of split A is a coefficient vector that vanishes outside a_idx (and likewise for B), so f's pair (va, vb) is
+    the generator's coefficient vector masked to either side. B(sigma_0) A(rho_0) ... A(rho_{s-1}) B(sigma_s) (:601-608)."""
+    if any(len(r) != len(c) for r in rho) or any(len(r) != len(c) for r in sigma) or len(sigma) != len(rho) + 1:
+        raise ValueError("split_cfm: Incompatible array dimensions")   # :587-592
+    t_arr = [t + ci * dt for ci in c]                                   # :597
+    full = f(t_arr)                                                     # :599
+    in_a = [m in a_idx for m in range(sp.M)]
+    va = [[coef[m] if in_a[m] else (0.0, 0.0) for m in range(sp.M)] for coef in full]
+    vb = [[(0.0, 0.0) if in_a[m] else coef[m] for m in range(sp.M)] for coef in full]
+    x = list(x0)
+    for i in range(len(rho)):                                           # :601-606
+        x = cfm_exp(sp, x, dt, vb, sigma[i])
+        x = cfm_exp(sp, x, dt, va, rho[i])
+    return cfm_exp(sp, x, dt, vb, sigma[len(rho)])                      # :607-608

@@ -57,3 +57,18 @@ def split_exp_midpoint_step(A_of_t, B_of_t, t, x, dt):
     """split_exp_midpoint (:520-562), literally: (la, lb) = f(t); UA0 = exp(dt/2 la); UB0 = exp(dt/2 lb); A B A."""
     ua, ub = expm(0.5 * dt * A_of_t(t)), expm(0.5 * dt * B_of_t(t))
     return ua @ (ub @ (ua @ x))
+
+
+def split_cfm_step(A_of_t, B_of_t, t, x, dt, c, rho, sigma):
+    """split_cfm (:568-609) with dense matrix exponentials: B(sigma_0) A(rho_0) ... A(rho_{s-1}) B(sigma_s), each exponent
+    dt * sum_q w_q L(t + c_q dt) (cfm_exp, src/exp/cfm.rs:20-40)."""
+    ts = [t + ci * dt for ci in c]
+    As, Bs = [A_of_t(tt) for tt in ts], [B_of_t(tt) for tt in ts]
+
+    def comb(mats, w):
+        return dt * sum(wq * m for wq, m in zip(w, mats))
+    y = x
+    for i in range(len(rho)):
+        y = expm(comb(Bs, sigma[i])) @ y
+        y = expm(comb(As, rho[i])) @ y
+    return expm(comb(Bs, sigma[len(rho)])) @ y

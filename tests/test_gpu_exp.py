@@ -240,3 +240,80 @@ def test_grouping_systems_by_drive_amplitude_keeps_the_callers_order(vo, ctx, or
     assert np.array_equal(st["accepted"], ref["accepted"])
     s.reset(psi0)
     assert s.run().kind == "Done" and np.array_equal(s.current()[1], psi)
+
+
+# ---- round 2: cfm_general with run-time tables, split_cfm, dense per-system operators ---------------------------------------
+GL6_NODES = [0.5 - np.sqrt(15.0) / 10.0, 0.5, 0.5 + np.sqrt(15.0) / 10.0]
+GL6_WEIGHTS = [[5.0 / 18.0, 4.0 / 9.0, 5.0 / 18.0]]  # exp(dt sum_q w_q L(t + c_q dt)): the 2nd-order exponential, as the embedded row
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_cfm_general_with_tables_matches_oracle(vo, ctx, oracle, n):
+    """cfm_general (exp/cfm.rs:43-100) with the caller's nodes and weights: BLANES17_R4_J4 (dat/mod.rs:76-80) on the three
+    6th-order Gauss-Legendre nodes, 4 exponentials per step; fixed steps <= 1e-12 against the oracle's cfm_general, and an
+    adaptive run with a one-exponential embedded row follows the oracle's step sequence."""
+    N = 24
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    alpha = vo.cfm_table("BLANES17_R4_J4")
+    assert alpha.shape == (4, 3) and np.array_equal(vo.cfm_table("CFM_R4_J2_GL"), [[0.53867513459481288225, -0.038675134594812882255], [-0.038675134594812882255, 0.53867513459481288225]])
+    s = vo.ExpCFMGeneralSolver(sp, gp, 0.0, 2.0, psi0, 0.1, GL6_NODES, alpha)
+    st = s.run()
+    assert st.kind == "Done"
+    ref = oracle.exp_ensemble("cfm_table", np.stack([B0, B1]), gp, psi0, 0.0, 2.0, 0.1, no_adaptive=True, tables=(GL6_NODES, alpha, None))
+    _, psi = s.current()
+    assert np.abs(psi - ref["psi"]).max() <= 1e-12 and np.array_equal(s.stats()["accepted"], ref["accepted"])
+    assert np.abs(np.linalg.norm(psi, axis=1) - 1.0).max() <= 1e-12
+    # the same tables through CFM4's own path: ExpCFMSolver is cfm_general with C_GAUSS_LEGENDRE_4 / CFM_R4_J2_GL / CFM_R2_J1_GL
+    a = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1).no_adaptive()
+    b = vo.ExpCFMGeneralSolver(sp, gp, 0.0, 1.0, psi0, 0.1, vo.cfm_table("C_GAUSS_LEGENDRE_4")[0], vo.cfm_table("CFM_R4_J2_GL"))
+    a.run(), b.run()
+    assert np.array_equal(a.current()[1].view(np.float64), b.current()[1].view(np.float64))
+    # adaptive
+    s = vo.ExpCFMGeneralSolver(sp, gp, 0.0, 2.0, psi0, 0.05, GL6_NODES, alpha, alph_err=GL6_WEIGHTS).with_tolerance(1e-6, 1e-6)
+    st = s.run(adaptive=True)
+    ref = oracle.exp_ensemble("cfm_table", np.stack([B0, B1]), gp, psi0, 0.0, 2.0, 0.05, adaptive=True, no_adaptive=False, rtol=1e-6,
+                              tables=(GL6_NODES, alpha, GL6_WEIGHTS))
+    stats = s.stats()
+    assert st.kind == "Done" and np.all(np.abs(stats["t"] - 2.0) <= 1e-13)
+    assert np.array_equal(stats["accepted"], ref["accepted"]) and np.array_equal(stats["rejected"], ref["rejected"])
+    assert np.abs(s.current()[1] - ref["psi"]).max() <= 1e-10
+    with pytest.raises(vo.VecOdeError) as e:
+        vo.ExpCFMGeneralSolver(sp, gp, 0.0, 1.0, psi0, 0.1, GL6_NODES, alpha[:, :2])
+    assert "Incompatible array dimensions" in e.value.msg
+
+
+def test_split_cfm_solver_matches_restatements(vo, ctx):
+    """split_cfm (exp/split_exp.rs:568-609): B(sigma_0) A(rho_0) B(sigma_1) A(rho_1) B(sigma_2) with commutator-free exponents
+    on the two Gauss-Legendre nodes. Against the pure-Python restatement of the same operations (scaled Taylor series, <= 1e-12)
+    and against dense matrix exponentials (scipy expm)."""
+    from oracle import exp_oracle as eo
+    from oracle import split_oracle as so
+    n, N, h, steps = 16, 5, 0.07, 3
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    basis = np.stack([B0, B1])
+    sp = vo.DenseBasisSplit(ctx, basis)
+    c = list(vo.cfm_table("C_GAUSS_LEGENDRE_4")[0])
+    # a 2-stage BAB composition whose A-weights and B-weights each sum to one over the step (consistency), asymmetric in the nodes
+    rho = [[0.30, 0.20], [0.20, 0.30]]
+    sigma = [[0.15, 0.05], [0.35, 0.25], [0.05, 0.15]]
+    s = vo.ExpSplitCFMSolver(sp, [0], gp, 0.0, steps * h, psi0, h, c, rho, sigma)
+    st = s.run()
+    assert st.kind == "Done" and np.all(s.stats()["accepted"] >= steps)
+    got = s.current()[1]
+    psp = eo.BasisSplit([[[(complex(z).real, complex(z).imag) for z in row] for row in B] for B in basis])
+    for i in range(N):
+        g = eo.gen_cos([tuple(r) for r in gp[i]], 2, 2)
+        x, t = [(z.real, z.imag) for z in psi0[i]], 0.0
+        y = psi0[i].copy()
+        for k in range(int(s.stats()["accepted"][i])):
+            dt = h if k < steps else steps * h - t  # the remainder step of the driver loop, if any
+            x = eo.split_cfm(psp, [0], lambda ts: [g(tt) for tt in ts], t, x, dt, c, rho, sigma)
+            y = so.split_cfm_step(lambda tt: B0, lambda tt: gp[i, 0, 0] * np.cos(gp[i, 0, 1] * tt + gp[i, 0, 2]) * B1, t, y, dt, c, rho, sigma)
+            t += dt
+        ref = np.array([complex(a, b) for a, b in x])
+        assert np.abs(got[i] - ref).max() <= 1e-12 and np.abs(got[i] - y).max() <= 1e-11
+    with pytest.raises(vo.VecOdeError):
+        vo.ExpSplitCFMSolver(sp, [0], gp, 0.0, 1.0, psi0, h, c, rho, sigma[:2])
+    with pytest.raises(vo.VecOdeError):
+        s.step_adaptive()

@@ -22,7 +22,8 @@ LAYOUT_SOA, LAYOUT_AOS = 0, 1
 NORM = {"L2": 0, "LINF": 1, "L1": 2, "HYPOT": 3}
 TABLEAU = {"RKF45_REF": 0, "RK4": 1, "DOPRI5": 2}
 RHS = {"DIAG_LINEAR": 0, "HARMONIC2D": 1, "LORENZ63": 2, "VDP": 3, "HEAT1D": 4, "CUSTOM": 5}
-EXP_SCHEME = {"midpoint": 0, "cfm4": 1, "magnus42": 2, "split_midpoint": 3}
+EXP_SCHEME = {"midpoint": 0, "cfm4": 1, "magnus42": 2, "split_midpoint": 3, "cfm_table": 4, "split_cfm": 5}
+CFM_TABLE = {"C_GAUSS_LEGENDRE_4": 0, "CFM_R2_J1_GL": 1, "CFM_R4_J2_GL": 2, "BLANES17_R4_J4": 3}
 EV_STEP, EV_CHKPT, EV_REJECT, EV_END, EV_ERR = range(5)
 STATE_OK, STATE_DONE, STATE_ERR = range(3)
 TRAJ_DONE, TRAJ_NONFINITE, TRAJ_STUCK = 1, 2, 4
@@ -134,6 +135,9 @@ SIGNATURES = {
     "vo_map_exp": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "vo_map_exp_seq": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
     "vo_exp_set_split_mask": (_i32, [_vp, C.c_uint32]),
+    "vo_exp_set_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32]),
+    "vo_exp_set_split_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32]),
+    "vo_cfm_builtin_table": (_i32, [_i32, _vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "vo_exp_create": (_i32, [_vp, _vp, _i32, _i32, _vp, _i64, _f64, _f64, _vp, _f64, _pvp]),
     "vo_exp_destroy": (_i32, [_vp]),
     "vo_exp_set_generator": (_i32, [_vp, C.c_char_p]),

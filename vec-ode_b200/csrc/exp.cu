@@ -56,7 +56,34 @@ struct vo_expsolver_s {
     double2* stage = nullptr;    // [N][n] staging for the reordering copies
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
+    // commutator-free schemes as tables (cfm_general's c / alpha / alph_err, exp/cfm.rs:43-53; split_cfm's rho / sigma)
+    int n_nodes = 0, n_rows = 0, n_rows_err = 0;
+    double tab_c[VO_EXP_MAX_NODES] = {};
+    double tab_alpha[VO_EXP_MAX_ROWS * VO_EXP_MAX_NODES] = {};
+    double tab_alpha_err[VO_EXP_MAX_ERR * VO_EXP_MAX_NODES] = {};
+    unsigned char row_split[VO_EXP_MAX_ROWS] = {};
 };
+
+// src/dat/mod.rs:4, 67-80 (same literals as the reference)
+static const double C_GAUSS_LEGENDRE_4[2] = {0.21132486540518711775, 0.78867513459481288225};
+static const double CFM_R2_J1_GL[2] = {0.5, 0.5};
+static const double CFM_R4_J2_GL[4] = {0.53867513459481288225, -0.038675134594812882255, -0.038675134594812882255, 0.53867513459481288225};
+static const double BLANES17_R4_J4[12] = {0.2463347584748155,  -0.0469610812011527, 0.0119511881315244,  0.0622500005170514, 0.2691833034233750,  -0.0427581693456134,
+                                          -0.0427581693456134, 0.2691833034233750,  0.0622500005170514,  0.0119511881315244, -0.0469610812011527, 0.2463347584748155};
+
+static int32_t exp_store_tables(vo_expsolver_s* s, const double* c, int k, const double* alpha, int rows, const double* alpha_err, int rows_err) {
+    if (!c || !alpha || k < 1 || k > VO_EXP_MAX_NODES || rows < 1 || rows > VO_EXP_MAX_ROWS || rows_err < 0 || rows_err > VO_EXP_MAX_ERR || (rows_err > 0 && !alpha_err))
+        return vo_fail(s->ctx, VO_ERR_SHAPE, "split_cfm: Incompatible array dimensions");  // the reference's panic message (cfm.rs:63, 86)
+    if (rows_err > rows) return vo_fail(s->ctx, VO_ERR_SHAPE, "split_cfm: Incompatible array dimensions for alph_err");  // cfm.rs:85-87
+    s->n_nodes = k, s->n_rows = rows, s->n_rows_err = rows_err;
+    std::memset(s->tab_alpha, 0, sizeof s->tab_alpha), std::memset(s->tab_alpha_err, 0, sizeof s->tab_alpha_err), std::memset(s->row_split, 0, sizeof s->row_split);
+    for (int q = 0; q < k; ++q) s->tab_c[q] = c[q];
+    for (int e = 0; e < rows; ++e)
+        for (int q = 0; q < k; ++q) s->tab_alpha[e * VO_EXP_MAX_NODES + q] = alpha[e * k + q];
+    for (int e = 0; e < rows_err; ++e)
+        for (int q = 0; q < k; ++q) s->tab_alpha_err[e * VO_EXP_MAX_NODES + q] = alpha_err[e * k + q];
+    return VO_OK;
+}
 
 namespace {
 
@@ -166,8 +193,11 @@ int32_t exp_ev_read(vo_expsolver_s* s, EvSlot* out) {
 int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     vo_ctx c = s->ctx;
     if (adaptive && !s->want_err) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // ode.rs:312
-    if (adaptive && (s->scheme == VO_EXP_MIDPOINT || s->scheme == VO_EXP_SPLIT_MIDPOINT))
+    if (adaptive && (s->scheme == VO_EXP_MIDPOINT || s->scheme == VO_EXP_SPLIT_MIDPOINT || s->scheme == VO_EXP_SPLIT_CFM))
         return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "this solver has no error estimate (it only implements ODESolver)");
+    const bool tables = s->scheme == VO_EXP_CFM4 || s->scheme == VO_EXP_CFM_TABLE || s->scheme == VO_EXP_SPLIT_CFM;
+    if (tables && s->n_rows < 1) return vo_fail(c, VO_ERR_STATE, "exp: the scheme's tables have not been set (vo_exp_set_cfm_tables / vo_exp_set_split_cfm_tables)");
+    if (adaptive && tables && s->n_rows_err < 1) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // alph_err is None (cfm.rs:214-222)
     ExpKP kp = make_kp(s->sp, 0);
     kp.M_gen = s->M_gen, kp.scheme = s->scheme, kp.adaptive = adaptive ? 1 : 0;
     kp.want_err = (s->want_err && adaptive) ? 1 : 0;  // the embedded solution only feeds the controller
@@ -175,6 +205,9 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     kp.rtol = s->rtol, kp.alpha = s->alpha, kp.pw = s->pw, kp.min_dt = s->min_dt, kp.max_dt = s->max_dt;
     kp.pw_is_third = s->pw == 1.0 / 3.0;
     kp.split_mask = s->split_mask;
+    kp.n_nodes = s->n_nodes, kp.n_rows = s->n_rows, kp.n_rows_err = s->n_rows_err;
+    std::memcpy(kp.tab_c, s->tab_c, sizeof kp.tab_c), std::memcpy(kp.tab_alpha, s->tab_alpha, sizeof kp.tab_alpha);
+    std::memcpy(kp.tab_alpha_err, s->tab_alpha_err, sizeof kp.tab_alpha_err), std::memcpy(kp.row_split, s->row_split, sizeof kp.row_split);
     return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn);
 }
 
@@ -320,12 +353,13 @@ int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask) {
 
 int32_t vo_exp_create(vo_ctx c, vo_split sp, int32_t scheme, int32_t M_gen, const double* gp_host, int64_t N, double t0, double tf,
                       const double* psi0_host, double h, vo_expsolver* out) {
-    if (!c || !sp || !out || !psi0_host || N < 1 || scheme < 0 || scheme > VO_EXP_SPLIT_MIDPOINT || M_gen < 1 || M_gen > sp->M || (M_gen > 1 && !gp_host))
+    if (!c || !sp || !out || !psi0_host || N < 1 || scheme < 0 || scheme > VO_EXP_SPLIT_CFM || M_gen < 1 || M_gen > sp->M || (M_gen > 1 && !gp_host))
         return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: bad argument");
     if (scheme == VO_EXP_MAGNUS42 && !sp->has_cs) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: Magnus needs vo_split_set_commutator (Commutator trait, exp/mod.rs:47-54)");
     DeviceGuard g(c->device);
     vo_expsolver s = new vo_expsolver_s();
     s->ctx = c, s->sp = sp, s->scheme = scheme, s->M_gen = M_gen, s->N = N, s->t0 = t0, s->tf = tf, s->h_init = h;
+    if (scheme == VO_EXP_CFM4) exp_store_tables(s, C_GAUSS_LEGENDRE_4, 2, CFM_R4_J2_GL, 2, CFM_R2_J1_GL, 1);  // ExpCFMSolver::new, cfm.rs:131-154
     const size_t nb = sizeof(double2) * (size_t)N * sp->n, ngp = sizeof(double) * (size_t)N * std::max(1, M_gen - 1) * 3;
     bool ok = cudaMalloc(&s->psi, nb) == cudaSuccess && cudaMalloc(&s->psi0, nb) == cudaSuccess && cudaMalloc(&s->gp, ngp) == cudaSuccess &&
               cudaMalloc(&s->ca.t, 8 * N) == cudaSuccess && cudaMalloc(&s->ca.h, 8 * N) == cudaSuccess && cudaMalloc(&s->ca.prev_h, 8 * N) == cudaSuccess &&
@@ -373,6 +407,43 @@ int32_t vo_exp_set_generator(vo_expsolver s, const char* body) {
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
     rtc_exp_unload(s->gen_module);
     s->gen_module = mod, s->gen_fn = fn;
+    return VO_OK;
+}
+
+int32_t vo_exp_set_cfm_tables(vo_expsolver s, const double* c, int32_t k, const double* alpha, int32_t rows, const double* alpha_err, int32_t rows_err) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (s->scheme != VO_EXP_CFM_TABLE && s->scheme != VO_EXP_CFM4) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_cfm_tables: the solver was not created with VO_EXP_CFM_TABLE");
+    return exp_store_tables(s, c, k, alpha, rows, alpha_err, rows_err);
+}
+
+int32_t vo_exp_set_split_cfm_tables(vo_expsolver s, const double* c, int32_t k, const double* rho, const double* sigma, int32_t stages) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (s->scheme != VO_EXP_SPLIT_CFM) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_split_cfm_tables: the solver was not created with VO_EXP_SPLIT_CFM");
+    if (!c || !rho || !sigma || stages < 1 || 2 * stages + 1 > VO_EXP_MAX_ROWS || k < 1 || k > VO_EXP_MAX_NODES)
+        return vo_fail(s->ctx, VO_ERR_SHAPE, "split_cfm: Incompatible array dimensions");  // split_exp.rs:587-592
+    // B(sigma_0) A(rho_0) B(sigma_1) ... A(rho_{s-1}) B(sigma_s), split_exp.rs:601-608
+    std::vector<double> rows((size_t)(2 * stages + 1) * k);
+    for (int i = 0; i <= stages; ++i) std::memcpy(&rows[(size_t)(2 * i) * k], &sigma[(size_t)i * k], sizeof(double) * k);
+    for (int i = 0; i < stages; ++i) std::memcpy(&rows[(size_t)(2 * i + 1) * k], &rho[(size_t)i * k], sizeof(double) * k);
+    int32_t r = exp_store_tables(s, c, k, rows.data(), 2 * stages + 1, nullptr, 0);
+    if (r != VO_OK) return r;
+    for (int e = 0; e < 2 * stages + 1; ++e) s->row_split[e] = (e % 2 == 0) ? 2 : 1;
+    return VO_OK;
+}
+
+int32_t vo_cfm_builtin_table(int32_t which, double* out, int32_t* rows, int32_t* cols) {
+    const double* src = nullptr;
+    int r = 0, k = 0;
+    switch (which) {
+        case VO_CFM_C_GAUSS_LEGENDRE_4: src = C_GAUSS_LEGENDRE_4, r = 1, k = 2; break;
+        case VO_CFM_R2_J1_GL: src = CFM_R2_J1_GL, r = 1, k = 2; break;
+        case VO_CFM_R4_J2_GL: src = CFM_R4_J2_GL, r = 2, k = 2; break;
+        case VO_CFM_BLANES17_R4_J4: src = BLANES17_R4_J4, r = 4, k = 3; break;
+        default: return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_cfm_builtin_table: unknown table");
+    }
+    if (out) std::memcpy(out, src, sizeof(double) * r * k);
+    if (rows) *rows = r;
+    if (cols) *cols = k;
     return VO_OK;
 }
 

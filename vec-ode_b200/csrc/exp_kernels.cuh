@@ -5,7 +5,10 @@
 #include "rk_small.cuh"  // CtlArrays / EvSlot / status-word layout shared with the RK solver
 
 #define VO_EXP_MAX_M 4
-#define VO_EXP_MAX_E 3  // exponentials per step: CFM4 adaptive = 2 + 1, Magnus adaptive = 1 + 1
+#define VO_EXP_MAX_NODES 4  // quadrature nodes of a commutator-free scheme (cfm_general's `c`, exp/cfm.rs:47)
+#define VO_EXP_MAX_ROWS 8   // exponentials of the propagated solution: rows of `alpha` (cfm.rs:48), or the 2 s + 1 factors of split_cfm
+#define VO_EXP_MAX_ERR 4    // exponentials of the embedded lower-order solution: rows of `alph_err` (cfm.rs:52)
+#define VO_EXP_MAX_E (VO_EXP_MAX_ROWS + VO_EXP_MAX_ERR)
 
 struct ExpKP {
     int n, M, M_gen, scheme, adaptive, want_err, taylor_deg, mode;  // mode 0: solver event, 1: bare map_exp
@@ -17,12 +20,18 @@ struct ExpKP {
     double norm1[VO_EXP_MAX_M];
     double cs[VO_EXP_MAX_M * VO_EXP_MAX_M * VO_EXP_MAX_M];
     int64_t N;
+    // commutator-free schemes as TABLES, the arguments of cfm_general (exp/cfm.rs:43-53) and split_cfm (exp/split_exp.rs:568-575):
+    // exponential e of a step is exp(dt * sum_q tab_alpha[e][q] L(t + tab_c[q] dt)), restricted to the basis matrices of split A
+    // (row_split 1) or of split B (2) or to none (0). VO_EXP_CFM4 is the tables of dat/mod.rs:4, 67-74 through the same code.
+    int n_nodes, n_rows, n_rows_err;
+    double tab_c[VO_EXP_MAX_NODES];
+    double tab_alpha[VO_EXP_MAX_ROWS * VO_EXP_MAX_NODES];
+    double tab_alpha_err[VO_EXP_MAX_ERR * VO_EXP_MAX_NODES];
+    unsigned char row_split[VO_EXP_MAX_ROWS];
 };
 
-// dat/mod.rs:4, 67-74 (same literals as the reference)
-__constant__ double C_GL4[2] = {0.21132486540518711775, 0.78867513459481288225};
-__constant__ double CFM_R4[4] = {0.53867513459481288225, -0.038675134594812882255, -0.038675134594812882255, 0.53867513459481288225};
-__constant__ double CFM_R2[2] = {0.5, 0.5};
+// (the literals of dat/mod.rs:4, 67-80 — C_GAUSS_LEGENDRE_4, CFM_R2_J1_GL, CFM_R4_J2_GL, BLANES17_R4_J4 — live in exp.cu, which
+// hands them to the kernel as tables)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -54,8 +63,9 @@ template <int NDIM, int M, int TB> struct Geo {
     static constexpr size_t SMEM_B = (size_t)M * 2 * NDIM * NDIM * sizeof(double);
     static constexpr size_t SMEM_T = (size_t)NBUF * 2 * TB * LDT * sizeof(double);
     static constexpr size_t SMEM_COEF = (size_t)VO_EXP_MAX_E * M * TB * sizeof(double2);
-    static constexpr size_t SMEM_MISC = (size_t)(NW * TB + 8 * TB) * sizeof(double) + 64 * sizeof(int);
+    static constexpr size_t SMEM_MISC = (size_t)(NW * TB + VO_EXP_MAX_E * TB + TB) * sizeof(double) + (size_t)(TB + 2 * VO_EXP_MAX_E + 8) * sizeof(int);
     static constexpr size_t SMEM = SMEM_B + SMEM_T + SMEM_COEF + SMEM_MISC;
+    static_assert(SMEM <= 227 * 1024, "exp_step_kernel: shared memory budget of one SM exceeded");
 };
 
 // x <- exp(sum_m coef[m][s] B_m) x for the tile, state in C-fragment layout:
@@ -175,7 +185,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     double* sNorm = reinterpret_cast<double*>(smem_raw + G::SMEM_B + G::SMEM_T + G::SMEM_COEF);  // [NW][TB]
     double* sTheta = sNorm + G::NW * TB;                                                         // [E][TB]
     double* sDt = sTheta + VO_EXP_MAX_E * TB;                                                    // [TB]
-    int* sEv = reinterpret_cast<int*>(sDt + TB + 4 * TB);                                        // [TB] event, then [8] plan, [1] any
+    int* sEv = reinterpret_cast<int*>(sDt + TB);                                                 // [TB] event, then [2 E] plan, [1] any
     int* sPlan = sEv + TB;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int w = wi % G::NW, cg = wi / G::NW;
@@ -191,25 +201,26 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TB;
-        const bool embedded = kp.mode == 0 && kp.want_err && (kp.scheme == VO_EXP_CFM4 || kp.scheme == VO_EXP_MAGNUS42);
-        const int nbase = kp.mode == 1 ? 1 : (kp.scheme == VO_EXP_CFM4 ? 2 : (kp.scheme == VO_EXP_SPLIT_MIDPOINT ? 3 : 1));
-        const int nexp = nbase + (embedded ? 1 : 0);
-        // ---- phase A: per-system control and exponent coefficients (one thread per system)
+        // exponentials of this event: nbase for the propagated solution, then nerr for the embedded lower-order one (from x0)
+        const bool tables = kp.scheme == VO_EXP_CFM4 || kp.scheme == VO_EXP_CFM_TABLE || kp.scheme == VO_EXP_SPLIT_CFM;
+        const int nbase = kp.mode == 1 ? 1 : (tables ? kp.n_rows : (kp.scheme == VO_EXP_SPLIT_MIDPOINT ? 3 : 1));
+        const int nerr = (kp.mode == 0 && kp.want_err) ? (tables ? kp.n_rows_err : (kp.scheme == VO_EXP_MAGNUS42 ? 1 : 0)) : 0;
+        const int nexp = nbase + nerr;
+        // ---- phase A: per-system control and exponent coefficients (one thread per system), written straight to shared memory
         if (threadIdx.x < TB) {
             const int s = threadIdx.x;
             const int64_t sys = base + s;
             int evk = 255;  // not live
             double dt = 0.0;
-            double2 ce[VO_EXP_MAX_E][M];
+            auto put = [&](int e, int m, double re, double im) { sCoef[(e * M + m) * TB + s] = make_double2(re, im); };
+            for (int e = 0; e < nexp; ++e)
 #pragma unroll
-            for (int e = 0; e < VO_EXP_MAX_E; ++e)
-#pragma unroll
-                for (int m = 0; m < M; ++m) ce[e][m] = make_double2(0.0, 0.0);
+                for (int m = 0; m < M; ++m) put(e, m, 0.0, 0.0);
             if (sys < kp.N) {
                 if (kp.mode == 1) {
                     evk = VO_EV_STEP;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) ce[0][m] = coef_in[sys * M + m];
+                    for (int m = 0; m < M; ++m) sCoef[m * TB + s] = coef_in[sys * M + m];
                 } else {
                     const uint32_t word = ca.word[sys];
                     if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
@@ -229,16 +240,27 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                                 double l[M];
                                 GEN::template coef<M>(g, kp.M_gen, t + dt * 0.5, l);
 #pragma unroll
-                                for (int m = 0; m < M; ++m) ce[0][m].x = l[m] * dt;
-                            } else if (kp.scheme == VO_EXP_CFM4) {  // exp/cfm.rs:43-100, cfm_exp :20-40
-                                double v0[M], v1[M];
-                                GEN::template coef<M>(g, kp.M_gen, t + C_GL4[0] * dt, v0);
-                                GEN::template coef<M>(g, kp.M_gen, t + C_GL4[1] * dt, v1);
+                                for (int m = 0; m < M; ++m) put(0, m, l[m] * dt, 0.0);
+                            } else if (tables) {
+                                // cfm_general (exp/cfm.rs:43-100) / split_cfm (exp/split_exp.rs:568-609): the generator at every node
+                                // (cfm.rs:70-72), then per exponential cfm_exp (cfm.rs:31-37): k = a_0 m_0; k += a_q m_q; k *= dt
+                                double v[VO_EXP_MAX_NODES][M];
 #pragma unroll
-                                for (int m = 0; m < M; ++m) {
-                                    ce[0][m].x = (CFM_R4[0] * v0[m] + (CFM_R4[1] * v1[m])) * dt;
-                                    ce[1][m].x = (CFM_R4[2] * v0[m] + (CFM_R4[3] * v1[m])) * dt;
-                                    ce[2][m].x = (CFM_R2[0] * v0[m] + (CFM_R2[1] * v1[m])) * dt;  // error scheme, :83-97
+                                for (int q = 0; q < VO_EXP_MAX_NODES; ++q)
+                                    if (q < kp.n_nodes) GEN::template coef<M>(g, kp.M_gen, t + kp.tab_c[q] * dt, v[q]);
+                                for (int e = 0; e < nexp; ++e) {
+                                    const double* a = e < nbase ? &kp.tab_alpha[e * VO_EXP_MAX_NODES] : &kp.tab_alpha_err[(e - nbase) * VO_EXP_MAX_NODES];
+                                    const int side = e < nbase ? kp.row_split[e] : 0;
+#pragma unroll
+                                    for (int m = 0; m < M; ++m) {
+                                        double k = a[0] * v[0][m];
+#pragma unroll
+                                        for (int q = 1; q < VO_EXP_MAX_NODES; ++q)
+                                            if (q < kp.n_nodes) k = k + (a[q] * v[q][m]);
+                                        const bool in_a = (kp.split_mask >> m) & 1u;
+                                        const bool keep = side == 0 || (side == 1 ? in_a : !in_a);
+                                        put(e, m, keep ? k * dt : 0.0, 0.0);
+                                    }
                                 }
                             } else if (kp.scheme == VO_EXP_SPLIT_MIDPOINT) {  // split_exp_midpoint, exp/split_exp.rs:520-562
                                 // literal: the generator is sampled at t (not t + dt/2) and BOTH splits are scaled by dt/2
@@ -249,9 +271,9 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
 #pragma unroll
                                 for (int m = 0; m < M; ++m) {
                                     const bool in_a = (kp.split_mask >> m) & 1u;
-                                    ce[0][m].x = in_a ? l[m] * dt0 : 0.0;
-                                    ce[1][m].x = in_a ? 0.0 : l[m] * dt0;
-                                    ce[2][m].x = ce[0][m].x;
+                                    put(0, m, in_a ? l[m] * dt0 : 0.0, 0.0);
+                                    put(1, m, in_a ? 0.0 : l[m] * dt0, 0.0);
+                                    put(2, m, in_a ? l[m] * dt0 : 0.0, 0.0);
                                 }
                             } else {  // magnus_42, exp/magnus.rs:28-83
                                 const double c_mid = 0.288675134594812882254574390251;
@@ -276,8 +298,8 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
 #pragma unroll
                                 for (int m = 0; m < M; ++m) {
                                     const double w1 = (l0[m] + l1[m]) * b1;
-                                    ce[0][m].x = w1 + w2[m] * b2;  // u = exp(w1 + w2)
-                                    ce[1][m].x = w1;               // u1 = exp(w1), the 2nd-order embedded solution
+                                    put(0, m, w1 + w2[m] * b2, 0.0);  // u = exp(w1 + w2)
+                                    if (nerr) put(1, m, w1, 0.0);     // u1 = exp(w1), the 2nd-order embedded solution
                                 }
                             }
                         }
@@ -285,28 +307,28 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                 }
             }
             sEv[s] = evk, sDt[s] = dt;
-#pragma unroll
-            for (int e = 0; e < VO_EXP_MAX_E; ++e) {
+            for (int e = 0; e < nexp; ++e) {
                 double th = 0.0;
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    sCoef[(e * M + m) * TB + s] = ce[e][m];
-                    th += hypot(ce[e][m].x, ce[e][m].y) * kp.norm1[m];
+                    const double2 c = sCoef[(e * M + m) * TB + s];
+                    th += hypot(c.x, c.y) * kp.norm1[m];
                 }
                 sTheta[e * TB + s] = evk == VO_EV_STEP ? th : 0.0;
             }
         }
         __syncthreads();
-        // ---- phase B: tile-uniform Taylor plan per exponential
-        if (threadIdx.x == 0) {
+        // ---- phase B: tile-uniform Taylor plan, one thread per exponential
+        if (threadIdx.x < nexp) {
+            const int e = threadIdx.x;
+            double th = 0.0;
+            for (int s = 0; s < TB; ++s) th = fmax(th, sTheta[e * TB + s]);
+            taylor_plan(th, kp.taylor_deg, &sPlan[2 * e], &sPlan[2 * e + 1]);
+        }
+        if (threadIdx.x == 32) {
             int any = 0;
             for (int s = 0; s < TB; ++s) any |= sEv[s] == VO_EV_STEP;
             sPlan[2 * VO_EXP_MAX_E] = any;
-            for (int e = 0; e < VO_EXP_MAX_E; ++e) {
-                double th = 0.0;
-                for (int s = 0; s < TB; ++s) th = fmax(th, sTheta[e * TB + s]);
-                taylor_plan(th, kp.taylor_deg, &sPlan[2 * e], &sPlan[2 * e + 1]);
-            }
         }
         __syncthreads();
         const bool any_step = sPlan[2 * VO_EXP_MAX_E] != 0;
@@ -322,9 +344,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                     x0r[j][q] = xfr[j][q] = v.x, x0i[j][q] = xfi[j][q] = v.y;
                     xer[j][q] = xei[j][q] = 0.0;
                 }
-            map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
-            if (kp.mode == 0 && nbase >= 2) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + M * TB, sPlan[2], sPlan[3], xfr, xfi, buf);
-            if (kp.mode == 0 && nbase >= 3) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + 2 * M * TB, sPlan[4], sPlan[5], xfr, xfi, buf);
+            for (int e = 0; e < nbase; ++e) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xfr, xfi, buf);
             for (int q = 1; kp.mode == 1 && q < kp.nseq; ++q) {  // vo_map_exp_seq: the next exponential of the composition
                 __syncthreads();
                 if (threadIdx.x < TB) {
@@ -347,13 +367,12 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                 __syncthreads();
                 map_exp_tile<NDIM, M, TB>(sB, sT, sCoef, sPlan[0], sPlan[1], xfr, xfi, buf);
             }
-            if (embedded) {  // embedded lower-order solution from x0, then x_err = that - xf
-                const int e = nexp - 1;
+            if (nerr) {  // embedded lower-order solution from x0 (cfm.rs:88-95, magnus.rs:76-78), then x_err = that - xf
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) xer[j][q] = x0r[j][q], xei[j][q] = x0i[j][q];
-                map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xer, xei, buf);
+                for (int e = nbase; e < nexp; ++e) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xer, xei, buf);
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -388,9 +407,9 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                             for (int ww = 0; ww < G::NW; ++ww) nn += sNorm[ww * TB + s];
                             const double dxn = sqrt(nn);
                             const double f = kp.rtol / dxn;
-                            const double mul = kp.alpha * pow(f, kp.pw);  // step_size_mul, ode.rs:133-135
-                            const double fp_lim = fmin(fmax(mul, 0.3), 2.0);
-                            const double new_h = fmin(fmax(fp_lim * h, kp.min_dt), kp.max_dt);
+                            const double mul = step_size_mul<true>(kp.alpha, f, kp.pw, kp.pw_is_third);  // ode.rs:133-135, powf correctly rounded (rk_small.cuh)
+                            const double fp_lim = at_most(at_least(mul, 0.3), 2.0);
+                            const double new_h = at_most(at_least(fp_lim * h, kp.min_dt), kp.max_dt);
                             if (!(dxn == dxn)) status |= VO_TRAJ_NONFINITE;
                             if (f <= 1.0) {
                                 evk = VO_EV_REJECT;

@@ -198,5 +198,33 @@ class ExpCFMSolver(_ExpSolver):
     SCHEME = "cfm4"
 
 
+def cfm_table(name: str) -> np.ndarray:
+    """The reference's coefficient statics (src/dat/mod.rs:3-6, 66-81): 'C_GAUSS_LEGENDRE_4', 'CFM_R2_J1_GL', 'CFM_R4_J2_GL',
+    'BLANES17_R4_J4', shaped [rows][nodes]."""
+    r, k = C.c_int32(), C.c_int32()
+    check(lib().vo_cfm_builtin_table(_cabi.CFM_TABLE[name], None, C.byref(r), C.byref(k)))
+    out = np.zeros((r.value, k.value))
+    check(lib().vo_cfm_builtin_table(_cabi.CFM_TABLE[name], _np_ptr(out), C.byref(r), C.byref(k)))
+    return out
+
+
+class ExpCFMGeneralSolver(_ExpSolver):
+    """cfm_general (exp/cfm.rs:43-100) as a solver with the caller's tables — what ExpCFMSolver is once `c`, `alpha`, `alph_err`
+    are arguments instead of the hard-wired CFM4 (cfm.rs:131-154): `c` [k] nodes, `alpha` [rows][k], `alph_err` [rows_err][k] | None."""
+    SCHEME = "cfm_table"
+
+    def __init__(self, sp, gp, t0, tf, psi0, h, c, alpha, alph_err=None, M_gen=None, group_similar=False):
+        super().__init__(sp, gp, t0, tf, psi0, h, M_gen, group_similar)
+        c = np.ascontiguousarray(c, dtype=np.float64).ravel()
+        a = np.ascontiguousarray(alpha, dtype=np.float64)
+        e = None if alph_err is None else np.ascontiguousarray(alph_err, dtype=np.float64)
+        if a.ndim != 2 or a.shape[1] != c.size or (e is not None and (e.ndim != 2 or e.shape[1] != c.size)):
+            raise _cabi.VecOdeError(_cabi.VO_ERR_SHAPE, "split_cfm: Incompatible array dimensions")  # cfm.rs:63
+        check(lib().vo_exp_set_cfm_tables(self._h, _np_ptr(c), c.size, _np_ptr(a), a.shape[0], None if e is None else _np_ptr(e), 0 if e is None else e.shape[0]),
+              self.ctx._h)
+        if e is None:
+            self.no_adaptive()
+
+
 class MagnusExpLinearSolver(_ExpSolver):
     SCHEME = "magnus42"

@@ -139,3 +139,26 @@ class ExpSplitMidpointSolver(_ExpSolver):
             mask |= 1 << m
         check(lib().vo_exp_set_split_mask(self._h, mask), self.ctx._h)
         check(lib().vo_exp_no_adaptive(self._h), self.ctx._h)  # it only implements ODESolver
+
+
+class ExpSplitCFMSolver(_ExpSolver):
+    """split_cfm (split_exp.rs:568-609) as a solver: per step B(sigma_0) A(rho_0) B(sigma_1) ... A(rho_{s-1}) B(sigma_s), every
+    exponent a commutator-free combination of the generator at the nodes `c` (cfm_exp, exp/cfm.rs:20-40). The reference declares
+    the struct (`ExpSplitCFMSolver`, :688-705) without an impl; this is the solver its fields and `split_cfm` describe.
+    `a_idx` = the basis matrices that form split A; `rho` [s][k], `sigma` [s + 1][k]."""
+    SCHEME = "split_cfm"
+
+    def __init__(self, sp: DenseBasisSplit, a_idx: Sequence[int], gp, t0, tf, psi0, h, c, rho, sigma, M_gen=None):
+        super().__init__(sp, gp, t0, tf, psi0, h, M_gen)
+        mask = 0
+        for m in a_idx:
+            mask |= 1 << m
+        check(lib().vo_exp_set_split_mask(self._h, mask), self.ctx._h)
+        c = np.ascontiguousarray(c, dtype=np.float64).ravel()
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+        if rho.ndim != 2 or sigma.ndim != 2 or rho.shape[1] != c.size or sigma.shape[1] != c.size or sigma.shape[0] != rho.shape[0] + 1:
+            from ._cabi import VO_ERR_SHAPE, VecOdeError
+            raise VecOdeError(VO_ERR_SHAPE, "split_cfm: Incompatible array dimensions")  # split_exp.rs:587-592
+        check(lib().vo_exp_set_split_cfm_tables(self._h, _np_ptr(c), c.size, _np_ptr(rho), _np_ptr(sigma), rho.shape[0]), self.ctx._h)
+        check(lib().vo_exp_no_adaptive(self._h), self.ctx._h)
