@@ -274,6 +274,22 @@ int32_t vo_split_norm(vo_split sp, const void* psi_dev, int64_t N, double* out_h
 /* Commutator::commutator (exp/mod.rs:47-54) on operators given as coefficient vectors la, lb, out: [N][M] complex (host). */
 int32_t vo_split_commutator(vo_split sp, const double* la, const double* lb, int64_t N, double* out);
 
+/* ---- the same traits for GENERAL dense operators: every system owns its n x n complex L and U (no shared basis, no closure
+ * under commutation assumed). An operator ensemble is a vo_ens of one row of 2 n^2 N doubles ([N][n][n] complex, row-major,
+ * interleaved), so LinearCombination on operators is vo_lc_* on those ensembles; n % 8 == 0, n <= 64. Products run on the FP64
+ * tensor cores (DMMA), one CTA per system with both operands in shared memory. -------------------------------------------------- */
+int32_t vo_split_dense_create(vo_ctx ctx, int32_t n, int64_t N, vo_split* out);
+int32_t vo_dense_lin_zero(vo_split sp, vo_ens* out);                                     /* lin_zero, exp/mod.rs:20 */
+/* L_i = sum_m coef[i][m] B_m: operators of a shared-basis split (coef [N][M] complex, host) as dense operators */
+int32_t vo_dense_assemble(vo_split sp, vo_split basis, const double* coef_host, vo_ens L);
+/* exp (exp/mod.rs:23): explicit U = exp(L) by scaling and squaring — L / 2^s with ||.||_1 <= 1/2, Taylor series to 2^-53, s
+ * squarings: (degree + s) complex GEMMs of 8 n^3 flops per system. */
+int32_t vo_dense_exp(vo_split sp, vo_ens L, vo_ens U);
+int32_t vo_dense_multi_exp(vo_split sp, vo_ens L, const double* k_arr, int32_t K, const vo_ens* U_out); /* exp(k l) for every k, exp/mod.rs:28-34 */
+int32_t vo_dense_map_exp(vo_split sp, vo_ens U, const void* psi_in_dev, void* psi_out_dev); /* map_exp, exp/mod.rs:25: y_i = U_i x_i */
+int32_t vo_dense_commutator(vo_split sp, vo_ens La, vo_ens Lb, vo_ens out);              /* commutator, exp/mod.rs:53: La Lb - Lb La */
+/* vo_split_norm (NormedExponentialSplit::norm) takes a dense split as well. */
+
 /* Generator family replacing the closures of exp/magnus.rs:12,32 and exp/cfm.rs:54:
  *   L_i(t) = B_0 + sum_{m=1}^{M_gen-1} amp_im * cos(omega_im * t + phase_im) * B_m ,  gp = [N][M_gen-1][3]. */
 #define VO_EXP_MIDPOINT 0 /* MidpointExpLinearSolver, exp/magnus.rs:85-148 */
@@ -315,6 +331,11 @@ int32_t vo_exp_set_split_cfm_tables(vo_expsolver s, const double* c, int32_t k, 
 int32_t vo_cfm_builtin_table(int32_t which, double* out /* [rows][cols], nullable */, int32_t* rows, int32_t* cols);
 /* VO_EXP_SPLIT_MIDPOINT: bit m of a_mask set <=> basis matrix m belongs to split A (the rest form split B). */
 int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
+/* VO_EXP_MAGNUS42 on generators that are NOT closed under commutation on the shared basis: 1 makes magnus_42 (exp/magnus.rs:28-83)
+ * assemble L(t) at its two nodes per system and form commutator(l0, l1) (magnus.rs:55) densely on the tensor cores — two
+ * n x n complex products per system and step — instead of expanding it through vo_split_set_commutator's structure tensor.
+ * n % 8 == 0, n <= 64; compiled-in generator family only. */
+int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */
 int32_t vo_exp_with_tolerance(vo_expsolver s, double atol, double rtol);
 int32_t vo_exp_with_step_range(vo_expsolver s, double dt_min, double dt_max);

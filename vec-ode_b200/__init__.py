@@ -5,12 +5,12 @@ The directory is `vec-ode_b200/` (not an importable name); `import vecode_b200` 
 """
 from . import _cabi, domain, group, pipeline, workloads
 from ._cabi import SO_PATH, StepResult, VecOdeError, build
-from .exp import DenseBasisSplit, ExpCFMGeneralSolver, ExpCFMSolver, MagnusExpLinearSolver, MidpointExpLinearSolver, cfm_table, with_commutator_slot
+from .exp import DenseBasisSplit, DenseSplit, ExpCFMGeneralSolver, ExpCFMSolver, MagnusExpLinearSolver, MidpointExpLinearSolver, cfm_table, with_commutator_slot
 from .split_exp import (CommutativeExpSplit, DirectSumL, ExpSplitCFMSolver, ExpSplitMidpointSolver, RKNR4ExpSplit, SemiComplexO4ExpSplit, StrangSplit,
                         TripleJumpExpSplit)
 from .base import (ButcherTableu, Context, Ensemble, LinearCombination, ODEError, ODEState, RK45Solver, Rhs, step_many)
 
-__all__ = ["ButcherTableu", "Context", "Ensemble", "LinearCombination", "ODEError", "ODEState", "RK45Solver", "Rhs", "step_many", "DenseBasisSplit", "ExpCFMSolver", "ExpCFMGeneralSolver", "ExpSplitCFMSolver", "cfm_table", "MagnusExpLinearSolver", "MidpointExpLinearSolver",
+__all__ = ["ButcherTableu", "Context", "Ensemble", "LinearCombination", "ODEError", "ODEState", "RK45Solver", "Rhs", "step_many", "DenseBasisSplit", "DenseSplit", "ExpCFMSolver", "ExpCFMGeneralSolver", "ExpSplitCFMSolver", "cfm_table", "MagnusExpLinearSolver", "MidpointExpLinearSolver",
            "with_commutator_slot", "CommutativeExpSplit", "DirectSumL", "ExpSplitMidpointSolver", "RKNR4ExpSplit",
            "SemiComplexO4ExpSplit", "StrangSplit", "TripleJumpExpSplit",
            "StepResult", "VecOdeError", "build", "workloads", "group", "domain", "pipeline", "SO_PATH"]

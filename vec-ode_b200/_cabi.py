@@ -134,6 +134,14 @@ SIGNATURES = {
     "vo_split_commutator": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "vo_map_exp": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "vo_map_exp_seq": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
+    "vo_split_dense_create": (_i32, [_vp, _i32, _i64, _pvp]),
+    "vo_dense_lin_zero": (_i32, [_vp, _pvp]),
+    "vo_dense_assemble": (_i32, [_vp, _vp, _vp, _vp]),
+    "vo_dense_exp": (_i32, [_vp, _vp, _vp]),
+    "vo_dense_multi_exp": (_i32, [_vp, _vp, _vp, _i32, _pvp]),
+    "vo_dense_map_exp": (_i32, [_vp, _vp, _vp, _vp]),
+    "vo_dense_commutator": (_i32, [_vp, _vp, _vp, _vp]),
+    "vo_exp_set_dense_commutator": (_i32, [_vp, _i32]),
     "vo_exp_set_split_mask": (_i32, [_vp, C.c_uint32]),
     "vo_exp_set_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32]),
     "vo_exp_set_split_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32]),

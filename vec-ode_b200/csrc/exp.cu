@@ -21,7 +21,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "exp_kernels.cuh"
+#include "exp_dense_kernels.cuh"
 
 
 struct vo_split_s {
@@ -32,6 +32,9 @@ struct vo_split_s {
     double cs[VO_EXP_MAX_M * VO_EXP_MAX_M * VO_EXP_MAX_M];
     bool has_cs = false;
     int taylor_deg = 0;
+    double2* basis_dev = nullptr;  // [M][n][n] row-major interleaved: what the dense kernels (exp_dense_kernels.cuh) assemble operators from
+    int kind = 0;                  // 0: shared-basis split (operators are coefficient vectors); 1: dense split (every system owns its n x n operators)
+    int64_t N = 0;                 // dense split: number of systems
 };
 
 struct vo_expsolver_s {
@@ -54,6 +57,7 @@ struct vo_expsolver_s {
     int64_t* perm = nullptr;     // vo_exp_set_order: device slot j holds the caller's system perm[j] (device copy)
     std::vector<int64_t> perm_host;
     double2* stage = nullptr;    // [N][n] staging for the reordering copies
+    int dense_comm = 0;          // vo_exp_set_dense_commutator: magnus_42 forms [L0, L1] densely per system (no structure tensor needed)
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
     // commutator-free schemes as tables (cfm_general's c / alpha / alph_err, exp/cfm.rs:43-53; split_cfm's rho / sigma)
@@ -175,6 +179,48 @@ ExpKP make_kp(const vo_split_s* sp, int mode) {
     return kp;
 }
 
+// ---- dense operators (exp_dense_kernels.cuh) --------------------------------------------------------------------------------------
+template <class K> int32_t dense_grid(vo_ctx c, K kernel, int threads, size_t smem, int64_t N, unsigned* grid) {
+    if (vo_ensure_smem_attr(c->device, (const void*)kernel, smem) != cudaSuccess) return vo_fail(c, VO_ERR_CUDA, "dense split: shared-memory carve-out rejected");
+    int bps = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem) != cudaSuccess || bps < 1) bps = 1;
+    *grid = (unsigned)std::min<int64_t>(N, (int64_t)c->sm_count * bps);
+    return VO_OK;
+}
+
+#define VO_DENSE_DISPATCH(nb, CALL)                                  \
+    switch (nb) {                                                    \
+        case 1: CALL(1) break;                                       \
+        case 2: CALL(2) break;                                       \
+        case 3: CALL(3) break;                                       \
+        case 4: CALL(4) break;                                       \
+        case 5: CALL(5) break;                                       \
+        case 6: CALL(6) break;                                       \
+        case 7: CALL(7) break;                                       \
+        case 8: CALL(8) break;                                       \
+        default: return vo_fail(c, VO_ERR_UNSUPPORTED, "dense split: n must be a multiple of 8, 8 <= n <= 64"); \
+    }
+
+int32_t launch_magnus_dense(vo_expsolver_s* s, const ExpKP& kp) {
+    vo_ctx c = s->ctx;
+    if (s->gen_fn) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_exp_set_dense_commutator: not available together with a run-time compiled generator");
+    const int nb = s->sp->n / 8;
+#define VO_CALL(NB)                                                                                                                        \
+    {                                                                                                                                      \
+        using G = DenseGeo<NB>;                                                                                                            \
+        auto k = magnus_dense_kernel<NB, GenCos>;                                                                                          \
+        const size_t smem = 2 * G::MAT + (G::N + 2) * sizeof(double) + 4 * G::N * sizeof(double2) + (2 * VO_EXP_MAX_M + 8) * sizeof(double) + 16 * sizeof(int); \
+        unsigned grid = 0;                                                                                                                 \
+        int32_t r = dense_grid(c, k, G::THREADS, smem, kp.N, &grid);                                                                       \
+        if (r != VO_OK) return r;                                                                                                          \
+        k<<<grid, G::THREADS, smem, c->stream>>>(kp, s->sp->basis_dev, s->psi, s->gp, s->ca, s->ev_dev);                                   \
+    }
+    VO_DENSE_DISPATCH(nb, VO_CALL)
+#undef VO_CALL
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
 int32_t exp_ev_read(vo_expsolver_s* s, EvSlot* out) {
     vo_ctx c = s->ctx;
     VO_CUDA(c, cudaMemcpyAsync(s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS, cudaMemcpyDeviceToHost, c->stream));
@@ -198,6 +244,8 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     const bool tables = s->scheme == VO_EXP_CFM4 || s->scheme == VO_EXP_CFM_TABLE || s->scheme == VO_EXP_SPLIT_CFM;
     if (tables && s->n_rows < 1) return vo_fail(c, VO_ERR_STATE, "exp: the scheme's tables have not been set (vo_exp_set_cfm_tables / vo_exp_set_split_cfm_tables)");
     if (adaptive && tables && s->n_rows_err < 1) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // alph_err is None (cfm.rs:214-222)
+    if (s->scheme == VO_EXP_MAGNUS42 && !s->sp->has_cs && !s->dense_comm)
+        return vo_fail(c, VO_ERR_BAD_ARG, "Magnus needs a Commutator (exp/mod.rs:47-54): vo_split_set_commutator for a basis closed under commutation, or vo_exp_set_dense_commutator");
     ExpKP kp = make_kp(s->sp, 0);
     kp.M_gen = s->M_gen, kp.scheme = s->scheme, kp.adaptive = adaptive ? 1 : 0;
     kp.want_err = (s->want_err && adaptive) ? 1 : 0;  // the embedded solution only feeds the controller
@@ -208,6 +256,7 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     kp.n_nodes = s->n_nodes, kp.n_rows = s->n_rows, kp.n_rows_err = s->n_rows_err;
     std::memcpy(kp.tab_c, s->tab_c, sizeof kp.tab_c), std::memcpy(kp.tab_alpha, s->tab_alpha, sizeof kp.tab_alpha);
     std::memcpy(kp.tab_alpha_err, s->tab_alpha_err, sizeof kp.tab_alpha_err), std::memcpy(kp.row_split, s->row_split, sizeof kp.row_split);
+    if (s->scheme == VO_EXP_MAGNUS42 && s->dense_comm) return launch_magnus_dense(s, kp);
     return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn);
 }
 
@@ -263,6 +312,11 @@ int32_t vo_split_basis_create(vo_ctx c, int32_t n, int32_t M, const double* basi
         return vo_fail(c, VO_ERR_ALLOC, "vo_split_basis_create: cudaMalloc failed");
     }
     VO_CUDA(c, cudaMemcpyAsync(sp->frag_dev, frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (cudaMalloc(&sp->basis_dev, sizeof(double2) * (size_t)M * n * n) != cudaSuccess) {
+        vo_split_destroy(sp);
+        return vo_fail(c, VO_ERR_ALLOC, "vo_split_basis_create: cudaMalloc failed");
+    }
+    VO_CUDA(c, cudaMemcpyAsync(sp->basis_dev, basis, sizeof(double2) * (size_t)M * n * n, cudaMemcpyHostToDevice, c->stream));
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
     *out = sp;
     return VO_OK;
@@ -272,7 +326,7 @@ int32_t vo_split_destroy(vo_split sp) {
     if (!sp) return VO_OK;
     DeviceGuard g(sp->ctx->device);
     cudaStreamSynchronize(sp->ctx->stream);
-    cudaFree(sp->frag_dev);
+    cudaFree(sp->frag_dev), cudaFree(sp->basis_dev);
     delete sp;
     return VO_OK;
 }
@@ -355,7 +409,7 @@ int32_t vo_exp_create(vo_ctx c, vo_split sp, int32_t scheme, int32_t M_gen, cons
                       const double* psi0_host, double h, vo_expsolver* out) {
     if (!c || !sp || !out || !psi0_host || N < 1 || scheme < 0 || scheme > VO_EXP_SPLIT_CFM || M_gen < 1 || M_gen > sp->M || (M_gen > 1 && !gp_host))
         return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: bad argument");
-    if (scheme == VO_EXP_MAGNUS42 && !sp->has_cs) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: Magnus needs vo_split_set_commutator (Commutator trait, exp/mod.rs:47-54)");
+    if (sp->kind != 0) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_create: the solvers take a shared-basis split (vo_split_basis_create)");
     DeviceGuard g(c->device);
     vo_expsolver s = new vo_expsolver_s();
     s->ctx = c, s->sp = sp, s->scheme = scheme, s->M_gen = M_gen, s->N = N, s->t0 = t0, s->tf = tf, s->h_init = h;
@@ -618,5 +672,113 @@ int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n) {
 }
 
 void* vo_exp_state_device_ptr(vo_expsolver s) { return s ? (void*)s->psi : nullptr; }
+
+
+// ---- dense split: ExponentialSplit / Commutator / NormedExponentialSplit (exp/mod.rs:11-54) with per-system n x n operators ------
+int32_t vo_split_dense_create(vo_ctx c, int32_t n, int64_t N, vo_split* out) {
+    if (!c || !out || n < 8 || n > 64 || n % 8 || N < 1) return vo_fail(c, VO_ERR_BAD_ARG, "vo_split_dense_create: need n % 8 == 0, 8 <= n <= 64 and N >= 1");
+    vo_split sp = new vo_split_s();
+    sp->ctx = c, sp->n = n, sp->M = 0, sp->kind = 1, sp->N = N;
+    std::memset(sp->cs, 0, sizeof sp->cs), std::memset(sp->norm1, 0, sizeof sp->norm1);
+    *out = sp;
+    return VO_OK;
+}
+
+static bool dense_op_ok(vo_split sp, vo_ens e) { return sp && sp->kind == 1 && e && e->d == 1 && e->n == 2 * (int64_t)sp->n * sp->n * sp->N && e->ctx->device == sp->ctx->device; }
+
+int32_t vo_dense_lin_zero(vo_split sp, vo_ens* out) {  // exp/mod.rs:20
+    if (!sp || sp->kind != 1 || !out) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_dense_lin_zero: needs a dense split");
+    return vo_ens_create(sp->ctx, 1, 2 * (int64_t)sp->n * sp->n * sp->N, out);
+}
+
+int32_t vo_dense_assemble(vo_split sp, vo_split basis, const double* coef_host, vo_ens L) {
+    if (!sp || !basis || basis->kind != 0 || !coef_host || !dense_op_ok(sp, L) || basis->n != sp->n) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_dense_assemble: bad argument");
+    vo_ctx c = sp->ctx;
+    DeviceGuard g(c->device);
+    double2* coef_dev = nullptr;
+    const size_t bytes = sizeof(double2) * (size_t)sp->N * basis->M;
+    VO_CUDA(c, cudaMallocAsync(&coef_dev, bytes, c->stream));
+    VO_CUDA(c, cudaMemcpyAsync(coef_dev, coef_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    dense_assemble_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)sp->n * sp->n * sp->N, 256), (int64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+        basis->basis_dev, coef_dev, basis->M, sp->n, sp->N, reinterpret_cast<double2*>(L->p));
+    VO_CHECK_LAUNCH(c);
+    cudaFreeAsync(coef_dev, c->stream);
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VO_OK;
+}
+
+static int32_t dense_exp_scaled(vo_split sp, vo_ens L, double k, vo_ens U) {
+    vo_ctx c = sp->ctx;
+    const int nb = sp->n / 8;
+#define VO_CALL(NB)                                                                                                 \
+    {                                                                                                               \
+        using G = DenseGeo<NB>;                                                                                     \
+        auto kf = dense_exp_kernel<NB>;                                                                             \
+        const size_t smem = 2 * G::MAT + (G::N + 2) * sizeof(double) + 8 * sizeof(int);                             \
+        unsigned grid = 0;                                                                                          \
+        int32_t r = dense_grid(c, kf, G::THREADS, smem, sp->N, &grid);                                              \
+        if (r != VO_OK) return r;                                                                                   \
+        kf<<<grid, G::THREADS, smem, c->stream>>>(reinterpret_cast<const double2*>(L->p), reinterpret_cast<double2*>(U->p), sp->N, k); \
+    }
+    VO_DENSE_DISPATCH(nb, VO_CALL)
+#undef VO_CALL
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_dense_exp(vo_split sp, vo_ens L, vo_ens U) {  // exp/mod.rs:23
+    if (!dense_op_ok(sp, L) || !dense_op_ok(sp, U)) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_SHAPE, "vo_dense_exp: operators must be [N][n][n] complex ensembles of this dense split");
+    DeviceGuard g(sp->ctx->device);
+    return dense_exp_scaled(sp, L, 1.0, U);
+}
+
+int32_t vo_dense_multi_exp(vo_split sp, vo_ens L, const double* k_arr, int32_t K, const vo_ens* U_out) {  // exp/mod.rs:28-34: exp(k l) for every k
+    if (!dense_op_ok(sp, L) || !k_arr || K < 1 || !U_out) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_dense_multi_exp: bad argument");
+    DeviceGuard g(sp->ctx->device);
+    for (int q = 0; q < K; ++q) {
+        if (!dense_op_ok(sp, U_out[q])) return vo_fail(sp->ctx, VO_ERR_SHAPE, "vo_dense_multi_exp: bad output operator");
+        int32_t r = dense_exp_scaled(sp, L, k_arr[q], U_out[q]);
+        if (r != VO_OK) return r;
+    }
+    return VO_OK;
+}
+
+int32_t vo_dense_map_exp(vo_split sp, vo_ens U, const void* psi_in_dev, void* psi_out_dev) {  // exp/mod.rs:25
+    if (!dense_op_ok(sp, U) || !psi_in_dev || !psi_out_dev || psi_in_dev == psi_out_dev) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_BAD_ARG, "vo_dense_map_exp: bad argument (in-place is not supported)");
+    vo_ctx c = sp->ctx;
+    DeviceGuard g(c->device);
+    dense_matvec_kernel<<<(unsigned)std::min<int64_t>(sp->N, (int64_t)c->sm_count * 8), 256, sizeof(double2) * sp->n, c->stream>>>(
+        reinterpret_cast<const double2*>(U->p), reinterpret_cast<const double2*>(psi_in_dev), reinterpret_cast<double2*>(psi_out_dev), sp->n, sp->N);
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_dense_commutator(vo_split sp, vo_ens La, vo_ens Lb, vo_ens out) {  // exp/mod.rs:47-54
+    if (!dense_op_ok(sp, La) || !dense_op_ok(sp, Lb) || !dense_op_ok(sp, out)) return vo_fail(sp ? sp->ctx : nullptr, VO_ERR_SHAPE, "vo_dense_commutator: operators must be [N][n][n] complex ensembles of this dense split");
+    vo_ctx c = sp->ctx;
+    DeviceGuard g(c->device);
+    const int nb = sp->n / 8;
+#define VO_CALL(NB)                                                                                                                          \
+    {                                                                                                                                        \
+        using G = DenseGeo<NB>;                                                                                                              \
+        auto kf = dense_commutator_kernel<NB>;                                                                                               \
+        unsigned grid = 0;                                                                                                                   \
+        int32_t r = dense_grid(c, kf, G::THREADS, 2 * G::MAT, sp->N, &grid);                                                                 \
+        if (r != VO_OK) return r;                                                                                                            \
+        kf<<<grid, G::THREADS, 2 * G::MAT, c->stream>>>(reinterpret_cast<const double2*>(La->p), reinterpret_cast<const double2*>(Lb->p), reinterpret_cast<double2*>(out->p), sp->N); \
+    }
+    VO_DENSE_DISPATCH(nb, VO_CALL)
+#undef VO_CALL
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (on && s->scheme != VO_EXP_MAGNUS42) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_dense_commutator: only the Magnus solver takes a commutator");
+    if (on && (s->sp->n > 64 || s->sp->n % 8)) return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "vo_exp_set_dense_commutator: n must be a multiple of 8, n <= 64");
+    s->dense_comm = on ? 1 : 0;
+    return VO_OK;
+}
 
 }  // extern "C"

@@ -79,6 +79,78 @@ class DenseBasisSplit:
             pass
 
 
+class DenseSplit:
+    """ExponentialSplit + Commutator + NormedExponentialSplit (src/exp/mod.rs:11-54) for GENERAL dense operators: every one of the
+    N systems owns its n x n complex `L` and its explicit `U = exp(L)` (vo_split_dense_*). Operators are `Ensemble`s of one row of
+    2 n^2 N doubles ([N][n][n] complex, row-major), so `LinearCombination` applies to them as to any other ensemble."""
+
+    def __init__(self, ctx: Context, n: int, n_systems: int):
+        self.ctx, self.n, self.N = ctx, n, n_systems
+        self._h = _vp()
+        check(lib().vo_split_dense_create(ctx._h, n, n_systems, C.byref(self._h)), ctx._h)
+
+    def _new(self):
+        from .base import Ensemble
+        return Ensemble(self.ctx, 1, 2 * self.n * self.n * self.N)
+
+    def operator(self, mats: np.ndarray):
+        """[N][n][n] complex host array -> operator ensemble"""
+        m = np.ascontiguousarray(mats, dtype=np.complex128)
+        assert m.shape == (self.N, self.n, self.n)
+        e = self._new()
+        e.upload(m.view(np.float64).reshape(1, -1), "soa")
+        return e
+
+    def to_host(self, op) -> np.ndarray:
+        return op.to_host("soa").reshape(-1).view(np.complex128).reshape(self.N, self.n, self.n)
+
+    def lin_zero(self):  # exp/mod.rs:20
+        from .base import Ensemble
+        h = _vp()
+        check(lib().vo_dense_lin_zero(self._h, C.byref(h)), self.ctx._h)
+        return Ensemble(self.ctx, 1, 2 * self.n * self.n * self.N, _handle=h)
+
+    def from_basis(self, basis_split: "DenseBasisSplit", coef: np.ndarray):
+        """L_i = sum_m coef[i][m] B_m as a dense operator ensemble (vo_dense_assemble)"""
+        coef = np.ascontiguousarray(coef, dtype=np.complex128)
+        out = self._new()
+        check(lib().vo_dense_assemble(self._h, basis_split._h, _np_ptr(coef.view(np.float64)), out._h), self.ctx._h)
+        return out
+
+    def exp(self, l):  # exp/mod.rs:23 — explicit U
+        u = self._new()
+        check(lib().vo_dense_exp(self._h, l._h, u._h), self.ctx._h)
+        return u
+
+    def multi_exp(self, l, k_arr):  # exp/mod.rs:28-34
+        ks = np.ascontiguousarray(k_arr, dtype=np.float64)
+        us = [self._new() for _ in ks]
+        hs = (C.c_void_p * len(us))(*[u._h.value for u in us])
+        check(lib().vo_dense_multi_exp(self._h, l._h, _np_ptr(ks), len(us), hs), self.ctx._h)
+        return us
+
+    def map_exp(self, u, psi_dev_in: int, psi_dev_out: int):  # exp/mod.rs:25
+        check(lib().vo_dense_map_exp(self._h, u._h, _vp(psi_dev_in), _vp(psi_dev_out)), self.ctx._h)
+
+    def commutator(self, la, lb):  # exp/mod.rs:53
+        out = self._new()
+        check(lib().vo_dense_commutator(self._h, la._h, lb._h, out._h), self.ctx._h)
+        return out
+
+    def norm(self, psi_dev: int, n_systems: Optional[int] = None) -> np.ndarray:  # exp/mod.rs:37-45
+        n_systems = self.N if n_systems is None else n_systems
+        out = np.empty(n_systems)
+        check(lib().vo_split_norm(self._h, _vp(psi_dev), n_systems, _np_ptr(out)), self.ctx._h)
+        return out
+
+    def __del__(self):
+        try:
+            if self._h and self.ctx._h:
+                lib().vo_split_destroy(self._h)
+        except Exception:
+            pass
+
+
 def with_commutator_slot(B0: np.ndarray, B1: np.ndarray):
     """Basis (B0, B1, [B0, B1]) and the structure tensor that closes ONE commutator of two generators from span{B0, B1}
     (all that magnus_42 takes, exp/magnus.rs:55)."""
@@ -227,4 +299,11 @@ class ExpCFMGeneralSolver(_ExpSolver):
 
 
 class MagnusExpLinearSolver(_ExpSolver):
+    """exp/magnus.rs:151-285. `dense_commutator=True`: commutator(l0, l1) (magnus.rs:55) is formed densely per system on the
+    tensor cores, so the generators need not be closed under commutation on the shared basis (vo_exp_set_dense_commutator)."""
     SCHEME = "magnus42"
+
+    def __init__(self, sp, gp, t0, tf, psi0, h, M_gen=None, group_similar=False, dense_commutator=False):
+        super().__init__(sp, gp, t0, tf, psi0, h, M_gen, group_similar)
+        if dense_commutator:
+            check(lib().vo_exp_set_dense_commutator(self._h, 1), self.ctx._h)
