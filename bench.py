@@ -386,7 +386,53 @@ class SchrodingerCFM4:
         return float(st.counts["Step"]), self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
-WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4)}
+class SchrodingerMagnusDense(SchrodingerCFM4):
+    """Config 5 with THREE generator matrices (H0 and two independently driven couplings) whose commutators leave their span: 4th-order
+    Magnus (exp/magnus.rs:28-83) with commutator(l0, l1) formed densely per system on the tensor cores (vo_exp_set_dense_commutator)."""
+    name = "schrodinger_magnus_dense"
+    label = ("config 5, generators not closed under commutation: Magnus-4 (one commutator), 10^5 driven 64-level systems with three generator "
+             "matrices, h = 0.1, fixed step; [L0, L1] = two dense 64 x 64 complex products per system and step on the FP64 tensor cores")
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        self.vo, self.ctx = vo, ctx
+        H0, H1 = vo.workloads.schrodinger_system(self.NDIM)
+        _, H2 = vo.workloads.schrodinger_system(self.NDIM, seed_h1=19)
+        self.basis = np.stack([-1j * H0, -1j * H1, -1j * H2])
+        self.sp = vo.DenseBasisSplit(ctx, self.basis)
+        g1 = vo.workloads.schrodinger_drive(self.N_SYS * world, self.N_SYS, rank * self.N_SYS)
+        g2 = vo.workloads.schrodinger_drive(self.N_SYS * world, self.N_SYS, rank * self.N_SYS, seed=23)
+        self.gp = np.concatenate([g1, g2 * np.array([0.5, 1.0, 1.0])], axis=1)
+        self.psi0 = np.zeros((self.N_SYS, self.NDIM), dtype=np.complex128)
+        self.psi0[:, 0] = 1.0
+        self.solver = vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1, dense_commutator=True).no_adaptive()
+        self.solver.step()  # Chkpt at t0
+        self.solvers = []
+        # algorithmic FLOPs per trajectory-step: the commutator (2 complex n x n products = 2 * 8 n^3) on the tensor cores, plus the Taylor
+        # series of exp(Omega) applied by matrix-vector products (m* terms of 8 n^2; m* at theta = ||Omega||_1 bounded by the generators' norms)
+        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
+        theta = 0.1 * (norm1[0] + self.gp[:, 0, 0] * norm1[1] + self.gp[:, 1, 0] * norm1[2])
+
+        def degree(th):
+            sq = max(1, int(np.ceil(th)))
+            x, term, k = th / sq, 1.0, 0
+            while k < 60:
+                k += 1
+                term = term * x / k
+                if term <= 1.1102230246251565e-16:
+                    break
+            return sq * k
+        self.m_star, self.theta = float(np.mean([degree(t) for t in theta[:: max(1, len(theta) // 512)]])), float(theta.max())
+        self.flops_per_unit = 2 * 8 * self.NDIM ** 3 + self.m_star * 8 * self.NDIM ** 2
+        self.bytes_per_unit = None
+
+    def e2e_setup(self, group=None):
+        import torch
+        self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_solver = self.vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0, self.psi0, 0.1, dense_commutator=True).no_adaptive()
+
+
+WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -503,7 +549,7 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
     """The `roofline` object of the dominant kernel from one timed region: algorithmic bytes (or FLOPs) per launch over the
     mean launch duration (CUDA events around the region, kernels back to back on the launching stream)."""
     kernel_ms = ms / max(launches, 1)
-    if W is SchrodingerCFM4:
+    if W in (SchrodingerCFM4, SchrodingerMagnusDense):
         p64 = os.path.join(ROOT, "profiles", "fp64_peaks.json")
         peak_tf, src = (json.load(open(p64))["dmma_tflops"], "measured by profiles/microbench/peaks.cu (profiles/fp64_peaks.json: dmma_tflops)") \
             if os.path.exists(p64) else (45.0, "nominal B200 FP64 tensor peak (no measured figure committed)")
@@ -511,7 +557,10 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
         return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": ncu_traffic(W.name),
                 "peak_source": src, "algorithmic_flops_per_unit": w.flops_per_unit, "taylor_degree": w.m_star, "theta": w.theta,
                 "kernel_us": kernel_ms * 1e3,
-                "note": "FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"}
+                "note": ("FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"
+                         if W is SchrodingerCFM4 else
+                         "algorithmic FLOPs = 2 x 8 n^3 (the dense commutator, on the FP64 tensor pipe) + m* x 8 n^2 (Taylor series of exp(Omega) by matrix-vector "
+                         "products, FP64 FMA pipe) per trajectory-step, against the DMMA peak")}
     bytes_per_launch = W.bytes_per_unit * (units_per_rank / max(launches, 1)) / events_per_launch
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(W.name),
@@ -521,7 +570,7 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
 
 def n_batches_for(W, n_traj):
     """Independent batches rotated per GPU so that the working set is >= 3x the L2 (each launch then streams from HBM)."""
-    if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4):
+    if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense):
         return 1
     if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
         return int(os.environ["VECODE_BENCH_BATCHES"])
@@ -856,19 +905,24 @@ def main():
             leg("heat_rk4_fused", HeatRK4Fused, "fast", 100)
         if W is not SchrodingerCFM4:
             leg("schrodinger_cfm4", SchrodingerCFM4, "fast", 10)
+        if W is not SchrodingerMagnusDense:
+            leg("schrodinger_magnus_dense", SchrodingerMagnusDense, "fast", 4)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args.workload)
+        try:
+            cpu = cpu_baseline(args.workload)
+        except KeyError:  # no CPU restatement of this variant (e.g. the dense-commutator Magnus)
+            cpu = None
 
     if rank == 0:
         line = {"metric": "ensemble trajectory-steps/sec", "value": value, "unit": f"{W.unit_name}s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if W is HeatRK4DD else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD) else SchrodingerCFM4.N_SYS if W is SchrodingerCFM4 else N_TRAJ),
+                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD) else SchrodingerCFM4.N_SYS if W in (SchrodingerCFM4, SchrodingerMagnusDense) else N_TRAJ),
                            "arith": args.arith, "events_per_launch": args.events_per_launch,
                            "l2": f"{n_batches} independent batches of {W.state_mb} MB rotated per GPU (> {L2_MB} MB L2), so each launch streams from HBM"
-                           if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
+                           if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
                            "warmup_note": f"every batch touched once, then ~{SPIN_UP_MS:.0f} ms of the same launches and the {args.warmup} warm-up steps, all untimed, before the {args.steps} timed steps",
