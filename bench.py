@@ -926,6 +926,9 @@ def main():
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
                            "warmup_note": f"every batch touched once, then ~{SPIN_UP_MS:.0f} ms of the same launches and the {args.warmup} warm-up steps, all untimed, before the {args.steps} timed steps",
+                           "timing": ("barrier + synchronize, event, steps, event, barrier + synchronize. A region of K launches costs about 14 us + K x the steady launch time "
+                                      "(tools/offset_probe.py): the first launch has no predecessor to overlap its ramp-up with and the last none to hide its tail; "
+                                      "queueing the launches behind a blocking kernel changes nothing (measured), so it is device time, not host latency"),
                            "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of {8 * DD_K} doubles per rank) every {DD_K} steps" if W is HeatRK4DD
                                            else f"trajectory-sharded x{world}, no data-path collective")},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}

@@ -49,6 +49,33 @@ def test_map_exp_against_eigendecomposition(vo, ctx, n):
         assert np.abs(got[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (i, np.abs(got[i] - ref).max())
 
 
+def test_map_exp_and_dense_exp_against_mpmath_50_digits(vo, ctx):
+    """map_exp of the lazy split and the explicit U = exp(L) of the dense split (scaling and squaring) against
+    exp(L) x summed as a plain Taylor series in 50-digit arithmetic (tests/_mp_expm.py), four systems of n = 16 with ||L||_1 from
+    0.3 to 6 (no sub-step to six sub-steps / three squarings)."""
+    import torch
+    from _mp_expm import map_exp_mp
+    n, N = 16, 4
+    B0, B1, _, psi0 = _system(vo, n, N)
+    coef = np.array([[0.1, 0.05 + 0.02j], [0.5, -0.2], [1.1, 0.3 - 0.05j], [2.4, 0.25]])
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    x = torch.from_numpy(psi0.view(np.float64).reshape(N, n, 2).copy()).cuda()
+    y = torch.empty_like(x)
+    sp.map_exp(sp.exp(coef), x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    got = y.cpu().numpy().reshape(N, n * 2).view(np.complex128)
+    Ls = np.einsum("nm,mij->nij", coef, np.stack([B0, B1]))
+    ref = np.stack([map_exp_mp(Ls[i], psi0[i]) for i in range(N)])
+    assert np.abs(got - ref).max() <= 5e-15, np.abs(got - ref).max()
+    ds = vo.DenseSplit(ctx, n, N)
+    U = ds.to_host(ds.exp(ds.operator(Ls)))
+    assert np.abs(np.einsum("nij,nj->ni", U, psi0) - ref).max() <= 2e-14
+    y2 = torch.empty_like(x)
+    ds.map_exp(ds.exp(ds.operator(Ls)), x.data_ptr(), y2.data_ptr())
+    torch.cuda.synchronize()
+    assert np.abs(y2.cpu().numpy().reshape(N, n * 2).view(np.complex128) - ref).max() <= 2e-14
+
+
 @pytest.mark.parametrize("scheme,cls", [("midpoint", "MidpointExpLinearSolver"), ("cfm4", "ExpCFMSolver"), ("magnus42", "MagnusExpLinearSolver")])
 @pytest.mark.parametrize("n", [16, 64])
 def test_fixed_step_schemes_match_oracle(vo, ctx, oracle, scheme, cls, n):
@@ -120,8 +147,10 @@ def test_exp_error_behaviour(vo, ctx):
     with pytest.raises(vo.VecOdeError) as e:
         s.step_adaptive()
     assert e.value.code == vo._cabi.VO_ERR_NOT_ADAPTIVE
-    with pytest.raises(vo.VecOdeError):
-        vo.MagnusExpLinearSolver(sp, gp, 0.0, 1.0, psi0, 0.1)  # no Commutator supplied
+    with pytest.raises(vo.VecOdeError) as e:  # no Commutator supplied (neither a structure tensor nor the dense one): refused at the first step
+        m = vo.MagnusExpLinearSolver(sp, gp, 0.0, 1.0, psi0, 0.1)
+        m.step(), m.step()
+    assert e.value.code == vo._cabi.VO_ERR_BAD_ARG
     with pytest.raises(vo.VecOdeError):
         s.with_tolerance(0.0, 1.0)
     first = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, 0.1).step()
