@@ -224,6 +224,15 @@ int32_t vo_solver_set_blocked(vo_solver s, int32_t on);
  * trajectory: ONE state-machine event per trajectory per call. res may be NULL. */
 int32_t vo_step(vo_solver s, vo_step_result* res);
 int32_t vo_step_adaptive(vo_solver s, vo_step_result* res);
+/* step_adaptive (ode.rs:336-344) in its two halves, for ONE state vector held in pieces by several solvers (grid slabs with
+ * ghost zones on several GPUs; single state N == 1, stage path). vo_adaptive_try runs step_size_of + try_step (rk.rs:90-155)
+ * and returns the norm ACCUMULATOR of this piece's components [lo, hi) of x_err — sum of squares (VO_NORM_L2), sum of
+ * magnitudes (L1) or maximum (LINF) — and the event; a Chkpt / End event is complete on return. After a Step event the caller
+ * combines the pieces' accumulators (sum / max over ranks, with vo_group_allreduce or any communicator), finishes the norm
+ * (square root for L2) and gives the SAME value to every piece: vo_adaptive_handle = handle_step_adaptive (ode.rs:311-334)
+ * + apply_step (ode.rs:402-428). */
+int32_t vo_adaptive_try(vo_solver s, int64_t lo, int64_t hi, double* acc, int32_t* event, vo_step_result* res /* filled for Chkpt / End */);
+int32_t vo_adaptive_handle(vo_solver s, double dx_norm, vo_step_result* res);
 /* `while let ODEState::Ok(_) = solver.step() {}` for the whole ensemble. max_calls <= 0: until Done.
  * res accumulates the event counts of all calls. */
 int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result* res);
@@ -336,6 +345,12 @@ int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
  * n x n complex products per system and step — instead of expanding it through vo_split_set_commutator's structure tensor.
  * n % 8 == 0, n <= 64; compiled-in generator family only. */
 int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on);
+/* MagnusExpLinearSolver::norm AS WRITTEN (exp/magnus.rs:274-276): it takes the norm of adaptive_dat.dx, a clone of x0 that
+ * try_step never writes (the embedded error goes to self.x_err, magnus.rs:249-250), so the controller sees the constant ||x0||:
+ * with rtol <= ||x0|| every attempt is rejected, with rtol > ||x0|| every attempt is accepted and h grows by
+ * clamp(0.9 (rtol / ||x0||)^(1/3), 0.3, 2) per step. Off by default: the solvers here give the controller the embedded error it
+ * was meant to see. On: the reference's literal behaviour, for comparisons. Magnus only. */
+int32_t vo_exp_set_literal_norm(vo_expsolver s, int32_t on);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */
 int32_t vo_exp_with_tolerance(vo_expsolver s, double atol, double rtol);
 int32_t vo_exp_with_step_range(vo_expsolver s, double dt_min, double dt_max);

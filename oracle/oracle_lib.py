@@ -41,7 +41,7 @@ class ExpCfg(C.Structure):
                 ("t0", C.c_double), ("tf", C.c_double), ("h0", C.c_double), ("rtol", C.c_double),
                 ("min_dt", C.c_double), ("max_dt", C.c_double), ("order", C.c_double), ("alpha", C.c_double),
                 ("max_calls", C.c_int64),
-                ("n_nodes", C.c_int32), ("n_rows", C.c_int32), ("n_rows_err", C.c_int32), ("pad_", C.c_int32),
+                ("n_nodes", C.c_int32), ("n_rows", C.c_int32), ("n_rows_err", C.c_int32), ("literal_norm", C.c_int32),
                 ("c", C.c_void_p), ("alpha_tab", C.c_void_p), ("alpha_err_tab", C.c_void_p)]
 
 
@@ -150,7 +150,7 @@ def rk_step(rhs, params, tableau, t, dt, x0, want_err=True):
 
 
 def exp_ensemble(scheme, basis, gp, psi0, t0, tf, h0, M_gen=None, cs=None, adaptive=False, no_adaptive=True,
-                 taylor_deg=0, rtol=1e-4, min_dt=1e-6, max_dt=1.0, order=3.0, alpha=0.9, max_calls=0, n_threads=1, tables=None):
+                 taylor_deg=0, rtol=1e-4, min_dt=1e-6, max_dt=1.0, order=3.0, alpha=0.9, max_calls=0, n_threads=1, tables=None, literal_norm=False):
     """basis: complex [M][n][n] (already -i*H_m); gp: [N][M_gen-1][3]; psi0: complex [N][n].
     scheme "cfm_table": cfm_general (cfm.rs:43-100) with tables = (c[k], alpha[s][k], alpha_err[s_err][k] | None)."""
     basis = np.ascontiguousarray(basis, dtype=np.complex128)
@@ -161,6 +161,7 @@ def exp_ensemble(scheme, basis, gp, psi0, t0, tf, h0, M_gen=None, cs=None, adapt
     gp = np.ascontiguousarray(gp, dtype=np.float64).reshape(N, max(M_gen - 1, 0), 3)
     cfg = ExpCfg(n, M, {"midpoint": 0, "cfm4": 1, "magnus42": 2, "cfm_table": 3}[scheme], int(adaptive), int(no_adaptive), taylor_deg,
                  t0, tf, h0, rtol, min_dt, max_dt, order, alpha, max_calls)
+    cfg.literal_norm = int(literal_norm)  # magnus.rs:274-276 as written
     keep = []
     if scheme == "cfm_table":
         c_t, a_t, e_t = tables

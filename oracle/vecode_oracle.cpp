@@ -652,7 +652,7 @@ struct ExpCfg {
     int64_t max_calls;
     // scheme 3: cfm_general (cfm.rs:43-100) with caller-supplied nodes c[n_nodes], alpha[n_rows][n_nodes] and the optional
     // lower-order alph_err[n_rows_err][n_nodes]
-    int32_t n_nodes, n_rows, n_rows_err, pad_;
+    int32_t n_nodes, n_rows, n_rows_err, literal_norm /* magnus.rs:274-276 as written: norm of adaptive_dat.dx = x0, never updated */;
     const double* c;
     const double* alpha_tab;
     const double* alpha_err_tab;
@@ -769,8 +769,9 @@ void orc_exp_ensemble(const ExpCfg* cfg, const double* basis /*[M][n][n] complex
                     dat.next_dt = dt;
                     try_step(dt);
                     if (cfg->adaptive) {  // ode.rs:311-334 with norm = 2-norm of dx
+                        const std::vector<cplx>& nv = (cfg->literal_norm && cfg->scheme == 2) ? x0 : dx;  // magnus.rs:274-276 reads adaptive_dat.dx (= x0)
                         double nn = 0.0;
-                        for (int r = 0; r < n; ++r) nn = nn + (dx[r].re * dx[r].re + dx[r].im * dx[r].im);
+                        for (int r = 0; r < n; ++r) nn = nn + (nv[r].re * nv[r].re + nv[r].im * nv[r].im);
                         ad.dx_norm = std::sqrt(nn);
                         const double f_ = ad.rtol / ad.dx_norm;
                         const double fp = rmin(rmax(ad.step_size_mul(f_), 0.3), 2.0);

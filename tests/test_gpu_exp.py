@@ -441,3 +441,36 @@ def test_magnus_with_dense_commutator(vo, ctx, oracle):
             x, t = expm(om) @ x, t + dt
         assert np.abs(got[i] - x).max() <= 1e-12, (i, np.abs(got[i] - x).max())
     assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() <= 1e-12
+
+
+def test_literal_magnus_norm_switch(vo, ctx, oracle):
+    """MagnusExpLinearSolver::norm as the reference writes it (magnus.rs:274-276: the norm of adaptive_dat.dx, a clone of x0 that no
+    step updates). With rtol <= ||x0|| = 1 every attempt is rejected until h reaches min_dt (flagged STUCK here; the reference loops
+    forever); with rtol = 8 every attempt is accepted and h doubles (0.9 * 8^(1/3) = 1.8 -> clamp 2 is not reached: factor 1.8).
+    Both must match the oracle's literal switch, and the default (off) stays the embedded-error controller."""
+    n, N, h = 16, 9, 0.01
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    basis3, cs = vo.with_commutator_slot(B0, B1)
+    sp = vo.DenseBasisSplit(ctx, basis3, commutator_structure=cs)
+    s = vo.MagnusExpLinearSolver(sp, gp, 0.0, 1.0, psi0, h, M_gen=2).with_tolerance(8.0, 8.0).literal_norm()
+    st = s.run(adaptive=True)
+    ref = oracle.exp_ensemble("magnus42", basis3, gp, psi0, 0.0, 1.0, h, M_gen=2, cs=cs, adaptive=True, no_adaptive=False, rtol=8.0, literal_norm=True)
+    stats = s.stats()
+    assert st.kind == "Done" and np.array_equal(stats["accepted"], ref["accepted"]) and not stats["rejected"].any() and not ref["rejected"].any()
+    assert np.abs(stats["dx_norm"] - 1.0).max() <= 1e-15  # ||x0||, every attempt
+    acc_literal = stats["accepted"].copy()
+    assert np.abs(s.current()[1] - ref["psi"]).max() <= 1e-12
+    # rtol below ||x0||: nothing but rejections
+    s = vo.MagnusExpLinearSolver(sp, gp, 0.0, 1.0, psi0, h, M_gen=2).with_tolerance(1e-4, 1e-4).literal_norm()
+    for _ in range(12):
+        st = s.step_adaptive()
+    stats = s.stats()
+    ref = oracle.exp_ensemble("magnus42", basis3, gp, psi0, 0.0, 1.0, h, M_gen=2, cs=cs, adaptive=True, no_adaptive=False, rtol=1e-4, literal_norm=True, max_calls=12)
+    assert not stats["accepted"].any() and np.array_equal(stats["rejected"], ref["rejected"]) and np.all(stats["rejected"] == 11)
+    assert np.allclose(stats["h"], ref["h"], rtol=1e-15) and np.all(stats["t"] == 0.0)
+    # the dense-commutator kernel honours the switch too
+    d = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, dense_commutator=True).with_tolerance(8.0, 8.0).literal_norm()
+    d.run(adaptive=True)
+    assert np.array_equal(d.stats()["accepted"], acc_literal) and not d.stats()["rejected"].any()
+    cfm = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, h)
+    assert vo._cabi.lib().vo_exp_set_literal_norm(cfm._h, 1) == vo._cabi.VO_ERR_STATE  # only the Magnus solver's norm() has the quirk

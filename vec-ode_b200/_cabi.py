@@ -118,6 +118,8 @@ SIGNATURES = {
     "vo_solver_set_blocked": (_i32, [_vp, _i32]),
     "vo_step": (_i32, [_vp, C.POINTER(StepResult)]),
     "vo_step_adaptive": (_i32, [_vp, C.POINTER(StepResult)]),
+    "vo_adaptive_try": (_i32, [_vp, _i64, _i64, C.POINTER(_f64), C.POINTER(_i32), C.POINTER(StepResult)]),
+    "vo_adaptive_handle": (_i32, [_vp, _f64, C.POINTER(StepResult)]),
     "vo_run": (_i32, [_vp, _i32, _i64, C.POINTER(StepResult)]),
     "vo_step_many": (_i32, [_pvp, _i32, _i32, _i64]),
     "vo_current": (_i32, [_vp, C.POINTER(_f64), C.POINTER(_f64), _pvp]),
@@ -142,6 +144,7 @@ SIGNATURES = {
     "vo_dense_map_exp": (_i32, [_vp, _vp, _vp, _vp]),
     "vo_dense_commutator": (_i32, [_vp, _vp, _vp, _vp]),
     "vo_exp_set_dense_commutator": (_i32, [_vp, _i32]),
+    "vo_exp_set_literal_norm": (_i32, [_vp, _i32]),
     "vo_exp_set_split_mask": (_i32, [_vp, C.c_uint32]),
     "vo_exp_set_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32]),
     "vo_exp_set_split_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32]),

@@ -406,6 +406,20 @@ class RK45Solver:
         check(lib().vo_step_adaptive(self._h, C.byref(res)), self.ctx._h)
         return _state_of(res)
 
+    def adaptive_try(self, lo: int, hi: int):
+        """First half of step_adaptive (ode.rs:336-344) for a state held in pieces: try_step + the norm accumulator of this piece's
+        components [lo, hi). Returns (acc, event, state): `state` is the finished ODEState when the event was Chkpt / End, else None
+        (combine the pieces' accumulators, then call adaptive_handle with the global norm)."""
+        acc, ev, res = C.c_double(), C.c_int32(), StepResult()
+        check(lib().vo_adaptive_try(self._h, lo, hi, C.byref(acc), C.byref(ev), C.byref(res)), self.ctx._h)
+        return acc.value, ev.value, (None if ev.value == 0 else _state_of(res))
+
+    def adaptive_handle(self, dx_norm: float) -> ODEState:
+        """Second half: handle_step_adaptive (ode.rs:311-334) with the global error norm, then apply_step."""
+        res = StepResult()
+        check(lib().vo_adaptive_handle(self._h, float(dx_norm), C.byref(res)), self.ctx._h)
+        return _state_of(res)
+
     def run(self, adaptive: bool = False, max_calls: int = 0) -> ODEState:
         """`while let ODEState::Ok(_) = solver.step() {}` for the whole ensemble."""
         res = StepResult()

@@ -57,6 +57,7 @@ struct vo_expsolver_s {
     int64_t* perm = nullptr;     // vo_exp_set_order: device slot j holds the caller's system perm[j] (device copy)
     std::vector<int64_t> perm_host;
     double2* stage = nullptr;    // [N][n] staging for the reordering copies
+    int literal_norm = 0;        // vo_exp_set_literal_norm: MagnusExpLinearSolver::norm as written (magnus.rs:274-276)
     int dense_comm = 0;          // vo_exp_set_dense_commutator: magnus_42 forms [L0, L1] densely per system (no structure tensor needed)
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
@@ -252,6 +253,7 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     kp.t_start = s->t0, kp.t_end = s->tf, kp.N = s->N, kp.count_events = 1;
     kp.rtol = s->rtol, kp.alpha = s->alpha, kp.pw = s->pw, kp.min_dt = s->min_dt, kp.max_dt = s->max_dt;
     kp.pw_is_third = s->pw == 1.0 / 3.0;
+    kp.literal_norm = (s->literal_norm && adaptive) ? 1 : 0;
     kp.split_mask = s->split_mask;
     kp.n_nodes = s->n_nodes, kp.n_rows = s->n_rows, kp.n_rows_err = s->n_rows_err;
     std::memcpy(kp.tab_c, s->tab_c, sizeof kp.tab_c), std::memcpy(kp.tab_alpha, s->tab_alpha, sizeof kp.tab_alpha);
@@ -633,6 +635,14 @@ int32_t vo_exp_stats(vo_expsolver s, int64_t* accepted, int64_t* rejected, doubl
     return VO_OK;
 }
 
+// adaptive_dat.dx is a clone of x0 that no step ever writes (magnus.rs:182-183, 249-250): its norm, per system, in ca.dx_norm
+static int32_t exp_fill_literal_norm(vo_expsolver_s* s) {
+    vo_ctx c = s->ctx;
+    exp_norm_kernel<<<(unsigned)ceil_div(s->N, 8), 256, 0, c->stream>>>(s->psi0, s->sp->n, s->N, s->ca.dx_norm);
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
 int32_t vo_exp_reset(vo_expsolver s, const double* psi0_host) {
     if (!s) return VO_ERR_BAD_ARG;
     vo_ctx c = s->ctx;
@@ -651,7 +661,16 @@ int32_t vo_exp_reset(vo_expsolver s, const double* psi0_host) {
     s->n_done = 0;
     exp_ctl_fill_kernel<<<(unsigned)ceil_div(s->N, 256), 256, 0, c->stream>>>(s->ca, s->N, s->t0, s->h_init);
     VO_CHECK_LAUNCH(c);
+    if (s->literal_norm) return exp_fill_literal_norm(s);
     return VO_OK;
+}
+
+int32_t vo_exp_set_literal_norm(vo_expsolver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (on && s->scheme != VO_EXP_MAGNUS42) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_literal_norm: only MagnusExpLinearSolver::norm reads adaptive_dat.dx (magnus.rs:274-276)");
+    DeviceGuard g(s->ctx->device);
+    s->literal_norm = on ? 1 : 0;
+    return on ? exp_fill_literal_norm(s) : VO_OK;
 }
 
 int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n) {

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(32 * NB) magnus_dense_kernel(const __grid_cons
                 if (kp.adaptive) {
                     double nn = 0.0;
                     for (int ww = 0; ww < NB; ++ww) nn += red[ww];
-                    const double dxn = sqrt(nn);
+                    const double dxn = kp.literal_norm ? ca.dx_norm[sys] : sqrt(nn);
                     const double f = kp.rtol / dxn;
                     const double fp_lim = at_most(at_least(step_size_mul<true>(kp.alpha, f, kp.pw, kp.pw_is_third), 0.3), 2.0);
                     const double new_h = at_most(at_least(fp_lim * h, kp.min_dt), kp.max_dt);

@@ -13,6 +13,7 @@
 struct ExpKP {
     int n, M, M_gen, scheme, adaptive, want_err, taylor_deg, mode;  // mode 0: solver event, 1: bare map_exp
     int pw_is_third, count_events;
+    int literal_norm;     // vo_exp_set_literal_norm: the controller reads ca.dx_norm (= ||x0||, never rewritten) instead of ||x_err||, magnus.rs:274-276
     int nseq;             // mode 1: exponentials applied one after the other, coefficient sets [nseq][N][M]
     unsigned split_mask;  // VO_EXP_SPLIT_MIDPOINT: bit m set <=> basis matrix m belongs to split A
     double t_end, t_start;
@@ -405,7 +406,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                         if (kp.adaptive) {  // handle_step_adaptive, ode.rs:311-334
                             double nn = 0.0;
                             for (int ww = 0; ww < G::NW; ++ww) nn += sNorm[ww * TB + s];
-                            const double dxn = sqrt(nn);
+                            const double dxn = kp.literal_norm ? ca.dx_norm[sys] : sqrt(nn);
                             const double f = kp.rtol / dxn;
                             const double mul = step_size_mul<true>(kp.alpha, f, kp.pw, kp.pw_is_third);  // ode.rs:133-135, powf correctly rounded (rk_small.cuh)
                             const double fp_lim = at_most(at_least(mul, 0.3), 2.0);

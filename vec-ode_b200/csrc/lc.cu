@@ -157,7 +157,7 @@ __device__ __forceinline__ double norm_term(double e, int kind) { return kind ==
 __device__ __forceinline__ double norm_join(double a, double b, int kind) { return kind == VO_NORM_LINF ? fmax(a, b) : a + b; }
 
 // d <= 64: one thread per trajectory, left-to-right over the components (coalesced over i).
-template <bool STRICT> __global__ void norm_small_kernel(const double* __restrict__ x, int64_t d, int64_t n, int kind, double* __restrict__ out) {
+template <bool STRICT> __global__ void norm_small_kernel(const double* __restrict__ x, int64_t d, int64_t n, int kind, double* __restrict__ out, bool finish) {
     using A = Ar<STRICT>;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -180,7 +180,7 @@ template <bool STRICT> __global__ void norm_small_kernel(const double* __restric
         else if (kind == VO_NORM_LINF) acc = fmax(acc, fabs(e));
         else acc = A::add(acc, fabs(e));
     }
-    out[i] = kind == VO_NORM_L2 ? sqrt(acc) : acc;
+    out[i] = (kind == VO_NORM_L2 && finish) ? sqrt(acc) : acc;
 }
 
 // large d: grid (chunks, trajectories); warp-shuffle tree inside each block; fixed order -> reproducible.
@@ -200,23 +200,24 @@ __global__ void __launch_bounds__(256) norm_partial_kernel(const double* __restr
         if (threadIdx.x == 0) partial[traj * gridDim.x + blockIdx.x] = acc;
     }
 }
-__global__ void norm_final_kernel(const double* __restrict__ partial, int chunks, int kind, double* __restrict__ out) {
+__global__ void norm_final_kernel(const double* __restrict__ partial, int chunks, int kind, double* __restrict__ out, bool finish) {
     const int64_t traj = blockIdx.x;
     double acc = 0.0;
     for (int c = threadIdx.x; c < chunks; c += 32) acc = norm_join(acc, partial[traj * chunks + c], kind);
     for (int off = 16; off > 0; off >>= 1) acc = norm_join(acc, __shfl_down_sync(0xffffffffu, acc, off), kind);
-    if (threadIdx.x == 0) out[traj] = kind == VO_NORM_L2 ? sqrt(acc) : acc;
+    if (threadIdx.x == 0) out[traj] = (kind == VO_NORM_L2 && finish) ? sqrt(acc) : acc;
 }
 
 }  // namespace
 
-// Device-side norm into a device buffer (used by the stage-path controller as well).
-int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap) {
+// Device-side norm into a device buffer (used by the stage-path controller as well). finish = false leaves the reduction
+// accumulator (sum of squares for L2) so that several partial states can be combined before the square root (vo_adaptive_try).
+int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap, bool finish) {
     vo_ctx c = e->ctx;
     if (e->d <= 64) {
         const int grid = (int)ceil_div(e->n, 256);
-        if (c->arith == VO_ARITH_STRICT) norm_small_kernel<true><<<grid, 256, 0, c->stream>>>(e->p, e->d, e->n, kind, out_dev);
-        else norm_small_kernel<false><<<grid, 256, 0, c->stream>>>(e->p, e->d, e->n, kind, out_dev);
+        if (c->arith == VO_ARITH_STRICT) norm_small_kernel<true><<<grid, 256, 0, c->stream>>>(e->p, e->d, e->n, kind, out_dev, finish);
+        else norm_small_kernel<false><<<grid, 256, 0, c->stream>>>(e->p, e->d, e->n, kind, out_dev, finish);
         VO_CHECK_LAUNCH(c);
         return VO_OK;
     }
@@ -227,7 +228,7 @@ int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_
     dim3 grid(chunks, (unsigned)e->n);
     norm_partial_kernel<<<grid, 256, 0, c->stream>>>(e->p, e->d, e->n, kind, partial_dev);
     VO_CHECK_LAUNCH(c);
-    norm_final_kernel<<<(unsigned)e->n, 32, 0, c->stream>>>(partial_dev, chunks, kind, out_dev);
+    norm_final_kernel<<<(unsigned)e->n, 32, 0, c->stream>>>(partial_dev, chunks, kind, out_dev, finish);
     VO_CHECK_LAUNCH(c);
     return VO_OK;
 }
@@ -269,7 +270,7 @@ int32_t vo_norm(vo_ens e, int32_t kind, double* out_host) {
     const int cap = 1 << 16;
     VO_CUDA(c, cudaMallocAsync(&out_dev, sizeof(double) * e->n, c->stream));
     VO_CUDA(c, cudaMallocAsync(&partial, sizeof(double) * cap, c->stream));
-    int32_t r = vo_norm_device(e, kind, out_dev, partial, cap);
+    int32_t r = vo_norm_device(e, kind, out_dev, partial, cap, true);
     if (r == VO_OK) {
         cudaError_t ce = cudaMemcpyAsync(out_host, out_dev, sizeof(double) * e->n, cudaMemcpyDeviceToHost, c->stream);
         if (ce != cudaSuccess) r = vo_fail(c, VO_ERR_CUDA, cudaGetErrorString(ce));

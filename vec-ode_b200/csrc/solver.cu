@@ -23,7 +23,7 @@
 #include "rk_stage.cuh"
 #include "rk_heat_fused.cuh"
 
-int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap);
+int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap, bool finish);
 int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t N, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
                             double* xe);  // nvrtc_rhs.cu
 
@@ -55,6 +55,9 @@ struct vo_solver_s {
     int u_tgt = 0;
     bool u_done = false;
     int64_t u_accept = 0, u_reject = 0;
+    bool try_pending = false;  // vo_adaptive_try has run rk_step and waits for vo_adaptive_handle
+    double try_dt = 0;
+    int try_launches = 0;
     // per-trajectory control
     CtlArrays ca{};
     uint8_t* evv = nullptr;  // stage path: event of the current call per trajectory
@@ -659,14 +662,36 @@ int32_t heat_fused_rk_step(vo_solver_s* s, double dt, double* nx, double* xe, in
     return r;
 }
 
+// handle_step_adaptive (ode.rs:311-334) for the shared scalars of a lock-step solver; true = rejected.
+bool uni_controller(vo_solver_s* s, double dxn) {
+    const double h = s->u_h;  // ode.rs:314
+    s->u_dx_norm = dxn;
+    const double f = s->rtol / dxn;                                                        // ode.rs:320
+    const double fp_lim = std::fmin(std::fmax(s->alpha * std::pow(f, s->pw), 0.3), 2.0);   // ode.rs:321-323
+    const double new_h = std::fmin(std::fmax(fp_lim * h, s->min_dt), s->max_dt);          // ode.rs:324
+    s->u_prev_h = s->u_h, s->u_h = new_h;                                                  // ode.rs:326
+    return f <= 1.0;                                                                       // ode.rs:328-330
+}
+// apply_step (ode.rs:402-428) of a Step / Reject event on the lock-step stage path
+void uni_apply(vo_solver_s* s, int ev, double dt, vo_step_result* res, int launches) {
+    if (ev == VO_EV_STEP) {
+        std::swap(s->x, s->next_x);  // advance, ode.rs:184-188
+        s->u_t += dt, s->u_accept += 1;
+        res_add(res, s->n, 0, 0, 0, launches);
+    } else {
+        s->u_reject += 1;
+        res_add(res, 0, 0, s->n, 0, launches);
+    }
+}
+
 // Lock-step stage path: one event, controller on the host (the norm is read back for adaptive steps).
 int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) {
     vo_ctx c = s->ctx;
     double dt = 0.0;
     int ev = uni_step_size(s, &dt);
     int launches = 0;
+    if (s->try_pending) return vo_fail(c, VO_ERR_STATE, "a vo_adaptive_try is waiting for its vo_adaptive_handle");
     if (ev == VO_EV_STEP) {
-        const double h = s->u_h;  // ode.rs:314
         double* xe_p = use_err(s) ? s->x_err->p : nullptr;
         int32_t r = heat_fused_ok(s) ? heat_fused_rk_step(s, dt, s->next_x->p, xe_p, &launches)
                                      : stage_rk_step(s, s->u_t, dt, false, s->next_x->p, xe_p, nullptr, &launches);
@@ -675,27 +700,14 @@ int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) 
             double* out = (double*)c->dscratch;
             if (s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: lock-step adaptive control needs N == 1");
             const int64_t launches_before = c->launches;
-            r = vo_norm_device(s->x_err, s->norm_kind, out, s->norm_partial, PARTIAL_CAP);
+            r = vo_norm_device(s->x_err, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, true);
             if (r != VO_OK) return r;
             launches += (int)(c->launches - launches_before);
             VO_CUDA(c, cudaMemcpyAsync(c->pinned, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             VO_CUDA(c, cudaStreamSynchronize(c->stream));
-            const double dxn = *(double*)c->pinned;
-            s->u_dx_norm = dxn;
-            const double f = s->rtol / dxn;                                                        // ode.rs:320
-            const double fp_lim = std::fmin(std::fmax(s->alpha * std::pow(f, s->pw), 0.3), 2.0);   // ode.rs:321-323
-            const double new_h = std::fmin(std::fmax(fp_lim * h, s->min_dt), s->max_dt);          // ode.rs:324
-            s->u_prev_h = s->u_h, s->u_h = new_h;                                                  // ode.rs:326
-            if (f <= 1.0) ev = VO_EV_REJECT;                                                       // ode.rs:328-330
+            if (uni_controller(s, *(double*)c->pinned)) ev = VO_EV_REJECT;
         }
-        if (ev == VO_EV_STEP) {
-            std::swap(s->x, s->next_x);  // advance, ode.rs:184-188
-            s->u_t += dt, s->u_accept += 1;
-            res_add(res, s->n, 0, 0, 0, launches);
-        } else {
-            s->u_reject += 1;
-            res_add(res, 0, 0, s->n, 0, launches);
-        }
+        uni_apply(s, ev, dt, res, launches);
     } else {
         uni_checkpoint(s, ev == VO_EV_END);
         res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
@@ -978,6 +990,66 @@ static int32_t step_impl(vo_solver s, bool adaptive, vo_step_result* res) {
 
 int32_t vo_step(vo_solver s, vo_step_result* res) { return step_impl(s, false, res); }
 int32_t vo_step_adaptive(vo_solver s, vo_step_result* res) { return step_impl(s, true, res); }
+
+// AdaptiveODESolver::step_adaptive (ode.rs:336-344) in its two halves — try_step + the error norm, then handle_step_adaptive +
+// apply_step — for a state that is ONE vector held in pieces by several solvers (slabs of a grid on several GPUs,
+// vec-ode_b200/domain.py): every piece reports the accumulator of its own components [lo, hi), the caller combines them
+// (sum or max over the pieces, any communicator) and hands the same global norm to every piece.
+int32_t vo_adaptive_try(vo_solver s, int64_t lo, int64_t hi, double* acc, int32_t* event, vo_step_result* res) {
+    if (!s || !acc || !event) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_adaptive_try: NULL argument");
+    vo_ctx c = s->ctx;
+    DeviceGuard g(c->device);
+    if (!s->uniform || use_small(s) || s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_adaptive_try: a single state (N == 1) on the stage path");
+    if (s->try_pending) return vo_fail(c, VO_ERR_STATE, "vo_adaptive_try: the previous attempt has not been handled");
+    if (lo < 0 || hi > s->d || lo >= hi) return vo_fail(c, VO_ERR_SHAPE, "vo_adaptive_try: bad component range");
+    if (s->norm_kind == VO_NORM_HYPOT) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_adaptive_try: L2, L1 or Linf norm");
+    int32_t r = prepare_mode(s, true);
+    if (r != VO_OK) return r;
+    *acc = 0.0;
+    if (res) std::memset(res, 0, sizeof *res);
+    if (s->u_done) {
+        *event = VO_EV_END;
+        finish_result(s, res);
+        return VO_OK;
+    }
+    double dt = 0.0;
+    const int ev = uni_step_size(s, &dt);
+    *event = ev;
+    if (ev != VO_EV_STEP) {  // Chkpt / End need no norm: done here, nothing to handle
+        uni_checkpoint(s, ev == VO_EV_END);
+        res_add(res, 0, ev == VO_EV_CHKPT ? s->n : 0, 0, ev == VO_EV_END ? s->n : 0, 0);
+        finish_result(s, res);
+        return VO_OK;
+    }
+    int launches = 0;
+    r = heat_fused_ok(s) ? heat_fused_rk_step(s, dt, s->next_x->p, s->x_err->p, &launches)
+                         : stage_rk_step(s, s->u_t, dt, false, s->next_x->p, s->x_err->p, nullptr, &launches);
+    if (r != VO_OK) return r;
+    vo_ens_s view;
+    view.ctx = c, view.p = s->x_err->p + lo, view.d = hi - lo, view.n = 1, view.owns = false;
+    double* out = (double*)c->dscratch;
+    const int64_t before = c->launches;
+    r = vo_norm_device(&view, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, false);
+    if (r != VO_OK) return r;
+    launches += (int)(c->launches - before);
+    VO_CUDA(c, cudaMemcpyAsync(c->pinned, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    *acc = *(double*)c->pinned;
+    s->try_pending = true, s->try_dt = dt, s->try_launches = launches;
+    return VO_OK;
+}
+
+int32_t vo_adaptive_handle(vo_solver s, double dx_norm, vo_step_result* res) {
+    if (!s) return VO_ERR_BAD_ARG;
+    vo_ctx c = s->ctx;
+    if (res) std::memset(res, 0, sizeof *res);
+    if (!s->try_pending) return vo_fail(c, VO_ERR_STATE, "vo_adaptive_handle: no attempt is pending (vo_adaptive_try returned Chkpt / End, or was not called)");
+    s->try_pending = false;
+    const int ev = uni_controller(s, dx_norm) ? VO_EV_REJECT : VO_EV_STEP;
+    uni_apply(s, ev, s->try_dt, res, s->try_launches);
+    finish_result(s, res);
+    return VO_OK;
+}
 
 int32_t vo_run(vo_solver s, int32_t adaptive, int64_t max_calls, vo_step_result* res) {
     if (!s) return VO_ERR_BAD_ARG;

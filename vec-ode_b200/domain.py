@@ -6,8 +6,14 @@ points plus H ghost points per side, copies of its periodic neighbours' edge poi
 3-point stencil reads one more neighbour per stage, so one step corrupts at most s points at each end of the local array
 (where the kernels' periodic wrap-around reads the wrong data) and leaves every other point with exactly the bits the
 single-GPU solve produces: same kernels, same operations, same order. With H = k*s the ranks exchange ghost points once
-every k steps — the only communication of the path: one all-gather of 2H doubles per rank (NCCL over NVLink on GPUs,
-gloo in the CPU tests). Fixed-step only: an adaptive step of one shared state would need a global error norm per attempt.
+every k steps — the only communication of the fixed-step path: one all-gather of 2H doubles per rank (NCCL over NVLink on
+GPUs, gloo in the CPU tests).
+
+Adaptive stepping (`step_adaptive`, ode.rs:311-344) needs ONE error norm of the whole state per attempt: every rank runs
+try_step on its slab and reduces x_err over its OWNED points only (vo_adaptive_try), the accumulators are combined with one
+all-reduce of a single double (sum of squares for the L2 norm, sum for L1, max for Linf), and every rank hands the same global
+norm to the controller (vo_adaptive_handle), so (t, h) and every accept / reject decision are identical on all ranks. A
+rejected attempt leaves the state untouched, so only ACCEPTED steps use up ghost points.
 """
 from __future__ import annotations
 
@@ -76,7 +82,7 @@ class HeatSlabSolver:
     the process group. Same stepping semantics as `RK45Solver.step()` for a single large state (N = 1, lock-step control on
     the host); every rank runs the same (t, dt) sequence, so the only data-path exchange is the ghost refresh."""
 
-    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4, fused: bool = False):
+    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4, fused: bool = False, adaptive: bool = False):
         from . import base
         rank, world = rank_world()
         self.ctx = ctx
@@ -86,7 +92,9 @@ class HeatSlabSolver:
         u0 = u0_global_fn(self.slab.global_index())  # every rank evaluates its own points (and ghosts) of the initial state
         self.rhs = base.Rhs(ctx, "HEAT1D", self.slab.local_len, [kappa])
         self.solver = base.RK45Solver(self.rhs, t0, tf, base.Ensemble.from_host(ctx, u0[None, :]), h, tableau=self.tableau)
-        self.solver.no_adaptive()
+        if not adaptive:
+            self.solver.no_adaptive()
+        self._norm_kind, self._adaptive = "L2", adaptive
         if fused:  # whole-step kernel (rk_heat_fused.cuh): its periodic wrap corrupts the same s points per step at the slab ends
             self.solver.set_fused_step()
         self._fused = fused
@@ -104,9 +112,16 @@ class HeatSlabSolver:
 
     def step(self):
         """One call of the reference's `step()` for the distributed state."""
+        # the exchange is torch work on torch's current stream; a ctx with a stream of its own is fenced on both sides
+        self._refresh_ghosts_if_due()
+        st = self.solver.step()
+        if st.counts["Step"]:
+            self._since_exchange += 1
+        return st
+
+    def _refresh_ghosts_if_due(self):
         if self._since_exchange == self.k:
             import torch
-            # the exchange is torch work on torch's current stream; a ctx with a stream of its own is fenced on both sides
             tstream = torch.cuda.current_stream(self.ctx.device)
             foreign = self.ctx.stream != (tstream.cuda_stream or 1)
             if foreign:
@@ -115,22 +130,48 @@ class HeatSlabSolver:
             if foreign:
                 tstream.synchronize()
             self._since_exchange, self.exchanges = 0, self.exchanges + 1
-        st = self.solver.step()
+
+    def step_adaptive(self):
+        """One call of the reference's `step_adaptive()` (ode.rs:336-344) for the distributed state: the error norm is taken over
+        the whole grid (one all-reduce of one double per attempt), the controller runs identically on every rank."""
+        import math
+        self._refresh_ghosts_if_due()
+        H, m = self.slab.halo, self.slab.m
+        acc, ev, done = self.solver.adaptive_try(H, H + m)
+        if done is not None:  # Chkpt / End: no norm, nothing to combine
+            return done
+        kind = self._norm_kind
+        if self.slab.world > 1 and is_distributed():
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([acc], dtype=torch.float64, device=("cpu" if dist.get_backend() == "gloo" else f"cuda:{self.ctx.device}"))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if kind == "LINF" else dist.ReduceOp.SUM)
+            acc = float(t.item())
+        st = self.solver.adaptive_handle(math.sqrt(acc) if kind == "L2" else acc)
         if st.counts["Step"]:
             self._since_exchange += 1
         return st
 
-    def run(self, max_calls: int = 0):
+    def with_tolerance(self, atol: float, rtol: float, norm: str = "L2"):
+        """with_tolerance (ode.rs:296-306) + the norm of the whole state: "L2", "L1" or "LINF"."""
+        self.solver.with_tolerance(atol, rtol)
+        self.solver.set_norm(norm)
+        self._norm_kind = norm
+        self._adaptive = True
+        return self
+
+    def run(self, max_calls: int = 0, adaptive: bool = False):
         st, calls = None, 0
         while st is None or (st.kind == "Ok" and (max_calls <= 0 or calls < max_calls)):
-            st = self.step()
+            st = self.step_adaptive() if adaptive else self.step()
             calls += 1
         return st
 
     def reset(self, x0):
         """Restart from the local state `x0` (an Ensemble of the slab's length, ghosts included and fresh)."""
         self.solver.reset(x0)
-        self.solver.no_adaptive()
+        if not self._adaptive:
+            self.solver.no_adaptive()
         if self._fused:
             self.solver.set_fused_step()
         self._since_exchange = 0

@@ -307,3 +307,9 @@ class MagnusExpLinearSolver(_ExpSolver):
         super().__init__(sp, gp, t0, tf, psi0, h, M_gen, group_similar)
         if dense_commutator:
             check(lib().vo_exp_set_dense_commutator(self._h, 1), self.ctx._h)
+
+    def literal_norm(self, on: bool = True):
+        """The reference's `norm()` as written (magnus.rs:274-276): the controller sees ||x0||, not the embedded error
+        (vo_exp_set_literal_norm). Off by default."""
+        check(lib().vo_exp_set_literal_norm(self._h, 1 if on else 0), self.ctx._h)
+        return self
