@@ -63,3 +63,38 @@ def test_product_never_imports_oracle():
                     code = line.split("//")[0].split("#", 1)[0] if not line.lstrip().startswith("#include") else line
                     bad = ("oracle" in code) and any(k in code for k in ("import", "#include", "CDLL", "dlopen", "subprocess"))
                     assert not bad and "libvecode_oracle" not in code, (f, line)
+
+
+def _build_harness(tmp_path):
+    """g++ on tests/harness/vo_harness.cpp against the shared object: what a compiled host does, no Python on the data path."""
+    import subprocess
+    exe = str(tmp_path / "vo_harness")
+    so_dir = os.path.join(ROOT, "vec-ode_b200")
+    cmd = ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "harness", "vo_harness.cpp"), "-o", exe,
+           "-L", so_dir, "-lvecode_b200", f"-Wl,-rpath,{so_dir}", "-Wl,-rpath-link,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_harness_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """The C++ harness compiles against include/vecode_b200.h as C++ and links every entry point it uses. Without a CUDA device the
+    library must refuse (exit code 3 of the harness, message 'no CPU fallback'); with one, the harness runs to 'harness ok'."""
+    import subprocess
+    import torch
+    exe = _build_harness(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "harness ok" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_harness_on_the_gpu(tmp_path):
+    """The reference's own three tests (src/impls/nalgebra.rs:52-107) and a bit-exact Lorenz-63 RK4 sweep, driven from C++."""
+    import subprocess
+    exe = _build_harness(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0 and "harness ok" in r.stdout and "bit-exact vs restatement: yes" in r.stdout, r.stdout + r.stderr
