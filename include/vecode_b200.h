@@ -46,6 +46,7 @@ typedef struct vo_solver_s* vo_solver;
 typedef struct vo_split_s* vo_split;
 typedef struct vo_expsolver_s* vo_expsolver;
 typedef struct vo_group_s* vo_group;
+typedef struct vo_normfn_s* vo_normfn;
 
 /* ---- context ---------------------------------------------------------------------------------- */
 /* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
@@ -110,7 +111,29 @@ int32_t vo_lc_stage_combine(vo_ens v, const vo_ens* v_arr, const double* k_arr, 
 #define VO_NORM_LINF 1  /* max_c |e_c| */
 #define VO_NORM_L1 2
 #define VO_NORM_HYPOT 3 /* complex scalar stored as (re, im): hypot (rk.rs:209-214) */
+#define VO_NORM_CUSTOM 4 /* a vo_normfn (below); set through vo_solver_set_norm_custom / vo_exp_set_norm_custom */
 int32_t vo_norm(vo_ens e, int32_t kind, double* out_host /* [N] */);
+/* User-defined norms. `Normed<T, V>` is the USER's trait impl (ode.rs:9-11; RK45Solver::norm, rk.rs:302-304) and ExpCFMSolver takes
+ * a NormFn closure (exp/cfm.rs:105, 214-216). Like the RHS closure it crosses the C ABI as SOURCE, in the shape
+ *     norm(e) = finish( JOIN_i map(e_i, i) ),   JOIN = VO_NORM_JOIN_SUM or VO_NORM_JOIN_MAX:
+ * `map_body`: CUDA C++ statements assigning `double m` (>= 0) from `const double e` (component i; the real part of a complex
+ * component), `const double im` (its imaginary part, 0 for real states), `const int i`, `const int n` (number of components);
+ * `finish_body`: statements assigning `double r` from `const double acc`, `const int n` (NULL or "": r = acc).
+ * E.g. a weighted RMS norm: map "m = (e * e) / (1.0 + i);", SUM, finish "r = sqrt(acc / n);".
+ * The functor is compiled at run time (NVRTC, sm_100a) into the same kernels that hold the built-in norms: the register-resident
+ * control kernels, the exponential-integrator kernel and the reduction kernels of the stage path. */
+#define VO_NORM_JOIN_SUM 0
+#define VO_NORM_JOIN_MAX 1
+int32_t vo_normfn_create(vo_ctx ctx, const char* map_body, int32_t join, const char* finish_body, vo_normfn* out);
+int32_t vo_normfn_destroy(vo_normfn f);
+/* Compile the functor without a ctx or a GPU (NVRTC only): cubin size (> 0), or VO_ERR_* with the compiler log in `log`. */
+int32_t vo_normfn_check(const char* map_body, int32_t join, const char* finish_body, char* log, int64_t log_cap);
+/* The same for the solver kernels the functor is compiled INTO: rhs_kind >= 0 compiles the register-resident kernels of that
+ * compiled-in family (d components, `stages`-stage tableau, VO_ARITH_* mode) with the norm; exp_n > 0 compiles
+ * exp_step_kernel<exp_n, exp_M> with it. Sum of the cubin sizes, or VO_ERR_* with the log. No ctx, no GPU. */
+int32_t vo_normfn_check_kernels(const char* map_body, int32_t join, const char* finish_body, int32_t rhs_kind, int32_t d, int32_t stages, int32_t arith,
+                                int32_t exp_n, int32_t exp_M, char* log, int64_t log_cap);
+int32_t vo_norm_custom(vo_ens e, vo_normfn f, double* out_host /* [N] */);  /* Normed::norm on its own */
 
 /* ---- ButcherTableu (src/base/rk.rs:22-78) ------------------------------------------------------ */
 #define VO_MAX_STAGES 16
@@ -192,6 +215,9 @@ int32_t vo_solver_with_init_step(vo_solver s, double h);                     /* 
 int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n);  /* pub field ODEData.t_list, ode.rs:89 */
 int32_t vo_solver_set_order_alpha(vo_solver s, double order, double alpha);  /* ODEAdaptiveData::new / with_alpha, ode.rs:114-131 */
 int32_t vo_solver_set_norm(vo_solver s, int32_t norm_kind);                  /* the user `Normed` impl, rk.rs:302 */
+/* ... as a user-defined functor (any RHS, compiled-in family or custom: the solver's control kernels are re-compiled at run time
+ * with the norm in them). `f` must outlive the solver. */
+int32_t vo_solver_set_norm_custom(vo_solver s, vo_normfn f);
 int32_t vo_solver_set_h_array(vo_solver s, const double* h_host, int64_t n); /* one initial step per trajectory */
 /* Events (calls of step()/step_adaptive()) fused per kernel launch on the register-resident path. 0 (default) =
  * automatic: one per launch for vo_step, vo_step_adaptive and vo_step_many, which expose every event; 16 (lock-step) or 8 (per-trajectory
@@ -351,6 +377,10 @@ int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on);
  * clamp(0.9 (rtol / ||x0||)^(1/3), 0.3, 2) per step. Off by default: the solvers here give the controller the embedded error it
  * was meant to see. On: the reference's literal behaviour, for comparisons. Magnus only. */
 int32_t vo_exp_set_literal_norm(vo_expsolver s, int32_t on);
+/* NormedExponentialSplit::norm / ExpCFMSolver's NormFn (exp/mod.rs:37-45, exp/cfm.rs:105, 214-216) as a user-defined functor:
+ * exp_step_kernel is re-compiled at run time with it (together with the generator of vo_exp_set_generator, if any).
+ * Not available with vo_exp_set_dense_commutator. */
+int32_t vo_exp_set_norm_custom(vo_expsolver s, vo_normfn f);
 int32_t vo_exp_no_adaptive(vo_expsolver s);                              /* exp/cfm.rs:157-161 */
 int32_t vo_exp_with_tolerance(vo_expsolver s, double atol, double rtol);
 int32_t vo_exp_with_step_range(vo_expsolver s, double dt_min, double dt_max);

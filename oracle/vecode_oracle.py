@@ -196,6 +196,8 @@ def _rmin(a, b):
 
 
 def norm_of(v, kind):
+    if callable(kind):  # the user's `Normed` impl (ode.rs:9-11): any function of the error vector
+        return kind(v)
     if kind == 0:  # L2
         acc = 0.0
         for e in v:

@@ -24,3 +24,28 @@ def test_user_generator_compiles_into_the_tensor_core_kernel(vo):
     with pytest.raises(vo.VecOdeError) as ei:
         vo.ExpCFMSolver.check_generator("g[1] = nope;", 16, 2)
     assert "generator_body(1)" in str(ei.value) and "nope" in str(ei.value)
+
+
+WRMS_MAP, WRMS_FINISH = "m = (e * e + im * im) / (1.0 + i);", "r = sqrt(acc / n);"
+
+
+def test_user_norm_compiles_alone_and_into_the_solver_kernels(vo):
+    """vo_normfn_check / vo_normfn_check_kernels: the user's `Normed` impl (ode.rs:9-11) and NormFn closure (cfm.rs:105) as source —
+    the reduction kernels, the register-resident control kernels of a compiled-in family (VdP, DoPri5, both arithmetic modes) and
+    the DMMA kernel of the exponential integrators, all without a GPU."""
+    assert vo.NormFn.check_source(WRMS_MAP, "sum", WRMS_FINISH) > 5_000
+    assert vo.NormFn.check_source("m = fabs(e);", "max") > 5_000
+    for arith in ("strict", "fast"):
+        assert vo.NormFn.check_kernels(WRMS_MAP, "sum", WRMS_FINISH, rhs_kind=3, d=2, stages=7, arith=arith) > 50_000
+    assert vo.NormFn.check_kernels(WRMS_MAP, "sum", WRMS_FINISH, rhs_kind=2, d=3, stages=5) > 50_000   # Lorenz, generic stage count
+    assert vo.NormFn.check_kernels("m = fabs(e) + fabs(im);", "max", "", exp_n=16, exp_M=2) > 10_000
+    assert vo.NormFn.check_kernels(WRMS_MAP, "sum", WRMS_FINISH, exp_n=64, exp_M=2) > 10_000
+
+
+def test_user_norm_compile_error_carries_the_log(vo):
+    with pytest.raises(vo.VecOdeError) as ei:
+        vo.NormFn.check_source("m = nope;", "sum")
+    assert "norm_map_body(1)" in str(ei.value) and "nope" in str(ei.value)
+    with pytest.raises(vo.VecOdeError) as ei:
+        vo.NormFn.check_source("m = e * e;", "sum", "r = sqrt(oops);")
+    assert "norm_finish_body(1)" in str(ei.value)

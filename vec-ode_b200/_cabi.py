@@ -110,6 +110,13 @@ SIGNATURES = {
     "vo_solver_set_t_list": (_i32, [_vp, _vp, _i32]),
     "vo_solver_set_order_alpha": (_i32, [_vp, _f64, _f64]),
     "vo_solver_set_norm": (_i32, [_vp, _i32]),
+    "vo_solver_set_norm_custom": (_i32, [_vp, _vp]),
+    "vo_normfn_create": (_i32, [_vp, C.c_char_p, _i32, C.c_char_p, _pvp]),
+    "vo_normfn_destroy": (_i32, [_vp]),
+    "vo_normfn_check": (_i32, [C.c_char_p, _i32, C.c_char_p, C.c_char_p, _i64]),
+    "vo_normfn_check_kernels": (_i32, [C.c_char_p, _i32, C.c_char_p, _i32, _i32, _i32, _i32, _i32, _i32, C.c_char_p, _i64]),
+    "vo_norm_custom": (_i32, [_vp, _vp, _vp]),
+    "vo_exp_set_norm_custom": (_i32, [_vp, _vp]),
     "vo_solver_set_h_array": (_i32, [_vp, _vp, _i64]),
     "vo_solver_set_events_per_launch": (_i32, [_vp, _i32]),
     "vo_solver_set_path": (_i32, [_vp, _i32]),

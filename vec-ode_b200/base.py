@@ -143,10 +143,13 @@ class Ensemble:
     def device_ptr(self) -> int:
         return int(lib().vo_ens_device_ptr(self._h) or 0)
 
-    def norm(self, kind: str = "L2") -> np.ndarray:
-        """Normed::norm (src/base/ode.rs:9-11) per trajectory."""
+    def norm(self, kind="L2") -> np.ndarray:
+        """Normed::norm (src/base/ode.rs:9-11) per trajectory: a built-in kind by name, or a NormFn."""
         out = np.empty(self.n)
-        check(lib().vo_norm(self._h, _cabi.NORM[kind], _np_ptr(out)), self.ctx._h)
+        if isinstance(kind, NormFn):
+            check(lib().vo_norm_custom(self._h, kind._h, _np_ptr(out)), self.ctx._h)
+        else:
+            check(lib().vo_norm(self._h, _cabi.NORM[kind], _np_ptr(out)), self.ctx._h)
         return out
 
     def __del__(self):
@@ -240,6 +243,51 @@ class ButcherTableu:
         try:
             if self._h:
                 lib().vo_tableau_destroy(self._h)
+        except Exception:
+            pass
+
+
+class NormFn:
+    """A user-defined norm, the reference's `Normed<T, V>` impl (src/base/ode.rs:9-11) or ExpCFMSolver's NormFn closure
+    (src/exp/cfm.rs:105, 214-216), as source (vo_normfn_create):  norm(e) = finish(JOIN_i map(e_i, i)).
+    `map_body` assigns `m` from `e` (`im`: imaginary part of a complex component), `i`, `n`; `join` is "sum" or "max"; `finish_body`
+    assigns `r` from `acc`, `n`. `finish_py(acc, n)` is the optional host-side twin of `finish_body` for norms combined across
+    ranks (domain.HeatSlabSolver)."""
+
+    def __init__(self, ctx: Context, map_body: str, join: str = "sum", finish_body: str = "", finish_py=None):
+        self.ctx, self.join, self.finish_py = ctx, join, finish_py
+        self._h = _vp()
+        check(lib().vo_normfn_create(ctx._h, map_body.encode(), {"sum": 0, "max": 1}[join], finish_body.encode(), C.byref(self._h)), ctx._h)
+
+    @staticmethod
+    def check_source(map_body: str, join: str = "sum", finish_body: str = "") -> int:
+        """Compile only (NVRTC, no GPU): the cubin size, or VecOdeError with the compiler log."""
+        log = C.create_string_buffer(8192)
+        rc = lib().vo_normfn_check(map_body.encode(), {"sum": 0, "max": 1}[join], finish_body.encode(), log, len(log))
+        if rc < 0:
+            raise VecOdeError(rc, log.value.decode(errors="replace"))
+        return rc
+
+    @staticmethod
+    def check_kernels(map_body: str, join: str = "sum", finish_body: str = "", rhs_kind: int = -1, d: int = 0, stages: int = 0, arith: str = "strict",
+                      exp_n: int = 0, exp_M: int = 0) -> int:
+        """Compile the solver kernels the functor goes INTO (vo_normfn_check_kernels; NVRTC, no GPU)."""
+        log = C.create_string_buffer(8192)
+        rc = lib().vo_normfn_check_kernels(map_body.encode(), {"sum": 0, "max": 1}[join], finish_body.encode(), rhs_kind, d, stages,
+                                           _cabi.ARITH_STRICT if arith == "strict" else _cabi.ARITH_FAST, exp_n, exp_M, log, len(log))
+        if rc < 0:
+            raise VecOdeError(rc, log.value.decode(errors="replace"))
+        return rc
+
+    def finish_host(self, acc: float, n: int) -> float:
+        if self.finish_py is None:
+            raise ValueError("this NormFn has no finish_py: give the host-side twin of finish_body to combine the norm across ranks")
+        return float(self.finish_py(acc, n))
+
+    def __del__(self):
+        try:
+            if self._h and self.ctx._h:
+                lib().vo_normfn_destroy(self._h)
         except Exception:
             pass
 
@@ -348,8 +396,12 @@ class RK45Solver:
         check(lib().vo_solver_with_init_step(self._h, h), self.ctx._h)
         return self
 
-    def with_norm(self, kind: str):  # the user-supplied `Normed` impl (rk.rs:302)
-        check(lib().vo_solver_set_norm(self._h, _cabi.NORM[kind]), self.ctx._h)
+    def with_norm(self, kind):  # the user-supplied `Normed` impl (rk.rs:302): a built-in kind by name, or a NormFn
+        if isinstance(kind, NormFn):
+            check(lib().vo_solver_set_norm_custom(self._h, kind._h), self.ctx._h)
+            self._norm_fn = kind  # keep the functor alive as long as the solver
+        else:
+            check(lib().vo_solver_set_norm(self._h, _cabi.NORM[kind]), self.ctx._h)
         return self
 
     def with_order_alpha(self, order: float, alpha: float):  # ode.rs:114-131

@@ -68,10 +68,26 @@ struct vo_rhs_s {
     uint64_t version = 0;              // bumped whenever a parameter changes (solvers that keep a packed copy of per-trajectory parameters re-pack)
     std::string body;                  // VO_RHS_CUSTOM: source of the RHS statements
     std::map<int, void*> modules;      // VO_RHS_CUSTOM: compiled modules keyed by (stage count, arithmetic mode)
+    int alias_kind = -1;               // >= 0: a compiled-in family re-compiled at run time (RhsCustom = RhsF<alias_kind, d>) to take a user norm
+    std::string norm_src;              // source of the VoUserNorm functor compiled into this RHS's modules (vo_solver_set_norm_custom)
 };
 void custom_rhs_release(vo_rhs_s* r);  // nvrtc_rhs.cu
+// user-defined norm (nvrtc_rhs.cu, norm_custom.cuh): the functor's source and the reduction kernels compiled from it
+struct vo_normfn_s {
+    vo_ctx ctx = nullptr;
+    std::string map_body, finish_body;
+    int join = 0;
+    void* module[2] = {nullptr, nullptr};  // per arithmetic mode (strict modules are compiled with --fmad=false)
+    void* fn[2][3] = {};                   // small / partial / final
+};
+std::string norm_source(const vo_normfn_s* f);
+// norm of x = [d][n] (components i_off .. i_off + d of a d_total-component vector) into out_dev[n]; finish = false leaves the accumulator
+int32_t norm_custom_device(vo_normfn_s* f, const double* x, int64_t d, int64_t n, int64_t i_off, int64_t d_total, double* out_dev, double* partial_dev,
+                           int partial_cap, bool finish);
+// a private RHS handle whose run-time modules carry the user's norm (for a compiled-in family: the family re-compiled with it)
+vo_rhs_s* custom_rhs_with_norm(const vo_rhs_s* base, const vo_normfn_s* f);
 // run-time compiled generator of the exponential integrators (nvrtc_rhs.cu): module + kernel handle for exp_step_kernel<n, M, 16, user GEN>
-int32_t rtc_exp_module(vo_ctx c, const std::string& body, int ndim, int M, size_t smem, void** module_out, void** fn_out);
+int32_t rtc_exp_module(vo_ctx c, const std::string& body, const std::string& norm_src, int ndim, int M, size_t smem, void** module_out, void** fn_out);
 int32_t rtc_exp_launch(vo_ctx c, void* fn, unsigned grid, unsigned block, size_t smem, void** args);
 void rtc_exp_unload(void* module);
 

@@ -61,6 +61,7 @@ struct vo_expsolver_s {
     int dense_comm = 0;          // vo_exp_set_dense_commutator: magnus_42 forms [L0, L1] densely per system (no structure tensor needed)
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
+    std::string gen_body, norm_src;  // sources of the run-time compiled kernel: the user's generator ("" = the cosine family) and norm ("" = 2-norm)
     // commutator-free schemes as tables (cfm_general's c / alpha / alph_err, exp/cfm.rs:43-53; split_cfm's rho / sigma)
     int n_nodes = 0, n_rows = 0, n_rows_err = 0;
     double tab_c[VO_EXP_MAX_NODES] = {};
@@ -450,20 +451,40 @@ int32_t vo_exp_destroy(vo_expsolver s) {
     return VO_OK;
 }
 
-int32_t vo_exp_set_generator(vo_expsolver s, const char* body) {
-    if (!s || !body) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_exp_set_generator: NULL argument");
+// (re)build the run-time compiled exp_step_kernel from the solver's generator and norm sources
+static int32_t exp_rebuild_rtc(vo_expsolver_s* s) {
     vo_ctx c = s->ctx;
-    DeviceGuard g(c->device);
     unsigned threads = 0;
     size_t smem = 0;
-    if (!exp_geometry(s->sp->n, s->sp->M, &threads, &smem)) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_exp_set_generator: unsupported shape");
+    if (!exp_geometry(s->sp->n, s->sp->M, &threads, &smem)) return vo_fail(c, VO_ERR_UNSUPPORTED, "exp: unsupported shape for a run-time compiled kernel");
     void *mod = nullptr, *fn = nullptr;
-    int32_t r = rtc_exp_module(c, body, s->sp->n, s->sp->M, smem, &mod, &fn);
+    int32_t r = rtc_exp_module(c, s->gen_body, s->norm_src, s->sp->n, s->sp->M, smem, &mod, &fn);
     if (r != VO_OK) return r;
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
     rtc_exp_unload(s->gen_module);
     s->gen_module = mod, s->gen_fn = fn;
     return VO_OK;
+}
+
+int32_t vo_exp_set_generator(vo_expsolver s, const char* body) {
+    if (!s || !body) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_exp_set_generator: NULL argument");
+    DeviceGuard g(s->ctx->device);
+    const std::string old = s->gen_body;
+    s->gen_body = body;
+    const int32_t r = exp_rebuild_rtc(s);
+    if (r != VO_OK) s->gen_body = old;
+    return r;
+}
+
+int32_t vo_exp_set_norm_custom(vo_expsolver s, vo_normfn f) {
+    if (!s || !f) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_exp_set_norm_custom: NULL argument");
+    if (s->dense_comm) return vo_fail(s->ctx, VO_ERR_UNSUPPORTED, "vo_exp_set_norm_custom: not available together with vo_exp_set_dense_commutator");
+    DeviceGuard g(s->ctx->device);
+    const std::string old = s->norm_src;
+    s->norm_src = norm_source(f);
+    const int32_t r = exp_rebuild_rtc(s);
+    if (r != VO_OK) s->norm_src = old;
+    return r;
 }
 
 int32_t vo_exp_set_cfm_tables(vo_expsolver s, const double* c, int32_t k, const double* alpha, int32_t rows, const double* alpha_err, int32_t rows_err) {

@@ -34,6 +34,10 @@ struct ExpKP {
 // (the literals of dat/mod.rs:4, 67-80 — C_GAUSS_LEGENDRE_4, CFM_R2_J1_GL, CFM_R4_J2_GL, BLANES17_R4_J4 — live in exp.cu, which
 // hands them to the kernel as tables)
 
+#ifdef VO_USER_NORM
+__device__ __forceinline__ double vo_user_join(double a, double b) { return VoUserNorm::JOIN == 1 ? fmax(a, b) : a + b; }
+#endif
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -387,8 +391,14 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
+#ifdef VO_USER_NORM  // the caller's norm (NormFn, exp/cfm.rs:105, 214-216): finish(JOIN_r map(x_err_r, r)); this lane holds row 8 w + lane / 4
+                        double v = VoUserNorm::map(xer[j][q], xei[j][q], 8 * w + (lane >> 2), NDIM);
+                        v = vo_user_join(v, __shfl_xor_sync(0xffffffffu, v, 4)), v = vo_user_join(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                        v = vo_user_join(v, __shfl_xor_sync(0xffffffffu, v, 16));
+#else
                         double v = xer[j][q] * xer[j][q] + xei[j][q] * xei[j][q];
                         v += __shfl_xor_sync(0xffffffffu, v, 4), v += __shfl_xor_sync(0xffffffffu, v, 8), v += __shfl_xor_sync(0xffffffffu, v, 16);
+#endif
                         if ((lane >> 2) == 0) sNorm[w * TB + 16 * cg + 8 * j + 2 * (lane & 3) + q] = v;
                     }
             }
@@ -405,8 +415,13 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                         const double h = ca.h[sys];
                         if (kp.adaptive) {  // handle_step_adaptive, ode.rs:311-334
                             double nn = 0.0;
+#ifdef VO_USER_NORM
+                            for (int ww = 0; ww < G::NW; ++ww) nn = vo_user_join(nn, sNorm[ww * TB + s]);
+                            const double dxn = kp.literal_norm ? ca.dx_norm[sys] : VoUserNorm::finish(nn, NDIM);
+#else
                             for (int ww = 0; ww < G::NW; ++ww) nn += sNorm[ww * TB + s];
                             const double dxn = kp.literal_norm ? ca.dx_norm[sys] : sqrt(nn);
+#endif
                             const double f = kp.rtol / dxn;
                             const double mul = step_size_mul<true>(kp.alpha, f, kp.pw, kp.pw_is_third);  // ode.rs:133-135, powf correctly rounded (rk_small.cuh)
                             const double fp_lim = at_most(at_least(mul, 0.3), 2.0);

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "norm_custom.cuh"
 #include "rk_small_launch.cuh"
 #include "rk_stage_pointwise.cuh"
 
@@ -141,11 +142,14 @@ struct CustomModule {
     size_t bps_smem[K_SMALL_COUNT] = {};
 };
 
-std::string rtc_source(const std::string& body, int d, int np, bool stage_module) {
-    std::string s = stage_module ? "#include \"rk_stage_pointwise.cuh\"\n" : "#include \"rk_small2.cuh\"\n";
+std::string rtc_source(const vo_rhs_s* r, bool stage_module) {
+    const int d = r->d, np = r->np;
+    std::string s = r->norm_src;  // the VoUserNorm functor, if any: non-dependent in err_norm, so it comes before the templates
+    s += stage_module ? "#include \"rk_stage_pointwise.cuh\"\n" : "#include \"rk_small2.cuh\"\n";
+    if (r->alias_kind >= 0) return s + "using RhsCustom = RhsF<" + std::to_string(r->alias_kind) + ", " + std::to_string(d) + ">;\n";
     s += "struct RhsCustom {\n    static constexpr int D = " + std::to_string(d) + ", NP = " + std::to_string(np > 0 ? np : 1) + ";\n";
     s += "    template <bool STRICT> static __device__ __forceinline__ void eval(const double t, const double (&x)[D], double (&dx)[D], const double (&p)[NP]) {\n";
-    s += "#line 1 \"rhs_body\"\n" + body + "\n    }\n};\n";
+    s += "#line 1 \"rhs_body\"\n" + r->body + "\n    }\n};\n";
     return s;
 }
 
@@ -212,10 +216,9 @@ int32_t rtc_compile(const std::string& src, const std::vector<std::string>& name
     return VO_OK;
 }
 
-int32_t compile_custom(const std::string& body, int d, int np, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered,
-                       std::string& log) {
+int32_t compile_custom(const vo_rhs_s* r, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered, std::string& log) {
     const bool stage_module = S == STAGE_MODULE;
-    return rtc_compile(rtc_source(body, d, np, stage_module), kernel_names(S, strict, stage_module), strict, cubin, lowered, log);
+    return rtc_compile(rtc_source(r, stage_module), kernel_names(S, strict, stage_module), strict, cubin, lowered, log);
 }
 
 int module_key(int S, bool strict) { return (S + 1) * 2 + (strict ? 1 : 0); }
@@ -231,7 +234,7 @@ int32_t get_module(vo_rhs_s* r, int S, bool strict, Driver** drv, CustomModule**
     }
     std::vector<char> cubin;
     std::vector<std::string> lowered;
-    int32_t rc = compile_custom(r->body, r->d, r->np, S, strict, cubin, lowered, err);
+    int32_t rc = compile_custom(r, S, strict, cubin, lowered, err);
     if (rc != VO_OK) return vo_fail(c, rc, err);
     cudaFree(0);  // make sure the primary context the runtime uses is current before the first driver call
     CustomModule* m = new CustomModule();
@@ -367,24 +370,27 @@ void custom_rhs_release(vo_rhs_s* r) {
 // ---- the same machinery for the generator closure of the exponential integrators (exp.cu) -------------------------------
 // The functor wraps statements that assign g[1] .. g[M_gen-1], the real coefficients of L(t) = B_0 + sum_m g[m] B_m, from the
 // time `t` and this system's parameter row `p` (the 3 (M_gen - 1) doubles per system handed to vo_exp_create).
-int32_t rtc_exp_compile(const std::string& body, int ndim, int M, std::vector<char>& cubin, std::string& lowered, std::string& log) {
-    std::string src = "#include \"exp_kernels.cuh\"\nstruct GenCustom {\n"
-                      "    template <int M> static __device__ __forceinline__ void coef(const double* __restrict__ p, int M_gen, const double t, double (&c)[M]) {\n"
-                      "        double g[M];\n#pragma unroll\n        for (int m = 0; m < M; ++m) g[m] = 0.0;\n        {\n#line 1 \"generator_body\"\n" +
-                      body +
-                      "\n        }\n#pragma unroll\n        for (int m = 0; m < M; ++m) c[m] = (m >= 1 && m < M_gen) ? g[m] : 0.0;\n        c[0] = 1.0;\n    }\n};\n";
-    std::vector<std::string> names = {"exp_step_kernel<" + std::to_string(ndim) + ", " + std::to_string(M) + ", 16, GenCustom>"}, low;
+int32_t rtc_exp_compile(const std::string& body, const std::string& norm_src, int ndim, int M, std::vector<char>& cubin, std::string& lowered, std::string& log) {
+    std::string src = norm_src + "#include \"exp_kernels.cuh\"\n";
+    const bool user_gen = !body.empty();
+    if (user_gen)
+        src += "struct GenCustom {\n"
+               "    template <int M> static __device__ __forceinline__ void coef(const double* __restrict__ p, int M_gen, const double t, double (&c)[M]) {\n"
+               "        double g[M];\n#pragma unroll\n        for (int m = 0; m < M; ++m) g[m] = 0.0;\n        {\n#line 1 \"generator_body\"\n" +
+               body +
+               "\n        }\n#pragma unroll\n        for (int m = 0; m < M; ++m) c[m] = (m >= 1 && m < M_gen) ? g[m] : 0.0;\n        c[0] = 1.0;\n    }\n};\n";
+    std::vector<std::string> names = {"exp_step_kernel<" + std::to_string(ndim) + ", " + std::to_string(M) + ", 16, " + (user_gen ? "GenCustom" : "GenCos") + ">"}, low;
     const int32_t rc = rtc_compile(src, names, false, cubin, low, log);
     if (rc == VO_OK) lowered = low[0];
     return rc;
 }
 
-int32_t rtc_exp_module(vo_ctx c, const std::string& body, int ndim, int M, size_t smem, void** module_out, void** fn_out) {
+int32_t rtc_exp_module(vo_ctx c, const std::string& body, const std::string& norm_src, int ndim, int M, size_t smem, void** module_out, void** fn_out) {
     std::string err, lowered;
     Driver* drv = nullptr;
     if (!driver_load(&drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
     std::vector<char> cubin;
-    int32_t rc = rtc_exp_compile(body, ndim, M, cubin, lowered, err);
+    int32_t rc = rtc_exp_compile(body, norm_src, ndim, M, cubin, lowered, err);
     if (rc != VO_OK) return vo_fail(c, rc, err);
     cudaFree(0);
     CUmodule mod = nullptr;
@@ -413,14 +419,189 @@ void rtc_exp_unload(void* module) {
     if (module && driver_load(&drv, err)) drv->moduleUnload((CUmodule)module);
 }
 
+
+// ---- user-defined norms (norm_custom.cuh) ------------------------------------------------------------------------------------
+std::string norm_source(const vo_normfn_s* f) {
+    std::string s = "#define VO_USER_NORM 1\nstruct VoUserNorm {\n    static constexpr int JOIN = " + std::to_string(f->join) + ";\n";
+    s += "    static __device__ __forceinline__ double map(const double e, const double im, const int i, const int n) {\n        double m = 0.0;\n        {\n"
+         "#line 1 \"norm_map_body\"\n" + f->map_body + "\n        }\n        return m;\n    }\n";
+    s += "    static __device__ __forceinline__ double finish(const double acc, const int n) {\n        double r = acc;\n        {\n"
+         "#line 1 \"norm_finish_body\"\n" + f->finish_body + "\n        }\n        return r;\n    }\n};\n";
+    return s;
+}
+
+namespace {
+int32_t norm_compile(const vo_normfn_s* f, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered, std::string& log) {
+    const std::string src = norm_source(f) + "#include \"norm_custom.cuh\"\n";
+    return rtc_compile(src, {"norm_small_custom_kernel<VoUserNorm>", "norm_partial_custom_kernel<VoUserNorm>", "norm_final_custom_kernel<VoUserNorm>"}, strict, cubin,
+                       lowered, log);
+}
+}  // namespace
+
+int32_t norm_custom_device(vo_normfn_s* f, const double* x, int64_t d, int64_t n, int64_t i_off, int64_t d_total, double* out_dev, double* partial_dev,
+                           int partial_cap, bool finish) {
+    vo_ctx c = f->ctx;
+    const int am = c->arith == VO_ARITH_STRICT ? 0 : 1;
+    std::string err;
+    Driver* drv = nullptr;
+    if (!driver_load(&drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
+    if (!f->module[am]) {
+        std::vector<char> cubin;
+        std::vector<std::string> lowered;
+        int32_t rc = norm_compile(f, am == 0, cubin, lowered, err);
+        if (rc != VO_OK) return vo_fail(c, rc, err);
+        cudaFree(0);
+        CUmodule mod = nullptr;
+        CUresult e = drv->moduleLoadData(&mod, cubin.data());
+        for (int k = 0; k < 3 && e == CUDA_SUCCESS; ++k) e = drv->moduleGetFunction((CUfunction*)&f->fn[am][k], mod, lowered[k].c_str());
+        if (e != CUDA_SUCCESS) {
+            if (mod) drv->moduleUnload(mod);
+            return vo_fail(c, VO_ERR_CUDA, "user norm: module load: " + cu_msg(drv, e));
+        }
+        f->module[am] = mod;
+    }
+    int fin = finish ? 1 : 0;
+    if (d <= 64) {  // one thread per trajectory, left to right (the order of a sequential norm), like the built-in norms
+        void* args[] = {&x, &d, &n, &out_dev, &fin};
+        // (the small kernel numbers components from 0; a window of a larger vector goes through the partial kernel below)
+        if (i_off == 0 && d == d_total) {
+            int32_t r = custom_launch(c, drv, (CUfunction)f->fn[am][0], (unsigned)ceil_div(n, 256), 256, 0, false, args);
+            if (r != VO_OK) return r;
+            VO_CHECK_LAUNCH(c);
+            return VO_OK;
+        }
+    }
+    int chunks = (int)std::min<int64_t>(std::max<int64_t>(1, d / 4096), std::max<int64_t>(1, (int64_t)c->sm_count * 4 / std::max<int64_t>(1, n)));
+    chunks = std::max(1, std::min(chunks, partial_cap / (int)std::max<int64_t>(1, n)));
+    if ((int64_t)chunks * n > partial_cap) return vo_fail(c, VO_ERR_UNSUPPORTED, "user norm: too many trajectories for the large-d path");
+    {
+        void* args[] = {&x, &d, &n, &i_off, &d_total, &partial_dev};
+        CUlaunchConfig cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDimX = (unsigned)chunks, cfg.gridDimY = (unsigned)n, cfg.gridDimZ = 1, cfg.blockDimX = 256, cfg.blockDimY = 1, cfg.blockDimZ = 1;
+        cfg.hStream = (CUstream)c->stream;
+        CUresult e = drv->launchKernelEx(&cfg, (CUfunction)f->fn[am][1], args, nullptr);
+        if (e != CUDA_SUCCESS) return vo_fail(c, VO_ERR_CUDA, "user norm: kernel launch: " + cu_msg(drv, e));
+        VO_CHECK_LAUNCH(c);
+    }
+    void* args[] = {&partial_dev, &chunks, &d_total, &out_dev, &fin};
+    int32_t r = custom_launch(c, drv, (CUfunction)f->fn[am][2], (unsigned)n, 32, 0, false, args);
+    if (r != VO_OK) return r;
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+vo_rhs_s* custom_rhs_with_norm(const vo_rhs_s* base, const vo_normfn_s* f) {
+    vo_rhs_s* r = new vo_rhs_s();
+    r->ctx = base->ctx, r->kind = VO_RHS_CUSTOM, r->d = base->d, r->np = base->np, r->body = base->body;
+    r->alias_kind = base->kind == VO_RHS_CUSTOM ? -1 : base->kind;
+    r->norm_src = norm_source(f);
+    for (int i = 0; i < VO_MAX_PARAMS; ++i) r->shared[i] = 0.0, r->per_traj[i] = nullptr, r->per_traj_n[i] = 0;  // parameters stay with the solver's own RHS
+    return r;
+}
+
 extern "C" {
+
+int32_t vo_normfn_create(vo_ctx c, const char* map_body, int32_t join, const char* finish_body, vo_normfn* out) {
+    if (!c || !map_body || !out || (join != VO_NORM_JOIN_SUM && join != VO_NORM_JOIN_MAX)) return vo_fail(c, VO_ERR_BAD_ARG, "vo_normfn_create: bad argument");
+    vo_normfn f = new vo_normfn_s();
+    f->ctx = c, f->map_body = map_body, f->finish_body = finish_body ? finish_body : "", f->join = join;
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    std::string log;
+    const int32_t rc = norm_compile(f, c->arith == VO_ARITH_STRICT, cubin, lowered, log);  // a source error is reported here, not at the first step
+    if (rc != VO_OK) {
+        delete f;
+        return vo_fail(c, rc, log);
+    }
+    *out = f;
+    return VO_OK;
+}
+
+int32_t vo_normfn_destroy(vo_normfn f) {
+    if (!f) return VO_OK;
+    std::string err;
+    Driver* drv = nullptr;
+    const bool have = driver_load(&drv, err);
+    for (int a = 0; a < 2; ++a)
+        if (have && f->module[a]) drv->moduleUnload((CUmodule)f->module[a]);
+    delete f;
+    return VO_OK;
+}
+
+int32_t vo_normfn_check(const char* map_body, int32_t join, const char* finish_body, char* log, int64_t log_cap) {
+    if (log && log_cap > 0) log[0] = '\0';
+    if (!map_body || (join != VO_NORM_JOIN_SUM && join != VO_NORM_JOIN_MAX)) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_normfn_check: bad argument");
+    vo_normfn_s f;
+    f.map_body = map_body, f.finish_body = finish_body ? finish_body : "", f.join = join;
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    std::string msg;
+    const int32_t rc = norm_compile(&f, true, cubin, lowered, msg);
+    if (rc != VO_OK) {
+        if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
+        return vo_fail(nullptr, rc, msg);
+    }
+    return (int32_t)std::min<size_t>(cubin.size(), 0x7fffffff);
+}
+
+int32_t vo_normfn_check_kernels(const char* map_body, int32_t join, const char* finish_body, int32_t rhs_kind, int32_t d, int32_t stages, int32_t arith, int32_t exp_n,
+                                int32_t exp_M, char* log, int64_t log_cap) {
+    if (log && log_cap > 0) log[0] = '\0';
+    if (!map_body || (join != VO_NORM_JOIN_SUM && join != VO_NORM_JOIN_MAX)) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_normfn_check_kernels: bad argument");
+    vo_normfn_s f;
+    f.map_body = map_body, f.finish_body = finish_body ? finish_body : "", f.join = join;
+    std::string msg;
+    size_t total = 0;
+    int32_t rc = VO_OK;
+    if (rhs_kind >= 0) {  // the register-resident kernels of a compiled-in family, re-compiled with the norm in them
+        vo_rhs_s base;
+        base.kind = rhs_kind, base.d = d, base.np = 0;
+        vo_rhs_s* r = custom_rhs_with_norm(&base, &f);
+        std::vector<char> cubin;
+        std::vector<std::string> lowered;
+        rc = compile_custom(r, stage_count_key(stages), arith == VO_ARITH_STRICT, cubin, lowered, msg);
+        total += cubin.size();
+        delete r;
+    }
+    if (rc == VO_OK && exp_n > 0) {
+        std::vector<char> cubin;
+        std::string lowered;
+        rc = rtc_exp_compile("", norm_source(&f), exp_n, exp_M, cubin, lowered, msg);
+        total += cubin.size();
+    }
+    if (rc != VO_OK) {
+        if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
+        return vo_fail(nullptr, rc, msg);
+    }
+    return (int32_t)std::min<size_t>(total, 0x7fffffff);
+}
+
+int32_t vo_norm_custom(vo_ens e, vo_normfn f, double* out_host) {
+    if (!e || !f || !out_host) return vo_fail(e ? e->ctx : nullptr, VO_ERR_BAD_ARG, "vo_norm_custom: bad argument");
+    vo_ctx c = e->ctx;
+    if (f->ctx != c) return vo_fail(c, VO_ERR_BAD_ARG, "vo_norm_custom: the norm belongs to another ctx");
+    DeviceGuard g(c->device);
+    double *out_dev = nullptr, *partial = nullptr;
+    const int cap = 1 << 16;
+    VO_CUDA(c, cudaMallocAsync(&out_dev, sizeof(double) * e->n, c->stream));
+    VO_CUDA(c, cudaMallocAsync(&partial, sizeof(double) * cap, c->stream));
+    int32_t r = norm_custom_device(f, e->p, e->d, e->n, 0, e->d, out_dev, partial, cap, true);
+    if (r == VO_OK) {
+        cudaError_t ce = cudaMemcpyAsync(out_host, out_dev, sizeof(double) * e->n, cudaMemcpyDeviceToHost, c->stream);
+        if (ce != cudaSuccess) r = vo_fail(c, VO_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    cudaFreeAsync(out_dev, c->stream), cudaFreeAsync(partial, c->stream);
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    return r;
+}
 
 int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap) {
     if (log && log_cap > 0) log[0] = '\0';
     if (!body || (n != 16 && n != 32 && n != 64) || M < 1 || M > 3) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_exp_generator_check: bad argument");
     std::vector<char> cubin;
     std::string lowered, msg;
-    const int32_t rc = rtc_exp_compile(body, n, M, cubin, lowered, msg);
+    const int32_t rc = rtc_exp_compile(body, "", n, M, cubin, lowered, msg);
     if (rc != VO_OK) {
         if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
         return vo_fail(nullptr, rc, msg);
@@ -455,7 +636,9 @@ int32_t vo_rhs_custom_check(const char* body, int32_t d, int32_t n_params, int32
     std::vector<char> cubin;
     std::vector<std::string> lowered;
     std::string msg;
-    const int32_t rc = compile_custom(body, d, n_params, stages < 0 ? STAGE_MODULE : stage_count_key(stages), arith == VO_ARITH_STRICT, cubin, lowered, msg);
+    vo_rhs_s tmp;
+    tmp.kind = VO_RHS_CUSTOM, tmp.d = d, tmp.np = n_params, tmp.body = body;
+    const int32_t rc = compile_custom(&tmp, stages < 0 ? STAGE_MODULE : stage_count_key(stages), arith == VO_ARITH_STRICT, cubin, lowered, msg);
     if (rc != VO_OK) {
         if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
         return vo_fail(nullptr, rc, msg);

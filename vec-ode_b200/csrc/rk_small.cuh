@@ -95,6 +95,16 @@ template <bool STRICT, int D> __device__ __forceinline__ double err_norm(const d
         for (int c = 0; c < D; ++c) acc = A::add(acc, fabs(e[c]));
         return acc;
     }
+#ifdef VO_USER_NORM  // the caller's `Normed` impl (ode.rs:9-11, rk.rs:302-304), compiled in with the kernel: finish(JOIN_c map(e_c, c))
+    if (kind == VO_NORM_CUSTOM) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double m = VoUserNorm::map(e[c], 0.0, c, D);
+            acc = VoUserNorm::JOIN == 1 ? fmax(acc, m) : A::add(acc, m);
+        }
+        return VoUserNorm::finish(acc, D);
+    }
+#endif
     // VO_NORM_HYPOT
     if (D == 2) return hypot(e[0], e[D - 1]);
 #pragma unroll

@@ -49,6 +49,9 @@ struct vo_solver_s {
     std::vector<double> t_list;
     double* t_list_dev = nullptr;
     int norm_kind = VO_NORM_L2;
+    vo_normfn norm_fn = nullptr;   // VO_NORM_CUSTOM: the caller's functor (borrowed)
+    vo_rhs_s* norm_rhs = nullptr;  // ... and the private RHS handle whose run-time modules carry it (register-resident path)
+    double* dxn_pre = nullptr;     // ... stage path, per-trajectory control: norms computed ahead of ctl_commit_kernel
     // lock-step control
     bool uniform = true;
     double u_t = 0, u_h = 0, u_prev_h = 0, u_dx_norm = 0;
@@ -186,7 +189,7 @@ __global__ void ctl_prepare_kernel(CtlArrays ca, const __grid_constant__ CtlShar
 template <bool STRICT>
 __global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restrict__ next_x, const double* __restrict__ x_err, int64_t d, int64_t N,
                                   CtlArrays ca, const __grid_constant__ CtlShared cs, const uint8_t* __restrict__ evv, const double* __restrict__ dtv,
-                                  EvSlot* __restrict__ ev) {
+                                  EvSlot* __restrict__ ev, const double* __restrict__ dxn_pre) {
     using A = Ar<STRICT>;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
@@ -198,7 +201,9 @@ __global__ void ctl_commit_kernel(double* __restrict__ x, const double* __restri
         if (evk == VO_EV_STEP) {
             if (cs.adaptive) {
                 double acc = 0.0;
-                if (cs.norm_kind == VO_NORM_HYPOT && d == 2) {
+                if (dxn_pre) {  // a user-defined norm, evaluated by its own run-time compiled kernel just before this one
+                    acc = dxn_pre[i];
+                } else if (cs.norm_kind == VO_NORM_HYPOT && d == 2) {
                     acc = hypot(x_err[i], x_err[N + i]);
                 } else if (cs.norm_kind == VO_NORM_HYPOT) {
                     for (int64_t c = 0; c + 1 < d; c += 2) {
@@ -411,7 +416,7 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     const TableauDev tb = make_tableau_dev(s->tab);
     const RhsParams rp = make_rhs_params(s->rhs);
     // the one-event adaptive sweep of a compiled-in family runs on the tile-blocked copy of the state; everything else on the public layout
-    const bool blocked = cs && !s->uniform && s->use_blocked && s->rhs->kind != VO_RHS_CUSTOM && small_path_blocked_ok(s->n, s->tab.s, *cs);
+    const bool blocked = cs && !s->uniform && s->use_blocked && s->rhs->kind != VO_RHS_CUSTOM && !s->norm_rhs && small_path_blocked_ok(s->n, s->tab.s, *cs);
     if (blocked) {
         int32_t br = ensure_blk(s);
         if (br != VO_OK) return br;
@@ -423,6 +428,10 @@ int32_t launch_small(vo_solver_s* s, const CtlShared* cs, const StepList* sl) {
     if (s->chain_epoch != c->epoch) s->cst.live = false;  // something else was enqueued on the ctx since our last launch
     SmallLaunch L{c, s->x->p, s->n, &tb, &rp, s->ca, cs, sl, s->ev_dev, &s->cst, blocked ? &s->bv : nullptr};
     int32_t r = VO_ERR_UNSUPPORTED;
+    if (s->norm_rhs) {  // a user-defined norm: the control kernels come from the run-time module that carries it
+        r = launch_small_custom(L, s->norm_rhs);
+        if (r != VO_OK) return r;
+    } else
     switch (s->rhs->kind) {
         case VO_RHS_DIAG_LINEAR: r = launch_small_diag(L, s->rhs->d); break;
         case VO_RHS_HARMONIC2D: r = launch_small_harmonic(L); break;
@@ -700,7 +709,8 @@ int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) 
             double* out = (double*)c->dscratch;
             if (s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: lock-step adaptive control needs N == 1");
             const int64_t launches_before = c->launches;
-            r = vo_norm_device(s->x_err, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, true);
+            r = s->norm_kind == VO_NORM_CUSTOM ? norm_custom_device(s->norm_fn, s->x_err->p, s->d, 1, 0, s->d, out, s->norm_partial, PARTIAL_CAP, true)
+                                               : vo_norm_device(s->x_err, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, true);
             if (r != VO_OK) return r;
             launches += (int)(c->launches - launches_before);
             VO_CUDA(c, cudaMemcpyAsync(c->pinned, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -734,8 +744,17 @@ int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
     int32_t r = stage_rk_step(s, 0.0, 0.0, true, s->next_x->p, use_err(s) ? s->x_err->p : nullptr, nullptr, launches);
     if (r != VO_OK) return r;
     const double* xe = use_err(s) ? s->x_err->p : nullptr;
-    if (c->arith == VO_ARITH_STRICT) ctl_commit_kernel<true><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev);
-    else ctl_commit_kernel<false><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev);
+    const double* dxn_pre = nullptr;
+    if (adaptive && xe && s->norm_kind == VO_NORM_CUSTOM) {
+        if (!s->dxn_pre && cudaMalloc(&s->dxn_pre, 8 * (size_t)s->n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "stage path: norm buffer");
+        const int64_t before = c->launches;
+        r = norm_custom_device(s->norm_fn, xe, s->d, s->n, 0, s->d, s->dxn_pre, s->norm_partial, PARTIAL_CAP, true);
+        if (r != VO_OK) return r;
+        *launches += (int)(c->launches - before);
+        dxn_pre = s->dxn_pre;
+    }
+    if (c->arith == VO_ARITH_STRICT) ctl_commit_kernel<true><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev, dxn_pre);
+    else ctl_commit_kernel<false><<<grid, 256, 0, c->stream>>>(s->x->p, s->next_x->p, xe, s->d, s->n, s->ca, cs, s->evv, s->dtv, s->ev_dev, dxn_pre);
     VO_CHECK_LAUNCH(c);
     ++*launches;
     return VO_OK;
@@ -867,6 +886,8 @@ int32_t vo_solver_destroy(vo_solver s) {
     free_ctl(s);
     cudaFree(s->bv.base), cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->cst.flags), cudaFree(s->snap);
     cudaFreeHost(s->ev_host);
+    cudaFree(s->dxn_pre);
+    if (s->norm_rhs) custom_rhs_release(s->norm_rhs), delete s->norm_rhs;
     delete s;
     return VO_OK;
 }
@@ -930,6 +951,26 @@ int32_t vo_solver_set_order_alpha(vo_solver s, double order, double alpha) {
 int32_t vo_solver_set_norm(vo_solver s, int32_t kind) {
     if (!s || kind < 0 || kind > VO_NORM_HYPOT) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_norm: bad norm kind");
     s->norm_kind = kind;
+    if (s->norm_rhs) {  // back to a compiled-in norm: drop the run-time modules that carried the user's
+        DeviceGuard g(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+        custom_rhs_release(s->norm_rhs), delete s->norm_rhs;
+        s->norm_rhs = nullptr, s->cst.live = false;
+    }
+    s->norm_fn = nullptr;
+    return VO_OK;
+}
+
+int32_t vo_solver_set_norm_custom(vo_solver s, vo_normfn f) {
+    if (!s || !f) return vo_fail(s ? s->ctx : nullptr, VO_ERR_BAD_ARG, "vo_solver_set_norm_custom: NULL argument");
+    vo_ctx c = s->ctx;
+    if (f->ctx != c) return vo_fail(c, VO_ERR_BAD_ARG, "vo_solver_set_norm_custom: the norm belongs to another ctx");
+    DeviceGuard g(c->device);
+    VO_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (s->norm_rhs) custom_rhs_release(s->norm_rhs), delete s->norm_rhs, s->norm_rhs = nullptr;
+    s->norm_kind = VO_NORM_CUSTOM, s->norm_fn = f, s->cst.live = false;
+    // register-resident path: the control kernels are re-compiled with the functor in them (a compiled-in family through an alias)
+    if (rhs_is_small(s->rhs)) s->norm_rhs = custom_rhs_with_norm(s->rhs, f);
     return VO_OK;
 }
 
@@ -1002,7 +1043,7 @@ int32_t vo_adaptive_try(vo_solver s, int64_t lo, int64_t hi, double* acc, int32_
     if (!s->uniform || use_small(s) || s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_adaptive_try: a single state (N == 1) on the stage path");
     if (s->try_pending) return vo_fail(c, VO_ERR_STATE, "vo_adaptive_try: the previous attempt has not been handled");
     if (lo < 0 || hi > s->d || lo >= hi) return vo_fail(c, VO_ERR_SHAPE, "vo_adaptive_try: bad component range");
-    if (s->norm_kind == VO_NORM_HYPOT) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_adaptive_try: L2, L1 or Linf norm");
+    if (s->norm_kind == VO_NORM_HYPOT) return vo_fail(c, VO_ERR_UNSUPPORTED, "vo_adaptive_try: L2, L1, Linf or a user-defined norm");
     int32_t r = prepare_mode(s, true);
     if (r != VO_OK) return r;
     *acc = 0.0;
@@ -1029,7 +1070,8 @@ int32_t vo_adaptive_try(vo_solver s, int64_t lo, int64_t hi, double* acc, int32_
     view.ctx = c, view.p = s->x_err->p + lo, view.d = hi - lo, view.n = 1, view.owns = false;
     double* out = (double*)c->dscratch;
     const int64_t before = c->launches;
-    r = vo_norm_device(&view, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, false);
+    r = s->norm_kind == VO_NORM_CUSTOM ? norm_custom_device(s->norm_fn, view.p, view.d, 1, lo, s->d, out, s->norm_partial, PARTIAL_CAP, false)
+                                       : vo_norm_device(&view, s->norm_kind, out, s->norm_partial, PARTIAL_CAP, false);
     if (r != VO_OK) return r;
     launches += (int)(c->launches - before);
     VO_CUDA(c, cudaMemcpyAsync(c->pinned, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

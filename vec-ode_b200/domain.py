@@ -141,21 +141,24 @@ class HeatSlabSolver:
         if done is not None:  # Chkpt / End: no norm, nothing to combine
             return done
         kind = self._norm_kind
+        custom = not isinstance(kind, str)  # a base.NormFn: its own join and finish
+        use_max = kind.join == "max" if custom else kind == "LINF"
         if self.slab.world > 1 and is_distributed():
             import torch
             import torch.distributed as dist
             t = torch.tensor([acc], dtype=torch.float64, device=("cpu" if dist.get_backend() == "gloo" else f"cuda:{self.ctx.device}"))
-            dist.all_reduce(t, op=dist.ReduceOp.MAX if kind == "LINF" else dist.ReduceOp.SUM)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if use_max else dist.ReduceOp.SUM)
             acc = float(t.item())
-        st = self.solver.adaptive_handle(math.sqrt(acc) if kind == "L2" else acc)
+        st = self.solver.adaptive_handle(kind.finish_host(acc, self.slab.d_total) if custom else (math.sqrt(acc) if kind == "L2" else acc))
         if st.counts["Step"]:
             self._since_exchange += 1
         return st
 
     def with_tolerance(self, atol: float, rtol: float, norm: str = "L2"):
-        """with_tolerance (ode.rs:296-306) + the norm of the whole state: "L2", "L1" or "LINF"."""
+        """with_tolerance (ode.rs:296-306) + the norm of the whole state: "L2", "L1", "LINF", or a base.NormFn built with `finish_py`
+        (the host-side twin of its finish statements, applied to the all-reduced accumulator)."""
         self.solver.with_tolerance(atol, rtol)
-        self.solver.set_norm(norm)
+        self.solver.with_norm(norm)
         self._norm_kind = norm
         self._adaptive = True
         return self

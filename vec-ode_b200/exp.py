@@ -200,6 +200,13 @@ class _ExpSolver:
             raise _cabi.VecOdeError(rc, log.value.decode("utf-8", "replace"))
         return rc
 
+    def with_norm(self, norm_fn):
+        """ExpCFMSolver's NormFn closure / NormedExponentialSplit::norm (exp/cfm.rs:105, 214-216, exp/mod.rs:37-45) as a
+        user-defined base.NormFn: the DMMA kernel is re-compiled with it (vo_exp_set_norm_custom)."""
+        check(lib().vo_exp_set_norm_custom(self._h, norm_fn._h), self.ctx._h)
+        self._norm_fn = norm_fn
+        return self
+
     def no_adaptive(self):  # exp/cfm.rs:157-161
         check(lib().vo_exp_no_adaptive(self._h), self.ctx._h)
         return self
