@@ -155,19 +155,30 @@ int32_t vo_tableau_destroy(vo_tableau t);
 #define VO_RHS_VDP 3         /* dx = v ; dv = (mu*(1-x*x))*v - x      params: mu                    */
 #define VO_RHS_HEAT1D 4      /* du_j = kappa*((u_{j-1}+u_{j+1}) - 2u_j), periodic in j; params: kappa */
 #define VO_RHS_CUSTOM 5      /* vo_rhs_create_custom */
+#define VO_RHS_CUSTOM_STENCIL 6 /* vo_rhs_create_custom_stencil */
 int32_t vo_rhs_create(vo_ctx ctx, int32_t kind, int32_t d, vo_rhs* out);
 /* User-defined right-hand side, the closest a C ABI gets to the reference's closure: `body` is CUDA C++ source for the
  * statements of f(t, &x, &mut dx). It sees `const double t`, `const double (&x)[D]`, `double (&dx)[D]`,
- * `const double (&p)[NP]` (D = d <= 8, NP = n_params <= 8, parameters shared or per-trajectory like the built-ins) and
+ * `const double (&p)[NP]` (D = d <= 32, NP = n_params <= 8, parameters shared or per-trajectory like the built-ins) and
  * must assign every dx[c]. It is compiled at run time with NVRTC for sm_100a INTO the fused register-resident kernels
  * (one module per stage count and arithmetic mode, cached): VO_ARITH_STRICT compiles with -fmad=false, so plain `a*b+c`
  * in the body stays an un-fused multiply and add like the reference's Rust. Compile errors come back through
- * vo_last_error. Runs on both kernel paths (register-resident and stage path), like a built-in family. */
+ * vo_last_error. d <= 8 runs on both kernel paths (register-resident and stage path) like a built-in family; 9 <= d <= 32
+ * runs on the stage path (one fused kernel per stage, the d components of a trajectory in one thread's registers). */
 int32_t vo_rhs_create_custom(vo_ctx ctx, const char* body, int32_t d, int32_t n_params, vo_rhs* out);
 /* Compile `body` exactly as vo_rhs_create_custom / the first step would, without a ctx or a GPU (NVRTC only): `stages` is the
  * tableau's stage count (-1 = the stage-path module), `arith` a VO_ARITH_* mode. Returns the size of the sm_100a cubin
  * (> 0), or a VO_ERR_* code with the compiler log copied to `log` (NUL-terminated, at most log_cap bytes; may be NULL). */
 int32_t vo_rhs_custom_check(const char* body, int32_t d, int32_t n_params, int32_t stages, int32_t arith, char* log, int64_t log_cap);
+/* User-defined STENCIL right-hand side for one large periodic grid state (N == 1; `V = Array1<f64>`, src/impls/ndarray.rs:8-33):
+ * dx_j = f(t, x_{j-R} .. x_{j+R}). `body`: CUDA C++ statements assigning `double du` from `const double (&u)[2 * R + 1]` (u[R] is the
+ * grid point itself, indices wrap periodically), `const double t`, `const long long j` (grid index), `const long long d` (grid size),
+ * `const double (&p)[NP]` (shared parameters, vo_rhs_set_param). 1 <= radius <= 8. Compiled at run time into the fused per-stage
+ * kernel of the stage path (rk_stage_stencil.cuh); fixed-step, adaptive (single-state controller) and domain-decomposed runs work
+ * as for the compiled-in heat equation, whose body would be "du = p[0] * ((u[0] + u[2]) - 2.0 * u[1]);" with radius 1 (the same
+ * bits in VO_ARITH_STRICT). */
+int32_t vo_rhs_create_custom_stencil(vo_ctx ctx, const char* body, int64_t d, int32_t radius, int32_t n_params, vo_rhs* out);
+int32_t vo_rhs_custom_stencil_check(const char* body, int32_t radius, int32_t n_params, int32_t arith, char* log, int64_t log_cap);
 int32_t vo_rhs_num_params(vo_rhs r);
 int32_t vo_rhs_set_param(vo_rhs r, int32_t idx, double value);                            /* shared by all trajectories */
 int32_t vo_rhs_set_param_array(vo_rhs r, int32_t idx, const double* host, int64_t n);     /* one value per trajectory */

@@ -49,3 +49,21 @@ def test_user_norm_compile_error_carries_the_log(vo):
     with pytest.raises(vo.VecOdeError) as ei:
         vo.NormFn.check_source("m = e * e;", "sum", "r = sqrt(oops);")
     assert "norm_finish_body(1)" in str(ei.value)
+
+
+HEAT_STENCIL = "du = p[0] * ((u[0] + u[2]) - 2.0 * u[1]);"
+
+
+def test_user_stencil_and_wide_pointwise_rhs_compile(vo):
+    """vo_rhs_custom_stencil_check (a grid stencil into the fused per-stage kernel of rk_stage_stencil.cuh) and a 24-component
+    pointwise right-hand side into the stage-path kernel: both without a GPU."""
+    for arith in ("strict", "fast"):
+        assert vo.Rhs.check_stencil_source(HEAT_STENCIL, 1, 1, arith) > 5_000
+    assert vo.Rhs.check_stencil_source("du = (-u[0] + 16.0 * u[1] - 30.0 * u[2] + 16.0 * u[3] - u[4]) * (p[0] / 12.0) + p[1] * sin(t) * (j == 0);", 2, 2) > 5_000
+    with pytest.raises(vo.VecOdeError) as ei:
+        vo.Rhs.check_stencil_source("du = u[7];\nnope();", 1, 0)
+    assert "rhs_body(2)" in str(ei.value)
+    ring = "\n".join(f"dx[{c}] = p[0] * (x[{(c + 1) % 24}] - x[{c}]) - x[{c}] * x[{c}] * x[{c}];" for c in range(24))
+    assert vo.Rhs.check_source(ring, 24, 1, -1, "strict") > 10_000
+    with pytest.raises(vo.VecOdeError):
+        vo.Rhs.check_source(ring, 24, 1, 7, "strict")  # the register-resident kernels stop at 8 components

@@ -5,6 +5,8 @@ Bars: a body that restates a built-in family gives the built-in kernel's bits on
 counterpart is bit-exact against the pure-Python restatement of rk.rs / ode.rs driving the same function (strict
 arithmetic, fixed step), and within rtol with equal accept / reject counts on adaptive runs.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -161,3 +163,82 @@ def test_custom_rhs_largest_shape_eight_components_eight_per_trajectory_paramete
         assert s.run().kind == "Done"
         out.append(s.current()[1].to_host())
     assert np.array_equal(out[0], out[1])
+
+
+# ---- user stencils on one grid state, and pointwise systems wider than the register-resident kernels take -----------------------
+HEAT_STENCIL = "du = p[0] * ((u[0] + u[2]) - 2.0 * u[1]);"
+
+
+@pytest.mark.parametrize("d", [1023, 4096, (1 << 18) + 5])
+@pytest.mark.parametrize("tab", ["RK4", "RKF45_REF"])
+def test_user_stencil_restating_the_heat_equation_gives_the_builtin_bits(vo, ctx, d, tab):
+    """The compiled-in HEAT1D family written as a user stencil (vo_rhs_create_custom_stencil): same operations, same order, so the
+    strict-arithmetic results are bit-identical — fixed steps with and without the error estimate, and vo_rhs_eval."""
+    u0 = vo.workloads.heat_u0(d)
+    outs = []
+    for rhs in (vo.Rhs(ctx, "HEAT1D", d, [0.7]), vo.Rhs.custom_stencil(ctx, HEAT_STENCIL, d, 1, [0.7])):
+        s = vo.RK45Solver(rhs, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, u0[None, :]), 0.2, tableau=vo.ButcherTableu.builtin(tab))
+        s.run(max_calls=8)
+        dx = vo.Ensemble(ctx, d, 1)
+        rhs(0.0, vo.Ensemble.from_host(ctx, u0[None, :]), dx)
+        outs.append((s.current()[1].to_host()[0], dx.to_host()[0]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_user_stencil_adaptive_and_fourth_order_laplacian(vo, ctx, oracle):
+    """A radius-2 stencil with a time-dependent source at one grid point, adaptive RKF45 on one state: against the pure-Python
+    restatement of rk.rs / ode.rs driving the same closure (accepted / rejected counts equal, states to rounding)."""
+    from oracle import vecode_oracle as po
+    d = 300
+    body = "du = (-u[0] + 16.0 * u[1] - 30.0 * u[2] + 16.0 * u[3] - u[4]) * (p[0] / 12.0) + (j == 7 ? p[1] * sin(3.0 * t) : 0.0);"
+    u0 = vo.workloads.heat_u0(d) + 0.2 * np.cos(np.pi * np.arange(d))
+    rhs = vo.Rhs.custom_stencil(ctx, body, d, 2, [0.6, 0.5])
+    s = vo.RK45Solver(rhs, 0.0, 1.5, vo.Ensemble.from_host(ctx, u0[None, :]), 0.01).with_tolerance(1e-7, 1e-7)
+    assert s.run(adaptive=True).kind == "Done"
+
+    def f(t, x, dx):
+        n = len(x)
+        for j in range(n):
+            dx[j] = (-x[j - 2] + 16.0 * x[j - 1] - 30.0 * x[j] + 16.0 * x[(j + 1) % n] - x[(j + 2) % n]) * (0.6 / 12.0) + (0.5 * math.sin(3.0 * t) if j == 7 else 0.0)
+    ac, b, be, ns = oracle.builtin_tableau(0)
+    r = po.RKSolver(f, (list(ac), list(b), list(be), ns), 0.0, 1.5, list(u0), 0.01).with_tolerance(1e-7, 1e-7)
+    r.run(adaptive=True)
+    st = s.stats()
+    assert (int(st["accepted"][0]), int(st["rejected"][0])) == (r.n_accept, r.n_reject)
+    assert np.abs(s.current()[1].to_host()[0] - np.array(r.x)).max() <= 1e-12
+    with pytest.raises(vo.VecOdeError):  # an ensemble of grids is not what a stencil handle is for
+        vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble(ctx, d, 3), 0.01).run(max_calls=3)
+
+
+def test_wide_pointwise_user_rhs_on_the_stage_path(vo, ctx, oracle):
+    """24 coupled components per trajectory (a ring of cubic oscillators): beyond the register-resident kernels (d <= 8), so the
+    solver takes the stage path — fixed-step bit-exact against the pure-Python restatement, adaptive with equal counts."""
+    from oracle import vecode_oracle as po
+    D, n = 24, 700
+    body = "\n".join(f"dx[{c}] = p[0] * (x[{(c + 1) % D}] - x[{c}]) - x[{c}] * x[{c}] * x[{c}];" for c in range(D))
+    rng = np.random.default_rng(8)
+    x0 = rng.uniform(-1.0, 1.0, (n, D))
+    kap = rng.uniform(0.5, 2.0, n)
+    rhs = vo.Rhs.custom(ctx, body, D, [kap])
+
+    def mk(k):
+        def f(t, x, dx):
+            for c in range(D):
+                dx[c] = k * (x[(c + 1) % D] - x[c]) - x[c] * x[c] * x[c]
+        return f
+    ac, b, be, ns = oracle.builtin_tableau(2)
+    s = vo.RK45Solver(rhs, 0.0, 0.2, vo.Ensemble.from_host(ctx, x0), 0.01, tableau=vo.ButcherTableu.builtin("DOPRI5"))
+    assert s.run().kind == "Done"
+    got = s.current()[1].to_host()
+    for i in range(0, n, 97):
+        r = po.RKSolver(mk(float(kap[i])), (list(ac), list(b), list(be), ns), 0.0, 0.2, list(x0[i]), 0.01)
+        r.run()
+        assert np.array_equal(got[i], np.array(r.x)), i
+    s = vo.RK45Solver(rhs, 0.0, 1.0, vo.Ensemble.from_host(ctx, x0), 0.01, tableau=vo.ButcherTableu.builtin("DOPRI5")).with_tolerance(1e-6, 1e-6)
+    assert s.run(adaptive=True).kind == "Done"
+    got, st = s.current()[1].to_host(), s.stats()
+    for i in range(0, n, 233):
+        r = po.RKSolver(mk(float(kap[i])), (list(ac), list(b), list(be), ns), 0.0, 1.0, list(x0[i]), 0.01).with_tolerance(1e-6, 1e-6)
+        r.run(adaptive=True)
+        assert (int(st["accepted"][i]), int(st["rejected"][i])) == (r.n_accept, r.n_reject)
+        assert np.abs(got[i] - np.array(r.x)).max() <= 1e-9

@@ -472,5 +472,5 @@ def test_literal_magnus_norm_switch(vo, ctx, oracle):
     d = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, dense_commutator=True).with_tolerance(8.0, 8.0).literal_norm()
     d.run(adaptive=True)
     assert np.array_equal(d.stats()["accepted"], acc_literal) and not d.stats()["rejected"].any()
-    cfm = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, h)
+    cfm = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, h, M_gen=2)
     assert vo._cabi.lib().vo_exp_set_literal_norm(cfm._h, 1) == vo._cabi.VO_ERR_STATE  # only the Magnus solver's norm() has the quirk

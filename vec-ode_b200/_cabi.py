@@ -21,7 +21,7 @@ ARITH_STRICT, ARITH_FAST = 0, 1
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 NORM = {"L2": 0, "LINF": 1, "L1": 2, "HYPOT": 3}
 TABLEAU = {"RKF45_REF": 0, "RK4": 1, "DOPRI5": 2}
-RHS = {"DIAG_LINEAR": 0, "HARMONIC2D": 1, "LORENZ63": 2, "VDP": 3, "HEAT1D": 4, "CUSTOM": 5}
+RHS = {"DIAG_LINEAR": 0, "HARMONIC2D": 1, "LORENZ63": 2, "VDP": 3, "HEAT1D": 4, "CUSTOM": 5, "CUSTOM_STENCIL": 6}
 EXP_SCHEME = {"midpoint": 0, "cfm4": 1, "magnus42": 2, "split_midpoint": 3, "cfm_table": 4, "split_cfm": 5}
 CFM_TABLE = {"C_GAUSS_LEGENDRE_4": 0, "CFM_R2_J1_GL": 1, "CFM_R4_J2_GL": 2, "BLANES17_R4_J4": 3}
 EV_STEP, EV_CHKPT, EV_REJECT, EV_END, EV_ERR = range(5)
@@ -94,6 +94,8 @@ SIGNATURES = {
     "vo_tableau_destroy": (_i32, [_vp]),
     "vo_rhs_create": (_i32, [_vp, _i32, _i32, _pvp]),
     "vo_rhs_create_custom": (_i32, [_vp, C.c_char_p, _i32, _i32, _pvp]),
+    "vo_rhs_create_custom_stencil": (_i32, [_vp, C.c_char_p, _i64, _i32, _i32, _pvp]),
+    "vo_rhs_custom_stencil_check": (_i32, [C.c_char_p, _i32, _i32, _i32, C.c_char_p, _i64]),
     "vo_rhs_custom_check": (_i32, [C.c_char_p, _i32, _i32, _i32, _i32, C.c_char_p, _i64]),
     "vo_rhs_num_params": (_i32, [_vp]),
     "vo_rhs_set_param": (_i32, [_vp, _i32, _f64]),

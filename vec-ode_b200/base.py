@@ -296,12 +296,15 @@ class Rhs:
     """Replaces the closure `FnMut(T, &V, &mut V) -> Result<(),()>` (src/base/rk.rs:97): a compiled-in device functor
     chosen by name, with parameters that are shared scalars or per-trajectory arrays."""
 
-    def __init__(self, ctx: Context, kind: str, d: int, params=None, body: str | None = None):
+    def __init__(self, ctx: Context, kind: str, d: int, params=None, body: str | None = None, radius: int = 0):
         self.ctx, self.kind, self.d = ctx, kind, d
         self._h = _vp()
         if kind == "CUSTOM":
             n_params = 0 if params is None else len(params)
             check(lib().vo_rhs_create_custom(ctx._h, body.encode(), d, n_params, C.byref(self._h)), ctx._h)
+        elif kind == "CUSTOM_STENCIL":
+            n_params = 0 if params is None else len(params)
+            check(lib().vo_rhs_create_custom_stencil(ctx._h, body.encode(), d, radius, n_params, C.byref(self._h)), ctx._h)
         else:
             check(lib().vo_rhs_create(ctx._h, _cabi.RHS[kind], d, C.byref(self._h)), ctx._h)
         self.num_params = int(lib().vo_rhs_num_params(self._h))
@@ -314,6 +317,20 @@ class Rhs:
         """The closure itself: `body` is CUDA C++ for the statements of `f(t, &x, &mut dx)` over `t`, `x[D]`, `dx[D]`, `p[NP]`;
         it is compiled at run time into the same fused kernels as the built-in families (vo_rhs_create_custom)."""
         return cls(ctx, "CUSTOM", d, list(params), body=body)
+
+    @classmethod
+    def custom_stencil(cls, ctx: Context, body: str, d: int, radius: int, params=()):
+        """A user stencil on one periodic grid state of d points: `body` assigns `du` from `u[0 .. 2R]` (u[R] is the point itself),
+        `t`, `j`, `d`, `p[NP]` (shared parameters); compiled at run time into the fused per-stage kernel (vo_rhs_create_custom_stencil)."""
+        return cls(ctx, "CUSTOM_STENCIL", d, list(params), body=body, radius=radius)
+
+    @staticmethod
+    def check_stencil_source(body: str, radius: int, n_params: int, arith: str = "strict") -> int:
+        log = C.create_string_buffer(1 << 16)
+        rc = lib().vo_rhs_custom_stencil_check(body.encode(), radius, n_params, _cabi.ARITH_STRICT if arith == "strict" else _cabi.ARITH_FAST, log, len(log))
+        if rc < 0:
+            raise VecOdeError(rc, log.value.decode("utf-8", "replace"))
+        return rc
 
     @staticmethod
     def check_source(body: str, d: int, n_params: int, stages: int = -1, arith: str = "strict") -> int:

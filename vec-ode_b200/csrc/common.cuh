@@ -68,6 +68,7 @@ struct vo_rhs_s {
     uint64_t version = 0;              // bumped whenever a parameter changes (solvers that keep a packed copy of per-trajectory parameters re-pack)
     std::string body;                  // VO_RHS_CUSTOM: source of the RHS statements
     std::map<int, void*> modules;      // VO_RHS_CUSTOM: compiled modules keyed by (stage count, arithmetic mode)
+    int radius = 0;                    // VO_RHS_CUSTOM_STENCIL: the stencil reaches `radius` grid points to each side
     int alias_kind = -1;               // >= 0: a compiled-in family re-compiled at run time (RhsCustom = RhsF<alias_kind, d>) to take a user norm
     std::string norm_src;              // source of the VoUserNorm functor compiled into this RHS's modules (vo_solver_set_norm_custom)
 };

@@ -21,6 +21,7 @@
 #include "norm_custom.cuh"
 #include "rk_small_launch.cuh"
 #include "rk_stage_pointwise.cuh"
+#include "rk_stage_stencil.cuh"
 
 namespace {
 
@@ -144,6 +145,13 @@ struct CustomModule {
 
 std::string rtc_source(const vo_rhs_s* r, bool stage_module) {
     const int d = r->d, np = r->np;
+    if (r->kind == VO_RHS_CUSTOM_STENCIL) {  // a grid stencil: the fused per-stage kernel of rk_stage_stencil.cuh
+        std::string st = "#include \"rk_stage_stencil.cuh\"\nstruct StencilCustom {\n    static constexpr int R = " + std::to_string(r->radius) +
+                         ", NP = " + std::to_string(np > 0 ? np : 1) + ";\n";
+        st += "    template <bool STRICT> static __device__ __forceinline__ double eval(const double t, const long long j, const long long d, const double (&u)[2 * R + 1], "
+              "const double (&p)[NP]) {\n        double du = 0.0;\n        {\n#line 1 \"rhs_body\"\n" + r->body + "\n        }\n        return du;\n    }\n};\n";
+        return st;
+    }
     std::string s = r->norm_src;  // the VoUserNorm functor, if any: non-dependent in err_norm, so it comes before the templates
     s += stage_module ? "#include \"rk_stage_pointwise.cuh\"\n" : "#include \"rk_small2.cuh\"\n";
     if (r->alias_kind >= 0) return s + "using RhsCustom = RhsF<" + std::to_string(r->alias_kind) + ", " + std::to_string(d) + ">;\n";
@@ -153,8 +161,9 @@ std::string rtc_source(const vo_rhs_s* r, bool stage_module) {
     return s;
 }
 
-std::vector<std::string> kernel_names(int S, bool strict, bool stage_module) {
+std::vector<std::string> kernel_names(int S, bool strict, bool stage_module, bool stencil = false) {
     const std::string st = strict ? "true" : "false", ss = std::to_string(S);
+    if (stencil) return {"stage_stencil_kernel<StencilCustom, " + st + ", false>", "stage_stencil_kernel<StencilCustom, " + st + ", true>"};
     if (stage_module) return {"stage_pointwise_kernel<RhsCustom, " + st + ", false>", "stage_pointwise_kernel<RhsCustom, " + st + ", true>"};
     std::vector<std::string> v(K_SMALL_COUNT);
     v[K_FIXED_STAGED] = "rk_fixed_staged_kernel<RhsCustom, " + ss + ", " + st + ">";
@@ -218,7 +227,7 @@ int32_t rtc_compile(const std::string& src, const std::vector<std::string>& name
 
 int32_t compile_custom(const vo_rhs_s* r, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered, std::string& log) {
     const bool stage_module = S == STAGE_MODULE;
-    return rtc_compile(rtc_source(r, stage_module), kernel_names(S, strict, stage_module), strict, cubin, lowered, log);
+    return rtc_compile(rtc_source(r, stage_module), kernel_names(S, strict, stage_module, r->kind == VO_RHS_CUSTOM_STENCIL), strict, cubin, lowered, log);
 }
 
 int module_key(int S, bool strict) { return (S + 1) * 2 + (strict ? 1 : 0); }
@@ -353,6 +362,21 @@ int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, 
     RhsParams rp = rp_in;
     void* args[] = {&x0, &N, &sa, &rp, &k_out, &nx, &xe};
     return custom_launch(c, drv, m->fn[tail ? K_STAGE_TAIL : K_STAGE], (unsigned)ceil_div(N, 128), 128, 0, false, args);
+}
+
+// The stage path for a user stencil on one grid state (rk_stage_stencil.cuh): persistent CTAs over 256-point tiles.
+int32_t launch_stage_stencil_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t d, const StageArgs& sa_in, const RhsParams& rp_in, double* k_out,
+                                    double* nx, double* xe) {
+    Driver* drv = nullptr;
+    CustomModule* m = nullptr;
+    int32_t rc = get_module(r, STAGE_MODULE, c->arith == VO_ARITH_STRICT, &drv, &m);
+    if (rc != VO_OK) return rc;
+    StageArgs sa = sa_in;
+    RhsParams rp = rp_in;
+    void* args[] = {&x0, &d, &sa, &rp, &k_out, &nx, &xe};
+    const int64_t tiles = ceil_div(d, ST_THREADS);
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
+    return custom_launch(c, drv, m->fn[tail ? K_STAGE_TAIL : K_STAGE], grid, ST_THREADS, 0, false, args);
 }
 
 void custom_rhs_release(vo_rhs_s* r) {
@@ -611,7 +635,7 @@ int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log
 
 int32_t vo_rhs_create_custom(vo_ctx c, const char* body, int32_t d, int32_t n_params, vo_rhs* out) {
     if (!c || !body || !out) return vo_fail(c, VO_ERR_BAD_ARG, "vo_rhs_create_custom: NULL argument");
-    if (d < 1 || d > 8 || n_params < 0 || n_params > VO_MAX_PARAMS) return vo_fail(c, VO_ERR_SHAPE, "vo_rhs_create_custom: needs 1 <= d <= 8 and 0 <= n_params <= 8");
+    if (d < 1 || d > 32 || n_params < 0 || n_params > VO_MAX_PARAMS) return vo_fail(c, VO_ERR_SHAPE, "vo_rhs_create_custom: needs 1 <= d <= 32 and 0 <= n_params <= 8");
     DeviceGuard g(c->device);
     vo_rhs r = new vo_rhs_s();
     r->ctx = c, r->kind = VO_RHS_CUSTOM, r->d = d, r->np = n_params, r->body = body;
@@ -629,9 +653,45 @@ int32_t vo_rhs_create_custom(vo_ctx c, const char* body, int32_t d, int32_t n_pa
     return VO_OK;
 }
 
+int32_t vo_rhs_create_custom_stencil(vo_ctx c, const char* body, int64_t d, int32_t radius, int32_t n_params, vo_rhs* out) {
+    if (!c || !body || !out) return vo_fail(c, VO_ERR_BAD_ARG, "vo_rhs_create_custom_stencil: NULL argument");
+    if (radius < 1 || radius > 8 || n_params < 0 || n_params > VO_MAX_PARAMS || d < 2 * radius + 1 || d > 0x7fffffff)
+        return vo_fail(c, VO_ERR_SHAPE, "vo_rhs_create_custom_stencil: needs 1 <= radius <= 8, 0 <= n_params <= 8 and 2 radius + 1 <= d < 2^31");
+    DeviceGuard g(c->device);
+    vo_rhs r = new vo_rhs_s();
+    r->ctx = c, r->kind = VO_RHS_CUSTOM_STENCIL, r->d = (int)d, r->np = n_params, r->body = body, r->radius = radius;
+    for (int i = 0; i < VO_MAX_PARAMS; ++i) r->shared[i] = 0.0, r->per_traj[i] = nullptr, r->per_traj_n[i] = 0;
+    Driver* drv = nullptr;
+    CustomModule* m = nullptr;
+    int32_t rc = get_module(r, STAGE_MODULE, c->arith == VO_ARITH_STRICT, &drv, &m);  // a source error is reported here
+    if (rc != VO_OK) {
+        custom_rhs_release(r);
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return VO_OK;
+}
+
+int32_t vo_rhs_custom_stencil_check(const char* body, int32_t radius, int32_t n_params, int32_t arith, char* log, int64_t log_cap) {
+    if (log && log_cap > 0) log[0] = '\0';
+    if (!body || radius < 1 || radius > 8 || n_params < 0 || n_params > VO_MAX_PARAMS) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_rhs_custom_stencil_check: bad argument");
+    vo_rhs_s tmp;
+    tmp.kind = VO_RHS_CUSTOM_STENCIL, tmp.d = 0, tmp.np = n_params, tmp.body = body, tmp.radius = radius;
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+    std::string msg;
+    const int32_t rc = compile_custom(&tmp, STAGE_MODULE, arith == VO_ARITH_STRICT, cubin, lowered, msg);
+    if (rc != VO_OK) {
+        if (log && log_cap > 0) std::strncpy(log, msg.c_str(), (size_t)log_cap - 1), log[log_cap - 1] = '\0';
+        return vo_fail(nullptr, rc, msg);
+    }
+    return (int32_t)std::min<size_t>(cubin.size(), 0x7fffffff);
+}
+
 int32_t vo_rhs_custom_check(const char* body, int32_t d, int32_t n_params, int32_t stages, int32_t arith, char* log, int64_t log_cap) {
     if (log && log_cap > 0) log[0] = '\0';
-    if (!body || d < 1 || d > 8 || n_params < 0 || n_params > VO_MAX_PARAMS || stages < -1 || stages > VO_MAX_STAGES)
+    if (!body || d < 1 || d > (stages < 0 ? 32 : 8) || n_params < 0 || n_params > VO_MAX_PARAMS || stages < -1 || stages > VO_MAX_STAGES)
         return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_rhs_custom_check: bad argument");
     std::vector<char> cubin;
     std::vector<std::string> lowered;

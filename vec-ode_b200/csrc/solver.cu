@@ -24,6 +24,8 @@
 #include "rk_heat_fused.cuh"
 
 int32_t vo_norm_device(vo_ens e, int32_t kind, double* out_dev, double* partial_dev, int partial_cap, bool finish);
+int32_t launch_stage_stencil_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t d, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
+                                    double* xe);
 int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t N, const StageArgs& sa, const RhsParams& rp, double* k_out, double* nx,
                             double* xe);  // nvrtc_rhs.cu
 
@@ -94,7 +96,11 @@ struct vo_solver_s {
 
 namespace {
 
-bool rhs_is_small(const vo_rhs_s* r) { return r->kind == VO_RHS_CUSTOM || (r->kind != VO_RHS_HEAT1D && r->d <= 4); }
+// register-resident whole-attempt kernels: compiled-in pointwise families up to 4 components, user right-hand sides up to 8
+bool rhs_is_small(const vo_rhs_s* r) {
+    if (r->kind == VO_RHS_CUSTOM) return r->d <= 8;
+    return r->kind != VO_RHS_HEAT1D && r->kind != VO_RHS_CUSTOM_STENCIL && r->d <= 4;
+}
 bool use_small(const vo_solver_s* s) { return !s->stage_path && rhs_is_small(s->rhs); }
 bool use_err(const vo_solver_s* s) { return s->tab.has_err && s->has_x_err; }
 // Events fused per launch. step()/vo_step_many expose every event, so they advance one at a time unless the caller
@@ -570,6 +576,11 @@ template <bool TAIL> int32_t launch_stage_kernel(vo_solver_s* s, const StageArgs
             int32_t cr = launch_stage_custom(c, s->rhs, TAIL, x0, s->n, sa, rp, k_out, nx, xe);
             if (cr != VO_OK) return cr;
         } break;
+        case VO_RHS_CUSTOM_STENCIL: {
+            if (s->n != 1) return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: a user stencil runs on ONE grid state (N == 1)");
+            int32_t cr = launch_stage_stencil_custom(c, s->rhs, TAIL, x0, s->d, sa, rp, k_out, nx, xe);
+            if (cr != VO_OK) return cr;
+        } break;
         case VO_RHS_HEAT1D: {
             const double kappa = r->shared[0];
             const bool strict = c->arith == VO_ARITH_STRICT;
@@ -728,7 +739,7 @@ int32_t stage_uniform_event(vo_solver_s* s, bool adaptive, vo_step_result* res) 
 // Per-trajectory stage path: prepare -> s stage kernels (masked) -> norm/controller/commit. One event per call.
 int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
     vo_ctx c = s->ctx;
-    if (s->d > 64 || s->rhs->kind == VO_RHS_HEAT1D)
+    if (s->d > 64 || s->rhs->kind == VO_RHS_HEAT1D || s->rhs->kind == VO_RHS_CUSTOM_STENCIL)
         return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: per-trajectory control needs a pointwise RHS with d <= 64");
     if (!s->evv) {
         if (cudaMalloc(&s->evv, (size_t)s->n) != cudaSuccess || cudaMalloc(&s->dtv, 8 * (size_t)s->n) != cudaSuccess)

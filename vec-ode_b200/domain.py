@@ -82,15 +82,18 @@ class HeatSlabSolver:
     the process group. Same stepping semantics as `RK45Solver.step()` for a single large state (N = 1, lock-step control on
     the host); every rank runs the same (t, dt) sequence, so the only data-path exchange is the ghost refresh."""
 
-    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4, fused: bool = False, adaptive: bool = False):
+    def __init__(self, ctx, d_total: int, u0_global_fn, kappa: float, t0: float, tf: float, h: float, tableau=None, steps_per_exchange: int = 4, fused: bool = False, adaptive: bool = False,
+                 rhs_factory=None, radius: int = 1):
         from . import base
         rank, world = rank_world()
         self.ctx = ctx
         self.tableau = tableau or base.ButcherTableu.builtin("RK4")
         self.k = int(steps_per_exchange)
-        self.slab = PeriodicSlab(d_total, rank, world, self.k * self.tableau.num_stages())
+        # a stencil of radius R corrupts R points per stage at each slab end: ghost zone = k * s * R
+        self.slab = PeriodicSlab(d_total, rank, world, self.k * self.tableau.num_stages() * radius)
         u0 = u0_global_fn(self.slab.global_index())  # every rank evaluates its own points (and ghosts) of the initial state
-        self.rhs = base.Rhs(ctx, "HEAT1D", self.slab.local_len, [kappa])
+        # rhs_factory(ctx, local_len): a user stencil (base.Rhs.custom_stencil) in place of the compiled-in heat equation
+        self.rhs = rhs_factory(ctx, self.slab.local_len) if rhs_factory else base.Rhs(ctx, "HEAT1D", self.slab.local_len, [kappa])
         self.solver = base.RK45Solver(self.rhs, t0, tf, base.Ensemble.from_host(ctx, u0[None, :]), h, tableau=self.tableau)
         if not adaptive:
             self.solver.no_adaptive()
