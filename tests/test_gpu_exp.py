@@ -49,6 +49,36 @@ def test_map_exp_against_eigendecomposition(vo, ctx, n):
         assert np.abs(got[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (i, np.abs(got[i] - ref).max())
 
 
+@pytest.mark.parametrize("n,M", [(8, 1), (8, 4), (16, 4), (24, 2), (24, 3), (32, 1), (32, 4), (40, 2), (48, 2), (48, 3), (64, 1), (64, 3)])
+def test_map_exp_on_every_compiled_shape_family(vo, ctx, n, M):
+    """The shared-basis split beyond config 5's (64, 2): every n that is a multiple of 8 up to 64 with the M values compiled in for it
+    (the whole basis has to fit one SM's shared memory) — map_exp against scipy expm per system, ragged batch."""
+    import torch
+    from scipy.linalg import expm
+    N = 19
+    rng = np.random.default_rng(100 * n + M)
+    Bs = []
+    for _ in range(M):
+        G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        Bs.append(-1j * (G + G.conj().T) / (2.0 * np.sqrt(n)))
+    basis = np.stack(Bs)
+    coef = (rng.uniform(-0.6, 0.6, (N, M)) + 0.1j * rng.uniform(-1, 1, (N, M))) * rng.choice([0.2, 1.0, 2.5], (N, 1))
+    psi = rng.standard_normal((N, n)) + 1j * rng.standard_normal((N, n))
+    sp = vo.DenseBasisSplit(ctx, basis)
+    x = torch.from_numpy(psi.view(np.float64).reshape(N, n, 2).copy()).cuda()
+    y = torch.empty_like(x)
+    sp.map_exp(sp.exp(coef), x.data_ptr(), y.data_ptr())
+    torch.cuda.synchronize()
+    got = y.cpu().numpy().reshape(N, n * 2).view(np.complex128)
+    for i in range(N):
+        ref = expm(np.einsum("m,mij->ij", coef[i], basis)) @ psi[i]
+        assert np.abs(got[i] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (i, np.abs(got[i] - ref).max())
+    with pytest.raises(vo.VecOdeError):  # (56, 2) is not compiled in: the error names the dense split
+        sp56 = vo.DenseBasisSplit(ctx, np.zeros((2, 56, 56), dtype=complex))
+        z = torch.zeros((1, 56, 2), dtype=torch.float64).cuda()
+        sp56.map_exp(sp56.exp(np.ones((1, 2), dtype=complex)), z.data_ptr(), z.clone().data_ptr())
+
+
 def test_map_exp_and_dense_exp_against_mpmath_50_digits(vo, ctx):
     """map_exp of the lazy split and the explicit U = exp(L) of the dense split (scaling and squaring) against
     exp(L) x summed as a plain Taylor series in 50-digit arithmetic (tests/_mp_expm.py), four systems of n = 16 with ||L||_1 from

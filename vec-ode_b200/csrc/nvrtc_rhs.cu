@@ -622,7 +622,7 @@ int32_t vo_norm_custom(vo_ens e, vo_normfn f, double* out_host) {
 
 int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap) {
     if (log && log_cap > 0) log[0] = '\0';
-    if (!body || (n != 16 && n != 32 && n != 64) || M < 1 || M > 3) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_exp_generator_check: bad argument");
+    if (!body || n < 8 || n > 64 || n % 8 || M < 1 || M > 4) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_exp_generator_check: bad argument");
     std::vector<char> cubin;
     std::string lowered, msg;
     const int32_t rc = rtc_exp_compile(body, "", n, M, cubin, lowered, msg);
