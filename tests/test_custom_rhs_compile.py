@@ -15,7 +15,7 @@ def test_user_rhs_compile_error_carries_the_log(vo):
         vo.Rhs.check_source("dx[0] = nope;", 1, 0)
     assert "rhs_body(1)" in str(ei.value) and "nope" in str(ei.value)
     with pytest.raises(vo.VecOdeError):
-        vo.Rhs.check_source("dx[0] = x[0];", 9, 0)
+        vo.Rhs.check_source("dx[0] = x[0];", 33, 0)
 
 
 def test_user_generator_compiles_into_the_tensor_core_kernel(vo):

@@ -136,7 +136,7 @@ def test_custom_rhs_compile_error_is_reported(vo, ctx):
         vo.Rhs.custom(ctx, "dx[0] = undefined_symbol;", 1, [])
     assert "rhs_body(1)" in str(ei.value) and "undefined_symbol" in str(ei.value)
     with pytest.raises(vo.VecOdeError):
-        vo.Rhs.custom(ctx, "dx[0] = x[0];", 9, [])  # d > 8
+        vo.Rhs.custom(ctx, "dx[0] = x[0];", 33, [])  # d > 32
 
 
 def test_custom_rhs_largest_shape_eight_components_eight_per_trajectory_parameters(vo, ctx):
