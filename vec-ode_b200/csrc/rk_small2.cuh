@@ -440,8 +440,26 @@ __global__ void __launch_bounds__(128, VO_CTL2_MIN_BLOCKS + 1) rk_ctl2w_staged_k
 #pragma unroll
             for (int u = 0; u < U; ++u) acc[u] = err_sumsq<STRICT, D>(xe[u]);
             controller_l2_n<STRICT, U>(acc, h, cs, cs.record_dx_norm != 0, dxn, new_h, rej, nonfin);  // handle_step_adaptive, ode.rs:311-334
+#ifdef VO_COMMIT_SELECT
+            // apply_step (ode.rs:402-428), branch-free: both trajectories always store — a rejected one stores back what it loaded
+            // (the same bits), an accepted one its new state. Whole 32-byte sectors of rejected trajectories are rare (the accept
+            // rate is ~2/3 and neighbours mix), so the masked version dirtied nearly every sector anyway, while its three-way
+            // branch (both accepted / both rejected / mixed) made most warps run all three paths one after the other.
+            {
+#pragma unroll
+                for (int c = 0; c < D; ++c)
+                    *reinterpret_cast<double2*>(x + c * N + i0) = make_double2(rej[0] ? xc[0][c] : xf[0][c], rej[1] ? xc[1][c] : xf[1][c]);
+                *reinterpret_cast<double2*>(ca.t + i0) = make_double2(rej[0] ? t[0] : t[0] + dt[0], rej[1] ? t[1] : t[1] + dt[1]);  // advance, ode.rs:184-188
+                *reinterpret_cast<uint2*>(ca.n_accept + i0) = make_uint2(n_acc[0] + (rej[0] ? 0u : 1u), n_acc[1] + (rej[1] ? 0u : 1u));
+                *reinterpret_cast<uint2*>(ca.n_reject + i0) = make_uint2(n_rej[0] + (rej[0] ? 1u : 0u), n_rej[1] + (rej[1] ? 1u : 0u));
+                const unsigned nr = (rej[0] ? 1u : 0u) + (rej[1] ? 1u : 0u);
+                c_rej += nr, c_step += 2u - nr;
+            }
+            if (false) {
+#else
             // apply_step (ode.rs:402-428) + masked write-back: 128-bit stores where both trajectories commit the same way
             if (!rej[0] && !rej[1]) {
+#endif
 #pragma unroll
                 for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(x + c * N + i0) = make_double2(xf[0][c], xf[1][c]);
                 *reinterpret_cast<double2*>(ca.t + i0) = make_double2(t[0] + dt[0], t[1] + dt[1]);  // advance, ode.rs:184-188

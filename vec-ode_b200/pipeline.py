@@ -107,15 +107,23 @@ class ShardedChunkedSolve:
             self.chunks.append((lo, hi, ctx, x0, make_solver(ctx, lo, hi, x0)))
         self.pool = ThreadPoolExecutor(max_workers=max(parts, 1))
         self._turn, self._cv = 0, threading.Condition()
+        self.trace = None  # set to a list to record (chunk, phase, t_begin, t_end) host timestamps of the next solve (tools/e2e_trace.py)
         self._placeholder = None  # a rank whose chunk is empty still takes part in the gather
 
     def _one(self, q, host_in, host_out, adaptive, root):
+        import time
         chunk, st = self.chunks[q], None
+        tr = self.trace
+        t0 = time.perf_counter()
         if chunk is not None:
             lo, hi, ctx, x0, solver = chunk
             x0.upload(host_in[lo:hi], "aos")
+            t1 = time.perf_counter()
             solver.reset(x0)
             st = solver.run(adaptive=adaptive)
+            if tr is not None:
+                tr.append((q, "upload", t0, t1)), tr.append((q, "run", t1, time.perf_counter()))
+        t2 = time.perf_counter()
         with self._cv:  # the gathers are enqueued in chunk order on every rank
             self._cv.wait_for(lambda: self._turn == q)
             if chunk is not None:
@@ -132,6 +140,8 @@ class ShardedChunkedSolve:
                 self.group.gather_placed([ens], args[0], args[1], host_out, root=root)
             self._turn += 1
             self._cv.notify_all()
+        if tr is not None:
+            tr.append((q, "gather_enqueue", t2, time.perf_counter()))
         return st
 
     def solve(self, host_in_local: np.ndarray, host_out_full, adaptive: bool = False, root: int = 0):
@@ -141,7 +151,13 @@ class ShardedChunkedSolve:
         self._turn = 0
         futs = [self.pool.submit(self._one, q, host_in_local, host_out_full, adaptive, root) for q in range(self.parts)]
         sts = [f.result() for f in futs]
-        self.group.sync()
+        if self.trace is not None:
+            import time
+            t0 = time.perf_counter()
+            self.group.sync()
+            self.trace.append((-1, "final_sync", t0, time.perf_counter()))
+        else:
+            self.group.sync()
         return [s for s in sts if s is not None]
 
     @property
