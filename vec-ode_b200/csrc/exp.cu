@@ -141,7 +141,7 @@ int32_t launch_exp(vo_ctx c, const ExpKP& kp, const double* frag, double2* psi, 
 // Shapes of the lazy shared-basis split that are compiled in: (n, M) with the whole basis (M n^2 complex) resident in one SM's
 // shared memory next to the term buffers. A run-time compiled generator or norm (nvrtc_rhs.cu) takes the same list.
 #define VO_EXP_SHAPES(X) \
-    X(64, 1) X(64, 2) X(64, 3) X(48, 2) X(48, 3) X(40, 2) X(32, 1) X(32, 2) X(32, 3) X(32, 4) X(24, 2) X(24, 3) X(16, 1) X(16, 2) X(16, 3) X(16, 4) X(8, 1) X(8, 2) X(8, 3) X(8, 4)
+    X(64, 1) X(64, 2) X(64, 3) X(48, 2) X(48, 3) X(40, 2) X(32, 1) X(32, 2) X(32, 3) X(32, 4) X(24, 2) X(24, 3) X(16, 1) X(16, 2) X(16, 3) X(16, 4)
 
 bool exp_geometry(int n, int M, unsigned* threads, size_t* smem) {
 #define VO_EXP_GEO(NDIM, MM) \
@@ -172,7 +172,7 @@ int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_ou
     if (sp->n == NDIM && sp->M == MM) return launch_exp<NDIM, MM, 16>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev);
     VO_EXP_SHAPES(VO_EXP_CASE)
 #undef VO_EXP_CASE
-    return vo_fail(c, VO_ERR_UNSUPPORTED, "exp: the shared-basis split is compiled for n in {8, 16, 32} with M <= 4, n in {24, 48} with M in {2, 3}, (40, 2) and n = 64 with M <= 3 "
+    return vo_fail(c, VO_ERR_UNSUPPORTED, "exp: the shared-basis split is compiled for n in {16, 32} with M <= 4, n in {24, 48} with M in {2, 3}, (40, 2) and n = 64 with M <= 3 "
                                           "(the whole basis stays in one SM's shared memory); other shapes: the dense split (vo_split_dense_create)");
 }
 
