@@ -828,7 +828,7 @@ def main():
     # e2e step ends with the final gather of the whole ensemble into rank 0's pinned host array, inside the timed region.
     group = None
     if world > 1:
-        group = vo.group.Group.from_torch_distributed(vo.Context(local, arith=args.arith))
+        group = vo.group.Group.from_torch_distributed(vo.Context(local, arith=args.arith, urgency=8))  # the gather stream goes ahead of the chunks still integrating
     w.e2e_setup(group)
     w.e2e_step()  # warm
     barrier()

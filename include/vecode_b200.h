@@ -52,6 +52,11 @@ typedef struct vo_normfn_s* vo_normfn;
 /* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to
  * let the ctx create its own non-blocking stream (use CUDA's cudaStreamLegacy handle, 0x1, to name the NULL stream). */
 int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out);
+/* A ctx on a stream of its own whose pending thread blocks are scheduled ahead of those of less urgent streams (CUDA stream
+ * priorities; urgency 0 = vo_ctx_create's default, higher = earlier, clamped to what the device offers). A solve cut into chunks
+ * on several contexts (vec-ode_b200/pipeline.py) gives chunk q urgency parts - q, so the chunks FINISH one after the other and
+ * the transfers of a finished chunk overlap the integration of the next instead of all chunks ending together. */
+int32_t vo_ctx_create_urgent(int32_t device, int32_t urgency, vo_ctx* out);
 int32_t vo_ctx_destroy(vo_ctx ctx);
 int32_t vo_ctx_sync(vo_ctx ctx);
 void* vo_ctx_stream(vo_ctx ctx);

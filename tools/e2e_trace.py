@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(local)
     bench.numa_bind(torch, local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    group = vo.group.Group.from_torch_distributed(vo.Context(local, arith="fast"))
+    group = vo.group.Group.from_torch_distributed(vo.Context(local, arith="fast", urgency=8))
     n_total = bench.N_TRAJ * world
     mu_il = vo.workloads.vdp_mu(n_total)[rank::world].copy()
     tab = vo.ButcherTableu.builtin("DOPRI5")

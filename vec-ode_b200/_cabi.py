@@ -61,6 +61,7 @@ _pvp = C.POINTER(C.c_void_p)
 # name -> (restype, argtypes): every entry point of include/vecode_b200.h
 SIGNATURES = {
     "vo_ctx_create": (_i32, [_i32, _vp, _pvp]),
+    "vo_ctx_create_urgent": (_i32, [_i32, _i32, _pvp]),
     "vo_ctx_destroy": (_i32, [_vp]),
     "vo_ctx_sync": (_i32, [_vp]),
     "vo_ctx_fence": (_i32, [_vp]),

@@ -31,9 +31,12 @@ def _np_ptr(a: Optional[np.ndarray]):
 class Context:
     """One CUDA device + one stream. `stream` may be a raw cudaStream_t (int), e.g. torch's current stream."""
 
-    def __init__(self, device: int = 0, stream: Optional[int] = None, arith: str = "strict"):
+    def __init__(self, device: int = 0, stream: Optional[int] = None, arith: str = "strict", urgency: int = 0):
         self._h = _vp()
-        check(lib().vo_ctx_create(device, _vp(stream) if stream else None, C.byref(self._h)))
+        if urgency > 0 and not stream:  # its own stream, scheduled ahead of less urgent ones (vo_ctx_create_urgent)
+            check(lib().vo_ctx_create_urgent(device, urgency, C.byref(self._h)))
+        else:
+            check(lib().vo_ctx_create(device, _vp(stream) if stream else None, C.byref(self._h)))
         self.device = device
         self.set_arith(arith)
 
@@ -494,6 +497,12 @@ class RK45Solver:
         res = StepResult()
         check(lib().vo_run(self._h, 1 if adaptive else 0, max_calls, C.byref(res)), self.ctx._h)
         return _state_of(res)
+
+    def state(self) -> "Ensemble":
+        """The borrowed state ensemble alone (vo_current without the time range: nothing is read back, nothing synchronises)."""
+        h = _vp()
+        check(lib().vo_current(self._h, None, None, C.byref(h)), self.ctx._h)
+        return Ensemble(self.ctx, self.d, self.n, _handle=h, _owner=self)
 
     def current(self):  # ode.rs:216-218 -> ((t_min, t_max), borrowed Ensemble)
         tmin, tmax, h = C.c_double(), C.c_double(), _vp()

@@ -25,7 +25,11 @@ extern "C" {
 
 int32_t vo_version(void) { return VO_VERSION; }
 
-int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out) {
+static int32_t ctx_create_impl(int32_t device, void* stream, int32_t urgency, vo_ctx* out);
+int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out) { return ctx_create_impl(device, stream, 0, out); }
+int32_t vo_ctx_create_urgent(int32_t device, int32_t urgency, vo_ctx* out) { return ctx_create_impl(device, nullptr, urgency < 0 ? 0 : urgency, out); }
+
+static int32_t ctx_create_impl(int32_t device, void* stream, int32_t urgency, vo_ctx* out) {
     if (!out) return vo_fail(nullptr, VO_ERR_BAD_ARG, "vo_ctx_create: out is NULL");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -40,7 +44,10 @@ int32_t vo_ctx_create(int32_t device, void* stream, vo_ctx* out) {
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
-        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        int lo = 0, hi = 0;  // numerically lower = scheduled first; the range is [greatest, least]
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int prio = std::max(hi, lo - urgency);  // urgency 0 = the default (least) priority, each step one level up
+        e = urgency > 0 ? cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio) : cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
             delete c;
             return vo_fail(nullptr, VO_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));

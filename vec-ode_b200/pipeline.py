@@ -27,7 +27,9 @@ class ChunkedSolve:
             lo, hi = shard_range(n, q, parts)
             if hi <= lo:
                 continue
-            ctx = Context(device, arith=arith)
+            # earlier chunks are more urgent: the chunks then finish one after the other (not all together at the end), so the
+            # download of a finished chunk overlaps the integration of the next
+            ctx = Context(device, arith=arith, urgency=parts - q)
             x0 = Ensemble(ctx, d, hi - lo)
             self.chunks.append((lo, hi, ctx, x0, make_solver(ctx, lo, hi, x0)))
         self.pool = ThreadPoolExecutor(max_workers=max(parts, 1))
@@ -38,7 +40,7 @@ class ChunkedSolve:
         x0.upload(host_in[lo:hi], "aos")
         solver.reset(x0)
         st = solver.run(adaptive=adaptive)
-        solver.current()[1].to_host("aos", out=host_out[lo:hi])
+        solver.state().to_host("aos", out=host_out[lo:hi])
         return st
 
     def solve(self, host_in: np.ndarray, host_out: np.ndarray, adaptive: bool = False):
@@ -102,7 +104,7 @@ class ShardedChunkedSolve:
             if hi <= lo:
                 self.chunks.append(None)
                 continue
-            ctx = Context(self.gctx.device, arith=arith)
+            ctx = Context(self.gctx.device, arith=arith, urgency=parts - len(self.chunks))  # chunk 0 first: its gather overlaps the rest
             x0 = Ensemble(ctx, d, hi - lo)
             self.chunks.append((lo, hi, ctx, x0, make_solver(ctx, lo, hi, x0)))
         self.pool = ThreadPoolExecutor(max_workers=max(parts, 1))
@@ -128,7 +130,7 @@ class ShardedChunkedSolve:
             self._cv.wait_for(lambda: self._turn == q)
             if chunk is not None:
                 self.gctx.wait_for(chunk[2])
-                ens = chunk[4].current()[1]
+                ens = chunk[4].state()  # no read-back: the gather is enqueued behind the chunk's stream
             else:
                 if self._placeholder is None:
                     self._placeholder = Ensemble(self.gctx, self.d, 1)
