@@ -15,6 +15,7 @@ typedef unsigned long size_t;
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #endif
@@ -80,6 +81,7 @@ struct vo_normfn_s {
     int join = 0;
     void* module[2] = {nullptr, nullptr};  // per arithmetic mode (strict modules are compiled with --fmad=false)
     void* fn[2][3] = {};                   // small / partial / final
+    std::mutex mu;                         // contexts may be driven from several host threads (pipeline.py): the lazy compile is serialised
 };
 std::string norm_source(const vo_normfn_s* f);
 // norm of x = [d][n] (components i_off .. i_off + d of a d_total-component vector) into out_dev[n]; finish = false leaves the accumulator

@@ -469,6 +469,7 @@ int32_t norm_custom_device(vo_normfn_s* f, const double* x, int64_t d, int64_t n
     std::string err;
     Driver* drv = nullptr;
     if (!driver_load(&drv, err)) return vo_fail(c, VO_ERR_UNSUPPORTED, err);
+    std::unique_lock<std::mutex> lock(f->mu);
     if (!f->module[am]) {
         std::vector<char> cubin;
         std::vector<std::string> lowered;
@@ -484,6 +485,7 @@ int32_t norm_custom_device(vo_normfn_s* f, const double* x, int64_t d, int64_t n
         }
         f->module[am] = mod;
     }
+    lock.unlock();
     int fin = finish ? 1 : 0;
     if (d <= 64) {  // one thread per trajectory, left to right (the order of a sequential norm), like the built-in norms
         void* args[] = {&x, &d, &n, &out_dev, &fin};

@@ -26,8 +26,9 @@ __global__ void __launch_bounds__(ST_THREADS) stage_stencil_kernel(const double*
     for (int64_t ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
         const int64_t base = ti * ST_THREADS;
         for (int k = threadIdx.x; k < W; k += ST_THREADS) {  // stage argument of the tile and its halo, periodic in the grid index
-            int64_t e = (base - R + k) % d;
-            if (e < 0) e += d;
+            int64_t e = base - R + k;  // periodic wrap without a 64-bit division: at most a few subtractions, and only at the grid's ends
+            while (e < 0) e += d;
+            while (e >= d) e -= d;
             const double xh = x0[e];
             tile[k] = sa.i == 0 ? xh : stage_elem<STRICT>(sa, sa.a, sa.i, e, xh, sa.dt);
         }
