@@ -172,7 +172,7 @@ std::vector<std::string> kernel_names(int S, bool strict, bool stage_module, boo
     v[K_CTL_STAGED_L2] = "rk_ctl_staged_kernel<RhsCustom, " + ss + ", " + st + ", 1>";
     v[K_CTL2_STAGED] = S > 0 ? "rk_ctl2w_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";
     v[K_CTL] = "rk_ctl_kernel<RhsCustom, " + ss + ", " + st + ">";
-    v[K_FIXED2_STAGED] = S > 0 ? "rk_fixed2_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";
+    v[K_FIXED2_STAGED] = S > 0 ? "rk_fixed2w_staged_kernel<RhsCustom, " + ss + ", " + st + ">" : "";  // warp-autonomous staging, as for the compiled-in families
     return v;
 }
 

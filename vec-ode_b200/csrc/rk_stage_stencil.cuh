@@ -23,18 +23,49 @@ __global__ void __launch_bounds__(ST_THREADS) stage_stencil_kernel(const double*
 #pragma unroll
     for (int q = 0; q < ST::NP; ++q) p[q] = rp.shared[q];
     const int64_t n_tiles = (d + ST_THREADS - 1) / ST_THREADS;
+    const int s_ = sa.s;
+    const int nload = TAIL ? (s_ - 1 < 8 ? s_ - 1 : 8) : (sa.i < 8 ? sa.i : 8);  // the tail also needs K_0..K_{s-2} for the b-combination
     for (int64_t ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
         const int64_t base = ti * ST_THREADS;
-        for (int k = threadIdx.x; k < W; k += ST_THREADS) {  // stage argument of the tile and its halo, periodic in the grid index
-            int64_t e = base - R + k;  // periodic wrap without a 64-bit division: at most a few subtractions, and only at the grid's ends
-            while (e < 0) e += d;
-            while (e >= d) e -= d;
-            const double xh = x0[e];
-            tile[k] = sa.i == 0 ? xh : stage_elem<STRICT>(sa, sa.a, sa.i, e, xh, sa.dt);
+        // own point: x0 and the stage derivatives it needs, fetched together (kept for the tail's b-combination)
+        int64_t e = base + threadIdx.x;
+        const bool act = e < d;
+        while (e >= d) e -= d;  // past the end of the grid (last tile only): a periodic image, needed as halo by the last points
+        const double xc = x0[e];
+        double kj[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) kj[j] = (j < nload && (STRICT || TAIL || sa.a[j] != 0.0)) ? sa.K[j][e] : 0.0;
+        {
+            double acc = xc;
+            if (sa.i > 0) {
+                if (STRICT) {
+                    acc = A::mul(sa.a[0], kj[0]);
+#pragma unroll
+                    for (int j = 1; j < 8; ++j)
+                        if (j < sa.i) acc = A::axpy(acc, sa.a[j], kj[j]);
+                    for (int j = 8; j < sa.i; ++j) acc = A::axpy(acc, sa.a[j], sa.K[j][e]);
+                } else {
+                    acc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < sa.i && sa.a[j] != 0.0) acc = fma(sa.a[j], kj[j], acc);
+                    for (int j = 8; j < sa.i; ++j)
+                        if (sa.a[j] != 0.0) acc = fma(sa.a[j], sa.K[j][e], acc);
+                }
+                acc = A::add(A::mul(acc, sa.dt), xc);  // rk.rs:123-124
+            }
+            tile[R + threadIdx.x] = acc;
+        }
+        if (threadIdx.x < 2 * R) {  // the 2R halo points of the tile (periodic), rebuilt from global memory: same operations, same order
+            const int k = threadIdx.x < R ? threadIdx.x : ST_THREADS + threadIdx.x;
+            int64_t eh = base - R + k;
+            while (eh < 0) eh += d;
+            while (eh >= d) eh -= d;
+            const double xh = x0[eh];
+            tile[k] = sa.i == 0 ? xh : stage_elem<STRICT>(sa, sa.a, sa.i, eh, xh, sa.dt);
         }
         __syncthreads();
-        const int64_t e = base + threadIdx.x;
-        if (e < d) {
+        if (act) {
             double u[2 * R + 1];
 #pragma unroll
             for (int k = 0; k < 2 * R + 1; ++k) u[k] = tile[threadIdx.x + k];
@@ -43,24 +74,36 @@ __global__ void __launch_bounds__(ST_THREADS) stage_stencil_kernel(const double*
                 k_out[e] = kl;
             } else {  // sum_j b_j K_j with K_{s-1} = kl in a register, left to right (lc.rs:20-35)
                 const int s = sa.s;
-                const double xc = x0[e];
+                auto kval = [&](int j) { return j == s - 1 ? kl : (j < 8 ? kj[j] : sa.K[j][e]); };
                 double xb, xbe = 0.0;
                 if (STRICT) {
-                    xb = A::mul(sa.b[0], s == 1 ? kl : sa.K[0][e]);
-                    for (int j = 1; j < s; ++j) xb = A::axpy(xb, sa.b[j], j == s - 1 ? kl : sa.K[j][e]);
+                    xb = A::mul(sa.b[0], kval(0));
+#pragma unroll
+                    for (int j = 1; j < 8; ++j)
+                        if (j < s) xb = A::axpy(xb, sa.b[j], kval(j));
+                    for (int j = 8; j < s; ++j) xb = A::axpy(xb, sa.b[j], kval(j));
                 } else {
                     xb = 0.0;
-                    for (int j = 0; j < s; ++j)
-                        if (sa.b[j] != 0.0) xb = fma(sa.b[j], j == s - 1 ? kl : sa.K[j][e], xb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < s && sa.b[j] != 0.0) xb = fma(sa.b[j], kval(j), xb);
+                    for (int j = 8; j < s; ++j)
+                        if (sa.b[j] != 0.0) xb = fma(sa.b[j], kval(j), xb);
                 }
                 xb = A::add(A::mul(xb, sa.dt), xc);
                 if (sa.use_err) {
                     if (STRICT) {
-                        xbe = A::mul(sa.b_err[0], s == 1 ? kl : sa.K[0][e]);
-                        for (int j = 1; j < s; ++j) xbe = A::axpy(xbe, sa.b_err[j], j == s - 1 ? kl : sa.K[j][e]);
+                        xbe = A::mul(sa.b_err[0], kval(0));
+#pragma unroll
+                        for (int j = 1; j < 8; ++j)
+                            if (j < s) xbe = A::axpy(xbe, sa.b_err[j], kval(j));
+                        for (int j = 8; j < s; ++j) xbe = A::axpy(xbe, sa.b_err[j], kval(j));
                     } else {
-                        for (int j = 0; j < s; ++j)
-                            if (sa.b_err[j] != 0.0) xbe = fma(sa.b_err[j], j == s - 1 ? kl : sa.K[j][e], xbe);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < s && sa.b_err[j] != 0.0) xbe = fma(sa.b_err[j], kval(j), xbe);
+                        for (int j = 8; j < s; ++j)
+                            if (sa.b_err[j] != 0.0) xbe = fma(sa.b_err[j], kval(j), xbe);
                     }
                     xbe = A::add(A::mul(xbe, sa.dt), xc);
                     next_x[e] = xbe;             // the reference propagates X_berr (rk.rs:142-146)
