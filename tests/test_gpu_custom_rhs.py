@@ -6,6 +6,7 @@ counterpart is bit-exact against the pure-Python restatement of rk.rs / ode.rs d
 arithmetic, fixed step), and within rtol with equal accept / reject counts on adaptive runs.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -242,3 +243,29 @@ def test_wide_pointwise_user_rhs_on_the_stage_path(vo, ctx, oracle):
         r.run(adaptive=True)
         assert (int(st["accepted"][i]), int(st["rejected"][i])) == (r.n_accept, r.n_reject)
         assert np.abs(got[i] - np.array(r.x)).max() <= 1e-9
+
+
+@pytest.mark.parametrize("radius,body", [(1, HEAT_STENCIL), (2, "du = (-u[0] + 16.0 * u[1] - 30.0 * u[2] + 16.0 * u[3] - u[4]) * (p[0] / 12.0) + 1e-3 * sin(t) * (j % 5);"),
+                                         (3, "du = p[0] * (u[0] - u[6]) + 0.1 * (u[2] + u[4] - 2.0 * u[3]);"), (4, "du = p[0] * (u[0] + u[8] - 2.0 * u[4]);")])
+@pytest.mark.parametrize("tab", ["RK4", "DOPRI5"])
+def test_user_stencil_tma_staged_kernel_equals_the_plain_kernel_bitwise(vo, ctx, radius, body, tab):
+    """Large even grids take the TMA-staged stencil kernel (rk_stage_stencil.cuh: stage_stencil_tma_kernel), everything else the
+    plain one: same operations per point, so the strict results must be the same bits — fixed steps with the error estimate on,
+    grid sizes that end in a full tile, a partial tile and a two-point remainder."""
+    for d in (8192, 8192 + 514, 4 * 1024 + 2):
+        u0 = vo.workloads.heat_u0(d) + 0.1 * np.cos(np.pi * np.arange(d))
+        outs = []
+        for plain in ("", "1"):
+            if plain:
+                os.environ["VECODE_STENCIL_PLAIN"] = "1"
+            else:
+                os.environ.pop("VECODE_STENCIL_PLAIN", None)
+            try:
+                rhs = vo.Rhs.custom_stencil(ctx, body, d, radius, [0.3])
+                s = vo.RK45Solver(rhs, 0.0, 1.0e9, vo.Ensemble.from_host(ctx, u0[None, :]), 0.05, tableau=vo.ButcherTableu.builtin(tab))
+                s.run(max_calls=6)
+                outs.append(s.current()[1].to_host()[0])
+            finally:
+                os.environ.pop("VECODE_STENCIL_PLAIN", None)
+        assert np.array_equal(outs[0], outs[1]), (d, np.abs(outs[0] - outs[1]).max())
+        assert np.isfinite(outs[0]).all() and np.abs(outs[0] - u0).max() > 1e-6

@@ -134,13 +134,16 @@ std::string cu_msg(Driver* dr, CUresult e) {
 // ---- one compiled module -----------------------------------------------------------------------------------------
 enum { K_FIXED_STAGED, K_FIXED, K_CTL_STAGED_GEN, K_CTL_STAGED_L2, K_CTL2_STAGED, K_CTL, K_FIXED2_STAGED, K_SMALL_COUNT };
 enum { K_STAGE, K_STAGE_TAIL, K_STAGE_COUNT };
+// stencil modules: the two plain kernels, then the TMA-staged ones indexed by (tail, number of stage-derivative rows read)
+constexpr int K_STENCIL_TMA = 2, K_FN_MAX = 2 + 2 * 8;
+static_assert(K_FN_MAX >= K_SMALL_COUNT, "CustomModule::fn too small");
 constexpr int STAGE_MODULE = -1;  // `S` key of the stage-path module (it does not depend on the stage count)
 
 struct CustomModule {
     CUmodule mod = nullptr;
-    CUfunction fn[K_SMALL_COUNT] = {};
-    int bps[K_SMALL_COUNT] = {};  // resident CTAs per SM at the shared-memory size last queried
-    size_t bps_smem[K_SMALL_COUNT] = {};
+    CUfunction fn[K_FN_MAX] = {};
+    int bps[K_FN_MAX] = {};  // resident CTAs per SM at the shared-memory size last queried
+    size_t bps_smem[K_FN_MAX] = {};
 };
 
 std::string rtc_source(const vo_rhs_s* r, bool stage_module) {
@@ -163,7 +166,14 @@ std::string rtc_source(const vo_rhs_s* r, bool stage_module) {
 
 std::vector<std::string> kernel_names(int S, bool strict, bool stage_module, bool stencil = false) {
     const std::string st = strict ? "true" : "false", ss = std::to_string(S);
-    if (stencil) return {"stage_stencil_kernel<StencilCustom, " + st + ", false>", "stage_stencil_kernel<StencilCustom, " + st + ", true>"};
+    if (stencil) {
+        std::vector<std::string> v = {"stage_stencil_kernel<StencilCustom, " + st + ", false>", "stage_stencil_kernel<StencilCustom, " + st + ", true>"};
+        if (S == 1)  // `S` doubles as "with the TMA-staged kernels" for a stencil module (radius <= 4)
+            for (int tail = 0; tail < 2; ++tail)
+                for (int nk = 0; nk < 8; ++nk)
+                    v.push_back("stage_stencil_tma_kernel<StencilCustom, " + st + ", " + (tail ? "true" : "false") + ", " + std::to_string(nk) + ">");
+        return v;
+    }
     if (stage_module) return {"stage_pointwise_kernel<RhsCustom, " + st + ", false>", "stage_pointwise_kernel<RhsCustom, " + st + ", true>"};
     std::vector<std::string> v(K_SMALL_COUNT);
     v[K_FIXED_STAGED] = "rk_fixed_staged_kernel<RhsCustom, " + ss + ", " + st + ">";
@@ -227,7 +237,8 @@ int32_t rtc_compile(const std::string& src, const std::vector<std::string>& name
 
 int32_t compile_custom(const vo_rhs_s* r, int S, bool strict, std::vector<char>& cubin, std::vector<std::string>& lowered, std::string& log) {
     const bool stage_module = S == STAGE_MODULE;
-    return rtc_compile(rtc_source(r, stage_module), kernel_names(S, strict, stage_module, r->kind == VO_RHS_CUSTOM_STENCIL), strict, cubin, lowered, log);
+    const bool stencil = r->kind == VO_RHS_CUSTOM_STENCIL;
+    return rtc_compile(rtc_source(r, stage_module), kernel_names(stencil ? (r->radius <= 4 ? 1 : 0) : S, strict, stage_module, stencil), strict, cubin, lowered, log);
 }
 
 int module_key(int S, bool strict) { return (S + 1) * 2 + (strict ? 1 : 0); }
@@ -364,15 +375,47 @@ int32_t launch_stage_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, 
     return custom_launch(c, drv, m->fn[tail ? K_STAGE_TAIL : K_STAGE], (unsigned)ceil_div(N, 128), 128, 0, false, args);
 }
 
-// The stage path for a user stencil on one grid state (rk_stage_stencil.cuh): persistent CTAs over 256-point tiles.
+// The stage path for a user stencil on one grid state (rk_stage_stencil.cuh). Large even grids with radius <= 4 take the TMA-staged
+// kernel (the K's this launch reads compacted exactly as for the compiled-in heat equation, solver.cu: launch_heat_tma); everything
+// else the plain kernel with persistent CTAs over 256-point tiles.
 int32_t launch_stage_stencil_custom(vo_ctx c, vo_rhs_s* r, bool tail, const double* x0, int64_t d, const StageArgs& sa_in, const RhsParams& rp_in, double* k_out,
                                     double* nx, double* xe) {
     Driver* drv = nullptr;
     CustomModule* m = nullptr;
-    int32_t rc = get_module(r, STAGE_MODULE, c->arith == VO_ARITH_STRICT, &drv, &m);
+    const bool strict = c->arith == VO_ARITH_STRICT;
+    int32_t rc = get_module(r, STAGE_MODULE, strict, &drv, &m);
     if (rc != VO_OK) return rc;
     StageArgs sa = sa_in;
     RhsParams rp = rp_in;
+    const int S = sa.s;
+    if (r->radius <= 4 && d % 2 == 0 && d >= 4 * SX_TILE && S <= 8 && !getenv("VECODE_STENCIL_PLAIN")) {
+        StencilArgs ha;
+        std::memset(&ha, 0, sizeof ha);
+        ha.dt = sa.dt, ha.t_i = sa.t_i, ha.use_err = sa.use_err;
+        const int nload = tail ? S - 1 : sa.i;
+        int nk = 0;
+        for (int j = 0; j < nload; ++j) {
+            if (!(strict || tail || sa.a[j] != 0.0)) continue;  // FAST non-tail stages drop zero coefficients; STRICT keeps them, like the reference
+            ha.K[nk] = sa.K[j], ha.a[nk] = j < sa.i ? sa.a[j] : 0.0, ha.b[nk] = sa.b[j], ha.b_err[nk] = sa.b_err[j];
+            ++nk;
+        }
+        ha.nterm = (strict || tail) ? sa.i : nk;
+        ha.b_last = sa.b[S - 1], ha.b_err_last = sa.b_err[S - 1];
+        const int HL = (r->radius + 1) & ~1, bps = (nk <= 3 && r->radius <= 2) ? 2 : 1;
+        const size_t row_bytes = (size_t)(nk + 1) * (SX_TILE + 2 * HL) * sizeof(double);
+        ha.nst = (int)std::max<size_t>(2, std::min<size_t>(SX_STAGES_MAX, (size_t)(208 * 1024 / bps) / row_bytes));
+        const size_t smem = (size_t)ha.nst * row_bytes;
+        const int k = K_STENCIL_TMA + (tail ? 8 : 0) + nk;
+        if (m->bps_smem[k] < smem) {
+            CUresult e = drv->funcSetAttribute(m->fn[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 216 * 1024);
+            if (e != CUDA_SUCCESS) return vo_fail(c, VO_ERR_CUDA, "user stencil: shared-memory attribute: " + cu_msg(drv, e));
+            m->bps_smem[k] = 216 * 1024;
+        }
+        const int64_t tiles = ceil_div(d, SX_TILE);
+        const int64_t iters = ceil_div(tiles, (int64_t)c->sm_count * bps);
+        void* args[] = {&x0, &d, &ha, &rp, &k_out, &nx, &xe};
+        return custom_launch(c, drv, m->fn[k], (unsigned)ceil_div(tiles, iters), SX_THREADS, smem, false, args);
+    }
     void* args[] = {&x0, &d, &sa, &rp, &k_out, &nx, &xe};
     const int64_t tiles = ceil_div(d, ST_THREADS);
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)c->sm_count * 8);
