@@ -169,14 +169,18 @@ __global__ void __launch_bounds__(SX_THREADS, ((NK <= 3 && ST::R <= 2) ? 2 : 1))
         const int64_t cnt = min((int64_t)SX_TILE, d - base);
         double* dst = sb + (size_t)st * NR * ROW;
         pipe::mbar_expect_tx(&full[st], (uint32_t)(NR * (cnt + 2 * HL) * sizeof(double)));
-        const int64_t lh = base == 0 ? d - HL : base - HL, rh = base + cnt >= d ? 0 : base + cnt;
+        // periodic halos: the left one never straddles the end of the grid (base is 0 or >= HL); the right one does when fewer than HL
+        // points remain after the tile (HL = 4 with a two-point last tile), and is then copied in two pieces (all counts are even)
+        const int64_t lh = base == 0 ? d - HL : base - HL, after = base + cnt;
+        const int64_t r1 = after >= d ? 0 : min((int64_t)HL, d - after);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const double* src = r == 0 ? x0 : ha.K[r - 1];
             double* rd = dst + (size_t)r * ROW;
             pipe::bulk_g2s(rd, src + lh, HL * sizeof(double), &full[st]);
             pipe::bulk_g2s(rd + HL, src + base, (uint32_t)(cnt * sizeof(double)), &full[st]);
-            pipe::bulk_g2s(rd + HL + cnt, src + rh, HL * sizeof(double), &full[st]);
+            if (r1 > 0) pipe::bulk_g2s(rd + HL + cnt, src + after, (uint32_t)(r1 * sizeof(double)), &full[st]);
+            if (r1 < HL) pipe::bulk_g2s(rd + HL + cnt + r1, src, (uint32_t)((HL - r1) * sizeof(double)), &full[st]);
         }
     };
     if (threadIdx.x == 0)
