@@ -187,8 +187,39 @@ std::vector<std::string> kernel_names(int S, bool strict, bool stage_module, boo
 }
 
 // Source -> cubin. Needs no GPU. `lowered[i]` is the mangled name of names[i] ("" where names[i] is "").
+struct RtcCached {
+    std::vector<char> cubin;
+    std::vector<std::string> lowered;
+};
+int32_t rtc_compile_uncached(const std::string& src, const std::vector<std::string>& names, bool fmad_off, std::vector<char>& cubin,
+                             std::vector<std::string>& lowered, std::string& log);
+
+// Process-wide cache of compiled sources: a pipelined solve builds one handle per chunk from the same body, tests build many.
 int32_t rtc_compile(const std::string& src, const std::vector<std::string>& names, bool fmad_off, std::vector<char>& cubin,
                     std::vector<std::string>& lowered, std::string& log) {
+    static std::map<std::string, RtcCached> cache;
+    static std::mutex mu;
+    std::string key = fmad_off ? "S\n" : "F\n";
+    for (const std::string& n : names) key += n + "\n";
+    key += src;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            cubin = it->second.cubin, lowered = it->second.lowered;
+            return VO_OK;
+        }
+    }
+    const int32_t rc = rtc_compile_uncached(src, names, fmad_off, cubin, lowered, log);
+    if (rc == VO_OK) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (cache.size() < 256) cache[key] = RtcCached{cubin, lowered};
+    }
+    return rc;
+}
+
+int32_t rtc_compile_uncached(const std::string& src, const std::vector<std::string>& names, bool fmad_off, std::vector<char>& cubin,
+                             std::vector<std::string>& lowered, std::string& log) {
     Nvrtc* nv = nullptr;
     if (!nvrtc_load(&nv, log)) return VO_ERR_UNSUPPORTED;
     const char* hdr_text[N_HEADERS];
