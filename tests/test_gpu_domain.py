@@ -129,3 +129,22 @@ def test_adaptive_two_ranks_on_one_gpu(tmp_path):
     mp.spawn(_adaptive_worker, args=(2, port, (1 << 15) + 6, 2, str(tmp_path)), nprocs=2, join=True)
     assert bool(np.load(tmp_path / "same_events.npy")[0])
     assert np.abs(np.load(tmp_path / "full.npy") - np.load(tmp_path / "ref.npy")).max() <= 1e-12
+
+
+def test_slab_with_a_user_stencil_of_radius_two_bitwise(vo, ctx):
+    """A user stencil (vo_rhs_create_custom_stencil) in place of the compiled-in heat equation: ghost zones of k * s * R points, the
+    owned points of the slab equal the single-state solve bit for bit (position-independent body: a slab sees local indices)."""
+    d_total, k, R = (1 << 16) + 4, 2, 2
+    body = "du = (-u[0] + 16.0 * u[1] - 30.0 * u[2] + 16.0 * u[3] - u[4]) * (p[0] / 12.0);"
+    u0 = vo.workloads.heat_u0(d_total)
+    s = vo.RK45Solver(vo.Rhs.custom_stencil(ctx, body, d_total, R, [0.4]), 0.0, 1.0e9, vo.Ensemble.from_host(ctx, u0[None, :]), H_STEP,
+                      tableau=vo.ButcherTableu.builtin("RK4")).no_adaptive()
+    for _ in range(N_STEPS + 1):
+        s.step()
+    ref = s.current()[1].to_host()[0]
+    ds = vo.domain.HeatSlabSolver(ctx, d_total, lambda j: vo.workloads.heat_u0_at(j, d_total), 1.0, 0.0, 1.0e9, H_STEP, steps_per_exchange=k,
+                                  rhs_factory=lambda c, n: vo.Rhs.custom_stencil(c, body, n, R, [0.4]), radius=R)
+    assert ds.slab.halo == k * 4 * R
+    for _ in range(N_STEPS + 1):
+        ds.step()
+    assert np.array_equal(ds.local_interior(), ref)
