@@ -51,6 +51,44 @@ def main():
         assert tot["accepted"] == int(rs["accepted"].sum()) and tot["rejected"] == int(rs["rejected"].sum()) and tot["n_done"] == n
     else:
         assert got is None
+    # ---- one grid state over the two GPUs, ADAPTIVE, with the library's own all-reduce between the two halves of step_adaptive
+    # (vo_adaptive_try -> vo_group_allreduce -> vo_adaptive_handle: what a compiled host without torch.distributed does)
+    import math
+    d_total, k_ex = (1 << 15) + 6, 2
+    tab = vo.ButcherTableu.builtin("RKF45_REF")
+
+    def rough(j):
+        j = np.asarray(j)
+        return vo.workloads.heat_u0_at(j, d_total) + 0.25 * np.cos(np.pi * j) + 0.1 * np.sin(2.0 * np.pi * 17.0 * j / d_total)
+    ds = vo.domain.HeatSlabSolver(ctx, d_total, rough, 1.0, 0.0, 3.0, 0.01, tableau=tab, steps_per_exchange=k_ex, adaptive=True)
+    ds.with_tolerance(1e-6, 1e-6)
+    ds.solver.with_step_range(1e-6, 1.0).with_init_step(0.01)
+    events, H, m = [], ds.slab.halo, ds.slab.m
+    while True:
+        ds._refresh_ghosts_if_due()
+        acc, ev, done = ds.solver.adaptive_try(H, H + m)
+        if done is None:
+            tot_acc = float(g.allreduce([[acc]], "sum")[0, 0])  # NCCL inside libvecode_b200.so
+            st = ds.solver.adaptive_handle(math.sqrt(tot_acc))
+            if st.counts["Step"]:
+                ds._since_exchange += 1
+        else:
+            st = done
+        events.append([kk for kk in ("Step", "Chkpt", "Reject", "End") if st.counts[kk]][0])
+        if st.kind != "Ok":
+            break
+    full_grid = ds.gather()
+    if rank == 0:
+        rs_ = vo.RK45Solver(vo.Rhs(ctx, "HEAT1D", d_total, [1.0]), 0.0, 3.0, vo.Ensemble.from_host(ctx, rough(np.arange(d_total))[None, :]), 0.01).with_tolerance(1e-6, 1e-6)
+        rs_.with_step_range(1e-6, 1.0).with_init_step(0.01)
+        ref_events = []
+        while True:
+            st = rs_.step_adaptive()
+            ref_events.append([kk for kk in ("Step", "Chkpt", "Reject", "End") if st.counts[kk]][0])
+            if st.kind != "Ok":
+                break
+        assert events == ref_events and "Reject" in events, "adaptive slabs: the event sequence differs from the single-state solve"
+        assert np.abs(full_grid - rs_.current()[1].to_host()[0]).max() <= 1e-12
     dist.barrier()
     if rank == 0:
         open(sys.argv[1], "w").write("ok")
