@@ -176,6 +176,8 @@ def gather_states(local, n_total: int, device=None, root=None):
     pad[: local.shape[0]] = local
     as_real = pad.view(np.float64) if np.iscomplexobj(pad) else pad
     t = torch.from_numpy(as_real.copy())
+    if device is None and dist.get_backend() == "nccl":  # NCCL moves device memory: stage on this process's current GPU
+        device = torch.device("cuda", torch.cuda.current_device())
     if device is not None:
         t = t.to(device)
     if root is None:
