@@ -1266,7 +1266,7 @@ int32_t vo_solver_reset(vo_solver s, vo_ens x0) {
     if (r != VO_OK) return r;
     s->uniform = true, s->cst.live = false, s->prev_h_stale = false;
     s->u_t = s->t0, s->u_h = s->h_init, s->u_prev_h = s->h_init, s->u_tgt = 0, s->u_done = false;
-    s->u_accept = s->u_reject = 0, s->u_dx_norm = 0.0, s->n_done = 0;
+    s->u_accept = s->u_reject = 0, s->u_dx_norm = 0.0, s->n_done = 0, s->try_pending = false;
     VO_CUDA(s->ctx, cudaMemsetAsync(s->ev_dev, 0, sizeof(EvSlot) * VO_EV_SLOTS, s->ctx->stream));
     std::memset(&s->ev_seen, 0, sizeof s->ev_seen);
     return VO_OK;
