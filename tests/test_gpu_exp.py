@@ -504,3 +504,49 @@ def test_literal_magnus_norm_switch(vo, ctx, oracle):
     assert np.array_equal(d.stats()["accepted"], acc_literal) and not d.stats()["rejected"].any()
     cfm = vo.ExpCFMSolver(sp, gp, 0.0, 1.0, psi0, h, M_gen=2)
     assert vo._cabi.lib().vo_exp_set_literal_norm(cfm._h, 1) == vo._cabi.VO_ERR_STATE  # only the Magnus solver's norm() has the quirk
+
+
+def test_exp_golden_fixtures_on_the_gpu(vo, ctx):
+    """The committed known answers of the exponential integrators (tests/golden/exp_known_answers.json: both CPU restatements bit for
+    bit, map_exp pinned to a 50-digit sum) against the kernels: <= 1e-13 on the states after the fixture's steps, 5e-15 on map_exp."""
+    import importlib.util
+    import json
+    import os
+    import torch
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_golden_exp", os.path.join(here, "golden", "make_golden_exp.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    G = json.load(open(os.path.join(here, "golden", "exp_known_answers.json")))
+    s15 = np.sqrt(15.0) / 10.0
+    for key, e in G.items():
+        if key.startswith("_"):
+            continue
+        basis, gp, psi0 = mod.case(e["n"], e["M"], e["seed"])
+        want = np.array(e["psi"]).reshape(psi0.shape[0], e["n"], 2).view(np.complex128)[..., 0]
+        tf = e["h"] * e["steps"]
+        if e["scheme"] == "magnus42":
+            basis3, cs = vo.with_commutator_slot(basis[0], basis[1])
+            s = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis3, commutator_structure=cs), gp, 0.0, 1.0e9, psi0, e["h"], M_gen=2).no_adaptive()
+        elif e["scheme"] == "midpoint":
+            s = vo.MidpointExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp, 0.0, 1.0e9, psi0, e["h"])
+        elif e["scheme"] == "cfm_table":
+            s = vo.ExpCFMGeneralSolver(vo.DenseBasisSplit(ctx, basis), gp, 0.0, 1.0e9, psi0, e["h"], [0.5 - s15, 0.5, 0.5 + s15], vo.cfm_table("BLANES17_R4_J4")).no_adaptive()
+        else:
+            s = vo.ExpCFMSolver(vo.DenseBasisSplit(ctx, basis), gp, 0.0, 1.0e9, psi0, e["h"]).no_adaptive()
+        s.run(max_calls=e["steps"] + 1)
+        got = s.current()[1]
+        assert np.abs(got - want).max() <= 1e-13, (key, np.abs(got - want).max())
+        # map_exp of the first system with the generator at t = 0 scaled by h, against the committed 50-digit answer
+        M = basis.shape[0]
+        coef = np.zeros((1, M), dtype=complex)
+        coef[0, 0] = e["h"]
+        for m in range(1, M):
+            coef[0, m] = e["h"] * gp[0, m - 1, 0] * np.cos(gp[0, m - 1, 2])
+        sp = vo.DenseBasisSplit(ctx, basis)
+        x = torch.from_numpy(psi0[:1].view(np.float64).reshape(1, e["n"], 2).copy()).cuda()
+        y = torch.empty_like(x)
+        sp.map_exp(sp.exp(coef), x.data_ptr(), y.data_ptr())
+        torch.cuda.synchronize()
+        mp_ref = np.array(e["map_exp_mp"]).view(np.complex128)[:, 0]
+        assert np.abs(y.cpu().numpy().reshape(e["n"] * 2).view(np.complex128) - mp_ref).max() <= 5e-15, key
