@@ -501,8 +501,14 @@ def cpu_baseline(workload, budget_s=12.0):
         n = int(min(N_TRAJ, max(n, target / steps)))
     units, dt = cpu_run(workload, n, steps, threads)
     what = f"{n} grid points x {steps} RK4 steps" if workload == "heat_rk4" else f"{n} trajectories x {steps} calls of step()"
-    return {"value": units / dt, "unit": f"{WORKLOADS[name].unit_name}s/s", "cores": threads, "kind": "port",
-            "sample": f"{what}, one solver object per trajectory, un-fused LinearCombination passes ({dt:.1f} s)"}
+    out = {"value": units / dt, "unit": f"{WORKLOADS[name].unit_name}s/s", "cores": threads, "kind": "port",
+           "sample": f"{what}, one solver object per trajectory, un-fused LinearCombination passes ({dt:.1f} s)"}
+    if threads > 1:  # the reference itself is single-threaded: the same code on ONE core, on a 1/threads share of the sample
+        n1 = max(1, n // threads)
+        u1, d1 = cpu_run(workload, n1, steps, 1)
+        out["single_core_value"] = u1 / d1
+        out["single_core_sample"] = f"{n1} trajectories x {steps} calls of step() on one core ({d1:.1f} s)"
+    return out
 
 
 def run_reference(args, rank):
