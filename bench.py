@@ -432,7 +432,43 @@ class SchrodingerMagnusDense(SchrodingerCFM4):
         self.e_solver = self.vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0, self.psi0, 0.1, dense_commutator=True).no_adaptive()
 
 
-WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense)}
+class SchrodingerMagnusApplied(SchrodingerMagnusDense):
+    """The same problem with the commutator APPLIED inside the Taylor series (vo_exp_set_applied_commutator): Omega T = W1 T + b2 (L0 (L1 T) -
+    L1 (L0 T)), three passes over the shared basis per term on the tensor cores, no matrix formed per system."""
+    name = "schrodinger_magnus_applied"
+    label = ("config 5, generators not closed under commutation: Magnus-4 with the commutator applied by products inside the Taylor series "
+             "(never formed), 10^5 driven 64-level systems with three generator matrices, h = 0.1, fixed step")
+
+    def __init__(self, vo, ctx, rank, world, n_batches):
+        super().__init__(vo, ctx, rank, world, n_batches)
+        self.solver = vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1, group_similar=GROUP_SIMILAR, applied_commutator=True).no_adaptive()
+        self.solver.step()
+        # algorithmic FLOPs per trajectory-step: 3 passes x M (3 basis matrices) x 8 n^2 per Taylor term; the degree follows the bound
+        # ||Omega||_1 <= ||W1|| + 2 |b2| ||L0|| ||L1|| the kernel plans with (generator amplitudes as upper bounds of |g(t)|)
+        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
+        nl = norm1[0] + self.gp[:, 0, 0] * norm1[1] + self.gp[:, 1, 0] * norm1[2]
+        theta = 0.1 * nl + 2.0 * (0.01 * 0.144337567297406441127287195125) * nl * nl
+
+        def degree(th):
+            sq = max(1, int(np.ceil(th)))
+            x, term, k = th / sq, 1.0, 0
+            while k < 60:
+                k += 1
+                term = term * x / k
+                if term <= 1.1102230246251565e-16:
+                    break
+            return sq * k
+        self.m_star, self.theta = float(np.mean([degree(t) for t in theta[:: max(1, len(theta) // 512)]])), float(theta.max())
+        self.flops_per_unit = 3 * 3 * self.m_star * 8 * self.NDIM ** 2
+
+    def e2e_setup(self, group=None):
+        import torch
+        self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
+        self.pin_out = torch.empty_like(self.pin_in).pin_memory()
+        self.e_solver = self.vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0, self.psi0, 0.1, applied_commutator=True).no_adaptive()
+
+
+WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -555,7 +591,7 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
     """The `roofline` object of the dominant kernel from one timed region: algorithmic bytes (or FLOPs) per launch over the
     mean launch duration (CUDA events around the region, kernels back to back on the launching stream)."""
     kernel_ms = ms / max(launches, 1)
-    if W in (SchrodingerCFM4, SchrodingerMagnusDense):
+    if W in (SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied):
         p64 = os.path.join(ROOT, "profiles", "fp64_peaks.json")
         peak_tf, src = (json.load(open(p64))["dmma_tflops"], "measured by profiles/microbench/peaks.cu (profiles/fp64_peaks.json: dmma_tflops)") \
             if os.path.exists(p64) else (45.0, "nominal B200 FP64 tensor peak (no measured figure committed)")
@@ -565,6 +601,8 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
                 "kernel_us": kernel_ms * 1e3,
                 "note": ("FP64 tensor pipe (mma.sync DMMA): algorithmic FLOPs = E(2 exponentials) x m* x M(2 basis matrices) x 8 n^2 per trajectory-step"
                          if W is SchrodingerCFM4 else
+                         "FP64 tensor pipe: algorithmic FLOPs = 3 passes x m* x M(3 basis matrices) x 8 n^2 per trajectory-step (the commutator is applied, never formed)"
+                         if W is SchrodingerMagnusApplied else
                          "algorithmic FLOPs = 2 x 8 n^3 (the dense commutator, on the FP64 tensor pipe) + m* x 8 n^2 (Taylor series of exp(Omega) by matrix-vector "
                          "products, FP64 FMA pipe) per trajectory-step, against the DMMA peak")}
     bytes_per_launch = W.bytes_per_unit * (units_per_rank / max(launches, 1)) / events_per_launch
@@ -576,7 +614,7 @@ def roofline_of(W, w, units_per_rank, ms, launches, events_per_launch, peak, pea
 
 def n_batches_for(W, n_traj):
     """Independent batches rotated per GPU so that the working set is >= 3x the L2 (each launch then streams from HBM)."""
-    if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense):
+    if W in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied):
         return 1
     if os.environ.get("VECODE_BENCH_BATCHES"):  # experiment switch (e.g. 1 = L2-resident state): the reported line says so in config.l2
         return int(os.environ["VECODE_BENCH_BATCHES"])
@@ -911,6 +949,8 @@ def main():
             leg("heat_rk4_fused", HeatRK4Fused, "fast", 100)
         if W is not SchrodingerCFM4:
             leg("schrodinger_cfm4", SchrodingerCFM4, "fast", 10)
+        if W is not SchrodingerMagnusApplied:
+            leg("schrodinger_magnus_applied", SchrodingerMagnusApplied, "fast", 6)
         if W is not SchrodingerMagnusDense:
             leg("schrodinger_magnus_dense", SchrodingerMagnusDense, "fast", 4)
 
@@ -925,10 +965,10 @@ def main():
         line = {"metric": "ensemble trajectory-steps/sec", "value": value, "unit": f"{W.unit_name}s/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong" if W is HeatRK4DD else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD) else SchrodingerCFM4.N_SYS if W in (SchrodingerCFM4, SchrodingerMagnusDense) else N_TRAJ),
+                "config": {"workload": W.name, "what": W.label, "trajectories_per_gpu": (1 if W in (HeatRK4, HeatRK4Fused, HeatRK4DD) else SchrodingerCFM4.N_SYS if W in (SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied) else N_TRAJ),
                            "arith": args.arith, "events_per_launch": args.events_per_launch,
                            "l2": f"{n_batches} independent batches of {W.state_mb} MB rotated per GPU (> {L2_MB} MB L2), so each launch streams from HBM"
-                           if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
+                           if W not in (HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied) else ("state 512 MB per buffer > 126 MB L2" if W in (HeatRK4, HeatRK4Fused) else
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
                            "warmup_note": f"every batch touched once, then ~{SPIN_UP_MS:.0f} ms of the same launches and the {args.warmup} warm-up steps, all untimed, before the {args.steps} timed steps",

@@ -387,6 +387,12 @@ int32_t vo_exp_set_split_mask(vo_expsolver s, uint32_t a_mask);
  * n x n complex products per system and step — instead of expanding it through vo_split_set_commutator's structure tensor.
  * n % 8 == 0, n <= 64; compiled-in generator family only. */
 int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on);
+/* ... or never formed at all: with L0, L1 the generator at the two Gauss nodes, a Taylor term of exp(Omega) needs only
+ * Omega T = b1 (L0 + L1) T + b2 (L0 (L1 T) - L1 (L0 T)) — three passes over the shared basis per term, each M tile products on the
+ * tensor cores inside exp_step_kernel (the same machinery as the commutator-free schemes: 16 systems per tile, basis resident in
+ * shared memory). No closure under commutation assumed, no structure tensor, no n x n matrix per system; works with a run-time
+ * compiled generator. About 2.5x the throughput of the dense commutator on config 5's shape. */
+int32_t vo_exp_set_applied_commutator(vo_expsolver s, int32_t on);
 /* MagnusExpLinearSolver::norm AS WRITTEN (exp/magnus.rs:274-276): it takes the norm of adaptive_dat.dx, a clone of x0 that
  * try_step never writes (the embedded error goes to self.x_err, magnus.rs:249-250), so the controller sees the constant ||x0||:
  * with rtol <= ||x0|| every attempt is rejected, with rtol > ||x0|| every attempt is accepted and h grows by

@@ -438,15 +438,19 @@ def test_magnus_with_dense_commutator(vo, ctx, oracle):
     basis3, cs = vo.with_commutator_slot(B0, B1)
     a = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis3, commutator_structure=cs), gp, 0.0, 1.0, psi0, h, M_gen=2).no_adaptive()
     b = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, dense_commutator=True).no_adaptive()
-    a.run(), b.run()
+    c = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, applied_commutator=True).no_adaptive()
+    a.run(), b.run(), c.run()
     assert np.abs(a.current()[1] - b.current()[1]).max() <= 1e-12
+    assert np.abs(a.current()[1] - c.current()[1]).max() <= 1e-12  # the commutator applied by products inside the Taylor series, never formed
     ref = oracle.exp_ensemble("magnus42", basis3, gp, psi0, 0.0, 1.0, h, M_gen=2, cs=cs, no_adaptive=True)
-    assert np.abs(b.current()[1] - ref["psi"]).max() <= 1e-12
+    assert np.abs(b.current()[1] - ref["psi"]).max() <= 1e-12 and np.abs(c.current()[1] - ref["psi"]).max() <= 1e-12
     a = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis3, commutator_structure=cs), gp, 0.0, 1.0, psi0, h, M_gen=2).with_tolerance(1e-7, 1e-7)
     b = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, dense_commutator=True).with_tolerance(1e-7, 1e-7)
-    a.run(adaptive=True), b.run(adaptive=True)
+    c = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, np.stack([B0, B1])), gp, 0.0, 1.0, psi0, h, applied_commutator=True).with_tolerance(1e-7, 1e-7)
+    a.run(adaptive=True), b.run(adaptive=True), c.run(adaptive=True)
     assert np.array_equal(a.stats()["accepted"], b.stats()["accepted"]) and np.array_equal(a.stats()["rejected"], b.stats()["rejected"])
-    assert np.abs(a.current()[1] - b.current()[1]).max() <= 1e-10
+    assert np.array_equal(a.stats()["accepted"], c.stats()["accepted"]) and np.array_equal(a.stats()["rejected"], c.stats()["rejected"])
+    assert np.abs(a.current()[1] - b.current()[1]).max() <= 1e-10 and np.abs(a.current()[1] - c.current()[1]).max() <= 1e-10
     # (ii) three generators, not closed under commutation
     rng = np.random.default_rng(12)
     G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
@@ -550,3 +554,47 @@ def test_exp_golden_fixtures_on_the_gpu(vo, ctx):
         torch.cuda.synchronize()
         mp_ref = np.array(e["map_exp_mp"]).view(np.complex128)[:, 0]
         assert np.abs(y.cpu().numpy().reshape(e["n"] * 2).view(np.complex128) - mp_ref).max() <= 5e-15, key
+
+
+@pytest.mark.parametrize("n", [16, 64])
+def test_magnus_with_applied_commutator_on_generators_not_closed_under_commutation(vo, ctx, n):
+    """Three generator matrices whose commutators leave their span, large steps (several sub-steps of the Taylor series): the
+    commutator applied by products inside exp_step_kernel (vo_exp_set_applied_commutator) against the per-system dense commutator
+    (vo_exp_set_dense_commutator) and against a dense restatement of magnus_42 with scipy expm; a run-time compiled generator too."""
+    from scipy.linalg import expm
+    N, h = 21, 0.35
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    rng = np.random.default_rng(12)
+    G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    B2 = -1j * (G + G.conj().T) / (2 * np.sqrt(n))
+    gp3 = np.concatenate([gp, gp * np.array([0.6, 1.7, 1.0]) + np.array([0.0, 0.0, 0.4])], axis=1)
+    basis = np.stack([B0, B1, B2])
+    a = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp3, 0.0, 1.05, psi0, h, applied_commutator=True).no_adaptive()
+    d = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp3, 0.0, 1.05, psi0, h, dense_commutator=True).no_adaptive()
+    assert a.run().kind == "Done" and d.run().kind == "Done"
+    got = a.current()[1]
+    assert np.abs(got - d.current()[1]).max() <= 1e-12
+    assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() <= 1e-12
+
+    def L(i, t):
+        return B0 + gp3[i, 0, 0] * np.cos(gp3[i, 0, 1] * t + gp3[i, 0, 2]) * B1 + gp3[i, 1, 0] * np.cos(gp3[i, 1, 1] * t + gp3[i, 1, 2]) * B2
+    c_mid = 0.288675134594812882254574390251
+    for i in range(0, N, 5):
+        x, t = psi0[i].copy(), 0.0
+        for dt in (h, h, h):
+            l0, l1 = L(i, t + dt / 2 - c_mid * dt), L(i, t + dt / 2 + c_mid * dt)
+            om = (l0 + l1) * (dt / 2) + (l0 @ l1 - l1 @ l0) * (dt * dt * -0.144337567297406441127287195125)
+            x, t = expm(om) @ x, t + dt
+        assert np.abs(got[i] - x).max() <= 1e-12, (i, np.abs(got[i] - x).max())
+    # adaptive: same accept / reject decisions as the dense route
+    a = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp3, 0.0, 1.0, psi0, 0.2, applied_commutator=True).with_tolerance(1e-6, 1e-6)
+    d = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp3, 0.0, 1.0, psi0, 0.2, dense_commutator=True).with_tolerance(1e-6, 1e-6)
+    a.run(adaptive=True), d.run(adaptive=True)
+    assert np.array_equal(a.stats()["accepted"], d.stats()["accepted"]) and np.array_equal(a.stats()["rejected"], d.stats()["rejected"])
+    assert np.abs(a.current()[1] - d.current()[1]).max() <= 1e-10
+    if n == 16:  # with the user's generator compiled at run time
+        body = "g[1] = p[0] * cos(p[1] * t + p[2]); g[2] = p[3] * cos(p[4] * t + p[5]);"
+        u = vo.MagnusExpLinearSolver(vo.DenseBasisSplit(ctx, basis), gp3, 0.0, 1.05, psi0, h, applied_commutator=True).no_adaptive()
+        u.set_generator(body)
+        u.run()
+        assert np.abs(u.current()[1] - got).max() <= 1e-13

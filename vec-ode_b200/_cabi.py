@@ -154,6 +154,7 @@ SIGNATURES = {
     "vo_dense_map_exp": (_i32, [_vp, _vp, _vp, _vp]),
     "vo_dense_commutator": (_i32, [_vp, _vp, _vp, _vp]),
     "vo_exp_set_dense_commutator": (_i32, [_vp, _i32]),
+    "vo_exp_set_applied_commutator": (_i32, [_vp, _i32]),
     "vo_exp_set_literal_norm": (_i32, [_vp, _i32]),
     "vo_exp_set_split_mask": (_i32, [_vp, C.c_uint32]),
     "vo_exp_set_cfm_tables": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32]),

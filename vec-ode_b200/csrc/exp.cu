@@ -58,6 +58,7 @@ struct vo_expsolver_s {
     std::vector<int64_t> perm_host;
     double2* stage = nullptr;    // [N][n] staging for the reordering copies
     int literal_norm = 0;        // vo_exp_set_literal_norm: MagnusExpLinearSolver::norm as written (magnus.rs:274-276)
+    int applied_comm = 0;        // vo_exp_set_applied_commutator: magnus_42's commutator applied by products inside the Taylor series, never formed
     int dense_comm = 0;          // vo_exp_set_dense_commutator: magnus_42 forms [L0, L1] densely per system (no structure tensor needed)
     void* gen_module = nullptr;  // vo_exp_set_generator: run-time compiled exp_step_kernel with the user's generator
     void* gen_fn = nullptr;
@@ -256,8 +257,8 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     const bool tables = s->scheme == VO_EXP_CFM4 || s->scheme == VO_EXP_CFM_TABLE || s->scheme == VO_EXP_SPLIT_CFM;
     if (tables && s->n_rows < 1) return vo_fail(c, VO_ERR_STATE, "exp: the scheme's tables have not been set (vo_exp_set_cfm_tables / vo_exp_set_split_cfm_tables)");
     if (adaptive && tables && s->n_rows_err < 1) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // alph_err is None (cfm.rs:214-222)
-    if (s->scheme == VO_EXP_MAGNUS42 && !s->sp->has_cs && !s->dense_comm)
-        return vo_fail(c, VO_ERR_BAD_ARG, "Magnus needs a Commutator (exp/mod.rs:47-54): vo_split_set_commutator for a basis closed under commutation, or vo_exp_set_dense_commutator");
+    if (s->scheme == VO_EXP_MAGNUS42 && !s->sp->has_cs && !s->dense_comm && !s->applied_comm)
+        return vo_fail(c, VO_ERR_BAD_ARG, "Magnus needs a Commutator (exp/mod.rs:47-54): vo_split_set_commutator for a basis closed under commutation, vo_exp_set_applied_commutator or vo_exp_set_dense_commutator");
     ExpKP kp = make_kp(s->sp, 0);
     kp.M_gen = s->M_gen, kp.scheme = s->scheme, kp.adaptive = adaptive ? 1 : 0;
     kp.want_err = (s->want_err && adaptive) ? 1 : 0;  // the embedded solution only feeds the controller
@@ -265,6 +266,7 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     kp.rtol = s->rtol, kp.alpha = s->alpha, kp.pw = s->pw, kp.min_dt = s->min_dt, kp.max_dt = s->max_dt;
     kp.pw_is_third = s->pw == 1.0 / 3.0;
     kp.literal_norm = (s->literal_norm && adaptive) ? 1 : 0;
+    kp.applied_comm = (s->scheme == VO_EXP_MAGNUS42 && s->applied_comm) ? 1 : 0;
     kp.split_mask = s->split_mask;
     kp.n_nodes = s->n_nodes, kp.n_rows = s->n_rows, kp.n_rows_err = s->n_rows_err;
     std::memcpy(kp.tab_c, s->tab_c, sizeof kp.tab_c), std::memcpy(kp.tab_alpha, s->tab_alpha, sizeof kp.tab_alpha);
@@ -820,6 +822,14 @@ int32_t vo_dense_commutator(vo_split sp, vo_ens La, vo_ens Lb, vo_ens out) {  //
     VO_DENSE_DISPATCH(nb, VO_CALL)
 #undef VO_CALL
     VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_exp_set_applied_commutator(vo_expsolver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    if (on && s->scheme != VO_EXP_MAGNUS42) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_applied_commutator: only the Magnus solver takes a commutator");
+    if (on && s->dense_comm) return vo_fail(s->ctx, VO_ERR_STATE, "vo_exp_set_applied_commutator: the dense commutator is already selected");
+    s->applied_comm = on ? 1 : 0;
     return VO_OK;
 }
 

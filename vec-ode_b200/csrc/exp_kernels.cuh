@@ -13,6 +13,7 @@
 struct ExpKP {
     int n, M, M_gen, scheme, adaptive, want_err, taylor_deg, mode;  // mode 0: solver event, 1: bare map_exp
     int pw_is_third, count_events;
+    int applied_comm;     // vo_exp_set_applied_commutator: magnus_42's commutator applied to the state by products, never formed (no structure tensor)
     int literal_norm;     // vo_exp_set_literal_norm: the controller reads ca.dx_norm (= ||x0||, never rewritten) instead of ||x_err||, magnus.rs:274-276
     int nseq;             // mode 1: exponentials applied one after the other, coefficient sets [nseq][N][M]
     unsigned split_mask;  // VO_EXP_SPLIT_MIDPOINT: bit m set <=> basis matrix m belongs to split A
@@ -164,6 +165,139 @@ __device__ __forceinline__ void map_exp_tile(const double* __restrict__ sB, doub
     }
 }
 
+// W_m = B_m T for every basis matrix, T the tile of column vectors held in C-fragment layout (tr, ti): the body of one Taylor term
+// of map_exp_tile as a function. Publishes T to the term buffer, one block barrier, NK k-steps of 8 M DMMAs.
+template <int NDIM, int M, int TB>
+__device__ __forceinline__ void basis_apply(const double* __restrict__ sB, double* __restrict__ sT, int& buf, const double (&tr)[2][2], const double (&ti)[2][2],
+                                            double (&Wr)[M][2][2], double (&Wi)[M][2][2]) {
+    using G = Geo<NDIM, M, TB>;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int w = wi % G::NW, cg = wi / G::NW;
+    const int row = 8 * w + (lane >> 2);
+    if (G::NBUF == 1) __syncthreads();
+    double* Tr = sT + (size_t)buf * 2 * TB * G::LDT;
+    double* Ti = Tr + TB * G::LDT;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
+            Tr[col * G::LDT + row] = tr[j][q], Ti[col * G::LDT + row] = ti[j][q];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Wr[m][j][0] = Wr[m][j][1] = Wi[m][j][0] = Wi[m][j][1] = 0.0;
+    const double* bA = sB + ((size_t)w * G::NK) * 32 + lane;
+    const double* bX = Tr + (16 * cg + (lane >> 2)) * G::LDT + (lane & 3);
+#pragma unroll 4
+    for (int kk = 0; kk < G::NK; ++kk) {
+        double fr[2], fi[2], nfi[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            fr[j] = bX[8 * j * G::LDT + 4 * kk];
+            fi[j] = bX[TB * G::LDT + 8 * j * G::LDT + 4 * kk];
+            nfi[j] = -fi[j];
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const double a_re = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
+            const double a_im = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                dmma(Wr[m][j][0], Wr[m][j][1], a_re, fr[j]);
+                dmma(Wr[m][j][0], Wr[m][j][1], a_im, nfi[j]);
+                dmma(Wi[m][j][0], Wi[m][j][1], a_im, fr[j]);
+                dmma(Wi[m][j][0], Wi[m][j][1], a_re, fi[j]);
+            }
+        }
+    }
+    if (G::NBUF == 2) buf ^= 1;
+}
+
+// x <- exp(Omega) x for magnus_42 (exp/magnus.rs:28-83) WITHOUT forming the commutator: with L0, L1 the generator at the two Gauss
+// nodes, Omega = W1 + b2 [L0, L1], W1 = b1 (L0 + L1), and a Taylor term needs only Omega T = W1 T + b2 (L0 (L1 T) - L1 (L0 T)): three
+// passes over the shared basis per term (T; L1 T; L0 T), each M tile products on the tensor cores, combined with the per-system REAL
+// coefficients of L0, L1 and W1. Nothing about closure under commutation is assumed and no n x n matrix is formed per system.
+// sW1 / sL0 / sL1: coefficient slots [M][TB] (imaginary parts ignored: the generator coefficients are real), sDt: the step per system.
+template <int NDIM, int M, int TB>
+__device__ __forceinline__ void map_exp_tile_comm(const double* __restrict__ sB, double* __restrict__ sT, const double2* __restrict__ sW1,
+                                                  const double2* __restrict__ sL0, const double2* __restrict__ sL1, const double* __restrict__ sDt, int sq, int deg,
+                                                  double (&xr)[2][2], double (&xi)[2][2], int& buf) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int cg = wi / Geo<NDIM, M, TB>::NW;
+    const double inv_sq = 1.0 / sq;
+    int col[2][2];
+    double b2[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            col[j][q] = 16 * cg + 8 * j + 2 * (lane & 3) + q;
+            const double dt = sDt[col[j][q]];
+            b2[j][q] = dt * dt * -0.144337567297406441127287195125 * inv_sq;  // magnus.rs:41 (b2 = -sqrt(3)/12 dt^2), per sub-step
+        }
+    for (int rep = 0; rep < sq; ++rep) {
+        double ar[2][2], ai[2][2], tr[2][2], ti[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) ar[j][q] = tr[j][q] = xr[j][q], ai[j][q] = ti[j][q] = xi[j][q];
+        for (int k = 1; k <= deg; ++k) {
+            double Wr[M][2][2], Wi[M][2][2];
+            double lr[2][2], li[2][2], u0r[2][2], u0i[2][2], u1r[2][2], u1i[2][2];
+            basis_apply<NDIM, M, TB>(sB, sT, buf, tr, ti, Wr, Wi);  // W_m = B_m T
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double a = 0.0, b = 0.0, c = 0.0, d = 0.0, e = 0.0, f = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const double w1 = sW1[m * TB + col[j][q]].x, l0 = sL0[m * TB + col[j][q]].x, l1 = sL1[m * TB + col[j][q]].x;
+                        a += w1 * Wr[m][j][q], b += w1 * Wi[m][j][q];
+                        c += l0 * Wr[m][j][q], d += l0 * Wi[m][j][q];
+                        e += l1 * Wr[m][j][q], f += l1 * Wi[m][j][q];
+                    }
+                    lr[j][q] = a * inv_sq, li[j][q] = b * inv_sq, u0r[j][q] = c, u0i[j][q] = d, u1r[j][q] = e, u1i[j][q] = f;
+                }
+            basis_apply<NDIM, M, TB>(sB, sT, buf, u1r, u1i, Wr, Wi);  // B_m (L1 T)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double c = 0.0, d = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const double l0 = sL0[m * TB + col[j][q]].x;
+                        c += l0 * Wr[m][j][q], d += l0 * Wi[m][j][q];
+                    }
+                    lr[j][q] += b2[j][q] * c, li[j][q] += b2[j][q] * d;  // + b2 L0 L1 T
+                }
+            basis_apply<NDIM, M, TB>(sB, sT, buf, u0r, u0i, Wr, Wi);  // B_m (L0 T)
+            const double ik = 1.0 / k;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double e = 0.0, f = 0.0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const double l1 = sL1[m * TB + col[j][q]].x;
+                        e += l1 * Wr[m][j][q], f += l1 * Wi[m][j][q];
+                    }
+                    tr[j][q] = (lr[j][q] - b2[j][q] * e) * ik, ti[j][q] = (li[j][q] - b2[j][q] * f) * ik;  // - b2 L1 L0 T, then / k
+                    ar[j][q] += tr[j][q], ai[j][q] += ti[j][q];
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) xr[j][q] = ar[j][q], xi[j][q] = ai[j][q];
+    }
+}
+
 // generator family: L(t) = B_0 + sum_{m=1}^{M_gen-1} amp_m cos(omega_m t + phase_m) B_m ; coefficients beyond M_gen are 0.
 // The generator closures of the reference (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32) are a functor GEN with this
 // shape; GenCos is the compiled-in family, a user-defined one is compiled at run time (vo_exp_set_generator).
@@ -218,7 +352,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             int evk = 255;  // not live
             double dt = 0.0;
             auto put = [&](int e, int m, double re, double im) { sCoef[(e * M + m) * TB + s] = make_double2(re, im); };
-            for (int e = 0; e < nexp; ++e)
+            for (int e = 0; e < (kp.applied_comm ? 4 : nexp); ++e)
 #pragma unroll
                 for (int m = 0; m < M; ++m) put(e, m, 0.0, 0.0);
             if (sys < kp.N) {
@@ -303,8 +437,9 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
 #pragma unroll
                                 for (int m = 0; m < M; ++m) {
                                     const double w1 = (l0[m] + l1[m]) * b1;
-                                    put(0, m, w1 + w2[m] * b2, 0.0);  // u = exp(w1 + w2)
+                                    put(0, m, kp.applied_comm ? w1 : w1 + w2[m] * b2, 0.0);  // u = exp(w1 + w2) (applied: w2 never formed)
                                     if (nerr) put(1, m, w1, 0.0);     // u1 = exp(w1), the 2nd-order embedded solution
+                                    if (kp.applied_comm) put(2, m, l0[m], 0.0), put(3, m, l1[m], 0.0);
                                 }
                             }
                         }
@@ -320,6 +455,12 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                     th += hypot(c.x, c.y) * kp.norm1[m];
                 }
                 sTheta[e * TB + s] = evk == VO_EV_STEP ? th : 0.0;
+            }
+            if (kp.applied_comm && kp.scheme == VO_EXP_MAGNUS42 && kp.mode == 0 && evk == VO_EV_STEP) {  // ||Omega||_1 <= ||W1|| + 2 |b2| ||L0|| ||L1||
+                double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) n0 += fabs(sCoef[(2 * M + m) * TB + s].x) * kp.norm1[m], n1 += fabs(sCoef[(3 * M + m) * TB + s].x) * kp.norm1[m];
+                sTheta[s] += 2.0 * (dt * dt * 0.144337567297406441127287195125) * n0 * n1;
             }
         }
         __syncthreads();
@@ -349,7 +490,10 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                     x0r[j][q] = xfr[j][q] = v.x, x0i[j][q] = xfi[j][q] = v.y;
                     xer[j][q] = xei[j][q] = 0.0;
                 }
-            for (int e = 0; e < nbase; ++e) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xfr, xfi, buf);
+            if (kp.applied_comm && kp.scheme == VO_EXP_MAGNUS42 && kp.mode == 0)
+                map_exp_tile_comm<NDIM, M, TB>(sB, sT, sCoef, sCoef + 2 * M * TB, sCoef + 3 * M * TB, sDt, sPlan[0], sPlan[1], xfr, xfi, buf);
+            else
+                for (int e = 0; e < nbase; ++e) map_exp_tile<NDIM, M, TB>(sB, sT, sCoef + e * M * TB, sPlan[2 * e], sPlan[2 * e + 1], xfr, xfi, buf);
             for (int q = 1; kp.mode == 1 && q < kp.nseq; ++q) {  // vo_map_exp_seq: the next exponential of the composition
                 __syncthreads();
                 if (threadIdx.x < TB) {

@@ -307,13 +307,17 @@ class ExpCFMGeneralSolver(_ExpSolver):
 
 class MagnusExpLinearSolver(_ExpSolver):
     """exp/magnus.rs:151-285. `dense_commutator=True`: commutator(l0, l1) (magnus.rs:55) is formed densely per system on the
-    tensor cores, so the generators need not be closed under commutation on the shared basis (vo_exp_set_dense_commutator)."""
+    tensor cores, so the generators need not be closed under commutation on the shared basis (vo_exp_set_dense_commutator).
+    `applied_commutator=True`: the commutator is applied to the state by products inside the Taylor series and never formed
+    (vo_exp_set_applied_commutator): no closure assumed either, and the work stays in the tiled shared-basis kernel."""
     SCHEME = "magnus42"
 
-    def __init__(self, sp, gp, t0, tf, psi0, h, M_gen=None, group_similar=False, dense_commutator=False):
+    def __init__(self, sp, gp, t0, tf, psi0, h, M_gen=None, group_similar=False, dense_commutator=False, applied_commutator=False):
         super().__init__(sp, gp, t0, tf, psi0, h, M_gen, group_similar)
         if dense_commutator:
             check(lib().vo_exp_set_dense_commutator(self._h, 1), self.ctx._h)
+        if applied_commutator:  # Omega T = W1 T + b2 (L0 (L1 T) - L1 (L0 T)) inside the Taylor series: the commutator is never formed
+            check(lib().vo_exp_set_applied_commutator(self._h, 1), self.ctx._h)
 
     def literal_norm(self, on: bool = True):
         """The reference's `norm()` as written (magnus.rs:274-276): the controller sees ||x0||, not the embedded error
