@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 N_TRAJ = 1_000_000
 GROUP_SIMILAR = os.environ.get("VECODE_BENCH_GROUP", "1") != "0"  # schrodinger_cfm4: tiles of systems with similar drive amplitude
+DYN_GROUP = os.environ.get("VECODE_BENCH_DYNGROUP", "1") != "0"  # ... re-sorted by the norm bound of the coming step before every event (vo_exp_set_dynamic_grouping)
 DD_K = int(os.environ.get("VECODE_BENCH_DD_K", "4"))  # heat_rk4_dd: RK steps between ghost refreshes (ghost zone = 4 * DD_K points per side)
 E2E_PARTS = int(os.environ.get("VECODE_BENCH_E2E_PARTS", "4"))  # chunks of the e2e solve (vec-ode_b200/pipeline.py); 1 = one solver
 L2_MB = 126
@@ -323,6 +324,65 @@ class HeatRK4DD:
         return float(n_steps) * self.e_ds.slab.m, self.pin_in.numel() * 8, self.pin_out.numel() * 8
 
 
+# ---- algorithmic Taylor degrees of the exponential integrators, exactly as the kernels plan them ------------------------------------
+def _plan_terms(theta):
+    """sub-steps x degree of the scaled Taylor series at theta = ||L||_1 (exp_kernels.cuh: taylor_plan), vectorised"""
+    theta = np.asarray(theta, dtype=np.float64)
+    sq = np.where(theta > 1.0, np.ceil(theta), 1.0)
+    x = theta / sq
+    term, deg, done = np.ones_like(x), np.zeros_like(x), np.zeros(x.shape, dtype=bool)
+    for k in range(1, 61):
+        term = np.where(done, term, term * x / k)
+        deg = np.where(done, deg, k)
+        done |= term <= 1.1102230246251565e-16
+    return sq * deg
+
+
+def exp_algorithmic_terms(scheme, basis, gp, h, n_sys=512, n_times=48, t_max=20.0):
+    """Mean number of Taylor terms per exponential-application that ONE system needs (its own theta, not its tile's), averaged over a
+    sample of systems and of step times t in [0, t_max), with the generator evaluated like the kernels do — the `m*` of SURVEY.md §8(d).
+    Returns (terms per trajectory-step summed over the exponentials of a step, largest theta)."""
+    rng = np.random.default_rng(5)
+    idx = np.linspace(0, gp.shape[0] - 1, n_sys).astype(np.int64)
+    t = rng.uniform(0.0, t_max, n_times)[None, :]                     # [1][T]
+    g = gp[idx]                                                       # [S][M-1][3]
+    norm1 = np.array([np.abs(b).sum(axis=0).max() for b in basis])    # induced 1-norms, as vo_split_basis_create computes them
+    M = basis.shape[0]
+
+    def gen(tt):  # [S][T][M] real coefficients of L(t) = B_0 + sum_m g_m(t) B_m
+        out = np.ones(g.shape[:1] + tt.shape[1:] + (M,))
+        for m in range(1, M):
+            out[..., m] = g[:, m - 1, 0, None] * np.cos(g[:, m - 1, 1, None] * tt + g[:, m - 1, 2, None])
+        return out
+    if scheme == "cfm4":  # cfm_general with the tables of dat/mod.rs:4, 67-74: two exponentials per step
+        c = (0.21132486540518711775, 0.78867513459481288225)
+        alpha = ((0.53867513459481288225, -0.038675134594812882255), (-0.038675134594812882255, 0.53867513459481288225))
+        v = [gen(t + cq * h) for cq in c]
+        terms, thmax = 0.0, 0.0
+        for row in alpha:
+            k = (row[0] * v[0] + row[1] * v[1]) * h
+            th = (np.abs(k) * norm1).sum(axis=-1)
+            terms, thmax = terms + _plan_terms(th).mean(), max(thmax, float(th.max()))
+        return float(terms), thmax
+    c_mid, b1, b2 = 0.288675134594812882254574390251, h * 0.5, h * h * 0.144337567297406441127287195125
+    l0, l1 = gen(t + b1 - c_mid * h), gen(t + b1 + c_mid * h)
+    if scheme == "magnus_applied":  # theta bound of exp_step_kernel: ||W1|| + 2 |b2| ||L0|| ||L1||
+        th = (np.abs((l0 + l1) * b1) * norm1).sum(axis=-1) + 2.0 * b2 * (np.abs(l0) * norm1).sum(axis=-1) * (np.abs(l1) * norm1).sum(axis=-1)
+        return float(_plan_terms(th).mean()), float(th.max())
+    if scheme == "magnus_dense":    # magnus_dense_kernel takes ||Omega||_1 of the matrix itself: form it for a smaller sample
+        ths = []
+        for si in range(0, l0.shape[0], 8):
+            for ti in range(0, l0.shape[1], 6):
+                L0 = np.tensordot(l0[si, ti], basis, axes=1)
+                L1 = np.tensordot(l1[si, ti], basis, axes=1)
+                om = (L0 + L1) * b1 - b2 * (L0 @ L1 - L1 @ L0)
+                ths.append(np.abs(om).sum(axis=0).max())
+        ths = np.array(ths)
+        return float(_plan_terms(ths).mean()), float(ths.max())
+    raise KeyError(scheme)
+
+
+
 class SchrodingerCFM4:
     name = "schrodinger_cfm4"
     label = ("config 5: commutator-free Magnus CFM4, 10^5 driven 64-level Schroedinger systems (complex f64) per GPU, h = 0.1, "
@@ -342,29 +402,17 @@ class SchrodingerCFM4:
         self.psi0 = np.zeros((self.N_SYS, self.NDIM), dtype=np.complex128)
         self.psi0[:, 0] = 1.0
         self.solver = vo.ExpCFMSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1, group_similar=GROUP_SIMILAR).no_adaptive()
+        if DYN_GROUP:
+            self.solver.dynamic_grouping()
         self.solver.step()  # Chkpt at t0
         self.solvers = []
-        # algorithmic FLOPs per trajectory-step: E * m* * M * 8 n^2 with m* from theta = ||L h||_1 of this config
-        # with m* the Taylor degree at theta_i = ||L_i h||_1 (bounded with |cos| <= 1), averaged over the systems: the
-        # kernel plans per 16-system tile with the tile's largest theta, so it never executes fewer terms than this.
-        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
-        a = 0.53867513459481288225 + 0.038675134594812882255
-        theta = 0.1 * a * (norm1[0] + self.gp[:, 0, 0] * norm1[1])
-
-        def degree(th):
-            sq = max(1, int(np.ceil(th)))
-            x, term, k = th / sq, 1.0, 0
-            while k < 60:
-                k += 1
-                term = term * x / k
-                if term <= 1.1102230246251565e-16:
-                    break
-            return sq * k
-
-        degs = np.array([degree(t) for t in np.unique(np.round(theta, 3))])
-        cnt = np.array([np.sum(np.round(theta, 3) == t) for t in np.unique(np.round(theta, 3))])
-        self.m_star, self.theta = float((degs * cnt).sum() / cnt.sum()), float(theta.max())
-        self.flops_per_unit = 2 * self.m_star * 2 * 8 * self.NDIM ** 2
+        # algorithmic FLOPs per trajectory-step: sum over the step's E = 2 exponentials of m*_e x M x 8 n^2, with m*_e the
+        # Taylor degree ONE system needs at its own theta = ||k_e||_1 (generator evaluated at the Gauss nodes like the kernel does),
+        # averaged over systems and step times. The kernel plans per 16-system tile with the tile's largest theta, so it executes
+        # at least this many terms.
+        terms, self.theta = exp_algorithmic_terms("cfm4", self.basis, self.gp, 0.1)
+        self.m_star = terms / 2.0
+        self.flops_per_unit = terms * 2 * 8 * self.NDIM ** 2
         self.bytes_per_unit = None
 
     def run_steps(self, k):
@@ -378,6 +426,8 @@ class SchrodingerCFM4:
         self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
         self.e_solver = self.vo.ExpCFMSolver(self.sp, self.gp, 0.0, 10.0, self.psi0, 0.1, group_similar=GROUP_SIMILAR).no_adaptive()
+        if DYN_GROUP:
+            self.e_solver.dynamic_grouping()
 
     def e2e_step(self):
         self.e_solver.reset(self.pin_in.numpy().view(np.complex128))  # H2D of the initial states
@@ -408,20 +458,8 @@ class SchrodingerMagnusDense(SchrodingerCFM4):
         self.solver.step()  # Chkpt at t0
         self.solvers = []
         # algorithmic FLOPs per trajectory-step: the commutator (2 complex n x n products = 2 * 8 n^3) on the tensor cores, plus the Taylor
-        # series of exp(Omega) applied by matrix-vector products (m* terms of 8 n^2; m* at theta = ||Omega||_1 bounded by the generators' norms)
-        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
-        theta = 0.1 * (norm1[0] + self.gp[:, 0, 0] * norm1[1] + self.gp[:, 1, 0] * norm1[2])
-
-        def degree(th):
-            sq = max(1, int(np.ceil(th)))
-            x, term, k = th / sq, 1.0, 0
-            while k < 60:
-                k += 1
-                term = term * x / k
-                if term <= 1.1102230246251565e-16:
-                    break
-            return sq * k
-        self.m_star, self.theta = float(np.mean([degree(t) for t in theta[:: max(1, len(theta) // 512)]])), float(theta.max())
+        # series of exp(Omega) applied by matrix-vector products (m* terms of 8 n^2, m* at the 1-norm of Omega itself, as the kernel plans)
+        self.m_star, self.theta = exp_algorithmic_terms("magnus_dense", self.basis, self.gp, 0.1)
         self.flops_per_unit = 2 * 8 * self.NDIM ** 3 + self.m_star * 8 * self.NDIM ** 2
         self.bytes_per_unit = None
 
@@ -442,23 +480,12 @@ class SchrodingerMagnusApplied(SchrodingerMagnusDense):
     def __init__(self, vo, ctx, rank, world, n_batches):
         super().__init__(vo, ctx, rank, world, n_batches)
         self.solver = vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0e9, self.psi0, 0.1, group_similar=GROUP_SIMILAR, applied_commutator=True).no_adaptive()
+        if DYN_GROUP:
+            self.solver.dynamic_grouping()
         self.solver.step()
-        # algorithmic FLOPs per trajectory-step: 3 passes x M (3 basis matrices) x 8 n^2 per Taylor term; the degree follows the bound
-        # ||Omega||_1 <= ||W1|| + 2 |b2| ||L0|| ||L1|| the kernel plans with (generator amplitudes as upper bounds of |g(t)|)
-        norm1 = [np.abs(b).sum(axis=0).max() for b in self.basis]
-        nl = norm1[0] + self.gp[:, 0, 0] * norm1[1] + self.gp[:, 1, 0] * norm1[2]
-        theta = 0.1 * nl + 2.0 * (0.01 * 0.144337567297406441127287195125) * nl * nl
-
-        def degree(th):
-            sq = max(1, int(np.ceil(th)))
-            x, term, k = th / sq, 1.0, 0
-            while k < 60:
-                k += 1
-                term = term * x / k
-                if term <= 1.1102230246251565e-16:
-                    break
-            return sq * k
-        self.m_star, self.theta = float(np.mean([degree(t) for t in theta[:: max(1, len(theta) // 512)]])), float(theta.max())
+        # algorithmic FLOPs per trajectory-step: 3 passes x M (3 basis matrices) x 8 n^2 per Taylor term; the degree is the one a system
+        # needs at the bound ||Omega||_1 <= ||W1|| + 2 |b2| ||L0|| ||L1|| the kernel plans with (generator at the Gauss nodes)
+        self.m_star, self.theta = exp_algorithmic_terms("magnus_applied", self.basis, self.gp, 0.1)
         self.flops_per_unit = 3 * 3 * self.m_star * 8 * self.NDIM ** 2
 
     def e2e_setup(self, group=None):

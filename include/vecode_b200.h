@@ -364,6 +364,12 @@ int32_t vo_exp_set_generator(vo_expsolver s, const char* body);
  * vo_exp_reset / vo_exp_current / vo_exp_stats speak the caller's order (the reordering runs on the device). The psi0 and gp
  * handed to vo_exp_create are in device order; call this right after creating the solver. */
 int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n);
+/* Dynamic grouping: before every event the systems are sorted on the device by the 1-norm bound of their exponent at the coming
+ * step (one small kernel + a radix sort of N keys, ~1 % of a step of config 5) and the kernel forms its 16-system tiles in that
+ * order. A tile runs the Taylor degree of its largest theta, so tiles of equal theta execute what their systems need and no more
+ * (static grouping by drive amplitude cannot follow the phases). Results are those of any other order to rounding; buffers and
+ * statistics stay in the caller's order. Compiled-in generator family only (a run-time compiled generator keeps the static order). */
+int32_t vo_exp_set_dynamic_grouping(vo_expsolver s, int32_t on);
 int32_t vo_exp_generator_check(const char* body, int32_t n, int32_t M, char* log, int64_t log_cap);
 /* The arguments `c`, `alpha`, `alph_err` of cfm_general (exp/cfm.rs:47-52): k <= 4 nodes, alpha [rows][k] with rows <= 8
  * exponentials per step, alph_err [rows_err][k] (rows_err <= min(rows, 4)) or NULL for no embedded solution. A step is

@@ -598,3 +598,30 @@ def test_magnus_with_applied_commutator_on_generators_not_closed_under_commutati
         u.set_generator(body)
         u.run()
         assert np.abs(u.current()[1] - got).max() <= 1e-13
+
+
+@pytest.mark.parametrize("scheme,cls,kw", [("cfm4", "ExpCFMSolver", {}), ("magnus42", "MagnusExpLinearSolver", {"applied_commutator": True})])
+def test_dynamic_grouping_changes_tiles_not_results(vo, ctx, scheme, cls, kw):
+    """vo_exp_set_dynamic_grouping: the systems are sorted by the norm bound of their coming exponent before every event and the
+    kernel forms its tiles in that order. Systems are independent, so states, times and counters must be those of the plain order
+    (to rounding: a system may run a different Taylor degree in different company), in the caller's order, fixed-step and adaptive,
+    with a ragged last tile and trajectories finishing at different times."""
+    n, N, h = 16, 1003, 0.2
+    B0, B1, gp, psi0 = _system(vo, n, N)
+    gp = gp * np.array([1.0 + 3.0 * (np.arange(N) % 7 == 0), 1.0, 1.0])[:, None, :].reshape(N, 1, 3)  # a few strongly driven systems scattered around
+    sp = vo.DenseBasisSplit(ctx, np.stack([B0, B1]))
+    runs = []
+    for dyn in (False, True):
+        s = getattr(vo, cls)(sp, gp, 0.0, 1.0, psi0, h, **kw).no_adaptive()
+        if dyn:
+            s.dynamic_grouping()
+        assert s.run().kind == "Done"
+        a = getattr(vo, cls)(sp, gp, 0.0, 1.0, psi0, h, **kw).with_tolerance(1e-6, 1e-6)
+        if dyn:
+            a.dynamic_grouping()
+        assert a.run(adaptive=True).kind == "Done"
+        runs.append((s.current()[1], s.stats(), a.current()[1], a.stats()))
+    assert np.abs(runs[0][0] - runs[1][0]).max() <= 1e-13 and np.array_equal(runs[0][1]["accepted"], runs[1][1]["accepted"])
+    assert np.abs(runs[0][2] - runs[1][2]).max() <= 1e-9
+    assert np.array_equal(runs[0][3]["accepted"], runs[1][3]["accepted"]) and np.array_equal(runs[0][3]["rejected"], runs[1][3]["rejected"])
+    assert np.all(runs[1][3]["t"] == 1.0)

@@ -164,6 +164,7 @@ SIGNATURES = {
     "vo_exp_destroy": (_i32, [_vp]),
     "vo_exp_set_generator": (_i32, [_vp, C.c_char_p]),
     "vo_exp_set_order": (_i32, [_vp, _vp, _i64]),
+    "vo_exp_set_dynamic_grouping": (_i32, [_vp, _i32]),
     "vo_exp_generator_check": (_i32, [C.c_char_p, _i32, _i32, C.c_char_p, _i64]),
     "vo_exp_no_adaptive": (_i32, [_vp]),
     "vo_exp_with_tolerance": (_i32, [_vp, _f64, _f64]),

@@ -23,6 +23,10 @@
 
 #include "exp_dense_kernels.cuh"
 
+// sort_keys.cu
+size_t vo_sort_pairs_tmp_bytes(int n);
+cudaError_t vo_sort_pairs(void* tmp, size_t tmp_bytes, const float* key_in, float* key_out, const int* idx_in, int* idx_out, int n, cudaStream_t stream);
+
 
 struct vo_split_s {
     vo_ctx ctx = nullptr;
@@ -57,6 +61,13 @@ struct vo_expsolver_s {
     int64_t* perm = nullptr;     // vo_exp_set_order: device slot j holds the caller's system perm[j] (device copy)
     std::vector<int64_t> perm_host;
     double2* stage = nullptr;    // [N][n] staging for the reordering copies
+    // dynamic grouping (vo_exp_set_dynamic_grouping): before every event the systems are sorted by the 1-norm bound of their generator
+    // at the coming step, and the kernel takes its tiles in that order (a tile runs the Taylor degree of its largest theta)
+    int dynamic_group = 0;
+    float *key_in = nullptr, *key_out = nullptr;
+    int *idx_in = nullptr, *idx_out = nullptr;
+    void* sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     int literal_norm = 0;        // vo_exp_set_literal_norm: MagnusExpLinearSolver::norm as written (magnus.rs:274-276)
     int applied_comm = 0;        // vo_exp_set_applied_commutator: magnus_42's commutator applied by products inside the Taylor series, never formed
     int dense_comm = 0;          // vo_exp_set_dense_commutator: magnus_42 forms [L0, L1] densely per system (no structure tensor needed)
@@ -127,13 +138,13 @@ __global__ void exp_ctl_fill_kernel(CtlArrays ca, int64_t N, double t, double h)
 
 template <int NDIM, int M, int TB>
 int32_t launch_exp(vo_ctx c, const ExpKP& kp, const double* frag, double2* psi, double2* psi_out, const double* gp, const double2* coef_in,
-                   const CtlArrays& ca, EvSlot* ev) {
+                   const CtlArrays& ca, EvSlot* ev, const int* order) {
     using G = Geo<NDIM, M, TB>;
     auto k = exp_step_kernel<NDIM, M, TB, GenCos>;
     if (vo_ensure_smem_attr(c->device, (const void*)k, G::SMEM) != cudaSuccess) return vo_fail(c, VO_ERR_CUDA, "exp: shared-memory carve-out rejected");
     const int64_t tiles = ceil_div(kp.N, TB);
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, c->sm_count);
-    k<<<grid, G::THREADS, G::SMEM, c->stream>>>(kp, frag, psi, psi_out, gp, coef_in, ca, ev);
+    k<<<grid, G::THREADS, G::SMEM, c->stream>>>(kp, frag, psi, psi_out, gp, coef_in, ca, ev, order);
     VO_CHECK_LAUNCH(c);
     return VO_OK;
 }
@@ -153,7 +164,7 @@ bool exp_geometry(int n, int M, unsigned* threads, size_t* smem) {
 }
 
 int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_out, const double* gp, const double2* coef_in, const CtlArrays& ca, EvSlot* ev,
-                     void* custom_fn = nullptr) {
+                     void* custom_fn = nullptr, const int* order = nullptr) {
     vo_ctx c = sp->ctx;
     if (custom_fn) {  // the user's generator: same kernel, compiled at run time
         unsigned threads = 0;
@@ -162,7 +173,7 @@ int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_ou
         ExpKP kpc = kp;
         const double* frag = sp->frag_dev;
         CtlArrays cac = ca;
-        void* args[] = {&kpc, &frag, &psi, &psi_out, &gp, &coef_in, &cac, &ev};
+        void* args[] = {&kpc, &frag, &psi, &psi_out, &gp, &coef_in, &cac, &ev, &order};
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(kp.N, 16), c->sm_count);
         int32_t r = rtc_exp_launch(c, custom_fn, grid, threads, smem, args);
         if (r != VO_OK) return r;
@@ -171,10 +182,10 @@ int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_ou
     }
     {   // experiment switch (A/B runs): config 5's shape with tiles of 32 systems on 16 warps, the basis shared by both column groups
         static const int tb = getenv("VECODE_EXP_TB") ? atoi(getenv("VECODE_EXP_TB")) : 16;
-        if (tb == 32 && sp->n == 64 && sp->M == 2) return launch_exp<64, 2, 32>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev);
+        if (tb == 32 && sp->n == 64 && sp->M == 2) return launch_exp<64, 2, 32>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order);
     }
 #define VO_EXP_CASE(NDIM, MM) \
-    if (sp->n == NDIM && sp->M == MM) return launch_exp<NDIM, MM, 16>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev);
+    if (sp->n == NDIM && sp->M == MM) return launch_exp<NDIM, MM, 16>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order);
     VO_EXP_SHAPES(VO_EXP_CASE)
 #undef VO_EXP_CASE
     return vo_fail(c, VO_ERR_UNSUPPORTED, "exp: the shared-basis split is compiled for n in {16, 32} with M <= 4, n in {24, 48} with M in {2, 3}, (40, 2) and n = 64 with M <= 3 "
@@ -249,6 +260,47 @@ int32_t exp_ev_read(vo_expsolver_s* s, EvSlot* out) {
     return VO_OK;
 }
 
+// Sort key of the dynamic grouping: the bound sum_m |g_m(t + dt/2)| ||B_m||_1 dt of the 1-norm of this system's exponent at its coming
+// step (the mid-point of the step stands in for the scheme's nodes: the key only has to ORDER systems, the kernel plans with the
+// exact exponents). Trajectories that are done sort first, together.
+__global__ void exp_group_key_kernel(const ExpKP kp, const double* __restrict__ gp, const CtlArrays ca, int64_t N, float* __restrict__ key, int* __restrict__ idx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    idx[i] = (int)i;
+    const uint32_t word = ca.word[i];
+    if ((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE) {
+        key[i] = 0.0f;
+        return;
+    }
+    const double t = ca.t[i], h = ca.h[i];
+    double l[VO_EXP_MAX_M];
+    GenCos::coef<VO_EXP_MAX_M>(gp + i * (kp.M_gen - 1) * 3, kp.M_gen, t + 0.5 * h, l);
+    double th = 0.0;
+    for (int m = 0; m < kp.M; ++m) th += fabs(l[m]) * kp.norm1[m];
+    key[i] = (float)(th * h);
+}
+
+// Order of the systems for the coming event: ascending key, so that every tile of 16 holds systems of similar theta.
+static int32_t exp_dynamic_order(vo_expsolver_s* s, const ExpKP& kp, const int** order) {
+    vo_ctx c = s->ctx;
+    *order = nullptr;
+    if (!s->dynamic_group || s->gen_fn || s->N < 64 || s->N > 0x7fffffff) return VO_OK;
+    const int n = (int)s->N;
+    if (!s->key_in) {
+        const size_t tmp = vo_sort_pairs_tmp_bytes(n);
+        if (cudaMalloc(&s->key_in, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->key_out, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->idx_in, 4 * (size_t)n) != cudaSuccess ||
+            cudaMalloc(&s->idx_out, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->sort_tmp, tmp) != cudaSuccess)
+            return vo_fail(c, VO_ERR_ALLOC, "exp: dynamic grouping buffers");
+        s->sort_tmp_bytes = tmp;
+    }
+    exp_group_key_kernel<<<(unsigned)ceil_div(s->N, 256), 256, 0, c->stream>>>(kp, s->gp, s->ca, s->N, s->key_in, s->idx_in);
+    VO_CHECK_LAUNCH(c);
+    if (vo_sort_pairs(s->sort_tmp, s->sort_tmp_bytes, s->key_in, s->key_out, s->idx_in, s->idx_out, n, c->stream) != cudaSuccess)
+        return vo_fail(c, VO_ERR_CUDA, "exp: dynamic grouping sort");
+    *order = s->idx_out;
+    return VO_OK;
+}
+
 int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     vo_ctx c = s->ctx;
     if (adaptive && !s->want_err) return vo_fail(c, VO_ERR_NOT_ADAPTIVE, "adaptive step validation failed");  // ode.rs:312
@@ -272,7 +324,10 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     std::memcpy(kp.tab_c, s->tab_c, sizeof kp.tab_c), std::memcpy(kp.tab_alpha, s->tab_alpha, sizeof kp.tab_alpha);
     std::memcpy(kp.tab_alpha_err, s->tab_alpha_err, sizeof kp.tab_alpha_err), std::memcpy(kp.row_split, s->row_split, sizeof kp.row_split);
     if (s->scheme == VO_EXP_MAGNUS42 && s->dense_comm) return launch_magnus_dense(s, kp);
-    return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn);
+    const int* order = nullptr;
+    int32_t orc = exp_dynamic_order(s, kp, &order);
+    if (orc != VO_OK) return orc;
+    return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn, order);
 }
 
 void exp_res_add(vo_step_result* res, const EvSlot& e, int launches) {
@@ -456,6 +511,7 @@ int32_t vo_exp_destroy(vo_expsolver s) {
     cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->psi), cudaFree(s->psi0), cudaFree(s->gp);
     cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm), cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
+    cudaFree(s->key_in), cudaFree(s->key_out), cudaFree(s->idx_in), cudaFree(s->idx_out), cudaFree(s->sort_tmp);
     cudaFree(s->ev_dev), cudaFreeHost(s->ev_host);
     rtc_exp_unload(s->gen_module);
     cudaFree(s->perm), cudaFree(s->stage);
@@ -822,6 +878,12 @@ int32_t vo_dense_commutator(vo_split sp, vo_ens La, vo_ens Lb, vo_ens out) {  //
     VO_DENSE_DISPATCH(nb, VO_CALL)
 #undef VO_CALL
     VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
+int32_t vo_exp_set_dynamic_grouping(vo_expsolver s, int32_t on) {
+    if (!s) return VO_ERR_BAD_ARG;
+    s->dynamic_group = on ? 1 : 0;
     return VO_OK;
 }
 

@@ -69,7 +69,7 @@ template <int NDIM, int M, int TB> struct Geo {
     static constexpr size_t SMEM_B = (size_t)M * 2 * NDIM * NDIM * sizeof(double);
     static constexpr size_t SMEM_T = (size_t)NBUF * 2 * TB * LDT * sizeof(double);
     static constexpr size_t SMEM_COEF = (size_t)VO_EXP_MAX_E * M * TB * sizeof(double2);
-    static constexpr size_t SMEM_MISC = (size_t)(NW * TB + VO_EXP_MAX_E * TB + TB) * sizeof(double) + (size_t)(TB + 2 * VO_EXP_MAX_E + 8) * sizeof(int);
+    static constexpr size_t SMEM_MISC = (size_t)(NW * TB + VO_EXP_MAX_E * TB + TB) * sizeof(double) + (size_t)(TB + 2 * VO_EXP_MAX_E + 8) * sizeof(int) + (size_t)TB * sizeof(long long);
     static constexpr size_t SMEM = SMEM_B + SMEM_T + SMEM_COEF + SMEM_MISC;
     static_assert(SMEM <= 227 * 1024, "exp_step_kernel: shared memory budget of one SM exceeded");
 };
@@ -315,7 +315,8 @@ struct GenCos {
 template <int NDIM, int M, int TB, class GEN>
 __global__ void __launch_bounds__(Geo<NDIM, M, TB>::THREADS, 1)
 exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ frag, double2* __restrict__ psi, double2* __restrict__ psi_out,
-                const double* __restrict__ gp, const double2* __restrict__ coef_in, const CtlArrays ca, EvSlot* __restrict__ ev) {
+                const double* __restrict__ gp, const double2* __restrict__ coef_in, const CtlArrays ca, EvSlot* __restrict__ ev,
+                const int* __restrict__ order /* nullable: slot -> system, tiles of systems with similar ||L h|| (exp.cu: dynamic grouping) */) {
     using G = Geo<NDIM, M, TB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sB = reinterpret_cast<double*>(smem_raw);
@@ -326,6 +327,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     double* sDt = sTheta + VO_EXP_MAX_E * TB;                                                    // [TB]
     int* sEv = reinterpret_cast<int*>(sDt + TB);                                                 // [TB] event, then [2 E] plan, [1] any
     int* sPlan = sEv + TB;
+    long long* sSys = reinterpret_cast<long long*>(smem_raw + G::SMEM - TB * sizeof(long long));  // [TB] system of each tile slot (kp.N = none)
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int w = wi % G::NW, cg = wi / G::NW;
     const int row = 8 * w + (lane >> 2);
@@ -348,7 +350,9 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
         // ---- phase A: per-system control and exponent coefficients (one thread per system), written straight to shared memory
         if (threadIdx.x < TB) {
             const int s = threadIdx.x;
-            const int64_t sys = base + s;
+            const int64_t slot = base + s;
+            const int64_t sys = slot < kp.N ? (order ? (int64_t)order[slot] : slot) : kp.N;
+            sSys[s] = sys;
             int evk = 255;  // not live
             double dt = 0.0;
             auto put = [&](int e, int m, double re, double im) { sCoef[(e * M + m) * TB + s] = make_double2(re, im); };
@@ -485,7 +489,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int64_t sys = base + 16 * cg + 8 * j + 2 * (lane & 3) + q;
+                    const int64_t sys = sSys[16 * cg + 8 * j + 2 * (lane & 3) + q];
                     const double2 v = sys < kp.N ? psi[sys * NDIM + row] : make_double2(0.0, 0.0);
                     x0r[j][q] = xfr[j][q] = v.x, x0i[j][q] = xfi[j][q] = v.y;
                     xer[j][q] = xei[j][q] = 0.0;
@@ -497,7 +501,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             for (int q = 1; kp.mode == 1 && q < kp.nseq; ++q) {  // vo_map_exp_seq: the next exponential of the composition
                 __syncthreads();
                 if (threadIdx.x < TB) {
-                    const int64_t sys = base + threadIdx.x;
+                    const int64_t sys = sSys[threadIdx.x];
                     double th = 0.0;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
@@ -549,7 +553,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             __syncthreads();
             if (threadIdx.x < TB) {
                 const int s = threadIdx.x;
-                const int64_t sys = base + s;
+                const int64_t sys = sSys[s];
                 int evk = sEv[s];
                 if (evk != 255) {
                     const uint32_t word = ca.word[sys];
@@ -599,7 +603,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
-                    const int64_t sys = base + col;
+                    const int64_t sys = sSys[col];
                     if (sys < kp.N && sEv[col] == VO_EV_STEP) dst[sys * NDIM + row] = make_double2(xfr[j][q], xfi[j][q]);
                 }
         }

@@ -184,6 +184,12 @@ class _ExpSolver:
         if self._perm is not None:  # from here on the C ABI speaks the caller's order (the reordering runs on the device)
             check(lib().vo_exp_set_order(self._h, _np_ptr(self._perm), self.N), self.ctx._h)
 
+    def dynamic_grouping(self, on: bool = True):
+        """Sort the systems by the norm bound of their exponent before every event, on the device, so that each 16-system tile runs the
+        Taylor degree its systems need (vo_exp_set_dynamic_grouping)."""
+        check(lib().vo_exp_set_dynamic_grouping(self._h, 1 if on else 0), self.ctx._h)
+        return self
+
     def set_generator(self, body: str):
         """The generator closure itself (`FnMut(T) -> L`, exp/cfm.rs:54, exp/magnus.rs:12,32): CUDA C++ statements assigning
         `g[1] .. g[M_gen-1]` of L(t) = B_0 + sum_m g[m] B_m from `t` and this system's parameter row `p` (the 3 (M_gen - 1)
