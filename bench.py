@@ -742,6 +742,8 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
         psi0 = np.zeros((hi - lo, 64), dtype=np.complex128)
         psi0[:, 0] = 1.0
         solver = vo.ExpCFMSolver(sp, gp, 0.0, 10.0, psi0, 0.1, group_similar=GROUP_SIMILAR).no_adaptive()
+        if DYN_GROUP:
+            solver.dynamic_grouping()
         pin_full = torch.empty((n_sys, 128), dtype=torch.float64).pin_memory() if rank == 0 else None
         rows = [vo.workloads.shard_range(n_sys, r, world) for r in range(world)]
 
