@@ -74,6 +74,15 @@ template <int NDIM, int M, int TB> struct Geo {
     static_assert(SMEM <= 227 * 1024, "exp_step_kernel: shared memory budget of one SM exceeded");
 };
 
+// Barrier among the NW warps of ONE column group (16 systems). A tile of TB = 16 NCG systems is NCG such groups that share the basis
+// in shared memory but nothing else inside a Taylor series: each republishes its own columns of the term buffer, so each can run
+// behind its own named barrier and the groups drift apart in phase — while one group waits at its barrier the other keeps the tensor
+// pipe busy. NCG == 1 is the plain block barrier.
+template <int NW, int NCG> __device__ __forceinline__ void group_sync(int cg) {
+    if (NCG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + cg), "r"(NW * 32) : "memory");
+}
+
 // x <- exp(sum_m coef[m][s] B_m) x for the tile, state in C-fragment layout:
 // lane l of warp (w, cg) owns row 8w + l/4 and columns 16cg + 8j + 2(l%4) + q, j,q in {0,1}.
 template <int NDIM, int M, int TB>
@@ -102,7 +111,7 @@ __device__ __forceinline__ void map_exp_tile(const double* __restrict__ sB, doub
             for (int q = 0; q < 2; ++q) ar[j][q] = tr[j][q] = xr[j][q], ai[j][q] = ti[j][q] = xi[j][q];
         for (int k = 1; k <= deg; ++k) {
             // publish the current term: planar [plane][column][LDT], row fastest
-            if (G::NBUF == 1) __syncthreads();
+            if (G::NBUF == 1) group_sync<G::NW, G::NCG>(cg);
             double* Tr = sT + (size_t)buf * 2 * TB * G::LDT;
             double* Ti = Tr + TB * G::LDT;
 #pragma unroll
@@ -112,7 +121,7 @@ __device__ __forceinline__ void map_exp_tile(const double* __restrict__ sB, doub
                     const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
                     Tr[col * G::LDT + row] = tr[j][q], Ti[col * G::LDT + row] = ti[j][q];
                 }
-            __syncthreads();
+            group_sync<G::NW, G::NCG>(cg);
             double Wr[M][2][2], Wi[M][2][2];
 #pragma unroll
             for (int m = 0; m < M; ++m)
@@ -174,7 +183,7 @@ __device__ __forceinline__ void basis_apply(const double* __restrict__ sB, doubl
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int w = wi % G::NW, cg = wi / G::NW;
     const int row = 8 * w + (lane >> 2);
-    if (G::NBUF == 1) __syncthreads();
+    if (G::NBUF == 1) group_sync<G::NW, G::NCG>(cg);
     double* Tr = sT + (size_t)buf * 2 * TB * G::LDT;
     double* Ti = Tr + TB * G::LDT;
 #pragma unroll
@@ -184,7 +193,7 @@ __device__ __forceinline__ void basis_apply(const double* __restrict__ sB, doubl
             const int col = 16 * cg + 8 * j + 2 * (lane & 3) + q;
             Tr[col * G::LDT + row] = tr[j][q], Ti[col * G::LDT + row] = ti[j][q];
         }
-    __syncthreads();
+    group_sync<G::NW, G::NCG>(cg);
 #pragma unroll
     for (int m = 0; m < M; ++m)
 #pragma unroll
