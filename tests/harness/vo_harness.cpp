@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -138,6 +139,70 @@ int main() {
                     (long long)res.n_step, (long long)vo_ctx_launch_count(ctx), same ? "yes" : "NO");
         if (!same || res.n_step != N * n_steps) return 1;
         vo_solver_destroy(s), vo_ens_destroy(x0), vo_tableau_destroy(tab), vo_rhs_destroy(rhs);
+    }
+    // ---- the multi-GPU entry points from one process (vo_group_create_local over the GPUs of the box, at least this one): scatter
+    // ---- from a host array, `while let Ok(_) = step()` on every shard, gather back to the host; must equal the single-ctx solve
+    {
+        int n_gpu = 1;
+        if (std::getenv("VO_HARNESS_GPUS")) n_gpu = std::atoi(std::getenv("VO_HARNESS_GPUS"));
+        std::vector<vo_ctx> ctxs((size_t)n_gpu);
+        ctxs[0] = ctx;
+        for (int g = 1; g < n_gpu; ++g) {
+            CHECK(nullptr, vo_ctx_create(g, nullptr, &ctxs[(size_t)g]));
+            CHECK(ctxs[(size_t)g], vo_ctx_set_arith(ctxs[(size_t)g], VO_ARITH_STRICT));
+        }
+        vo_group grp = nullptr;
+        CHECK(ctx, vo_group_create_local(ctxs.data(), n_gpu, &grp));
+        const int64_t N = 5001;
+        const double dt = 1.0e-3;
+        std::vector<double> x((size_t)N * 3), whole((size_t)N * 3), got((size_t)N * 3);
+        for (int64_t i = 0; i < N; ++i) x[3 * i] = 1.0 + 1e-4 * i, x[3 * i + 1] = 1.0, x[3 * i + 2] = 1.0 - 1e-5 * i;
+        vo_tableau tab = nullptr;
+        CHECK(ctx, vo_tableau_builtin(VO_TABLEAU_RK4, &tab));
+        std::vector<vo_ens> shard((size_t)n_gpu), fin((size_t)n_gpu);
+        std::vector<vo_rhs> rhs((size_t)n_gpu);
+        std::vector<vo_solver> sol((size_t)n_gpu);
+        for (int g = 0; g < n_gpu; ++g) {
+            int64_t lo = 0, hi = 0;
+            CHECK(ctx, vo_group_shard_range(N, g, n_gpu, &lo, &hi));
+            CHECK(ctxs[(size_t)g], vo_ens_create(ctxs[(size_t)g], 3, hi - lo, &shard[(size_t)g]));
+        }
+        CHECK(ctx, vo_group_scatter(grp, x.data(), VO_LAYOUT_AOS, 3, N, 0, shard.data()));
+        for (int g = 0; g < n_gpu; ++g) {
+            vo_ctx c = ctxs[(size_t)g];
+            CHECK(c, vo_rhs_create(c, VO_RHS_LORENZ63, 3, &rhs[(size_t)g]));
+            CHECK(c, vo_rhs_set_param(rhs[(size_t)g], 0, 10.0));
+            CHECK(c, vo_rhs_set_param(rhs[(size_t)g], 1, 28.0));
+            CHECK(c, vo_rhs_set_param(rhs[(size_t)g], 2, 8.0 / 3.0));
+            CHECK(c, vo_rk_create(c, tab, rhs[(size_t)g], 0.0, 0.02, shard[(size_t)g], dt, &sol[(size_t)g]));
+        }
+        vo_group_stats tot;
+        CHECK(ctx, vo_group_run(grp, sol.data(), 0, 0, &tot));
+        for (int g = 0; g < n_gpu; ++g) CHECK(ctxs[(size_t)g], vo_current(sol[(size_t)g], nullptr, nullptr, &fin[(size_t)g]));
+        CHECK(ctx, vo_group_gather(grp, fin.data(), N, 0, got.data(), VO_LAYOUT_AOS));
+        // the same ensemble on one ctx
+        vo_ens x0 = nullptr;
+        vo_solver one = nullptr;
+        vo_rhs r1 = nullptr;
+        CHECK(ctx, vo_rhs_create(ctx, VO_RHS_LORENZ63, 3, &r1));
+        CHECK(ctx, vo_rhs_set_param(r1, 0, 10.0));
+        CHECK(ctx, vo_rhs_set_param(r1, 1, 28.0));
+        CHECK(ctx, vo_rhs_set_param(r1, 2, 8.0 / 3.0));
+        CHECK(ctx, vo_ens_create(ctx, 3, N, &x0));
+        CHECK(ctx, vo_ens_upload(x0, x.data(), VO_LAYOUT_AOS));
+        CHECK(ctx, vo_rk_create(ctx, tab, r1, 0.0, 0.02, x0, dt, &one));
+        vo_step_result res;
+        CHECK(ctx, vo_run(one, 0, 0, &res));
+        vo_ens cur = nullptr;
+        CHECK(ctx, vo_current(one, nullptr, nullptr, &cur));
+        CHECK(ctx, vo_ens_download(cur, whole.data(), VO_LAYOUT_AOS));
+        const bool same = std::memcmp(whole.data(), got.data(), sizeof(double) * whole.size()) == 0;
+        std::printf("group of %d GPU(s): %lld trajectories done, accepted %lld, gathered ensemble == single-ctx solve: %s\n", vo_group_world(grp), (long long)tot.n_done,
+                    (long long)tot.accepted, same ? "yes" : "NO");
+        if (!same || tot.n_done != N || tot.t_max != 0.02) return 1;
+        for (int g = 0; g < n_gpu; ++g) vo_solver_destroy(sol[(size_t)g]), vo_rhs_destroy(rhs[(size_t)g]), vo_ens_destroy(shard[(size_t)g]);
+        vo_solver_destroy(one), vo_ens_destroy(x0), vo_rhs_destroy(r1), vo_tableau_destroy(tab), vo_group_destroy(grp);
+        for (int g = 1; g < n_gpu; ++g) vo_ctx_destroy(ctxs[(size_t)g]);
     }
     vo_ctx_destroy(ctx);
     std::printf("harness ok\n");

@@ -98,3 +98,9 @@ def test_cpp_harness_on_the_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0 and "harness ok" in r.stdout and "bit-exact vs restatement: yes" in r.stdout, r.stdout + r.stderr
+    assert "gathered ensemble == single-ctx solve: yes" in r.stdout  # vo_group_* (NCCL inside the library) from plain C++
+    import torch
+    if torch.cuda.device_count() >= 2:  # one process driving two GPUs
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, VO_HARNESS_GPUS="2"))
+        print(r.stdout)
+        assert r.returncode == 0 and "group of 2 GPU(s)" in r.stdout and "gathered ensemble == single-ctx solve: yes" in r.stdout, r.stdout + r.stderr
