@@ -797,6 +797,12 @@ def numa_bind(torch, local):
     return None
 
 
+# Blocking kernel (nvbench's method): after the synchronize and BEFORE the first event a spin kernel of this many microseconds is enqueued
+# on the launching stream, so that the K timed launches are already queued when the device reaches the first event and the events
+# bracket DEVICE time of the K steps — not the host's luck in getting its first launches out. One process on an idle box shows no
+# difference (0.725 vs 0.731, r2h / r2i); with 2-8 processes per box the host side jitters (17.4 / 17.5 us per step without, 17.1 / 16.5
+# with, 2 GPUs). 0 switches it off.
+GATE_US = float(os.environ.get("VECODE_BENCH_GATE_US", "150"))
 SPIN_UP_MS = 40.0  # untimed load right before the timed region, whatever --warmup says: clocks and caches in their steady state
 
 
@@ -876,6 +882,10 @@ def main():
         else:
             torch.cuda.synchronize()
         l0 = c2.launch_count
+        if GATE_US > 0:
+            # torch's spin kernel, untimed, not counted in gpu_launches; it touches no solver state, so no vo_ctx_fence(): the first timed launch
+            # follows it in stream order and finds its own predecessor's generation flag already published
+            torch.cuda._sleep(int(GATE_US * 1.9e3))
         ev0.record()
         w2.run_steps(steps)
         ev1.record()
@@ -1012,9 +1022,11 @@ def main():
                                                                         f"slab of {512 // world} MB per buffer per GPU" if W is HeatRK4DD else
                                                                         "compute-bound: 102 MB of state per launch, streamed once"),
                            "warmup_note": f"every batch touched once, then ~{SPIN_UP_MS:.0f} ms of the same launches and the {args.warmup} warm-up steps, all untimed, before the {args.steps} timed steps",
-                           "timing": ("barrier + synchronize, event, steps, event, barrier + synchronize. A region of K launches costs about 14 us + K x the steady launch time "
-                                      "(tools/offset_probe.py): the first launch has no predecessor to overlap its ramp-up with and the last none to hide its tail; "
-                                      "queueing the launches behind a blocking kernel changes nothing (measured), so it is device time, not host latency"),
+                           "timing": ((f"barrier + synchronize, a {GATE_US:.0f} us blocking kernel (torch.cuda._sleep, untimed), event, {args.steps} steps, event, barrier + synchronize: the "
+                                       "launches are queued behind the blocking kernel, so the events bracket device time of the steps (VECODE_BENCH_GATE_US=0: without). "
+                                       if GATE_US > 0 else "barrier + synchronize, event, steps, event, barrier + synchronize (no blocking kernel). ") +
+                                      "A region of K launches costs about 14 us + K x the steady launch time (tools/offset_probe.py): the first launch has no predecessor "
+                                      "to overlap its ramp-up with and the last none to hide its tail"),
                            "parallelism": (f"domain-decomposed x{world}: ghost refresh (all-gather of {8 * DD_K} doubles per rank) every {DD_K} steps" if W is HeatRK4DD
                                            else f"trajectory-sharded x{world}, no data-path collective")},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
