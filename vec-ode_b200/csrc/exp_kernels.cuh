@@ -138,18 +138,28 @@ __device__ __forceinline__ void map_exp_tile(const double* __restrict__ sB, doub
                     fi[j] = bX[TB * G::LDT + 8 * j * G::LDT + 4 * kk];
                     nfi[j] = -fi[j];
                 }
+                // the asm statements are volatile, so the DMMAs issue in program order: every accumulator is written twice per k-step, and the
+                // two writes are kept 4 M instructions apart (first the products with Xr, then those with Xi) instead of back to back
+                double a_re[M], a_im[M];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    const double a_re = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
-                    const double a_im = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+                    a_re[m] = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
+                    a_im[m] = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+                }
+#pragma unroll
+                for (int m = 0; m < M; ++m)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        dmma(Wr[m][j][0], Wr[m][j][1], a_re, fr[j]);   // Re += Br Xr
-                        dmma(Wr[m][j][0], Wr[m][j][1], a_im, nfi[j]);  // Re -= Bi Xi
-                        dmma(Wi[m][j][0], Wi[m][j][1], a_im, fr[j]);   // Im += Bi Xr
-                        dmma(Wi[m][j][0], Wi[m][j][1], a_re, fi[j]);   // Im += Br Xi
+                        dmma(Wr[m][j][0], Wr[m][j][1], a_re[m], fr[j]);   // Re += Br Xr
+                        dmma(Wi[m][j][0], Wi[m][j][1], a_im[m], fr[j]);   // Im += Bi Xr
                     }
-                }
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        dmma(Wr[m][j][0], Wr[m][j][1], a_im[m], nfi[j]);  // Re -= Bi Xi
+                        dmma(Wi[m][j][0], Wi[m][j][1], a_re[m], fi[j]);   // Im += Br Xi
+                    }
             }
             const double ik = 1.0 / k;
 #pragma unroll
@@ -209,18 +219,26 @@ __device__ __forceinline__ void basis_apply(const double* __restrict__ sB, doubl
             fi[j] = bX[TB * G::LDT + 8 * j * G::LDT + 4 * kk];
             nfi[j] = -fi[j];
         }
+        double a_re[M], a_im[M];  // dependent DMMAs 4 M instructions apart, as in map_exp_tile
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const double a_re = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
-            const double a_im = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+            a_re[m] = bA[((size_t)(m * 2 + 0) * G::NW) * G::NK * 32 + kk * 32];
+            a_im[m] = bA[((size_t)(m * 2 + 1) * G::NW) * G::NK * 32 + kk * 32];
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m)
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                dmma(Wr[m][j][0], Wr[m][j][1], a_re, fr[j]);
-                dmma(Wr[m][j][0], Wr[m][j][1], a_im, nfi[j]);
-                dmma(Wi[m][j][0], Wi[m][j][1], a_im, fr[j]);
-                dmma(Wi[m][j][0], Wi[m][j][1], a_re, fi[j]);
+                dmma(Wr[m][j][0], Wr[m][j][1], a_re[m], fr[j]);
+                dmma(Wi[m][j][0], Wi[m][j][1], a_im[m], fr[j]);
             }
-        }
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                dmma(Wr[m][j][0], Wr[m][j][1], a_im[m], nfi[j]);
+                dmma(Wi[m][j][0], Wi[m][j][1], a_re[m], fi[j]);
+            }
     }
     if (G::NBUF == 2) buf ^= 1;
 }
