@@ -397,7 +397,7 @@ int32_t vo_exp_set_dense_commutator(vo_expsolver s, int32_t on);
  * Omega T = b1 (L0 + L1) T + b2 (L0 (L1 T) - L1 (L0 T)) — three passes over the shared basis per term, each M tile products on the
  * tensor cores inside exp_step_kernel (the same machinery as the commutator-free schemes: 16 systems per tile, basis resident in
  * shared memory). No closure under commutation assumed, no structure tensor, no n x n matrix per system; works with a run-time
- * compiled generator. About 2.5x the throughput of the dense commutator on config 5's shape. */
+ * compiled generator. 1.8x the throughput of the dense commutator on config 5's shape (18.0 against 32.4 ms per step of 10^5 systems). */
 int32_t vo_exp_set_applied_commutator(vo_expsolver s, int32_t on);
 /* MagnusExpLinearSolver::norm AS WRITTEN (exp/magnus.rs:274-276): it takes the norm of adaptive_dat.dx, a clone of x0 that
  * try_step never writes (the embedded error goes to self.x_err, magnus.rs:249-250), so the controller sees the constant ||x0||:
