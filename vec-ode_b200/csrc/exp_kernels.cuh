@@ -367,8 +367,34 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     const int64_t n_tiles = (kp.N + TB - 1) / TB;
     int buf = 0;
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    // Control data of a tile's systems (solver events): which system sits in the slot, its status word, t, h and generator parameters.
+    // The thread that owns slot s fetches them for the NEXT tile of this CTA while the current tile's exponentials run, so that phase A
+    // starts from registers instead of a chain of four dependent global loads (order -> word -> t, h -> parameters) per tile.
+    constexpr int PG = 3 * (VO_EXP_MAX_M - 1);
+    long long p_sys = kp.N;
+    uint32_t p_word = 0;
+    double p_t = 0.0, p_h = 0.0, p_g[PG];
+#pragma unroll
+    for (int q = 0; q < PG; ++q) p_g[q] = 0.0;
+    auto prefetch_ctl = [&](int64_t tl) {
+        p_sys = kp.N;
+        if (tl < n_tiles) {
+            const int64_t slot = tl * TB + threadIdx.x;
+            if (slot < kp.N) p_sys = order ? (long long)order[slot] : slot;
+        }
+        if (p_sys < kp.N) {
+            p_word = ca.word[p_sys], p_t = ca.t[p_sys], p_h = ca.h[p_sys];
+            const double* g = gp + p_sys * (kp.M_gen - 1) * 3;
+#pragma unroll
+            for (int q = 0; q < PG; ++q)
+                if (q < 3 * (kp.M_gen - 1)) p_g[q] = g[q];
+        }
+    };
+    if (kp.mode == 0 && threadIdx.x < TB) prefetch_ctl(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TB;
+        uint32_t a_word = 0;  // this slot's status word and step size, from phase A to phase D (same thread)
+        double a_h = 0.0;
         // exponentials of this event: nbase for the propagated solution, then nerr for the embedded lower-order one (from x0)
         const bool tables = kp.scheme == VO_EXP_CFM4 || kp.scheme == VO_EXP_CFM_TABLE || kp.scheme == VO_EXP_SPLIT_CFM;
         const int nbase = kp.mode == 1 ? 1 : (tables ? kp.n_rows : (kp.scheme == VO_EXP_SPLIT_MIDPOINT ? 3 : 1));
@@ -378,7 +404,18 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
         if (threadIdx.x < TB) {
             const int s = threadIdx.x;
             const int64_t slot = base + s;
-            const int64_t sys = slot < kp.N ? (order ? (int64_t)order[slot] : slot) : kp.N;
+            int64_t sys;
+            double a_t = 0.0, a_g[PG];
+            if (kp.mode == 0) {  // from the prefetch of the previous iteration; the next tile's loads go out now
+                sys = p_sys, a_word = p_word, a_t = p_t, a_h = p_h;
+#pragma unroll
+                for (int q = 0; q < PG; ++q) a_g[q] = p_g[q];
+                prefetch_ctl(tile + gridDim.x);
+            } else {
+                sys = slot < kp.N ? (order ? (int64_t)order[slot] : slot) : kp.N;
+#pragma unroll
+                for (int q = 0; q < PG; ++q) a_g[q] = 0.0;
+            }
             sSys[s] = sys;
             int evk = 255;  // not live
             double dt = 0.0;
@@ -392,10 +429,10 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
 #pragma unroll
                     for (int m = 0; m < M; ++m) sCoef[m * TB + s] = coef_in[sys * M + m];
                 } else {
-                    const uint32_t word = ca.word[sys];
+                    const uint32_t word = a_word;
                     if (!((word >> VO_WORD_STATUS_SHIFT) & VO_TRAJ_DONE)) {
                         const int tgt = (int)(word & VO_WORD_TGT_MASK);
-                        const double t = ca.t[sys], h = ca.h[sys];
+                        const double t = a_t, h = a_h;
                         // step_size_of (ode.rs:165-176) with t_list = [t0, tf]
                         if (tgt >= 2) {
                             evk = VO_EV_END;
@@ -405,7 +442,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                             else dt = rem < h ? rem : h, evk = VO_EV_STEP;
                         }
                         if (evk == VO_EV_STEP) {
-                            const double* g = gp + sys * (kp.M_gen - 1) * 3;
+                            const double* g = a_g;  // this system's generator parameters (prefetched)
                             if (kp.scheme == VO_EXP_MIDPOINT) {  // exp/magnus.rs:10-26
                                 double l[M];
                                 GEN::template coef<M>(g, kp.M_gen, t + dt * 0.5, l);
@@ -583,11 +620,11 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                 const int64_t sys = sSys[s];
                 int evk = sEv[s];
                 if (evk != 255) {
-                    const uint32_t word = ca.word[sys];
+                    const uint32_t word = a_word;  // read in phase A by this thread; nothing has written it since
                     int tgt = (int)(word & VO_WORD_TGT_MASK);
                     uint32_t status = word >> VO_WORD_STATUS_SHIFT;
                     if (evk == VO_EV_STEP) {
-                        const double h = ca.h[sys];
+                        const double h = a_h;
                         if (kp.adaptive) {  // handle_step_adaptive, ode.rs:311-334
                             double nn = 0.0;
 #ifdef VO_USER_NORM
