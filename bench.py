@@ -497,7 +497,9 @@ class SchrodingerMagnusApplied(SchrodingerMagnusDense):
         import torch
         self.pin_in = torch.from_numpy(self.psi0.view(np.float64).copy()).pin_memory()
         self.pin_out = torch.empty_like(self.pin_in).pin_memory()
-        self.e_solver = self.vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0, self.psi0, 0.1, applied_commutator=True).no_adaptive()
+        self.e_solver = self.vo.MagnusExpLinearSolver(self.sp, self.gp, 0.0, 1.0, self.psi0, 0.1, group_similar=GROUP_SIMILAR, applied_commutator=True).no_adaptive()
+        if DYN_GROUP:
+            self.e_solver.dynamic_grouping()
 
 
 WORKLOADS = {w.name: w for w in (LorenzRK4, VdpDopri5, HeatRK4, HeatRK4Fused, HeatRK4DD, SchrodingerCFM4, SchrodingerMagnusDense, SchrodingerMagnusApplied)}
