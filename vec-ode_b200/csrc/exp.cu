@@ -67,6 +67,7 @@ struct vo_expsolver_s {
     float *key_in = nullptr, *key_out = nullptr;
     int *idx_in = nullptr, *idx_out = nullptr;
     void* sort_tmp = nullptr;
+    int* tile_ctr = nullptr;  // tile counter of the kernel's largest-theta-first schedule, zeroed before every launch
     size_t sort_tmp_bytes = 0;
     int literal_norm = 0;        // vo_exp_set_literal_norm: MagnusExpLinearSolver::norm as written (magnus.rs:274-276)
     int applied_comm = 0;        // vo_exp_set_applied_commutator: magnus_42's commutator applied by products inside the Taylor series, never formed
@@ -138,13 +139,13 @@ __global__ void exp_ctl_fill_kernel(CtlArrays ca, int64_t N, double t, double h)
 
 template <int NDIM, int M, int TB>
 int32_t launch_exp(vo_ctx c, const ExpKP& kp, const double* frag, double2* psi, double2* psi_out, const double* gp, const double2* coef_in,
-                   const CtlArrays& ca, EvSlot* ev, const int* order) {
+                   const CtlArrays& ca, EvSlot* ev, const int* order, int* tile_ctr) {
     using G = Geo<NDIM, M, TB>;
     auto k = exp_step_kernel<NDIM, M, TB, GenCos>;
     if (vo_ensure_smem_attr(c->device, (const void*)k, G::SMEM) != cudaSuccess) return vo_fail(c, VO_ERR_CUDA, "exp: shared-memory carve-out rejected");
     const int64_t tiles = ceil_div(kp.N, TB);
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, c->sm_count);
-    k<<<grid, G::THREADS, G::SMEM, c->stream>>>(kp, frag, psi, psi_out, gp, coef_in, ca, ev, order);
+    k<<<grid, G::THREADS, G::SMEM, c->stream>>>(kp, frag, psi, psi_out, gp, coef_in, ca, ev, order, tile_ctr);
     VO_CHECK_LAUNCH(c);
     return VO_OK;
 }
@@ -164,7 +165,7 @@ bool exp_geometry(int n, int M, unsigned* threads, size_t* smem) {
 }
 
 int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_out, const double* gp, const double2* coef_in, const CtlArrays& ca, EvSlot* ev,
-                     void* custom_fn = nullptr, const int* order = nullptr) {
+                     void* custom_fn = nullptr, const int* order = nullptr, int* tile_ctr = nullptr) {
     vo_ctx c = sp->ctx;
     if (custom_fn) {  // the user's generator: same kernel, compiled at run time
         unsigned threads = 0;
@@ -173,7 +174,7 @@ int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_ou
         ExpKP kpc = kp;
         const double* frag = sp->frag_dev;
         CtlArrays cac = ca;
-        void* args[] = {&kpc, &frag, &psi, &psi_out, &gp, &coef_in, &cac, &ev, &order};
+        void* args[] = {&kpc, &frag, &psi, &psi_out, &gp, &coef_in, &cac, &ev, &order, &tile_ctr};
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(kp.N, 16), c->sm_count);
         int32_t r = rtc_exp_launch(c, custom_fn, grid, threads, smem, args);
         if (r != VO_OK) return r;
@@ -182,10 +183,10 @@ int32_t dispatch_exp(vo_split sp, const ExpKP& kp, double2* psi, double2* psi_ou
     }
     {   // experiment switch (A/B runs): config 5's shape with tiles of 32 systems on 16 warps, the basis shared by both column groups
         static const int tb = getenv("VECODE_EXP_TB") ? atoi(getenv("VECODE_EXP_TB")) : 16;
-        if (tb == 32 && sp->n == 64 && sp->M == 2) return launch_exp<64, 2, 32>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order);
+        if (tb == 32 && sp->n == 64 && sp->M == 2) return launch_exp<64, 2, 32>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order, tile_ctr);
     }
 #define VO_EXP_CASE(NDIM, MM) \
-    if (sp->n == NDIM && sp->M == MM) return launch_exp<NDIM, MM, 16>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order);
+    if (sp->n == NDIM && sp->M == MM) return launch_exp<NDIM, MM, 16>(c, kp, sp->frag_dev, psi, psi_out, gp, coef_in, ca, ev, order, tile_ctr);
     VO_EXP_SHAPES(VO_EXP_CASE)
 #undef VO_EXP_CASE
     return vo_fail(c, VO_ERR_UNSUPPORTED, "exp: the shared-basis split is compiled for n in {16, 32} with M <= 4, n in {24, 48} with M in {2, 3}, (40, 2) and n = 64 with M <= 3 "
@@ -297,6 +298,8 @@ static int32_t exp_dynamic_order(vo_expsolver_s* s, const ExpKP& kp, const int**
     VO_CHECK_LAUNCH(c);
     if (vo_sort_pairs(s->sort_tmp, s->sort_tmp_bytes, s->key_in, s->key_out, s->idx_in, s->idx_out, n, c->stream) != cudaSuccess)
         return vo_fail(c, VO_ERR_CUDA, "exp: dynamic grouping sort");
+    if (!s->tile_ctr && cudaMalloc(&s->tile_ctr, sizeof(int)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "exp: tile counter");
+    VO_CUDA(c, cudaMemsetAsync(s->tile_ctr, 0, sizeof(int), c->stream));
     *order = s->idx_out;
     return VO_OK;
 }
@@ -327,7 +330,7 @@ int32_t exp_launch_event(vo_expsolver_s* s, bool adaptive) {
     const int* order = nullptr;
     int32_t orc = exp_dynamic_order(s, kp, &order);
     if (orc != VO_OK) return orc;
-    return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn, order);
+    return dispatch_exp(s->sp, kp, s->psi, nullptr, s->gp, nullptr, s->ca, s->ev_dev, s->gen_fn, order, order ? s->tile_ctr : nullptr);
 }
 
 void exp_res_add(vo_step_result* res, const EvSlot& e, int launches) {
@@ -511,7 +514,7 @@ int32_t vo_exp_destroy(vo_expsolver s) {
     cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->psi), cudaFree(s->psi0), cudaFree(s->gp);
     cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm), cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
-    cudaFree(s->key_in), cudaFree(s->key_out), cudaFree(s->idx_in), cudaFree(s->idx_out), cudaFree(s->sort_tmp);
+    cudaFree(s->key_in), cudaFree(s->key_out), cudaFree(s->idx_in), cudaFree(s->idx_out), cudaFree(s->sort_tmp), cudaFree(s->tile_ctr);
     cudaFree(s->ev_dev), cudaFreeHost(s->ev_host);
     rtc_exp_unload(s->gen_module);
     cudaFree(s->perm), cudaFree(s->stage);

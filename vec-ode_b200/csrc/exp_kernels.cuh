@@ -343,7 +343,8 @@ template <int NDIM, int M, int TB, class GEN>
 __global__ void __launch_bounds__(Geo<NDIM, M, TB>::THREADS, 1)
 exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ frag, double2* __restrict__ psi, double2* __restrict__ psi_out,
                 const double* __restrict__ gp, const double2* __restrict__ coef_in, const CtlArrays ca, EvSlot* __restrict__ ev,
-                const int* __restrict__ order /* nullable: slot -> system, tiles of systems with similar ||L h|| (exp.cu: dynamic grouping) */) {
+                const int* __restrict__ order /* nullable: slot -> system, tiles of systems with similar ||L h|| (exp.cu: dynamic grouping) */,
+                int* __restrict__ tile_ctr /* nullable: with `order`, tiles are handed out by this counter, largest theta first */) {
     using G = Geo<NDIM, M, TB>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sB = reinterpret_cast<double*>(smem_raw);
@@ -367,6 +368,11 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     const int64_t n_tiles = (kp.N + TB - 1) / TB;
     int buf = 0;
     unsigned c_step = 0, c_chkpt = 0, c_rej = 0, c_end = 0, c_stuck = 0;
+    // Tile -> slots. With the dynamic grouping the slots are sorted by ascending theta, so tiles differ in cost: they are then taken from
+    // the expensive end and handed out by an atomic counter as CTAs become free (longest-processing-time-first), which also removes the
+    // 42-or-43-tiles-per-CTA quantisation of a static stride. Without it: the static stride.
+    const bool dyn_tiles = order != nullptr && tile_ctr != nullptr;
+    auto tile_base = [&](int64_t tl) { return (dyn_tiles ? n_tiles - 1 - tl : tl) * TB; };
     // Control data of a tile's systems (solver events): which system sits in the slot, its status word, t, h and generator parameters.
     // The thread that owns slot s fetches them for the NEXT tile of this CTA while the current tile's exponentials run, so that phase A
     // starts from registers instead of a chain of four dependent global loads (order -> word -> t, h -> parameters) per tile.
@@ -379,7 +385,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
     auto prefetch_ctl = [&](int64_t tl) {
         p_sys = kp.N;
         if (tl < n_tiles) {
-            const int64_t slot = tl * TB + threadIdx.x;
+            const int64_t slot = tile_base(tl) + threadIdx.x;
             if (slot < kp.N) p_sys = order ? (long long)order[slot] : slot;
         }
         if (p_sys < kp.N) {
@@ -390,9 +396,10 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
                 if (q < 3 * (kp.M_gen - 1)) p_g[q] = g[q];
         }
     };
+    int64_t next_tile = 0;
     if (kp.mode == 0 && threadIdx.x < TB) prefetch_ctl(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * TB;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile = next_tile) {
+        const int64_t base = tile_base(tile);
         uint32_t a_word = 0;  // this slot's status word and step size, from phase A to phase D (same thread)
         double a_h = 0.0;
         // exponentials of this event: nbase for the propagated solution, then nerr for the embedded lower-order one (from x0)
@@ -406,7 +413,7 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             const int64_t slot = base + s;
             int64_t sys;
             double a_t = 0.0, a_g[PG];
-            if (kp.mode == 0) {  // from the prefetch of the previous iteration; the next tile's loads go out now
+            if (kp.mode == 0) {  // from the prefetch of the previous iteration (the next tile's loads go out after phase B)
                 sys = p_sys, a_word = p_word, a_t = p_t, a_h = p_h;
 #pragma unroll
                 for (int q = 0; q < PG; ++q) a_g[q] = p_g[q];
@@ -543,9 +550,12 @@ exp_step_kernel(const __grid_constant__ ExpKP kp, const double* __restrict__ fra
             int any = 0;
             for (int s = 0; s < TB; ++s) any |= sEv[s] == VO_EV_STEP;
             sPlan[2 * VO_EXP_MAX_E] = any;
+            sPlan[2 * VO_EXP_MAX_E + 1] = dyn_tiles ? (int)gridDim.x + atomicAdd(tile_ctr, 1) : (int)(tile + gridDim.x);  // this CTA's next tile
         }
         __syncthreads();
         const bool any_step = sPlan[2 * VO_EXP_MAX_E] != 0;
+        next_tile = sPlan[2 * VO_EXP_MAX_E + 1];
+        if (kp.mode == 0 && threadIdx.x < TB) prefetch_ctl(next_tile);  // in flight during the exponentials below
         // ---- phase C: the exponentials
         double x0r[2][2], x0i[2][2], xfr[2][2], xfi[2][2], xer[2][2], xei[2][2];
         if (any_step) {
