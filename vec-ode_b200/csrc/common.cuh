@@ -73,6 +73,7 @@ struct vo_rhs_s {
     int alias_kind = -1;               // >= 0: a compiled-in family re-compiled at run time (RhsCustom = RhsF<alias_kind, d>) to take a user norm
     std::string norm_src;              // source of the VoUserNorm functor compiled into this RHS's modules (vo_solver_set_norm_custom)
 };
+cudaError_t vo_small_readback(vo_ctx c, void* host_pinned, const void* dev, size_t bytes);  // ctx.cu: bytes % 8 == 0, pinned (mapped) destination
 void custom_rhs_release(vo_rhs_s* r);  // nvrtc_rhs.cu
 // user-defined norm (nvrtc_rhs.cu, norm_custom.cuh): the functor's source and the reduction kernels compiled from it
 struct vo_normfn_s {

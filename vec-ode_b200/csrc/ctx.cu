@@ -21,6 +21,17 @@ cudaError_t vo_ensure_smem_attr(int device, const void* func, size_t bytes) {
     return e;
 }
 
+// Small device -> pinned-host read-backs (event counters) as a KERNEL that stores into the mapped host buffer, not as a copy: a
+// cudaMemcpyAsync queues on the device-to-host copy engine behind whatever else is there — on the root of a sharded solve the
+// 32 MB pieces of the final gather — and a solver's control loop then idles for the length of that transfer at every read-back.
+__global__ void vo_small_readback_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst_host, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst_host[i] = src[i];
+}
+cudaError_t vo_small_readback(vo_ctx c, void* host_pinned, const void* dev, size_t bytes) {
+    vo_small_readback_kernel<<<1, 256, 0, c->stream>>>((const unsigned long long*)dev, (unsigned long long*)host_pinned, (int)(bytes / 8));
+    return cudaGetLastError();
+}
+
 extern "C" {
 
 int32_t vo_version(void) { return VO_VERSION; }

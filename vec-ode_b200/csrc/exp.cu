@@ -248,7 +248,7 @@ int32_t launch_magnus_dense(vo_expsolver_s* s, const ExpKP& kp) {
 
 int32_t exp_ev_read(vo_expsolver_s* s, EvSlot* out) {
     vo_ctx c = s->ctx;
-    VO_CUDA(c, cudaMemcpyAsync(s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(c, vo_small_readback(c, s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS));  // not a copy: see ctx.cu
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
     EvSlot tot;
     std::memset(&tot, 0, sizeof tot);

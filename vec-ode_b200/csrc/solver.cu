@@ -399,7 +399,7 @@ void ev_sum(const EvSlot* h, EvSlot* out) {
 int32_t ev_read(vo_solver_s* s, EvSlot* out) {
     vo_ctx c = s->ctx;
     const uint64_t epoch = c->epoch;
-    VO_CUDA(c, cudaMemcpyAsync(s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(c, vo_small_readback(c, s->ev_host, s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS));  // not a copy: see ctx.cu
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
     c->epoch = epoch;  // reading the counters touches no solver state: the CTA chains stay alive
     EvSlot tot;
