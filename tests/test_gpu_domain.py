@@ -148,3 +148,32 @@ def test_slab_with_a_user_stencil_of_radius_two_bitwise(vo, ctx):
     for _ in range(N_STEPS + 1):
         ds.step()
     assert np.array_equal(ds.local_interior(), ref)
+
+
+def test_adaptive_slab_with_a_user_norm(vo, ctx):
+    """The user's norm on a distributed state: every piece reports the accumulator of the functor's `map` over its own points
+    (vo_adaptive_try with VO_NORM_CUSTOM numbers the components globally within the slab), the pieces are joined and the host applies
+    the functor's `finish` twin — same Step / Reject sequence as the single-state solve with the same norm."""
+    d_total, tf, rtol = 1 << 14, 2.0, 1e-6
+    mk = lambda: vo.NormFn(ctx, "m = e * e;", "sum", "r = sqrt(acc / n);", finish_py=lambda acc, n: float(np.sqrt(acc / n)))
+    rhs = vo.Rhs(ctx, "HEAT1D", d_total, [1.0])
+    s = vo.RK45Solver(rhs, 0.0, tf, vo.Ensemble.from_host(ctx, _rough_u0_at(vo, np.arange(d_total), d_total)[None, :]), 0.01).with_tolerance(rtol, rtol)
+    s.with_step_range(1e-6, 1.0).with_init_step(0.01).with_norm(mk())
+    ref_events = []
+    while True:
+        st = s.step_adaptive()
+        ref_events.append([k for k in ("Step", "Chkpt", "Reject", "End") if st.counts[k]][0])
+        if st.kind != "Ok":
+            break
+    ds = vo.domain.HeatSlabSolver(ctx, d_total, lambda j: _rough_u0_at(vo, j, d_total), 1.0, 0.0, tf, 0.01, tableau=vo.ButcherTableu.builtin("RKF45_REF"),
+                                  steps_per_exchange=2, adaptive=True)
+    ds.with_tolerance(rtol, rtol, norm=mk())
+    ds.solver.with_step_range(1e-6, 1.0).with_init_step(0.01)
+    events = []
+    while True:
+        st = ds.step_adaptive()
+        events.append([k for k in ("Step", "Chkpt", "Reject", "End") if st.counts[k]][0])
+        if st.kind != "Ok":
+            break
+    assert events == ref_events
+    assert np.abs(ds.local_interior() - s.current()[1].to_host()[0]).max() <= 1e-12
