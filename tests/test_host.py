@@ -42,3 +42,32 @@ def test_schrodinger_system_is_hermitian(vo):
     assert np.array_equal(H0, H0.conj().T) and np.allclose(H1, H1.conj().T, atol=0)
     gp = vo.workloads.schrodinger_drive(100)
     assert gp.shape == (100, 1, 3) and np.all(gp[:, 0, 0] >= 0.5) and np.all(gp[:, 0, 1] < 3.0)
+
+
+def test_chunk_range_partitions_and_tapers(vo):
+    """pipeline.chunk_range: the chunks of a pipelined solve tile [0, n) exactly, in order, and get smaller towards the end (the last
+    chunk's transfer is the one nothing overlaps)."""
+    from vecode_b200.pipeline import chunk_range
+    for n in (1_000_000, 125_000, 40_003, 1001, 7, 3, 1):
+        for parts in (1, 2, 3, 4, 8):
+            r = [chunk_range(n, q, parts) for q in range(parts)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(parts - 1)), (n, parts, r)
+            sizes = [b - a for a, b in r]
+            assert all(x >= 0 for x in sizes)
+            if n >= 1000 and parts > 1:
+                assert sizes == sorted(sizes, reverse=True) and sizes[-1] < sizes[0]
+    assert [b - a for a, b in (chunk_range(1_000_000, q, 4) for q in range(4))] == [320000, 280000, 240000, 160000]
+
+
+def test_bench_taylor_plan_matches_the_oracles_plan():
+    """bench.py's vectorised Taylor plan (the algorithmic term count of the roofline of config 5) against the pure-Python oracle's
+    plan, which the kernels are tested against."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import exp_oracle as eo
+    import numpy as np
+    thetas = np.array([1e-9, 1e-3, 0.05, 0.3, 0.477, 0.999, 1.0, 1.0001, 1.7, 2.0, 3.3, 6.02, 11.5])
+    want = [np.prod(eo.BasisSplit.plan(float(t))) for t in thetas]
+    assert list(bench._plan_terms(thetas)) == [float(w) for w in want]
