@@ -777,6 +777,24 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
     return out
 
 
+def blocking_sync(local):
+    """Make this process's synchronisations SLEEP instead of spin (CU_CTX_SCHED_BLOCKING_SYNC on the device's primary context, set before
+    anything initialises it). A rank's e2e pipeline runs four chunk threads that wait in stream synchronisations; with 4-8 ranks per box
+    that is 20-40 spinning threads on the box's 16 hardware threads, and some rank's last chunk is late in most solves.
+    A solve synchronises a handful of times per chunk, so the wake-up latency of a blocking wait costs next to nothing."""
+    import ctypes
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        dev = ctypes.c_int()
+        if cu.cuInit(0) != 0 or cu.cuDeviceGet(ctypes.byref(dev), int(local)) != 0:
+            return "spin (driver API unavailable)"
+        fn = getattr(cu, "cuDevicePrimaryCtxSetFlags_v2", None) or cu.cuDevicePrimaryCtxSetFlags
+        rc = fn(dev, 4)  # CU_CTX_SCHED_BLOCKING_SYNC
+        return "blocking (CU_CTX_SCHED_BLOCKING_SYNC)" if rc == 0 else f"spin (cuDevicePrimaryCtxSetFlags -> {rc})"
+    except Exception as e:  # noqa: BLE001
+        return f"spin ({e!r})"
+
+
 def numa_bind(torch, local):
     """Run this rank's host threads on the CPUs of its GPU's NUMA node, so that the pinned staging buffers it allocates
     (first touch) and the threads that drive its copies are local to the GPU's PCIe root. Returns the node, or None."""
@@ -839,6 +857,7 @@ def main():
     import torch.distributed as dist
     import vecode_b200 as vo
 
+    host_sync = blocking_sync(local) if (world >= 4 or os.environ.get("VECODE_BENCH_BLOCKING_SYNC") == "1") else "spin (CUDA default)"
     torch.cuda.set_device(local)
     numa = numa_bind(torch, local) if world > 1 else None  # pinned buffers and copy threads next to this rank's GPU
     if world > 1:
@@ -1034,6 +1053,7 @@ def main():
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step, "clocks": clocks}
         if numa is not None:
             line["config"]["numa_node_rank0"] = numa
+        line["config"]["host_sync"] = host_sync
         if gather_ms is not None:
             line["final_gather_ms"] = gather_ms
             line["final_gather_note"] = (f"vo_group_gather of the whole ensemble ({world} x {W.state_mb if W is LorenzRK4 else 16} MB of state) on its own: NCCL into rank 0's "
