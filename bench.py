@@ -857,7 +857,9 @@ def main():
     import torch.distributed as dist
     import vecode_b200 as vo
 
-    host_sync = blocking_sync(local) if (world >= 4 or os.environ.get("VECODE_BENCH_BLOCKING_SYNC") == "1") else "spin (CUDA default)"
+    # experiment switch: measured 6.5 -> 7.8 ms per e2e solve at 2 GPUs (the wake-up latency of a blocking wait is paid at every upload, reset and
+    # read-back), so it stays off; whether it wins at 8 ranks per box, where 40 spinning chunk threads share 16 hardware threads, is unmeasured
+    host_sync = blocking_sync(local) if os.environ.get("VECODE_BENCH_BLOCKING_SYNC") == "1" else "spin (CUDA default)"
     torch.cuda.set_device(local)
     numa = numa_bind(torch, local) if world > 1 else None  # pinned buffers and copy threads next to this rank's GPU
     if world > 1:
