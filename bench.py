@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — ensemble trajectory-steps/s of the time-stepping hot path on N B200s (BASELINE.json's metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vdp_dopri5|lorenz_rk4|heat_rk4|heat_rk4_fused|heat_rk4_dd|schrodinger_cfm4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vdp_dopri5|lorenz_rk4|heat_rk4|heat_rk4_fused|heat_rk4_dd|schrodinger_cfm4|
+                   schrodinger_magnus_applied|schrodinger_magnus_dense]
                   [--arith strict|fast]
 The default workload is config 3 (adaptive DoPri5, 10^6 Van der Pol oscillators), the configuration the north-star target is
 quoted on; at N = 1 the other configs are measured in the same run and reported under `also`, each with its own roofline.
