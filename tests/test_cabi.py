@@ -104,3 +104,20 @@ def test_cpp_harness_on_the_gpu(tmp_path):
         r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, VO_HARNESS_GPUS="2"))
         print(r.stdout)
         assert r.returncode == 0 and "group of 2 GPU(s)" in r.stdout and "gathered ensemble == single-ctx solve: yes" in r.stdout, r.stdout + r.stderr
+
+
+def test_generated_rust_ffi_is_current_and_complete():
+    """bindings/rust/vecode_b200_sys.rs (tools/gen_rust_ffi.py): the raw `extern "C"` half of the Rust binding a maintainer of the
+    reference would add. No rustc here, so the check is textual: regenerating gives the committed file, and every function the header
+    declares has exactly one `pub fn`."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    committed = open(mod.OUT).read()
+    text, names = mod.main()
+    assert text == committed, "bindings/rust/vecode_b200_sys.rs is stale: run python tools/gen_rust_ffi.py"
+    assert sorted(names) == _declared()
+    for n in names:
+        assert len(re.findall(rf"pub fn {n}\(", text)) == 1
+    assert "pub const VO_ERR_BAD_ARG: i32 = -1;" in text and "pub struct VoGroupStats" in text
