@@ -121,3 +121,17 @@ def test_generated_rust_ffi_is_current_and_complete():
     for n in names:
         assert len(re.findall(rf"pub fn {n}\(", text)) == 1
     assert "pub const VO_ERR_BAD_ARG: i32 = -1;" in text and "pub struct VoGroupStats" in text
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/vecode_b200.h must compile as C99 (no C++-isms, no torch or CUDA types in the signatures) and a C
+    program must link against the shared object."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "vecode_b200.h"\nint main(void) { vo_step_result r; vo_group_stats g; (void)r; (void)g; return vo_version() > 0 ? 0 : 1; }\n')
+    so_dir = os.path.join(ROOT, "vec-ode_b200")
+    exe = str(tmp_path / "hdr")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe, "-L", so_dir,
+                        "-lvecode_b200", f"-Wl,-rpath,{so_dir}", "-Wl,-rpath-link,/usr/local/cuda/lib64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([exe]).returncode == 0  # vo_version needs no GPU
