@@ -77,6 +77,14 @@ int32_t vo_version(void);
 /* Number of kernels this ctx has launched since creation (bench.py's `gpu_launches`). */
 int64_t vo_ctx_launch_count(vo_ctx ctx);
 
+/* The library's own bounds check (compute-sanitizer's stand-in on pools where it is closed). With VECODE_GUARD=1 in the environment
+ * when the library is loaded, every device block the library allocates lies between two 4 KiB guard zones filled with a byte
+ * pattern. vo_guard_check synchronises, inspects the zones of every live block and returns the number of blocks found damaged since
+ * load (blocks already freed were inspected when freed); *live_blocks (may be NULL) receives the number of blocks checked. Returns 0
+ * and checks nothing when the switch is off (vo_guard_enabled() == 0). Diagnostics go to stderr. */
+int32_t vo_guard_enabled(void);
+int64_t vo_guard_check(int64_t* live_blocks);
+
 /* Arithmetic mode of every kernel launched on the ctx.
  * VO_ARITH_STRICT: separate IEEE multiply and add in the reference's operation order, zero coefficients
  *   kept — bit-identical to rustc's un-fused f64 code (src/impls/ndarray.rs:14-32).

@@ -70,6 +70,8 @@ SIGNATURES = {
     "vo_last_error": (C.c_char_p, [_vp]),
     "vo_version": (_i32, []),
     "vo_ctx_launch_count": (_i64, [_vp]),
+    "vo_guard_enabled": (_i32, []),
+    "vo_guard_check": (_i64, [C.POINTER(_i64)]),
     "vo_ctx_set_arith": (_i32, [_vp, _i32]),
     "vo_ens_create": (_i32, [_vp, _i64, _i64, _pvp]),
     "vo_ens_wrap": (_i32, [_vp, _vp, _i64, _i64, _pvp]),

@@ -73,6 +73,13 @@ struct vo_rhs_s {
     int alias_kind = -1;               // >= 0: a compiled-in family re-compiled at run time (RhsCustom = RhsF<alias_kind, d>) to take a user norm
     std::string norm_src;              // source of the VoUserNorm functor compiled into this RHS's modules (vo_solver_set_norm_custom)
 };
+// Device allocations of the library (ctx.cu). Ordinary cudaMalloc / cudaFree unless the process runs with VECODE_GUARD=1: then every
+// allocation sits between two 4 KiB guard zones filled with a byte pattern, checked when the block is freed and by vo_guard_check —
+// a write past either end of a state, control or scratch array by any kernel shows up as a violation (tests/conftest.py asserts zero
+// after every GPU test when the switch is on). compute-sanitizer is closed on the GPU pool; this is the library's own bounds check.
+cudaError_t vo_dmalloc_impl(void** p, size_t bytes);
+cudaError_t vo_dfree(void* p);
+template <class T> static inline cudaError_t vo_dmalloc(T** p, size_t bytes) { return vo_dmalloc_impl((void**)p, bytes); }
 cudaError_t vo_small_readback(vo_ctx c, void* host_pinned, const void* dev, size_t bytes);  // ctx.cu: bytes % 8 == 0, pinned (mapped) destination
 void custom_rhs_release(vo_rhs_s* r);  // nvrtc_rhs.cu
 // user-defined norm (nvrtc_rhs.cu, norm_custom.cuh): the functor's source and the reduction kernels compiled from it

@@ -1,5 +1,6 @@
 // ctx.cu — contexts, ensembles (SoA device buffers), tableaux and RHS handles.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <set>
@@ -19,6 +20,116 @@ cudaError_t vo_ensure_smem_attr(int device, const void* func, size_t bytes) {
     const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) have = bytes;
     return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Guarded device allocations (VECODE_GUARD=1), see common.cuh
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t GUARD_BYTES = 4096;
+constexpr unsigned char GUARD_PATTERN = 0xA5;
+struct GuardBlock {
+    void* base;
+    size_t bytes;
+    int device;
+};
+std::mutex g_guard_mu;
+std::map<void*, GuardBlock> g_guard_live;  // user pointer -> block
+int64_t g_guard_violations = 0;            // blocks found damaged so far (each block counted once per check)
+int64_t g_guard_allocs = 0;
+
+bool guard_on() {
+    static const bool on = [] {
+        const char* e = getenv("VECODE_GUARD");
+        return e && e[0] && e[0] != '0';
+    }();
+    return on;
+}
+
+// Reads both guard zones of one block back; returns the number of damaged bytes and repairs them so that a later check reports new damage only.
+size_t guard_damage(void* user, const GuardBlock& b) {
+    std::vector<unsigned char> host(2 * GUARD_BYTES);
+    DeviceGuard g(b.device);
+    cudaDeviceSynchronize();
+    unsigned char* lo = (unsigned char*)b.base;
+    unsigned char* hi = (unsigned char*)user + b.bytes;
+    if (cudaMemcpy(host.data(), lo, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(host.data() + GUARD_BYTES, hi, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    size_t bad = 0, first = 0;
+    for (size_t i = 0; i < host.size(); ++i)
+        if (host[i] != GUARD_PATTERN) {
+            if (!bad) first = i;
+            ++bad;
+        }
+    if (bad) {
+        const long off = first < GUARD_BYTES ? (long)first - (long)GUARD_BYTES : (long)(first - GUARD_BYTES);
+        fprintf(stderr, "vecode guard: %zu byte(s) written outside a %zu-byte device block; first at %s%ld\n", bad, b.bytes, first < GUARD_BYTES ? "start" : "end+",
+                off);
+        cudaMemset(lo, GUARD_PATTERN, GUARD_BYTES), cudaMemset(hi, GUARD_PATTERN, GUARD_BYTES);
+    }
+    return bad;
+}
+}  // namespace
+
+cudaError_t vo_dmalloc_impl(void** p, size_t bytes) {
+    if (!guard_on()) return cudaMalloc(p, bytes);
+    // the user block keeps cudaMalloc's alignment (the front guard is a multiple of 512 bytes); its END is padded to 16 bytes only, so that
+    // the rear guard starts as close behind the last element as the bulk-copy granularity of the kernels allows
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    void* base = nullptr;
+    const cudaError_t e = cudaMalloc(&base, padded + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    unsigned char* user = (unsigned char*)base + GUARD_BYTES;
+    cudaMemset(base, GUARD_PATTERN, GUARD_BYTES);
+    cudaMemset(user + bytes, GUARD_PATTERN, padded - bytes + GUARD_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    g_guard_live[user] = GuardBlock{base, bytes, dev};
+    ++g_guard_allocs;
+    *p = user;
+    return cudaSuccess;
+}
+
+cudaError_t vo_dfree(void* p) {
+    if (!p || !guard_on()) return cudaFree(p);
+    GuardBlock b{};
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        auto it = g_guard_live.find(p);
+        if (it == g_guard_live.end()) return cudaFree(p);  // not ours (allocated before the switch was read: cannot happen) — plain free
+        b = it->second;
+        g_guard_live.erase(it);
+    }
+    if (guard_damage(p, b)) {
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        ++g_guard_violations;
+    }
+    DeviceGuard g(b.device);
+    return cudaFree(b.base);
+}
+
+extern "C" int32_t vo_guard_enabled(void) { return guard_on() ? 1 : 0; }
+
+// Checks the guard zones of every live block (synchronises the devices) and returns the number of damaged blocks found since the
+// library was loaded, freed ones included; 0 when the switch is off. live_blocks (may be NULL): blocks currently allocated.
+extern "C" int64_t vo_guard_check(int64_t* live_blocks) {
+    if (live_blocks) *live_blocks = 0;
+    if (!guard_on()) return 0;
+    std::vector<std::pair<void*, GuardBlock>> blocks;
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mu);
+        blocks.assign(g_guard_live.begin(), g_guard_live.end());
+    }
+    int64_t found = 0;
+    for (auto& kv : blocks) found += guard_damage(kv.first, kv.second) ? 1 : 0;
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    g_guard_violations += found;
+    if (live_blocks) *live_blocks = (int64_t)g_guard_live.size();
+    return g_guard_violations;
 }
 
 // Small device -> pinned-host read-backs (event counters) as a KERNEL that stores into the mapped host buffer, not as a copy: a
@@ -75,7 +186,7 @@ static int32_t ctx_create_impl(int32_t device, void* stream, int32_t urgency, vo
         }
         cudaGetLastError();
     }
-    if (cudaMallocHost(&c->pinned, 4096) != cudaSuccess || cudaMalloc(&c->dscratch, 4096) != cudaSuccess) {
+    if (cudaMallocHost(&c->pinned, 4096) != cudaSuccess || vo_dmalloc(&c->dscratch, 4096) != cudaSuccess) {
         delete c;
         return vo_fail(nullptr, VO_ERR_ALLOC, "vo_ctx_create: scratch allocation failed");
     }
@@ -89,7 +200,7 @@ int32_t vo_ctx_destroy(vo_ctx c) {
     cudaStreamSynchronize(c->stream);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     cudaFreeHost(c->pinned);
-    cudaFree(c->dscratch);
+    vo_dfree(c->dscratch);
     delete c;
     return VO_OK;
 }
@@ -146,7 +257,7 @@ int32_t vo_ens_create(vo_ctx c, int64_t d, int64_t n, vo_ens* out) {
     DeviceGuard g(c->device);
     vo_ens e = new vo_ens_s();
     e->ctx = c, e->d = d, e->n = n, e->owns = true;
-    if (cudaMalloc(&e->p, sizeof(double) * d * n) != cudaSuccess) {
+    if (vo_dmalloc(&e->p, sizeof(double) * d * n) != cudaSuccess) {
         cudaGetLastError();
         delete e;
         return vo_fail(c, VO_ERR_ALLOC, "vo_ens_create: cudaMalloc failed");
@@ -185,7 +296,7 @@ int32_t vo_ens_destroy(vo_ens e) {
     DeviceGuard g(e->ctx->device);
     if (e->owns && e->p) {
         cudaStreamSynchronize(e->ctx->stream);
-        cudaFree(e->p);
+        vo_dfree(e->p);
     }
     delete e;
     return VO_OK;
@@ -363,7 +474,7 @@ int32_t vo_rhs_set_param(vo_rhs r, int32_t idx, double value) {
     if (r->per_traj[idx]) {
         DeviceGuard g(r->ctx->device);
         cudaStreamSynchronize(r->ctx->stream);
-        cudaFree(r->per_traj[idx]);
+        vo_dfree(r->per_traj[idx]);
         r->per_traj[idx] = nullptr, r->per_traj_n[idx] = 0;
     }
     return VO_OK;
@@ -376,11 +487,11 @@ int32_t vo_rhs_set_param_array(vo_rhs r, int32_t idx, const double* host, int64_
     DeviceGuard g(c->device);
     if (r->per_traj[idx] && r->per_traj_n[idx] != n) {
         cudaStreamSynchronize(c->stream);
-        cudaFree(r->per_traj[idx]);
+        vo_dfree(r->per_traj[idx]);
         r->per_traj[idx] = nullptr;
     }
     if (!r->per_traj[idx]) {
-        if (cudaMalloc(&r->per_traj[idx], sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_rhs_set_param_array: cudaMalloc failed");
+        if (vo_dmalloc(&r->per_traj[idx], sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_rhs_set_param_array: cudaMalloc failed");
         r->per_traj_n[idx] = n;
     }
     VO_CUDA(c, cudaMemcpyAsync(r->per_traj[idx], host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -394,7 +505,7 @@ int32_t vo_rhs_destroy(vo_rhs r) {
     DeviceGuard g(r->ctx->device);
     cudaStreamSynchronize(r->ctx->stream);
     for (int i = 0; i < VO_MAX_PARAMS; ++i)
-        if (r->per_traj[i]) cudaFree(r->per_traj[i]);
+        if (r->per_traj[i]) vo_dfree(r->per_traj[i]);
     if (r->kind == VO_RHS_CUSTOM) custom_rhs_release(r);
     delete r;
     return VO_OK;

@@ -289,8 +289,8 @@ static int32_t exp_dynamic_order(vo_expsolver_s* s, const ExpKP& kp, const int**
     const int n = (int)s->N;
     if (!s->key_in) {
         const size_t tmp = vo_sort_pairs_tmp_bytes(n);
-        if (cudaMalloc(&s->key_in, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->key_out, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->idx_in, 4 * (size_t)n) != cudaSuccess ||
-            cudaMalloc(&s->idx_out, 4 * (size_t)n) != cudaSuccess || cudaMalloc(&s->sort_tmp, tmp) != cudaSuccess)
+        if (vo_dmalloc(&s->key_in, 4 * (size_t)n) != cudaSuccess || vo_dmalloc(&s->key_out, 4 * (size_t)n) != cudaSuccess || vo_dmalloc(&s->idx_in, 4 * (size_t)n) != cudaSuccess ||
+            vo_dmalloc(&s->idx_out, 4 * (size_t)n) != cudaSuccess || vo_dmalloc(&s->sort_tmp, tmp) != cudaSuccess)
             return vo_fail(c, VO_ERR_ALLOC, "exp: dynamic grouping buffers");
         s->sort_tmp_bytes = tmp;
     }
@@ -298,7 +298,7 @@ static int32_t exp_dynamic_order(vo_expsolver_s* s, const ExpKP& kp, const int**
     VO_CHECK_LAUNCH(c);
     if (vo_sort_pairs(s->sort_tmp, s->sort_tmp_bytes, s->key_in, s->key_out, s->idx_in, s->idx_out, n, c->stream) != cudaSuccess)
         return vo_fail(c, VO_ERR_CUDA, "exp: dynamic grouping sort");
-    if (!s->tile_ctr && cudaMalloc(&s->tile_ctr, sizeof(int)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "exp: tile counter");
+    if (!s->tile_ctr && vo_dmalloc(&s->tile_ctr, sizeof(int)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "exp: tile counter");
     VO_CUDA(c, cudaMemsetAsync(s->tile_ctr, 0, sizeof(int), c->stream));
     *order = s->idx_out;
     return VO_OK;
@@ -380,12 +380,12 @@ int32_t vo_split_basis_create(vo_ctx c, int32_t n, int32_t M, const double* basi
                     for (int l = 0; l < 32; ++l)  // A fragment of mma.m8n8k4: lane l holds A[l/4][l%4]
                         frag[((((size_t)(m * 2 + p) * NW + w) * NK + kk) * 32) + l] = basis[(((size_t)m * n + 8 * w + l / 4) * n + 4 * kk + l % 4) * 2 + p];
     }
-    if (cudaMalloc(&sp->frag_dev, frag.size() * sizeof(double)) != cudaSuccess) {
+    if (vo_dmalloc(&sp->frag_dev, frag.size() * sizeof(double)) != cudaSuccess) {
         delete sp;
         return vo_fail(c, VO_ERR_ALLOC, "vo_split_basis_create: cudaMalloc failed");
     }
     VO_CUDA(c, cudaMemcpyAsync(sp->frag_dev, frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (cudaMalloc(&sp->basis_dev, sizeof(double2) * (size_t)M * n * n) != cudaSuccess) {
+    if (vo_dmalloc(&sp->basis_dev, sizeof(double2) * (size_t)M * n * n) != cudaSuccess) {
         vo_split_destroy(sp);
         return vo_fail(c, VO_ERR_ALLOC, "vo_split_basis_create: cudaMalloc failed");
     }
@@ -399,7 +399,7 @@ int32_t vo_split_destroy(vo_split sp) {
     if (!sp) return VO_OK;
     DeviceGuard g(sp->ctx->device);
     cudaStreamSynchronize(sp->ctx->stream);
-    cudaFree(sp->frag_dev), cudaFree(sp->basis_dev);
+    vo_dfree(sp->frag_dev), vo_dfree(sp->basis_dev);
     delete sp;
     return VO_OK;
 }
@@ -488,11 +488,11 @@ int32_t vo_exp_create(vo_ctx c, vo_split sp, int32_t scheme, int32_t M_gen, cons
     s->ctx = c, s->sp = sp, s->scheme = scheme, s->M_gen = M_gen, s->N = N, s->t0 = t0, s->tf = tf, s->h_init = h;
     if (scheme == VO_EXP_CFM4) exp_store_tables(s, C_GAUSS_LEGENDRE_4, 2, CFM_R4_J2_GL, 2, CFM_R2_J1_GL, 1);  // ExpCFMSolver::new, cfm.rs:131-154
     const size_t nb = sizeof(double2) * (size_t)N * sp->n, ngp = sizeof(double) * (size_t)N * std::max(1, M_gen - 1) * 3;
-    bool ok = cudaMalloc(&s->psi, nb) == cudaSuccess && cudaMalloc(&s->psi0, nb) == cudaSuccess && cudaMalloc(&s->gp, ngp) == cudaSuccess &&
-              cudaMalloc(&s->ca.t, 8 * N) == cudaSuccess && cudaMalloc(&s->ca.h, 8 * N) == cudaSuccess && cudaMalloc(&s->ca.prev_h, 8 * N) == cudaSuccess &&
-              cudaMalloc(&s->ca.dx_norm, 8 * N) == cudaSuccess && cudaMalloc(&s->ca.n_accept, 4 * N) == cudaSuccess &&
-              cudaMalloc(&s->ca.n_reject, 4 * N) == cudaSuccess && cudaMalloc(&s->ca.word, 4 * N) == cudaSuccess &&
-              cudaMalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) == cudaSuccess && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) == cudaSuccess;
+    bool ok = vo_dmalloc(&s->psi, nb) == cudaSuccess && vo_dmalloc(&s->psi0, nb) == cudaSuccess && vo_dmalloc(&s->gp, ngp) == cudaSuccess &&
+              vo_dmalloc(&s->ca.t, 8 * N) == cudaSuccess && vo_dmalloc(&s->ca.h, 8 * N) == cudaSuccess && vo_dmalloc(&s->ca.prev_h, 8 * N) == cudaSuccess &&
+              vo_dmalloc(&s->ca.dx_norm, 8 * N) == cudaSuccess && vo_dmalloc(&s->ca.n_accept, 4 * N) == cudaSuccess &&
+              vo_dmalloc(&s->ca.n_reject, 4 * N) == cudaSuccess && vo_dmalloc(&s->ca.word, 4 * N) == cudaSuccess &&
+              vo_dmalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) == cudaSuccess && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) == cudaSuccess;
     if (!ok) {
         vo_exp_destroy(s);
         return vo_fail(c, VO_ERR_ALLOC, "vo_exp_create: allocation failed");
@@ -512,12 +512,12 @@ int32_t vo_exp_destroy(vo_expsolver s) {
     if (!s) return VO_OK;
     DeviceGuard g(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->psi), cudaFree(s->psi0), cudaFree(s->gp);
-    cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm), cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
-    cudaFree(s->key_in), cudaFree(s->key_out), cudaFree(s->idx_in), cudaFree(s->idx_out), cudaFree(s->sort_tmp), cudaFree(s->tile_ctr);
-    cudaFree(s->ev_dev), cudaFreeHost(s->ev_host);
+    vo_dfree(s->psi), vo_dfree(s->psi0), vo_dfree(s->gp);
+    vo_dfree(s->ca.t), vo_dfree(s->ca.h), vo_dfree(s->ca.prev_h), vo_dfree(s->ca.dx_norm), vo_dfree(s->ca.n_accept), vo_dfree(s->ca.n_reject), vo_dfree(s->ca.word);
+    vo_dfree(s->key_in), vo_dfree(s->key_out), vo_dfree(s->idx_in), vo_dfree(s->idx_out), vo_dfree(s->sort_tmp), vo_dfree(s->tile_ctr);
+    vo_dfree(s->ev_dev), cudaFreeHost(s->ev_host);
     rtc_exp_unload(s->gen_module);
-    cudaFree(s->perm), cudaFree(s->stage);
+    vo_dfree(s->perm), vo_dfree(s->stage);
     delete s;
     return VO_OK;
 }
@@ -774,7 +774,7 @@ int32_t vo_exp_set_order(vo_expsolver s, const int64_t* perm, int64_t n) {
         if (perm[j] < 0 || perm[j] >= n || seen[(size_t)perm[j]]) return vo_fail(c, VO_ERR_BAD_ARG, "vo_exp_set_order: not a permutation");
         seen[(size_t)perm[j]] = 1;
     }
-    if (!s->perm && (cudaMalloc(&s->perm, 8 * (size_t)n) != cudaSuccess || cudaMalloc(&s->stage, sizeof(double2) * (size_t)n * s->sp->n) != cudaSuccess))
+    if (!s->perm && (vo_dmalloc(&s->perm, 8 * (size_t)n) != cudaSuccess || vo_dmalloc(&s->stage, sizeof(double2) * (size_t)n * s->sp->n) != cudaSuccess))
         return vo_fail(c, VO_ERR_ALLOC, "vo_exp_set_order: cudaMalloc failed");
     s->perm_host.assign(perm, perm + n);
     VO_CUDA(c, cudaMemcpyAsync(s->perm, perm, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));

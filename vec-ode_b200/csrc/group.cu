@@ -124,7 +124,7 @@ int32_t g_fail(vo_group g, int32_t code, const std::string& msg) {
 int32_t member_alloc(vo_group g) {
     for (Member& mb : g->m) {
         DeviceGuard dg(mb.ctx->device);
-        if (cudaMalloc(&mb.scratch, 256) != cudaSuccess || cudaMallocHost(&mb.pinned, 256) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group: scratch allocation failed");
+        if (vo_dmalloc(&mb.scratch, 256) != cudaSuccess || cudaMallocHost(&mb.pinned, 256) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group: scratch allocation failed");
     }
     return VO_OK;
 }
@@ -229,7 +229,7 @@ int32_t vo_group_destroy(vo_group g) {
         DeviceGuard dg(mb.ctx->device);
         cudaStreamSynchronize(mb.ctx->stream);
         if (mb.comm) g->nc->commDestroy(mb.comm);
-        cudaFree(mb.gbuf), cudaFree(mb.scratch), cudaFreeHost(mb.pinned);
+        vo_dfree(mb.gbuf), vo_dfree(mb.scratch), cudaFreeHost(mb.pinned);
     }
     delete g;
     return VO_OK;
@@ -272,8 +272,8 @@ int32_t vo_group_gather_device(vo_group g, const vo_ens* local, int64_t n_total,
         DeviceGuard dg(rm->ctx->device);
         if (rm->gbuf_elems < (size_t)(d * n_total)) {
             cudaStreamSynchronize(rm->ctx->stream);
-            cudaFree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
-            if (cudaMalloc(&rm->gbuf, sizeof(double) * d * n_total) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather: gather buffer");
+            vo_dfree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
+            if (vo_dmalloc(&rm->gbuf, sizeof(double) * d * n_total) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather: gather buffer");
             rm->gbuf_elems = (size_t)(d * n_total);
         }
     }
@@ -342,8 +342,8 @@ int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, co
         const size_t need = (size_t)(d * total) * (aos ? 2 : 1);  // second half: the AoS images
         if (rm->gbuf_elems < need) {
             cudaStreamSynchronize(rm->ctx->stream);
-            cudaFree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
-            if (cudaMalloc(&rm->gbuf, sizeof(double) * need) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather_placed: gather buffer");
+            vo_dfree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
+            if (vo_dmalloc(&rm->gbuf, sizeof(double) * need) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather_placed: gather buffer");
             rm->gbuf_elems = need;
         }
     }
@@ -425,8 +425,8 @@ int32_t vo_group_gather_interleaved(vo_group g, const vo_ens* local, int32_t roo
         const size_t need = (size_t)(d * total) * 2;
         if (rm->gbuf_elems < need) {
             cudaStreamSynchronize(rm->ctx->stream);
-            cudaFree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
-            if (cudaMalloc(&rm->gbuf, sizeof(double) * need) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather_interleaved: gather buffer");
+            vo_dfree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
+            if (vo_dmalloc(&rm->gbuf, sizeof(double) * need) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_gather_interleaved: gather buffer");
             rm->gbuf_elems = need;
         }
     }
@@ -502,8 +502,8 @@ int32_t vo_group_scatter(vo_group g, const double* host_in, int32_t layout, int6
         DeviceGuard dg(rm->ctx->device);
         if (rm->gbuf_elems < (size_t)(d * n_total)) {
             cudaStreamSynchronize(rm->ctx->stream);
-            cudaFree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
-            if (cudaMalloc(&rm->gbuf, sizeof(double) * d * n_total) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_scatter: staging buffer");
+            vo_dfree(rm->gbuf), rm->gbuf = nullptr, rm->gbuf_elems = 0;
+            if (vo_dmalloc(&rm->gbuf, sizeof(double) * d * n_total) != cudaSuccess) return g_fail(g, VO_ERR_ALLOC, "vo_group_scatter: staging buffer");
             rm->gbuf_elems = (size_t)(d * n_total);
         }
         vo_ens whole = nullptr;

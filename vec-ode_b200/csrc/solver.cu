@@ -271,16 +271,16 @@ int32_t alloc_ctl(vo_solver_s* s) {
     if (s->ca.t) return VO_OK;
     vo_ctx c = s->ctx;
     const size_t n = (size_t)s->n;
-    if (cudaMalloc(&s->ca.t, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.h, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.prev_h, 8 * n) != cudaSuccess ||
-        cudaMalloc(&s->ca.dx_norm, 8 * n) != cudaSuccess || cudaMalloc(&s->ca.n_accept, 4 * n) != cudaSuccess ||
-        cudaMalloc(&s->ca.n_reject, 4 * n) != cudaSuccess || cudaMalloc(&s->ca.word, 4 * n) != cudaSuccess)
+    if (vo_dmalloc(&s->ca.t, 8 * n) != cudaSuccess || vo_dmalloc(&s->ca.h, 8 * n) != cudaSuccess || vo_dmalloc(&s->ca.prev_h, 8 * n) != cudaSuccess ||
+        vo_dmalloc(&s->ca.dx_norm, 8 * n) != cudaSuccess || vo_dmalloc(&s->ca.n_accept, 4 * n) != cudaSuccess ||
+        vo_dmalloc(&s->ca.n_reject, 4 * n) != cudaSuccess || vo_dmalloc(&s->ca.word, 4 * n) != cudaSuccess)
         return vo_fail(c, VO_ERR_ALLOC, "solver: per-trajectory control allocation failed");
     return VO_OK;
 }
 
 void free_ctl(vo_solver_s* s) {
-    cudaFree(s->ca.t), cudaFree(s->ca.h), cudaFree(s->ca.prev_h), cudaFree(s->ca.dx_norm);
-    cudaFree(s->ca.n_accept), cudaFree(s->ca.n_reject), cudaFree(s->ca.word);
+    vo_dfree(s->ca.t), vo_dfree(s->ca.h), vo_dfree(s->ca.prev_h), vo_dfree(s->ca.dx_norm);
+    vo_dfree(s->ca.n_accept), vo_dfree(s->ca.n_reject), vo_dfree(s->ca.word);
     s->ca = CtlArrays{};
 }
 
@@ -348,9 +348,9 @@ int32_t ensure_blk(vo_solver_s* s) {
     const int64_t n_wtiles = ceil_div(s->n, VO_TILE_CTL) * (VO_TILE_CTL / VO_BLK_WT);
     if (!s->bv.base || s->bv.R != R || s->bv.n_wtiles != n_wtiles) {
         VO_CUDA(c, cudaStreamSynchronize(c->stream));
-        cudaFree(s->bv.base), s->bv = BlkView{};
+        vo_dfree(s->bv.base), s->bv = BlkView{};
         const uint32_t rb = blk_read_bytes(R);
-        if (cudaMalloc(&s->bv.base, (size_t)n_wtiles * (rb + 1024u)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "solver: tile-blocked state allocation failed");
+        if (vo_dmalloc(&s->bv.base, (size_t)n_wtiles * (rb + 1024u)) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "solver: tile-blocked state allocation failed");
         s->bv.n_wtiles = n_wtiles, s->bv.read_bytes = rb, s->bv.stride = rb + 1024u, s->bv.R = R;
     }
     blk_pack_kernel<<<(unsigned)ceil_div(n_wtiles * VO_BLK_WT, 256), 256, 0, c->stream>>>(s->bv, a);
@@ -742,7 +742,7 @@ int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
     if (s->d > 64 || s->rhs->kind == VO_RHS_HEAT1D || s->rhs->kind == VO_RHS_CUSTOM_STENCIL)
         return vo_fail(c, VO_ERR_UNSUPPORTED, "stage path: per-trajectory control needs a pointwise RHS with d <= 64");
     if (!s->evv) {
-        if (cudaMalloc(&s->evv, (size_t)s->n) != cudaSuccess || cudaMalloc(&s->dtv, 8 * (size_t)s->n) != cudaSuccess)
+        if (vo_dmalloc(&s->evv, (size_t)s->n) != cudaSuccess || vo_dmalloc(&s->dtv, 8 * (size_t)s->n) != cudaSuccess)
             return vo_fail(c, VO_ERR_ALLOC, "stage path: event buffers");
     }
     const CtlShared cs = make_ctl_shared(s, adaptive ? 1 : 0, 1);
@@ -757,7 +757,7 @@ int32_t stage_pertraj_event(vo_solver_s* s, bool adaptive, int* launches) {
     const double* xe = use_err(s) ? s->x_err->p : nullptr;
     const double* dxn_pre = nullptr;
     if (adaptive && xe && s->norm_kind == VO_NORM_CUSTOM) {
-        if (!s->dxn_pre && cudaMalloc(&s->dxn_pre, 8 * (size_t)s->n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "stage path: norm buffer");
+        if (!s->dxn_pre && vo_dmalloc(&s->dxn_pre, 8 * (size_t)s->n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "stage path: norm buffer");
         const int64_t before = c->launches;
         r = norm_custom_device(s->norm_fn, xe, s->d, s->n, 0, s->d, s->dxn_pre, s->norm_partial, PARTIAL_CAP, true);
         if (r != VO_OK) return r;
@@ -837,9 +837,9 @@ void finish_result(vo_solver_s* s, vo_step_result* res) {
 static int32_t alloc_snapshots(vo_solver s) {
     vo_ctx c = s->ctx;
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(s->snap), s->snap = nullptr;
+    vo_dfree(s->snap), s->snap = nullptr;
     const size_t bytes = sizeof(double) * s->t_list.size() * (size_t)s->d * (size_t)s->n;
-    if (cudaMalloc(&s->snap, bytes) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_enable_snapshots: cudaMalloc failed");
+    if (vo_dmalloc(&s->snap, bytes) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_enable_snapshots: cudaMalloc failed");
     VO_CUDA(c, cudaMemsetAsync(s->snap, 0, bytes, c->stream));
     return VO_OK;
 }
@@ -861,10 +861,10 @@ int32_t vo_rk_create(vo_ctx c, vo_tableau tableau, vo_rhs rhs, double t0, double
     int32_t r = vo_ens_clone(x0, &s->x);                      // ODEData::new clones x0 into x and next_x (ode.rs:141-150)
     if (r == VO_OK) r = vo_ens_clone(x0, &s->next_x);
     if (r == VO_OK && tableau->has_err) r = vo_ens_clone(x0, &s->x_err);  // Some(x0.clone()), rk.rs:249
-    if (r == VO_OK && cudaMalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: counters");
+    if (r == VO_OK && vo_dmalloc(&s->ev_dev, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: counters");
     if (r == VO_OK && cudaMallocHost(&s->ev_host, sizeof(EvSlot) * VO_EV_SLOTS) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: pinned counters");
-    if (r == VO_OK && cudaMalloc(&s->norm_partial, sizeof(double) * PARTIAL_CAP) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: norm scratch");
-    if (r == VO_OK && (cudaMalloc(&s->cst.flags, sizeof(uint32_t) * CHAIN_FLAGS) != cudaSuccess ||
+    if (r == VO_OK && vo_dmalloc(&s->norm_partial, sizeof(double) * PARTIAL_CAP) != cudaSuccess) r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: norm scratch");
+    if (r == VO_OK && (vo_dmalloc(&s->cst.flags, sizeof(uint32_t) * CHAIN_FLAGS) != cudaSuccess ||
                        cudaMemsetAsync(s->cst.flags, 0, sizeof(uint32_t) * CHAIN_FLAGS, c->stream) != cudaSuccess))
         r = vo_fail(c, VO_ERR_ALLOC, "vo_rk_create: chain flags");
     if (r == VO_OK) {
@@ -895,9 +895,9 @@ int32_t vo_solver_destroy(vo_solver s) {
     vo_ens_destroy(s->x), vo_ens_destroy(s->next_x), vo_ens_destroy(s->x_err);
     for (vo_ens k : s->K) vo_ens_destroy(k);
     free_ctl(s);
-    cudaFree(s->bv.base), cudaFree(s->evv), cudaFree(s->dtv), cudaFree(s->norm_partial), cudaFree(s->ev_dev), cudaFree(s->t_list_dev), cudaFree(s->cst.flags), cudaFree(s->snap);
+    vo_dfree(s->bv.base), vo_dfree(s->evv), vo_dfree(s->dtv), vo_dfree(s->norm_partial), vo_dfree(s->ev_dev), vo_dfree(s->t_list_dev), vo_dfree(s->cst.flags), vo_dfree(s->snap);
     cudaFreeHost(s->ev_host);
-    cudaFree(s->dxn_pre);
+    vo_dfree(s->dxn_pre);
     if (s->norm_rhs) custom_rhs_release(s->norm_rhs), delete s->norm_rhs;
     delete s;
     return VO_OK;
@@ -944,9 +944,9 @@ int32_t vo_solver_set_t_list(vo_solver s, const double* t_list, int32_t n) {
     DeviceGuard g(c->device);
     s->t_list.assign(t_list, t_list + n);
     VO_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(s->t_list_dev), s->t_list_dev = nullptr;
+    vo_dfree(s->t_list_dev), s->t_list_dev = nullptr;
     if (n > VO_INLINE_TLIST) {
-        if (cudaMalloc(&s->t_list_dev, sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_set_t_list: cudaMalloc");
+        if (vo_dmalloc(&s->t_list_dev, sizeof(double) * n) != cudaSuccess) return vo_fail(c, VO_ERR_ALLOC, "vo_solver_set_t_list: cudaMalloc");
         VO_CUDA(c, cudaMemcpy(s->t_list_dev, t_list, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
     if (s->snap) return alloc_snapshots(s);
