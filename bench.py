@@ -778,20 +778,30 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
     return out
 
 
-def blocking_sync(local):
-    """Make this process's synchronisations SLEEP instead of spin (CU_CTX_SCHED_BLOCKING_SYNC on the device's primary context, set before
-    anything initialises it). A rank's e2e pipeline runs four chunk threads that wait in stream synchronisations; with 4-8 ranks per box
-    that is 20-40 spinning threads on the box's 16 hardware threads, and some rank's last chunk is late in most solves.
-    A solve synchronises a handful of times per chunk, so the wake-up latency of a blocking wait costs next to nothing."""
+def HOST_SYNC_DEFAULT(world):
+    return "spin"
+
+
+def host_sync_policy(local, mode):
+    """How this process's synchronisations wait (flags of the device's primary context, set before anything initialises it):
+    "spin" = CUDA's default, "yield" = spin but give the hardware thread away between polls (CU_CTX_SCHED_YIELD), "blocking" = sleep on
+    an interrupt (CU_CTX_SCHED_BLOCKING_SYNC). A rank's e2e pipeline runs four chunk threads that wait in stream synchronisations; with
+    4-8 ranks per box that is 20-40 waiting threads on the box's 16 hardware threads, and some rank's last chunk is late in most solves
+    (DESIGN.md §6). Yielding keeps the wake-up latency of a spin when hardware threads are free and lets the threads that have launches
+    or copies to issue run when they are not; a blocking wait pays its wake-up latency at every upload, reset and read-back."""
     import ctypes
+    flag = {"yield": 2, "blocking": 4}.get(mode)
+    if flag is None:
+        return "spin (CUDA default)"
     try:
         cu = ctypes.CDLL("libcuda.so.1")
         dev = ctypes.c_int()
         if cu.cuInit(0) != 0 or cu.cuDeviceGet(ctypes.byref(dev), int(local)) != 0:
             return "spin (driver API unavailable)"
         fn = getattr(cu, "cuDevicePrimaryCtxSetFlags_v2", None) or cu.cuDevicePrimaryCtxSetFlags
-        rc = fn(dev, 4)  # CU_CTX_SCHED_BLOCKING_SYNC
-        return "blocking (CU_CTX_SCHED_BLOCKING_SYNC)" if rc == 0 else f"spin (cuDevicePrimaryCtxSetFlags -> {rc})"
+        rc = fn(dev, flag)
+        name = "yield (CU_CTX_SCHED_YIELD)" if flag == 2 else "blocking (CU_CTX_SCHED_BLOCKING_SYNC)"
+        return name if rc == 0 else f"spin (cuDevicePrimaryCtxSetFlags -> {rc})"
     except Exception as e:  # noqa: BLE001
         return f"spin ({e!r})"
 
@@ -858,9 +868,10 @@ def main():
     import torch.distributed as dist
     import vecode_b200 as vo
 
-    # experiment switch: measured 6.5 -> 7.8 ms per e2e solve at 2 GPUs (the wake-up latency of a blocking wait is paid at every upload, reset and
-    # read-back), so it stays off; whether it wins at 8 ranks per box, where 40 spinning chunk threads share 16 hardware threads, is unmeasured
-    host_sync = blocking_sync(local) if os.environ.get("VECODE_BENCH_BLOCKING_SYNC") == "1" else "spin (CUDA default)"
+    # VECODE_BENCH_HOST_SYNC = spin | yield | blocking (VECODE_BENCH_BLOCKING_SYNC=1: the older name of "blocking"). Blocking waits measured
+    # 6.5 -> 7.8 ms per e2e solve at 2 GPUs, so they stay an experiment switch.
+    sync_mode = os.environ.get("VECODE_BENCH_HOST_SYNC", "blocking" if os.environ.get("VECODE_BENCH_BLOCKING_SYNC") == "1" else HOST_SYNC_DEFAULT(world))
+    host_sync = host_sync_policy(local, sync_mode)
     torch.cuda.set_device(local)
     numa = numa_bind(torch, local) if world > 1 else None  # pinned buffers and copy threads next to this rank's GPU
     if world > 1:
