@@ -779,7 +779,10 @@ def multi_gpu_legs(vo, torch, dist, args, W, group, rank, world, local, barrier,
 
 
 def HOST_SYNC_DEFAULT(world):
-    return "spin"
+    """Several ranks per box share the host's hardware threads (8 ranks x 5 threads on 16): waits yield there. Measured on one GPU
+    (profiles/r02_host_sync.md): with all hardware threads free spin 6.46 / yield 6.48 / blocking 7.81 ms per e2e solve, pinned to two
+    hardware threads 6.73 / 6.49 / 7.25 ms."""
+    return "yield" if world > 1 else "spin"
 
 
 def host_sync_policy(local, mode):
