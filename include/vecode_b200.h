@@ -118,6 +118,15 @@ int32_t vo_lc_delta(vo_ens v, vo_ens y);                                /* lc.rs
 int32_t vo_lc_linear_combination(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n);
 /* Fused RK stage argument (rk.rs:121-124): v = (sum_j k_j v_j) * dt + x0, same operation order. */
 int32_t vo_lc_stage_combine(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n, double dt, vo_ens x0);
+/* LinearCombination<Complex<f64>, V> — the same trait with the scalar type of a complex vector space (src/impls/ndarray.rs:8-33 is
+ * generic over the element type; the exponential integrators' states and dense operators are such vectors). v, u, target: ensembles
+ * whose rows hold interleaved (re, im) pairs (n even), e.g. the view vo_exp_current_device hands out or the operator ensembles of vo_split_dense_*. Arithmetic as
+ * num-complex writes it (Mul: re = a.re b.re - a.im b.im, im = a.re b.im + a.im b.re), un-fused in strict mode. add_assign_ref and
+ * delta are vo_lc_add_assign_ref / vo_lc_delta unchanged. k_arr of the n-term reducer: [n][2] (re, im). */
+int32_t vo_lc_scale_z(vo_ens v, double k_re, double k_im);                                 /* lc.rs:10 */
+int32_t vo_lc_scalar_multiply_to_z(vo_ens v, double k_re, double k_im, vo_ens target);     /* lc.rs:12 */
+int32_t vo_lc_add_scalar_mul_z(vo_ens v, double k_re, double k_im, vo_ens u);              /* lc.rs:14 */
+int32_t vo_lc_linear_combination_z(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n);  /* lc.rs:20-54 */
 
 /* ---- Normed (src/base/ode.rs:9-11): per-trajectory norm over the d components ------------------ */
 #define VO_NORM_L2 0    /* sqrt(sum_c e_c^2), left-to-right for d <= 64, tree-reduced above that */

@@ -643,6 +643,31 @@ void orc_lc_linear_combination(double* v, const double* const* v_arr, const doub
     for (int j = 1; j < m; ++j) orc_lc_add_scalar_mul(v, k_arr[j], v_arr[j], n);
 }
 
+// The same primitives with A = num_complex::Complex<f64> (src/impls/ndarray.rs:8-33 is generic over the element type), vectors of nz
+// interleaved (re, im) pairs. num-complex 0.4 (third-party, not under /root/reference; restated from its published source):
+// Mul: (a.re b.re - a.im b.im, a.re b.im + a.im b.re); MulAssign: re = re k.re - im k.im, im = im k.re + re k.im; Add componentwise.
+static inline void zmul(double ar, double ai, double br, double bi, double* re, double* im) { *re = ar * br - ai * bi, *im = ar * bi + ai * br; }
+void orc_lcz_scale(double* v, double kr, double ki, int64_t nz) {
+    for (int64_t i = 0; i < nz; ++i) {  // *self *= k (MulAssign)
+        const double a = v[2 * i], re = v[2 * i] * kr - v[2 * i + 1] * ki, im = v[2 * i + 1] * kr + a * ki;
+        v[2 * i] = re, v[2 * i + 1] = im;
+    }
+}
+void orc_lcz_scalar_multiply_to(const double* v, double kr, double ki, double* t, int64_t nz) {
+    for (int64_t i = 0; i < nz; ++i) zmul(kr, ki, v[2 * i], v[2 * i + 1], &t[2 * i], &t[2 * i + 1]);  // *t = k * s
+}
+void orc_lcz_add_scalar_mul(double* v, double kr, double ki, const double* u, int64_t nz) {
+    for (int64_t i = 0; i < nz; ++i) {  // *y = *y + (k * *x)
+        double pr, pi;
+        zmul(kr, ki, u[2 * i], u[2 * i + 1], &pr, &pi);
+        v[2 * i] = v[2 * i] + pr, v[2 * i + 1] = v[2 * i + 1] + pi;
+    }
+}
+void orc_lcz_linear_combination(double* v, const double* const* v_arr, const double* k_arr, int32_t m, int64_t nz) {
+    orc_lcz_scalar_multiply_to(v_arr[0], k_arr[0], k_arr[1], v, nz);
+    for (int j = 1; j < m; ++j) orc_lcz_add_scalar_mul(v, k_arr[2 * j], k_arr[2 * j + 1], v_arr[j], nz);
+}
+
 // ---- exponential integrators on the shared-basis dense split ---------------------------------------
 // Generator family: L_i(t) = -i * (H_0 + sum_{m>=1} g_m(t; p_i) H_m), g_m(t) = amp_{i,m} * cos(omega_{i,m} t + phase_{i,m}).
 // Basis handed in as B_m = -i * H_m so coefficients are real; gp: [N][M-1][3] = (amp, omega, phase).

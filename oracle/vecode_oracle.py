@@ -131,6 +131,37 @@ def lc_linear_combination(v, v_arr, k_arr):
         lc_add_scalar_mul(v, k, vi)
 
 
+# --- the same with A = Complex<f64> (ndarray.rs:8-33 is generic over the element type): vectors of (re, im) tuples, k = (re, im).
+# num-complex 0.4 (third-party; restated): Mul = (a.re b.re - a.im b.im, a.re b.im + a.im b.re), MulAssign the same two sums.
+def _zmul(a, b):
+    return (a[0] * b[0] - a[1] * b[1], a[0] * b[1] + a[1] * b[0])
+
+
+def lcz_scale(v, k):
+    for i in range(len(v)):
+        re, im = v[i]
+        v[i] = (re * k[0] - im * k[1], im * k[0] + re * k[1])  # MulAssign
+
+
+def lcz_scalar_multiply_to(v, k, target):
+    for i in range(len(v)):
+        target[i] = _zmul(k, v[i])
+
+
+def lcz_add_scalar_mul(v, k, u):
+    for i in range(len(v)):
+        p = _zmul(k, u[i])
+        v[i] = (v[i][0] + p[0], v[i][1] + p[1])
+
+
+def lcz_linear_combination(v, v_arr, k_arr):
+    if not v_arr or not k_arr:
+        raise ValueError("linear_combination: slices cannot be empty")  # lc.rs:21-23
+    lcz_scalar_multiply_to(v_arr[0], k_arr[0], v)
+    for vi, k in zip(v_arr[1:], k_arr[1:]):
+        lcz_add_scalar_mul(v, k, vi)
+
+
 # --- rk_step: src/base/rk.rs:90-155 ------------------------------------------------------------------
 def rk_step(f, t, x0, xf, x_err, dt, ac, b, b_err, s, K):
     """Returns (xf, x_err) because the reference swaps the two buffers (rk.rs:142)."""

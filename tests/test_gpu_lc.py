@@ -118,3 +118,58 @@ def test_norm_large_state(vo, ctx):
     np.testing.assert_allclose(e.norm("L2")[0], np.sqrt(np.sum(a * a)), rtol=1e-13)
     assert e.norm("LINF")[0] == np.abs(a).max()
     np.testing.assert_allclose(e.norm("L1")[0], np.abs(a).sum(), rtol=1e-13)
+
+
+@pytest.mark.parametrize("d,n", [(1, 2), (1, 2002), (3, 4098), (1, 1 << 20), (2, 33334)])
+def test_complex_lc_primitives_bit_exact(vo, ctx, oracle, d, n):
+    """LinearCombination<Complex<f64>, V> (ndarray.rs:8-33 with complex elements): rows of interleaved (re, im) pairs, complex scalars,
+    num-complex's product written out; strict arithmetic must give the bits of the C++ restatement."""
+    LC = vo.ComplexLinearCombination
+    a, b, c3 = _rand((d, n), 11), _rand((d, n), 12), _rand((d, n), 13)
+    k = complex(0.7310585786300049, -1.2345678901234567)
+    lib = oracle.lib()
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    nz = C.c_int64(a.size // 2)
+    kr, ki = C.c_double(k.real), C.c_double(k.imag)
+
+    v = vo.Ensemble.from_host(ctx, a, layout="soa")
+    LC.scale(v, k)
+    ref = a.copy(); lib.orc_lcz_scale(P(ref), kr, ki, nz)
+    assert np.array_equal(v.to_host(layout="soa"), ref)
+    z = (a.reshape(-1, 2)[:, 0] + 1j * a.reshape(-1, 2)[:, 1]) * k  # numpy's own complex product as a sanity bound
+    assert np.allclose(ref.reshape(-1, 2)[:, 0] + 1j * ref.reshape(-1, 2)[:, 1], z, rtol=1e-15, atol=1e-15)
+
+    u = vo.Ensemble.from_host(ctx, b, layout="soa")
+    t = vo.Ensemble(ctx, d, n)
+    LC.scalar_multiply_to(u, k, t)
+    ref = np.empty_like(b); lib.orc_lcz_scalar_multiply_to(P(b), kr, ki, P(ref), nz)
+    assert np.array_equal(t.to_host(layout="soa"), ref)
+
+    v = vo.Ensemble.from_host(ctx, a, layout="soa")
+    LC.add_scalar_mul(v, k, u)
+    ref = a.copy(); lib.orc_lcz_add_scalar_mul(P(ref), kr, ki, P(b), nz)
+    assert np.array_equal(v.to_host(layout="soa"), ref)
+
+    # n-term reducer in one pass against the chain of the reference (lc.rs:20-35)
+    w = vo.Ensemble.from_host(ctx, c3, layout="soa")
+    ks = [k, complex(-0.25, 0.5), complex(0.0, 1.0)]
+    LC.linear_combination(t, [v, u, w], ks)
+    va = v.to_host(layout="soa")
+    ptrs = (C.c_void_p * 3)(P(va), P(b), P(c3))
+    kflat = np.array([[q.real, q.imag] for q in ks]).ravel()
+    ref = np.empty_like(a); lib.orc_lcz_linear_combination(P(ref), ptrs, P(kflat), 3, nz)
+    assert np.array_equal(t.to_host(layout="soa"), ref)
+
+    # fast arithmetic (FMA): same values to rounding
+    fast = vo.Context(0, arith="fast")
+    v = vo.Ensemble.from_host(fast, a, layout="soa")
+    LC.scale(v, k)
+    ref = a.copy(); lib.orc_lcz_scale(P(ref), kr, ki, nz)
+    assert np.allclose(v.to_host(layout="soa"), ref, rtol=0, atol=8e-16 * np.abs(a).max() * abs(k))
+    fast.close()
+
+
+def test_complex_lc_rejects_odd_rows(vo, ctx):
+    v = vo.Ensemble.from_host(ctx, np.ones((1, 3)), layout="soa")
+    with pytest.raises(Exception):
+        vo.ComplexLinearCombination.scale(v, 1j)

@@ -22,6 +22,16 @@ for arith in ("strict", "fast"):
         "linear_combination, 5 terms: 6 passes (the reference's chain: 14)": (6, lambda: LC.linear_combination(vs[6], vs[1:6], [0.1, 0.2, 0.3, 0.4, 0.5])),
         "stage_combine, 5 terms + x0: 7 passes": (7, lambda: LC.stage_combine(vs[6], vs[1:6], [0.1, 0.2, 0.3, 0.4, 0.5], 1e-3, vs[0])),
     }
+    if "--complex" in sys.argv:  # LinearCombination<Complex<f64>, V>: rows of interleaved (re, im) pairs (d = 1, n = D doubles = D/2 elements)
+        del vs
+        vs = [vo.Ensemble.wrap_tensor(ctx, torch.rand(1, D, device="cuda", dtype=torch.float64)) for _ in range(5)]
+        ZC = vo.ComplexLinearCombination
+        ops = {
+            "complex scale (v *= k): 2 passes": (2, lambda: ZC.scale(vs[0], 1.0000001 + 1e-9j)),
+            "complex scalar_multiply_to (t = k v): 2 passes": (2, lambda: ZC.scalar_multiply_to(vs[0], 0.5 - 0.25j, vs[1])),
+            "complex add_scalar_mul (v = v + k u): 3 passes": (3, lambda: ZC.add_scalar_mul(vs[0], 1e-9 + 1e-9j, vs[1])),
+            "complex linear_combination, 3 terms: 4 passes": (4, lambda: ZC.linear_combination(vs[4], vs[1:4], [0.1 + 0.2j, 0.3j, -0.5])),
+        }
     for name, (passes, fn) in ops.items():
         for _ in range(3):
             fn()

@@ -89,6 +89,10 @@ SIGNATURES = {
     "vo_lc_delta": (_i32, [_vp, _vp]),
     "vo_lc_linear_combination": (_i32, [_vp, _pvp, C.POINTER(_f64), _i32]),
     "vo_lc_stage_combine": (_i32, [_vp, _pvp, C.POINTER(_f64), _i32, _f64, _vp]),
+    "vo_lc_scale_z": (_i32, [_vp, _f64, _f64]),
+    "vo_lc_scalar_multiply_to_z": (_i32, [_vp, _f64, _f64, _vp]),
+    "vo_lc_add_scalar_mul_z": (_i32, [_vp, _f64, _f64, _vp]),
+    "vo_lc_linear_combination_z": (_i32, [_vp, _pvp, C.POINTER(_f64), _i32]),
     "vo_norm": (_i32, [_vp, _i32, _vp]),
     "vo_tableau_create": (_i32, [_vp, _vp, _vp, _i32, _pvp]),
     "vo_tableau_builtin": (_i32, [_i32, _pvp]),

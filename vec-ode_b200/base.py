@@ -208,6 +208,37 @@ class LinearCombination:
         check(lib().vo_lc_stage_combine(v._h, hs, ks, n, dt, x0._h), v.ctx._h)
 
 
+class ComplexLinearCombination:
+    """`LinearCombination<Complex<f64>, V>`: the same trait on vectors of interleaved (re, im) pairs with complex scalars (the element
+    type of src/impls/ndarray.rs:8-33 is generic). `add_assign_ref` / `delta` are the real ones."""
+
+    add_assign_ref = LinearCombination.add_assign_ref
+    delta = LinearCombination.delta
+
+    @staticmethod
+    def scale(v: Ensemble, k: complex):
+        k = complex(k)
+        check(lib().vo_lc_scale_z(v._h, k.real, k.imag), v.ctx._h)
+
+    @staticmethod
+    def scalar_multiply_to(v: Ensemble, k: complex, target: Ensemble):
+        k = complex(k)
+        check(lib().vo_lc_scalar_multiply_to_z(v._h, k.real, k.imag, target._h), v.ctx._h)
+
+    @staticmethod
+    def add_scalar_mul(v: Ensemble, k: complex, other: Ensemble):
+        k = complex(k)
+        check(lib().vo_lc_add_scalar_mul_z(v._h, k.real, k.imag, other._h), v.ctx._h)
+
+    @staticmethod
+    def linear_combination(v: Ensemble, v_arr: Sequence[Ensemble], k_arr: Sequence[complex]):
+        n = min(len(v_arr), len(k_arr))
+        hs = (C.c_void_p * max(n, 1))(*[e._h.value for e in v_arr[:n]])
+        flat = [c for k in k_arr[:n] for c in (complex(k).real, complex(k).imag)]
+        ks = (C.c_double * max(2 * n, 2))(*flat)
+        check(lib().vo_lc_linear_combination_z(v._h, hs, ks, n), v.ctx._h)
+
+
 class ButcherTableu:
     """src/base/rk.rs:22-78 (the reference's spelling). `ac` is s*s row-major with c_i ON the diagonal."""
 

@@ -152,6 +152,78 @@ int32_t lincomb_impl(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t
     return VO_OK;
 }
 
+// ---- complex scalars: LinearCombination<Complex<f64>, V> -------------------------------------------------------------------
+// src/impls/ndarray.rs:8-33 is generic over the element type A, and with A = num_complex::Complex<f64> the scalar k is complex too
+// (the states and operators of the exponential integrators are such vectors). Elements are stored interleaved (re, im), one
+// 16-byte vector per element. Arithmetic as num-complex 0.4 writes it: Mul is (a.re b.re - a.im b.im, a.re b.im + a.im b.re),
+// MulAssign is re = re k.re - im k.im, im = im k.re + re k.im (the same two sums; IEEE addition commutes), Add is componentwise.
+struct LcTermsZ {
+    const double2* v[VO_MAX_TERMS];
+    double2 k[VO_MAX_TERMS];
+    int n;
+};
+
+enum LcOpZ { ZOP_SCALE, ZOP_SMUL_TO, ZOP_AXPY };
+
+template <bool STRICT> __device__ __forceinline__ double2 zmul(double2 a, double2 b) {  // a * b
+    using A = Ar<STRICT>;
+    return make_double2(A::sub(A::mul(a.x, b.x), A::mul(a.y, b.y)), A::add(A::mul(a.x, b.y), A::mul(a.y, b.x)));
+}
+template <int OP, bool STRICT> __device__ __forceinline__ double2 lcz_apply(double2 v, double2 u, double2 k) {
+    using A = Ar<STRICT>;
+    if (OP == ZOP_SCALE) return zmul<STRICT>(v, k);  // *self *= k           ndarray.rs:15
+    const double2 p = zmul<STRICT>(k, u);            // k * s                ndarray.rs:19
+    if (OP == ZOP_SMUL_TO) return p;
+    return make_double2(A::add(v.x, p.x), A::add(v.y, p.y));  // *y = *y + (k * *x)   ndarray.rs:23
+}
+
+// nz complex elements; v in/out (write-only for ZOP_SMUL_TO), u in. Two 16-byte elements in flight per thread and iteration.
+template <int OP, bool STRICT>
+__global__ void __launch_bounds__(LC_THREADS) lcz_binary_kernel(double2* __restrict__ v, const double2* __restrict__ u, double2 k, int64_t nz) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + stride < nz; i += 2 * stride) {
+        double2 a0 = {0, 0}, a1 = {0, 0}, b0 = {0, 0}, b1 = {0, 0};
+        if (OP != ZOP_SMUL_TO) a0 = v[i], a1 = v[i + stride];
+        if (OP != ZOP_SCALE) b0 = u[i], b1 = u[i + stride];
+        v[i] = lcz_apply<OP, STRICT>(a0, b0, k), v[i + stride] = lcz_apply<OP, STRICT>(a1, b1, k);
+    }
+    for (; i < nz; i += stride) {
+        double2 a0 = {0, 0}, b0 = {0, 0};
+        if (OP != ZOP_SMUL_TO) a0 = v[i];
+        if (OP != ZOP_SCALE) b0 = u[i];
+        v[i] = lcz_apply<OP, STRICT>(a0, b0, k);
+    }
+}
+
+// v = k0*v0; v = v + (kj*vj) left to right (lc.rs:20-54), one pass
+template <bool STRICT> __global__ void __launch_bounds__(LC_THREADS) lcz_lincomb_kernel(double2* __restrict__ v, const __grid_constant__ LcTermsZ tm, int64_t nz) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nz; i += stride) {
+        double2 acc = zmul<STRICT>(tm.k[0], tm.v[0][i]);
+        for (int j = 1; j < tm.n; ++j) acc = lcz_apply<ZOP_AXPY, STRICT>(acc, tm.v[j][i], tm.k[j]);
+        v[i] = acc;
+    }
+}
+
+// a complex vector is any ensemble whose rows hold whole (re, im) pairs
+bool complex_ok(vo_ens e) { return e && e->n % 2 == 0; }
+
+template <int OP> int32_t launch_binary_z(vo_ens v, vo_ens u, double kr, double ki) {
+    vo_ctx c = v->ctx;
+    if (!complex_ok(v)) return vo_fail(c, VO_ERR_SHAPE, "complex LinearCombination: rows must hold whole (re, im) pairs (n even)");
+    DeviceGuard g(c->device);
+    const int64_t nz = v->elems() / 2;
+    const int grid = lc_grid(c, 2 * nz);
+    const double2 k = make_double2(kr, ki);
+    if (c->arith == VO_ARITH_STRICT)
+        lcz_binary_kernel<OP, true><<<grid, LC_THREADS, 0, c->stream>>>(reinterpret_cast<double2*>(v->p), u ? reinterpret_cast<const double2*>(u->p) : nullptr, k, nz);
+    else
+        lcz_binary_kernel<OP, false><<<grid, LC_THREADS, 0, c->stream>>>(reinterpret_cast<double2*>(v->p), u ? reinterpret_cast<const double2*>(u->p) : nullptr, k, nz);
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
+}
+
 // ---- norms -------------------------------------------------------------------------------------------
 __device__ __forceinline__ double norm_term(double e, int kind) { return kind == VO_NORM_L2 ? e * e : fabs(e); }
 __device__ __forceinline__ double norm_join(double a, double b, int kind) { return kind == VO_NORM_LINF ? fmax(a, b) : a + b; }
@@ -260,6 +332,40 @@ int32_t vo_lc_linear_combination(vo_ens v, const vo_ens* v_arr, const double* k_
 }
 int32_t vo_lc_stage_combine(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n, double dt, vo_ens x0) {
     return lincomb_impl(v, v_arr, k_arr, n, true, dt, x0);
+}
+
+int32_t vo_lc_scale_z(vo_ens v, double k_re, double k_im) {
+    if (!v) return VO_ERR_BAD_ARG;
+    return launch_binary_z<ZOP_SCALE>(v, nullptr, k_re, k_im);
+}
+int32_t vo_lc_scalar_multiply_to_z(vo_ens v, double k_re, double k_im, vo_ens target) {
+    if (!same_shape(v, target)) return vo_fail(v ? v->ctx : nullptr, VO_ERR_SHAPE, "scalar_multiply_to: shape mismatch");
+    return launch_binary_z<ZOP_SMUL_TO>(target, v, k_re, k_im);
+}
+int32_t vo_lc_add_scalar_mul_z(vo_ens v, double k_re, double k_im, vo_ens u) {
+    if (!same_shape(v, u)) return vo_fail(v ? v->ctx : nullptr, VO_ERR_SHAPE, "add_scalar_mul: shape mismatch");
+    return launch_binary_z<ZOP_AXPY>(v, u, k_re, k_im);
+}
+int32_t vo_lc_linear_combination_z(vo_ens v, const vo_ens* v_arr, const double* k_arr, int32_t n) {
+    if (!v) return VO_ERR_BAD_ARG;
+    vo_ctx c = v->ctx;
+    if (!v_arr || !k_arr || n <= 0) return vo_fail(c, VO_ERR_BAD_ARG, "linear_combination: slices cannot be empty");  // lc.rs:21-23
+    if (n > VO_MAX_TERMS) return vo_fail(c, VO_ERR_UNSUPPORTED, "linear_combination: more than VO_MAX_TERMS terms");
+    if (!complex_ok(v)) return vo_fail(c, VO_ERR_SHAPE, "complex LinearCombination: rows must hold whole (re, im) pairs (n even)");
+    LcTermsZ tm;
+    tm.n = n;
+    for (int j = 0; j < n; ++j) {
+        if (!same_shape(v, v_arr[j])) return vo_fail(c, VO_ERR_SHAPE, "linear_combination: operand shape mismatch");
+        if (v_arr[j]->p == v->p) return vo_fail(c, VO_ERR_BAD_ARG, "linear_combination: target aliases an operand");
+        tm.v[j] = reinterpret_cast<const double2*>(v_arr[j]->p), tm.k[j] = make_double2(k_arr[2 * j], k_arr[2 * j + 1]);
+    }
+    DeviceGuard g(c->device);
+    const int64_t nz = v->elems() / 2;
+    const int grid = lc_grid(c, 2 * nz);
+    if (c->arith == VO_ARITH_STRICT) lcz_lincomb_kernel<true><<<grid, LC_THREADS, 0, c->stream>>>(reinterpret_cast<double2*>(v->p), tm, nz);
+    else lcz_lincomb_kernel<false><<<grid, LC_THREADS, 0, c->stream>>>(reinterpret_cast<double2*>(v->p), tm, nz);
+    VO_CHECK_LAUNCH(c);
+    return VO_OK;
 }
 
 int32_t vo_norm(vo_ens e, int32_t kind, double* out_host) {
