@@ -59,7 +59,8 @@ bool nccl_load(Nccl** out, std::string& err) {
             if (n.h) break;
         }
         if (!n.h) {
-            why = std::string("NCCL is not available (dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?") + ")";
+            const char* de = dlerror();  // one call: dlerror() clears the message it returns
+            why = std::string("NCCL is not available (dlopen libnccl.so.2: ") + (de ? de : "?") + ")";
         } else {
             ok = true;
 #define VO_NCCL_SYM(field, sym)                                  \
@@ -120,6 +121,26 @@ int32_t g_fail(vo_group g, int32_t code, const std::string& msg) {
         ncclResult_t _r = (call);                                                                                         \
         if (_r != ncclSuccess) return g_fail((g), VO_ERR_NCCL, std::string(#call) + ": " + (g)->nc->getErrorString(_r)); \
     } while (0)
+
+// ncclGroupStart / ncclGroupEnd as a scope: an error return between the two must not leave the NCCL group open (every later NCCL call
+// of the process would be queued into it and never issued).
+struct GroupScope {
+    Nccl* nc = nullptr;
+    bool open = false;
+    ncclResult_t start(Nccl* n) {
+        nc = n;
+        const ncclResult_t r = nc->groupStart();
+        open = r == ncclSuccess;
+        return r;
+    }
+    ncclResult_t end() {
+        open = false;
+        return nc->groupEnd();
+    }
+    ~GroupScope() {
+        if (open) nc->groupEnd();
+    }
+};
 
 int32_t member_alloc(vo_group g) {
     for (Member& mb : g->m) {
@@ -277,7 +298,8 @@ int32_t vo_group_gather_device(vo_group g, const vo_ens* local, int64_t n_total,
             rm->gbuf_elems = (size_t)(d * n_total);
         }
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupStart());
+    GroupScope gs;
+    if (g->world > 1) VO_NCCL(g, gs.start(g->nc));
     for (size_t i = 0; i < g->m.size(); ++i) {
         Member& mb = g->m[i];
         DeviceGuard dg(mb.ctx->device);
@@ -302,7 +324,7 @@ int32_t vo_group_gather_device(vo_group g, const vo_ens* local, int64_t n_total,
                 VO_NCCL(g, g->nc->send(local[i]->p + c * (hi - lo), (size_t)(hi - lo), ncclDouble, root, mb.comm, mb.ctx->stream));
         }
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupEnd());
+    if (g->world > 1) VO_NCCL(g, gs.end());
     if (out) *out = nullptr;
     if (rm && out) return vo_ens_wrap(rm->ctx, rm->gbuf, d, n_total, out);
     return VO_OK;
@@ -347,7 +369,8 @@ int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, co
             rm->gbuf_elems = need;
         }
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupStart());
+    GroupScope gs;
+    if (g->world > 1) VO_NCCL(g, gs.start(g->nc));
     for (size_t i = 0; i < g->m.size(); ++i) {
         Member& mb = g->m[i];
         DeviceGuard dg(mb.ctx->device);
@@ -364,7 +387,7 @@ int32_t vo_group_gather_placed(vo_group g, const vo_ens* local, int32_t root, co
             VO_NCCL(g, g->nc->send(local[i]->p, (size_t)(d * n_i), ncclDouble, root, mb.comm, mb.ctx->stream));
         }
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupEnd());
+    if (g->world > 1) VO_NCCL(g, gs.end());
     if (rm) {
         DeviceGuard dg(rm->ctx->device);
         cudaStream_t st = rm->ctx->stream;
@@ -430,7 +453,8 @@ int32_t vo_group_gather_interleaved(vo_group g, const vo_ens* local, int32_t roo
             rm->gbuf_elems = need;
         }
     }
-    if (G > 1) VO_NCCL(g, g->nc->groupStart());
+    GroupScope gs;
+    if (G > 1) VO_NCCL(g, gs.start(g->nc));
     for (size_t i = 0; i < g->m.size(); ++i) {
         Member& mb = g->m[i];
         DeviceGuard dg(mb.ctx->device);
@@ -447,7 +471,7 @@ int32_t vo_group_gather_interleaved(vo_group g, const vo_ens* local, int32_t roo
             VO_NCCL(g, g->nc->send(local[i]->p, (size_t)(d * n_i), ncclDouble, root, mb.comm, mb.ctx->stream));
         }
     }
-    if (G > 1) VO_NCCL(g, g->nc->groupEnd());
+    if (G > 1) VO_NCCL(g, gs.end());
     if (rm && tot > 0) {
         DeviceGuard dg(rm->ctx->device);
         cudaStream_t st = rm->ctx->stream;
@@ -512,7 +536,8 @@ int32_t vo_group_scatter(vo_group g, const double* host_in, int32_t layout, int6
         vo_ens_destroy(whole);
         if (rc != VO_OK) return rc;
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupStart());
+    GroupScope gs;
+    if (g->world > 1) VO_NCCL(g, gs.start(g->nc));
     for (size_t i = 0; i < g->m.size(); ++i) {
         Member& mb = g->m[i];
         DeviceGuard dg(mb.ctx->device);
@@ -537,7 +562,7 @@ int32_t vo_group_scatter(vo_group g, const double* host_in, int32_t layout, int6
                 VO_NCCL(g, g->nc->recv(local_out[i]->p + c * (hi - lo), (size_t)(hi - lo), ncclDouble, root, mb.comm, mb.ctx->stream));
         }
     }
-    if (g->world > 1) VO_NCCL(g, g->nc->groupEnd());
+    if (g->world > 1) VO_NCCL(g, gs.end());
     for (Member& mb : g->m) {
         DeviceGuard dg(mb.ctx->device);
         cudaError_t e = cudaStreamSynchronize(mb.ctx->stream);
@@ -557,12 +582,13 @@ int32_t vo_group_allreduce(vo_group g, double* host_inout /* [members][n] */, in
         std::memcpy(mb.pinned, host_inout + i * n, sizeof(double) * n);
         cudaMemcpyAsync(mb.scratch, mb.pinned, sizeof(double) * n, cudaMemcpyHostToDevice, mb.ctx->stream);
     }
-    VO_NCCL(g, g->nc->groupStart());
+    GroupScope gs;
+    VO_NCCL(g, gs.start(g->nc));
     for (Member& mb : g->m) {
         DeviceGuard dg(mb.ctx->device);
         VO_NCCL(g, g->nc->allReduce(mb.scratch, mb.scratch, (size_t)n, ncclDouble, op == 0 ? ncclSum : op == 1 ? ncclMax : ncclMin, mb.comm, mb.ctx->stream));
     }
-    VO_NCCL(g, g->nc->groupEnd());
+    VO_NCCL(g, gs.end());
     for (size_t i = 0; i < nm; ++i) {
         Member& mb = g->m[i];
         DeviceGuard dg(mb.ctx->device);
@@ -586,13 +612,14 @@ int32_t vo_group_reduce_stats(vo_group g, const vo_solver* local, vo_group_stats
         if (rc != VO_OK) return rc;
     }
     if (g->world > 1) {
-        VO_NCCL(g, g->nc->groupStart());
+        GroupScope gs;
+        VO_NCCL(g, gs.start(g->nc));
         for (Member& mb : g->m) {
             DeviceGuard dg(mb.ctx->device);
             VO_NCCL(g, g->nc->allReduce(mb.scratch, mb.scratch, 6, ncclUint64, ncclSum, mb.comm, mb.ctx->stream));
             VO_NCCL(g, g->nc->allReduce((char*)mb.scratch + 64, (char*)mb.scratch + 64, 2, ncclDouble, ncclMax, mb.comm, mb.ctx->stream));
         }
-        VO_NCCL(g, g->nc->groupEnd());
+        VO_NCCL(g, gs.end());
     }
     Member& m0 = g->m[0];
     DeviceGuard dg(m0.ctx->device);
