@@ -71,3 +71,32 @@ def test_bench_taylor_plan_matches_the_oracles_plan():
     thetas = np.array([1e-9, 1e-3, 0.05, 0.3, 0.477, 0.999, 1.0, 1.0001, 1.7, 2.0, 3.3, 6.02, 11.5])
     want = [np.prod(eo.BasisSplit.plan(float(t))) for t in thetas]
     assert list(bench._plan_terms(thetas)) == [float(w) for w in want]
+
+
+def test_odestep_mirror_and_check_step():
+    """ODEStep<T> (src/base/ode.rs:41-77) and check_step (ode.rs:389-399) on the host: the enum's helpers behave as the reference's, and
+    check_step agrees with the oracle's restatement on its edge cases (zero remainder, remainder below / above dt, negative micro-step)."""
+    import math
+    import vecode_b200 as vo
+    from oracle import vecode_oracle as po
+    s = vo.ODEStep.Step(0.25)
+    assert s.kind == "Step" and s.unwrap_dt() == 0.25 and s.unwrap_dt_or(1.0) == 0.25
+    seen = []
+    assert s.map_dt(seen.append) is s and seen == [0.25]                       # Ok(_) keeps the step
+
+    def fail(dt):
+        raise vo.ODEError("rhs failed")
+    e = s.map_dt(fail)
+    assert e.kind == "Err" and e.err.msg == "rhs failed"                       # Err(e) => ODEStep::Err(e)
+    for other in (vo.ODEStep.Chkpt, vo.ODEStep.Reject, vo.ODEStep.End):
+        assert other.map_dt(fail) is other and other.unwrap_dt_or(3.0) == 3.0  # every other variant passes through
+        try:
+            other.unwrap_dt()
+            assert False
+        except RuntimeError as ex:
+            assert "expected Step(T)" in str(ex)
+    eps = 2.220446049250313e-16
+    cases = [(0.0, 1.0, 0.1), (0.95, 1.0, 0.1), (1.0, 1.0, 0.1), (1.0 - eps / 2, 1.0, 0.1), (1.0 + 1e-12, 1.0, 0.1), (0.0, 1e-300, 0.1),
+             (3.0, 3.0 + 4 * eps, 1.0), (math.pi, 10.0, 7.0)]
+    for t0, tf, dt in cases:
+        assert vo.check_step(t0, tf, dt) == po.check_step(t0, tf, dt), (t0, tf, dt)

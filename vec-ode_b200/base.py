@@ -399,6 +399,50 @@ class ODEError(Exception):
     msg: str
 
 
+@dataclass(frozen=True)
+class ODEStep:
+    """`enum ODEStep<T>` (src/base/ode.rs:41-77) for ONE trajectory: kind in 'Step' | 'Chkpt' | 'Reject' | 'End' | 'Err', with the step
+    size for 'Step' and the error for 'Err'. The device keeps one of these per trajectory in its status word; the host mirror is for
+    callers that drive `try_step` themselves (rk.rs:287-293) or port code written against the enum."""
+    kind: str
+    dt: Optional[float] = None
+    err: Optional["ODEError"] = None
+
+    @staticmethod
+    def Step(dt: float) -> "ODEStep":
+        return ODEStep("Step", float(dt))
+
+    def map_dt(self, f) -> "ODEStep":
+        """ode.rs:53-61: run `f(dt)` on a Step; an ODEError it raises (Rust: returns) turns the step into Err, anything else passes."""
+        if self.kind != "Step":
+            return self
+        try:
+            f(self.dt)
+        except ODEError as e:
+            return ODEStep("Err", None, e)
+        return self
+
+    def unwrap_dt(self) -> float:  # ode.rs:63-68
+        if self.kind != "Step":
+            raise RuntimeError("ODEStep::unwrap_dt expected Step(T) in enum")
+        return self.dt
+
+    def unwrap_dt_or(self, dt2: float) -> float:  # ode.rs:70-75
+        return self.dt if self.kind == "Step" else dt2
+
+
+ODEStep.Chkpt, ODEStep.Reject, ODEStep.End = ODEStep("Chkpt"), ODEStep("Reject"), ODEStep("End")
+
+
+def check_step(t0: float, tf: float, dt: float) -> Optional[float]:
+    """src/base/ode.rs:389-399: None when tf - t0 is zero to `relative_eq` (approx 0.5: equal, or |rem| <= 2^-52), else the remainder if
+    it is shorter than dt, else dt — the rule the kernels apply per trajectory (rk_small.cuh: ctl_lane)."""
+    rem = tf - t0
+    if rem == 0.0 or abs(rem) <= 2.220446049250313e-16:
+        return None
+    return rem if rem < dt else dt
+
+
 @dataclass
 class ODEState:
     """kind: 'Ok' while any trajectory still steps, 'Done' when all have emitted End, 'Err'. `counts` holds how many
@@ -539,6 +583,13 @@ class RK45Solver:
         tmin, tmax, h = C.c_double(), C.c_double(), _vp()
         check(lib().vo_current(self._h, C.byref(tmin), C.byref(tmax), C.byref(h)), self.ctx._h)
         return (tmin.value, tmax.value), Ensemble(self.ctx, self.d, self.n, _handle=h, _owner=self)
+
+    def into_current(self):  # ode.rs:219-221: the state by value — a copy the solver no longer owns
+        (t_min, t_max), x = self.current()
+        return (t_min, t_max), x.clone()
+
+    def validate_adaptive(self) -> None:  # ode.rs:263-265: the reference's default accepts every configuration
+        return None
 
     def stats(self) -> dict:
         n = self.n
