@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: synthetic workload generators, sharding, the import shim."""
 import numpy as np
+import pytest
 
 from oracle import vecode_oracle as po
 
@@ -100,3 +101,69 @@ def test_odestep_mirror_and_check_step():
              (3.0, 3.0 + 4 * eps, 1.0), (math.pi, 10.0, 7.0)]
     for t0, tf, dt in cases:
         assert vo.check_step(t0, tf, dt) == po.check_step(t0, tf, dt), (t0, tf, dt)
+
+
+@pytest.mark.parametrize("interleave", [False, True])
+def test_sharded_chunk_plan_tiles_the_ensemble(vo, monkeypatch, interleave):
+    """pipeline.ShardedChunkedSolve's plan (which local trajectories form chunk q on rank r, and where the root places them) for ragged
+    ensemble sizes, every rank of 1..8 and 1..5 chunks, with the device objects replaced by stand-ins: every rank derives the SAME gather
+    arguments for a chunk, the per-rank counts match what the gather entry points expect (vo_group_gather_placed: rows[rank];
+    vo_group_gather_interleaved: ceil((tot - rank) / G)), and the chunks tile [0, n_total) exactly once."""
+    from vecode_b200 import pipeline
+    from vecode_b200.workloads import shard_range
+
+    class FakeCtx:
+        device = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+    class FakeEns:
+        def __init__(self, ctx, d, n):
+            self.d, self.n = d, n
+
+    class FakeGroup:
+        def __init__(self, rank, world):
+            self.ctxs, self.ranks, self.world = [FakeCtx()], [rank], world
+
+    monkeypatch.setattr(pipeline, "Context", FakeCtx)
+    monkeypatch.setattr(pipeline, "Ensemble", FakeEns)
+    for n_total in (1, 7, 64, 1000, 1001, 12345):
+        for G in (1, 2, 3, 4, 8):
+            for parts in (1, 2, 4, 5):
+                made = {}
+                plans = []
+                for r in range(G):
+                    sc = pipeline.ShardedChunkedSolve(FakeGroup(r, G), n_total, 2, lambda ctx, lo, hi, x0, r=r: made.setdefault((r, lo, hi), x0.n), parts=parts,
+                                                      interleave=interleave)
+                    plans.append(sc)
+                    sc.pool.shutdown()
+                    # this rank's chunks tile its shard in order
+                    edges = [(lo, hi) for lo, hi, _ in sc.plan]
+                    full = [e for e in edges if e[1] > e[0]]  # (an empty chunk of the round-robin plan carries no meaningful offset)
+                    assert (not full and sc.n_local == 0) or (full[0][0] == 0 and full[-1][1] == sc.n_local and all(a[1] == b[0] for a, b in zip(full, full[1:]))), \
+                        (n_total, G, parts, r, edges)
+                    assert sum(hi - lo for lo, hi in edges) == sc.n_local
+                    for (lo, hi), ch in zip(edges, sc.chunks):
+                        assert (ch is None) == (hi <= lo) and (ch is None or (ch[0], ch[1], ch[3].n) == (lo, hi, hi - lo))
+                covered = np.zeros(n_total, dtype=np.int64)
+                for q in range(parts):
+                    args = [p.plan[q][2] for p in plans]
+                    assert all(a == args[0] for a in args)  # a collective: same arguments on every rank
+                    if interleave:
+                        tot, row0 = args[0]
+                        assert 0 <= row0 and row0 + tot <= n_total
+                        covered[row0:row0 + tot] += 1
+                        for r, p in enumerate(plans):
+                            lo, hi, _ = p.plan[q]
+                            assert hi - lo == max(0, -(-(tot - r) // G))           # what vo_group_gather_interleaved expects from rank r
+                            assert tot == 0 or hi == lo or row0 == lo * G           # local index i of rank r is trajectory r + G i
+                    else:
+                        rows, off = args[0]
+                        for r, p in enumerate(plans):
+                            lo, hi, _ = p.plan[q]
+                            slo, shi = shard_range(n_total, r, G)
+                            assert rows[r] == hi - lo and (rows[r] == 0 or off[r] == slo + lo) and off[r] + rows[r] <= n_total
+                            covered[off[r]:off[r] + rows[r]] += 1
+                assert np.all(covered == 1), (n_total, G, parts, interleave)
+                assert sum(p.n_local for p in plans) == n_total

@@ -98,7 +98,8 @@ class ShardedChunkedSolve:
             n0 = -(-n_total // G)  # rank 0's count, the largest: chunk boundaries in units of G consecutive trajectories
             for q in range(parts):
                 lo, hi = chunk_range(n0, q, parts)
-                row0, tot = lo * G, max(0, min(hi * G, n_total) - lo * G)
+                row0 = min(lo * G, n_total)  # (an empty trailing chunk of a tiny ensemble must still name a row inside the host array)
+                tot = max(0, min(hi * G, n_total) - row0)
                 mine = max(0, -(-(tot - r) // G))
                 self.plan.append((lo, lo + mine, (tot, row0)))
         else:
