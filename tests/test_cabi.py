@@ -135,3 +135,33 @@ def test_header_is_plain_c(tmp_path):
                         "-lvecode_b200", f"-Wl,-rpath,{so_dir}", "-Wl,-rpath-link,/usr/local/cuda/lib64"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([exe]).returncode == 0  # vo_version needs no GPU
+
+
+def test_builtin_cfm_tables_of_the_library_equal_the_oracles():
+    """vo_cfm_builtin_table needs no GPU: the literals of src/dat/mod.rs:4, 67-80 as the LIBRARY holds them (csrc/exp.cu) are those of the
+    oracle's restatement (oracle/exp_oracle.py), bit for bit — the tables the CFM kernels are driven by."""
+    import numpy as np
+    import vecode_b200 as vo
+    from oracle import exp_oracle as eo
+    assert np.array_equal(vo.cfm_table("C_GAUSS_LEGENDRE_4")[0], eo.C_GAUSS_LEGENDRE_4)
+    assert np.array_equal(vo.cfm_table("CFM_R2_J1_GL"), eo.CFM_R2_J1_GL)
+    assert np.array_equal(vo.cfm_table("CFM_R4_J2_GL"), eo.CFM_R4_J2_GL)
+    assert np.array_equal(vo.cfm_table("BLANES17_R4_J4"), eo.BLANES17_R4_J4)
+
+
+def test_guard_switch_is_read_from_the_environment_without_a_gpu():
+    """vo_guard_enabled / vo_guard_check (the library's own bounds check) touch no device while nothing is allocated: off by default, on
+    with VECODE_GUARD=1 in the environment of the process that loads the library."""
+    import ctypes as C
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); from vecode_b200 import _cabi; l = _cabi.lib(); n = C.c_int64(-1); "
+            "print(l.vo_guard_enabled(), l.vo_guard_check(C.byref(n)), n.value)" % ROOT)
+    for env_val, want in (("", "0 0 0"), ("1", "1 0 0"), ("0", "0 0 0")):
+        env = dict(os.environ)
+        env.pop("VECODE_GUARD", None)
+        if env_val:
+            env["VECODE_GUARD"] = env_val
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0 and r.stdout.split() == want.split(), (env_val, r.stdout, r.stderr)
